@@ -1,0 +1,549 @@
+/* TEST INFRASTRUCTURE ONLY — see vpic_oracle.h.  CPU restatement of the
+ * reference hot path (scalar pipelines), one function per reference routine,
+ * citing the reference file:line it follows.  Built with -ffp-contract=off. */
+#include "vpic_oracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define VOX(x, y, z) ((x) + (nx + 2) * ((y) + (ny + 2) * (z)))   /* grid.h:136 */
+
+/* interpolator member offsets (sf_interface.h:62-74) */
+enum { I_EX = 0, I_DEXDY, I_DEXDZ, I_D2EXDYDZ, I_EY, I_DEYDZ, I_DEYDX, I_D2EYDZDX,
+       I_EZ, I_DEZDX, I_DEZDY, I_D2EZDXDY, I_CBX, I_DCBXDX, I_CBY, I_DCBYDY, I_CBZ, I_DCBZDZ };
+/* field_t member offsets in floats (field_advance.h:152-160) */
+enum { F_EX = 0, F_EY, F_EZ, F_DIVE, F_CBX, F_CBY, F_CBZ, F_DIVB,
+       F_TCAX, F_TCAY, F_TCAZ, F_RHOB, F_JFX, F_JFY, F_JFZ, F_RHOF, F_STRIDE = 20 };
+
+/* ------------------------------------------------------------------------ */
+/* move_p, scalar variant: move_p.cc:216-378                                 */
+
+int vpo_move_p(vpo_particle_t *p0, vpo_mover_t *pm, float *accum, int32_t accum_stride,
+               const int64_t *neighbor, int64_t rangel, int64_t rangeh, float qsp) {
+  float s_midx, s_midy, s_midz, s_dispx, s_dispy, s_dispz, s_dir[3];
+  float v0, v1, v2, v3, v4, v5, q;
+  int axis, face;
+  int64_t nb;
+  float *a;
+  vpo_particle_t *p = p0 + pm->i;
+
+  q = qsp * p->w;                                                   /* :233 */
+  for (;;) {
+    s_midx = p->dx; s_midy = p->dy; s_midz = p->dz;
+    s_dispx = pm->dispx; s_dispy = pm->dispy; s_dispz = pm->dispz;
+
+    s_dir[0] = (s_dispx > 0.0f) ? 1.0f : -1.0f;                     /* :245-247 */
+    s_dir[1] = (s_dispy > 0.0f) ? 1.0f : -1.0f;
+    s_dir[2] = (s_dispz > 0.0f) ? 1.0f : -1.0f;
+
+    v0 = (s_dispx == 0.0f) ? 3.4e38f : (s_dir[0] - s_midx) / s_dispx;   /* :251-253 */
+    v1 = (s_dispy == 0.0f) ? 3.4e38f : (s_dir[1] - s_midy) / s_dispy;
+    v2 = (s_dispz == 0.0f) ? 3.4e38f : (s_dir[2] - s_midz) / s_dispz;
+
+    v3 = 2.0f; axis = 3;                                             /* :262-266 */
+    if (v0 < v3) { v3 = v0; axis = 0; }
+    if (v1 < v3) { v3 = v1; axis = 1; }
+    if (v2 < v3) { v3 = v2; axis = 2; }
+    v3 *= 0.5f;
+
+    s_dispx *= v3; s_dispy *= v3; s_dispz *= v3;                     /* :269-275 */
+    s_midx += s_dispx; s_midy += s_dispy; s_midz += s_dispz;
+
+    /* :280 — the 1/3 is a double constant: one double multiply, then back to float */
+    v5 = (float)((double)(q * s_dispx * s_dispy * s_dispz) * (1.0 / 3.0));
+
+    a = accum + (size_t)p->i * accum_stride;
+#   define ACC(sd, mY, mZ)                                            \
+    v4 = q * (sd); v1 = v4 * (mY); v0 = v4 - v1; v1 += v4;            \
+    v4 = 1 + (mZ); v2 = v0 * v4; v3 = v1 * v4;                        \
+    v4 = 1 - (mZ); v0 *= v4; v1 *= v4;                                \
+    v0 += v5; v1 -= v5; v2 -= v5; v3 += v5;                           \
+    a[0] += v0; a[1] += v1; a[2] += v2; a[3] += v3
+    ACC(s_dispx, s_midy, s_midz); a += 4;                            /* :284-305 */
+    ACC(s_dispy, s_midz, s_midx); a += 4;
+    ACC(s_dispz, s_midx, s_midy);
+#   undef ACC
+
+    pm->dispx -= s_dispx; pm->dispy -= s_dispy; pm->dispz -= s_dispz;   /* :310-312 */
+    p->dx += s_dispx + s_dispx;                                      /* :315-317 */
+    p->dy += s_dispy + s_dispy;
+    p->dz += s_dispz + s_dispz;
+
+    if (axis == 3) break;                                            /* :323 */
+
+    v0 = s_dir[axis];
+    (&p->dx)[axis] = v0;                                             /* :337 exactly on the face */
+    face = axis;
+    if (v0 > 0.0f) face += 3;
+    nb = neighbor[6 * (int64_t)p->i + face];                         /* :347 */
+
+    if (nb == -1) {                                                  /* reflect_particles :349-358 */
+      (&p->ux)[axis] = -(&p->ux)[axis];
+      (&pm->dispx)[axis] = -(&pm->dispx)[axis];
+      continue;
+    }
+    if (nb < rangel || nb > rangeh) {                                /* :360-369 */
+      p->i = 8 * p->i + face;
+      return 1;
+    }
+    p->i = (int32_t)(nb - rangel);                                   /* :374-376 */
+    (&p->dx)[axis] = -v0;
+  }
+  return 0;
+}
+
+/* ------------------------------------------------------------------------ */
+/* advance_p_pipeline_scalar: advance_p_pipeline.cc:20-245 (one pipeline, one accumulator block) */
+
+int32_t vpo_advance_p(const vpo_push_args_t *A, int32_t *n_ignored) {
+  const float qdt_2mc = A->qdt_2mc, cdt_dx = A->cdt_dx, cdt_dy = A->cdt_dy, cdt_dz = A->cdt_dz, qsp = A->qsp;
+  const float one = 1.0, one_third = 1.0 / 3.0, two_fifteenths = 2.0 / 15.0;   /* :39-42 */
+  float dx, dy, dz, ux, uy, uz, q, hax, hay, haz, cbx, cby, cbz, v0, v1, v2, v3, v4, v5;
+  int32_t ii, nm = 0, ign = 0;
+  vpo_particle_t *p = A->p;
+  vpo_mover_t local_pm[1];
+
+  for (int32_t n = 0; n < A->np; n++, p++) {
+    dx = p->dx; dy = p->dy; dz = p->dz; ii = p->i;                  /* :91-94 */
+    const float *f = A->interp + (size_t)ii * A->interp_stride;
+
+    hax = qdt_2mc * ((f[I_EX] + dy * f[I_DEXDY]) + dz * (f[I_DEXDZ] + dy * f[I_D2EXDYDZ]));   /* :98-105 */
+    hay = qdt_2mc * ((f[I_EY] + dz * f[I_DEYDZ]) + dx * (f[I_DEYDX] + dz * f[I_D2EYDZDX]));
+    haz = qdt_2mc * ((f[I_EZ] + dx * f[I_DEZDX]) + dy * (f[I_DEZDY] + dx * f[I_D2EZDXDY]));
+    cbx = f[I_CBX] + dx * f[I_DCBXDX];                               /* :107-109 */
+    cby = f[I_CBY] + dy * f[I_DCBYDY];
+    cbz = f[I_CBZ] + dz * f[I_DCBZDZ];
+
+    ux = p->ux; uy = p->uy; uz = p->uz; q = p->w;
+    ux += hax; uy += hay; uz += haz;                                 /* :116-118 */
+
+    v0 = qdt_2mc / sqrtf(one + (ux * ux + (uy * uy + uz * uz)));     /* :120 */
+    v1 = cbx * cbx + (cby * cby + cbz * cbz);                        /* :123-127 */
+    v2 = (v0 * v0) * v1;
+    v3 = v0 * (one + v2 * (one_third + v2 * two_fifteenths));
+    v4 = v3 / (one + v1 * (v3 * v3));
+    v4 += v4;
+    v0 = ux + v3 * (uy * cbz - uz * cby);                            /* :129-131 */
+    v1 = uy + v3 * (uz * cbx - ux * cbz);
+    v2 = uz + v3 * (ux * cby - uy * cbx);
+    ux += v4 * (v1 * cbz - v2 * cby);                                /* :133-135 */
+    uy += v4 * (v2 * cbx - v0 * cbz);
+    uz += v4 * (v0 * cby - v1 * cbx);
+    ux += hax; uy += hay; uz += haz;                                 /* :137-139 */
+    p->ux = ux; p->uy = uy; p->uz = uz;                              /* :141-143 */
+
+    v0 = one / sqrtf(one + (ux * ux + (uy * uy + uz * uz)));         /* :145 */
+    ux *= cdt_dx; uy *= cdt_dy; uz *= cdt_dz;
+    ux *= v0; uy *= v0; uz *= v0;
+    v0 = dx + ux; v1 = dy + uy; v2 = dz + uz;                        /* :156-158 */
+    v3 = v0 + ux; v4 = v1 + uy; v5 = v2 + uz;                        /* :160-162 */
+
+    if (v3 <= one && v4 <= one && v5 <= one && -v3 <= one && -v4 <= one && -v5 <= one) {   /* :165-166 */
+      q *= qsp;
+      p->dx = v3; p->dy = v4; p->dz = v5;
+      dx = v0; dy = v1; dz = v2;
+      v5 = q * ux * uy * uz * one_third;                             /* :183 */
+      float *a = A->accum + (size_t)ii * A->accum_stride;
+#     define ACCUMULATE_J(uX, dY, dZ, off)                            \
+      v4 = q * (uX); v1 = v4 * (dY); v0 = v4 - v1; v1 += v4;          \
+      v4 = one + (dZ); v2 = v0 * v4; v3 = v1 * v4;                    \
+      v4 = one - (dZ); v0 *= v4; v1 *= v4;                            \
+      v0 += v5; v1 -= v5; v2 -= v5; v3 += v5;                         \
+      a[off + 0] += v0; a[off + 1] += v1; a[off + 2] += v2; a[off + 3] += v3
+      ACCUMULATE_J(ux, dy, dz, 0);                                   /* :187-208 */
+      ACCUMULATE_J(uy, dz, dx, 4);
+      ACCUMULATE_J(uz, dx, dy, 8);
+#     undef ACCUMULATE_J
+    } else {                                                         /* :213-238 */
+      local_pm->dispx = ux; local_pm->dispy = uy; local_pm->dispz = uz;
+      local_pm->i = (int32_t)(p - A->p);
+      if (vpo_move_p(A->p, local_pm, A->accum, A->accum_stride, A->neighbor, A->rangel, A->rangeh, qsp)) {
+        if (nm < A->max_nm) A->pm[nm++] = local_pm[0];
+        else { ign++; p->i = p->i >> 3; }
+      }
+    }
+  }
+  if (n_ignored) *n_ignored = ign;
+  return nm;
+}
+
+/* ------------------------------------------------------------------------ */
+/* sort_p_pipeline, single-subsort branch: sort_p_pipeline.cc:142-214,345-370.
+ * The multi-threaded branch is two stable passes, so the result is the same
+ * stable counting sort for any thread count. */
+
+void vpo_sort_p(vpo_particle_t *p, int32_t np, vpo_particle_t *aux, int32_t *partition,
+                int32_t nx, int32_t ny, int32_t nz) {
+  const int32_t nv = (nx + 2) * (ny + 2) * (nz + 2);
+  const int32_t vl = VOX(1, 1, 1), vh = VOX(nx, ny, nz);
+  int32_t *next = (int32_t *)calloc((size_t)nv + 1, sizeof(int32_t));
+  int32_t sum = 0, v, i;
+  for (i = 0; i < np; i++) next[p[i].i]++;                           /* :178-181 */
+  for (v = vl; v < vh + 1; v++) {                                    /* :184-191 */
+    int32_t count = next[v];
+    next[v] = sum; partition[v] = sum; sum += count;
+  }
+  partition[vh + 1] = sum;                                           /* :193 */
+  for (i = 0; i < np; i++) aux[next[p[i].i]++] = p[i];               /* :196-212 */
+  for (v = 0; v < vl; v++) partition[v] = 0;                         /* :357 */
+  for (v = vh + 1; v < nv; v++) partition[v] = np;                   /* :359-362 */
+  memcpy(p, aux, (size_t)np * sizeof *p);                            /* :369 */
+  free(next);
+}
+
+/* ------------------------------------------------------------------------ */
+/* load_interpolator_pipeline_scalar: interpolator_array_pipeline.cc:21-135 */
+
+void vpo_load_interpolator(float *interp, int32_t is, const float *fld, int32_t nx, int32_t ny, int32_t nz) {
+  const float fourth = 0.25, half = 0.50;
+  for (int z = 1; z <= nz; z++) for (int y = 1; y <= ny; y++) for (int x = 1; x <= nx; x++) {
+    float *pi = interp + (size_t)VOX(x, y, z) * is;
+    const float *pf0 = fld + (size_t)VOX(x, y, z) * F_STRIDE;
+    const float *pfx = fld + (size_t)VOX(x + 1, y, z) * F_STRIDE;
+    const float *pfy = fld + (size_t)VOX(x, y + 1, z) * F_STRIDE;
+    const float *pfz = fld + (size_t)VOX(x, y, z + 1) * F_STRIDE;
+    const float *pfyz = fld + (size_t)VOX(x, y + 1, z + 1) * F_STRIDE;
+    const float *pfzx = fld + (size_t)VOX(x + 1, y, z + 1) * F_STRIDE;
+    const float *pfxy = fld + (size_t)VOX(x + 1, y + 1, z) * F_STRIDE;
+    float w0, w1, w2, w3;
+    w0 = pf0[F_EX]; w1 = pfy[F_EX]; w2 = pfz[F_EX]; w3 = pfyz[F_EX];              /* :67-79 */
+    pi[I_EX] = fourth * ((w3 + w0) + (w1 + w2));
+    pi[I_DEXDY] = fourth * ((w3 - w0) + (w1 - w2));
+    pi[I_DEXDZ] = fourth * ((w3 - w0) - (w1 - w2));
+    pi[I_D2EXDYDZ] = fourth * ((w3 + w0) - (w1 + w2));
+    w0 = pf0[F_EY]; w1 = pfz[F_EY]; w2 = pfx[F_EY]; w3 = pfzx[F_EY];              /* :82-90 */
+    pi[I_EY] = fourth * ((w3 + w0) + (w1 + w2));
+    pi[I_DEYDZ] = fourth * ((w3 - w0) + (w1 - w2));
+    pi[I_DEYDX] = fourth * ((w3 - w0) - (w1 - w2));
+    pi[I_D2EYDZDX] = fourth * ((w3 + w0) - (w1 + w2));
+    w0 = pf0[F_EZ]; w1 = pfx[F_EZ]; w2 = pfy[F_EZ]; w3 = pfxy[F_EZ];              /* :93-101 */
+    pi[I_EZ] = fourth * ((w3 + w0) + (w1 + w2));
+    pi[I_DEZDX] = fourth * ((w3 - w0) + (w1 - w2));
+    pi[I_DEZDY] = fourth * ((w3 - w0) - (w1 - w2));
+    pi[I_D2EZDXDY] = fourth * ((w3 + w0) - (w1 + w2));
+    w0 = pf0[F_CBX]; w1 = pfx[F_CBX]; pi[I_CBX] = half * (w1 + w0); pi[I_DCBXDX] = half * (w1 - w0);   /* :104-121 */
+    w0 = pf0[F_CBY]; w1 = pfy[F_CBY]; pi[I_CBY] = half * (w1 + w0); pi[I_DCBYDY] = half * (w1 - w0);
+    w0 = pf0[F_CBZ]; w1 = pfz[F_CBZ]; pi[I_CBZ] = half * (w1 + w0); pi[I_DCBZDZ] = half * (w1 - w0);
+  }
+}
+
+/* ------------------------------------------------------------------------ */
+/* clear_accumulator_array_pipeline (block 0): clear_array_pipeline.cc:40-67 */
+
+void vpo_clear_accumulator(float *accum, int32_t as, int32_t nx, int32_t ny, int32_t nz) {
+  int32_t i0 = (VOX(1, 1, 1) / 2) * 2;
+  int32_t na = (((VOX(nx, ny, nz) - i0 + 1) + 1) / 2) * 2;
+  memset(accum + (size_t)i0 * as, 0, (size_t)na * as * sizeof(float));
+}
+
+/* unload_accumulator_pipeline_scalar: unload_accumulator_pipeline.cc:18-82; coefficients :137-139 */
+
+void vpo_unload_accumulator(float *fld, const float *accum, int32_t as, int32_t nx, int32_t ny, int32_t nz,
+                            float rdx, float rdy, float rdz, float dt) {
+  const float cx = 0.25 * rdy * rdz / dt;   /* double 0.25 * float ... evaluated in double, stored to float */
+  const float cy = 0.25 * rdz * rdx / dt;
+  const float cz = 0.25 * rdx * rdy / dt;
+  for (int z = 1; z <= nz + 1; z++) for (int y = 1; y <= ny + 1; y++) for (int x = 1; x <= nx + 1; x++) {
+    float *f0 = fld + (size_t)VOX(x, y, z) * F_STRIDE;
+    const float *a0 = accum + (size_t)VOX(x, y, z) * as;
+    const float *ax = accum + (size_t)VOX(x - 1, y, z) * as;
+    const float *ay = accum + (size_t)VOX(x, y - 1, z) * as;
+    const float *az = accum + (size_t)VOX(x, y, z - 1) * as;
+    const float *ayz = accum + (size_t)VOX(x, y - 1, z - 1) * as;
+    const float *azx = accum + (size_t)VOX(x - 1, y, z - 1) * as;
+    const float *axy = accum + (size_t)VOX(x - 1, y - 1, z) * as;
+    f0[F_JFX] += cx * (a0[0] + ay[1] + az[2] + ayz[3]);              /* :65-67 */
+    f0[F_JFY] += cy * (a0[4] + az[5] + ax[6] + azx[7]);
+    f0[F_JFZ] += cz * (a0[8] + ax[9] + ay[10] + axy[11]);
+  }
+}
+
+/* ------------------------------------------------------------------------ */
+/* energy_p: energy_p_pipeline.cc:18-115 (single pipeline order, no cross-rank sum) */
+
+double vpo_energy_p(const vpo_particle_t *p, int32_t np, const float *interp, int32_t is,
+                    float q, float m, float dt, float cvac) {
+  const float qdt_2mc = (q * dt) / (2 * m * cvac);                  /* :98 */
+  const float msp = m, one = 1.0;
+  double en = 0.0;
+  for (int32_t n = 0; n < np; n++) {
+    float dx = p[n].dx, dy = p[n].dy, dz = p[n].dz, v0, v1, v2;
+    const float *f = interp + (size_t)p[n].i * is;
+    v0 = p[n].ux + qdt_2mc * ((f[I_EX] + dy * f[I_DEXDY]) + dz * (f[I_DEXDZ] + dy * f[I_D2EXDYDZ]));
+    v1 = p[n].uy + qdt_2mc * ((f[I_EY] + dz * f[I_DEYDZ]) + dx * (f[I_DEYDX] + dz * f[I_D2EYDZDX]));
+    v2 = p[n].uz + qdt_2mc * ((f[I_EZ] + dx * f[I_DEZDX]) + dy * (f[I_DEZDY] + dx * f[I_D2EZDXDY]));
+    v0 = v0 * v0 + v1 * v1 + v2 * v2;                                /* :62 */
+    v0 = (msp * p[n].w) * (v0 / (one + sqrtf(one + v0)));            /* :64 */
+    en += (double)v0;
+  }
+  return en * ((double)cvac * (double)cvac);
+}
+
+/* center_p / uncenter_p scalar pipelines: center_p_pipeline.cc:17-96, uncenter_p_pipeline.cc:17-98 */
+
+void vpo_center_p(vpo_particle_t *p, int32_t np, const float *interp, int32_t is, float qdt_2mc) {
+  const float qdt_4mc = 0.5 * qdt_2mc, one = 1.0, one_third = 1.0 / 3.0, two_fifteenths = 2.0 / 15.0;
+  for (int32_t n = 0; n < np; n++, p++) {
+    float dx = p->dx, dy = p->dy, dz = p->dz, hax, hay, haz, cbx, cby, cbz, ux, uy, uz, v0, v1, v2, v3, v4;
+    const float *f = interp + (size_t)p->i * is;
+    hax = qdt_2mc * ((f[I_EX] + dy * f[I_DEXDY]) + dz * (f[I_DEXDZ] + dy * f[I_D2EXDYDZ]));
+    hay = qdt_2mc * ((f[I_EY] + dz * f[I_DEYDZ]) + dx * (f[I_DEYDX] + dz * f[I_D2EYDZDX]));
+    haz = qdt_2mc * ((f[I_EZ] + dx * f[I_DEZDX]) + dy * (f[I_DEZDY] + dx * f[I_D2EZDXDY]));
+    cbx = f[I_CBX] + dx * f[I_DCBXDX]; cby = f[I_CBY] + dy * f[I_DCBYDY]; cbz = f[I_CBZ] + dz * f[I_DCBZDZ];
+    ux = p->ux; uy = p->uy; uz = p->uz;
+    ux += hax; uy += hay; uz += haz;
+    v0 = qdt_4mc / (float)sqrt(one + (ux * ux + (uy * uy + uz * uz)));   /* double sqrt of a float expr */
+    v1 = cbx * cbx + (cby * cby + cbz * cbz);
+    v2 = (v0 * v0) * v1;
+    v3 = v0 * (one + v2 * (one_third + v2 * two_fifteenths));
+    v4 = v3 / (one + v1 * (v3 * v3)); v4 += v4;
+    v0 = ux + v3 * (uy * cbz - uz * cby);
+    v1 = uy + v3 * (uz * cbx - ux * cbz);
+    v2 = uz + v3 * (ux * cby - uy * cbx);
+    ux += v4 * (v1 * cbz - v2 * cby);
+    uy += v4 * (v2 * cbx - v0 * cbz);
+    uz += v4 * (v0 * cby - v1 * cbx);
+    p->ux = ux; p->uy = uy; p->uz = uz;
+  }
+}
+
+void vpo_uncenter_p(vpo_particle_t *p, int32_t np, const float *interp, int32_t is, float qdt_2mc_in) {
+  const float qdt_2mc = -qdt_2mc_in;            /* uncenter_p_pipeline.cc: caller passes -q dt/2mc ... see .cc:120 */
+  const float qdt_4mc = 0.5 * qdt_2mc, one = 1.0, one_third = 1.0 / 3.0, two_fifteenths = 2.0 / 15.0;
+  for (int32_t n = 0; n < np; n++, p++) {
+    float dx = p->dx, dy = p->dy, dz = p->dz, hax, hay, haz, cbx, cby, cbz, ux, uy, uz, v0, v1, v2, v3, v4;
+    const float *f = interp + (size_t)p->i * is;
+    hax = qdt_2mc * ((f[I_EX] + dy * f[I_DEXDY]) + dz * (f[I_DEXDZ] + dy * f[I_D2EXDYDZ]));
+    hay = qdt_2mc * ((f[I_EY] + dz * f[I_DEYDZ]) + dx * (f[I_DEYDX] + dz * f[I_D2EYDZDX]));
+    haz = qdt_2mc * ((f[I_EZ] + dx * f[I_DEZDX]) + dy * (f[I_DEZDY] + dx * f[I_D2EZDXDY]));
+    cbx = f[I_CBX] + dx * f[I_DCBXDX]; cby = f[I_CBY] + dy * f[I_DCBYDY]; cbz = f[I_CBZ] + dz * f[I_DCBZDZ];
+    ux = p->ux; uy = p->uy; uz = p->uz;
+    v0 = qdt_4mc / (float)sqrt(one + (ux * ux + (uy * uy + uz * uz)));
+    v1 = cbx * cbx + (cby * cby + cbz * cbz);
+    v2 = (v0 * v0) * v1;
+    v3 = v0 * (one + v2 * (one_third + v2 * two_fifteenths));
+    v4 = v3 / (one + v1 * (v3 * v3)); v4 += v4;
+    v0 = ux + v3 * (uy * cbz - uz * cby);
+    v1 = uy + v3 * (uz * cbx - ux * cbz);
+    v2 = uz + v3 * (ux * cby - uy * cbx);
+    ux += v4 * (v1 * cbz - v2 * cby);
+    uy += v4 * (v2 * cbx - v0 * cbz);
+    uz += v4 * (v0 * cby - v1 * cbx);
+    ux += hax; uy += hay; uz += haz;
+    p->ux = ux; p->uy = uy; p->uz = uz;
+  }
+}
+
+/* ======================================================================== */
+/* Standard field advance, vacuum material, single local domain.            */
+
+typedef struct { int n[3]; int s[3]; } dims_t;   /* n = cells per axis, s = voxel stride per axis */
+
+static dims_t mkdims(const vpo_field_args_t *a) {
+  dims_t d; d.n[0] = a->nx; d.n[1] = a->ny; d.n[2] = a->nz;
+  d.s[0] = 1; d.s[1] = a->nx + 2; d.s[2] = (a->nx + 2) * (a->ny + 2);
+  return d;
+}
+static float axis_d(const vpo_field_args_t *a, int X) { return X == 0 ? a->dx : X == 1 ? a->dy : a->dz; }
+static float axis_rd(const vpo_field_args_t *a, int X) { return X == 0 ? a->rdx : X == 1 ? a->rdy : a->rdz; }
+
+/* Loop over plane X=xp with Y in [yl,yh], Z in [zl,zh] (cyclic axis naming as in local.cc/remote.cc macros:
+ * the reference's XYZ_LOOP always iterates z outer, y middle, x inner in *physical* axes; message packing
+ * order therefore depends on the physical order, reproduced here). */
+#define PLANE_LOOP(X, xp, Y, yl, yh, Z, zl, zh, body) do {                                   \
+    int lo_[3], hi_[3], c_[3];                                                               \
+    lo_[X] = hi_[X] = (xp); lo_[Y] = (yl); hi_[Y] = (yh); lo_[Z] = (zl); hi_[Z] = (zh);      \
+    for (c_[2] = lo_[2]; c_[2] <= hi_[2]; c_[2]++)                                           \
+      for (c_[1] = lo_[1]; c_[1] <= hi_[1]; c_[1]++)                                         \
+        for (c_[0] = lo_[0]; c_[0] <= hi_[0]; c_[0]++) {                                     \
+          int v = c_[0] * d.s[0] + c_[1] * d.s[1] + c_[2] * d.s[2]; (void)v; body; } } while (0)
+
+void vpo_clear_jf(const vpo_field_args_t *a) {                       /* sfa.cc:231-237 */
+  int nv = (a->nx + 2) * (a->ny + 2) * (a->nz + 2);
+  for (int v = 0; v < nv; v++) { float *f = a->f + (size_t)v * F_STRIDE; f[F_JFX] = 0; f[F_JFY] = 0; f[F_JFZ] = 0; }
+}
+
+/* advance_b: advance_b_pipeline.cc:20-125, stencil advance_b_pipeline.h:26-28,57-59; local_adjust_norm_b local.cc:268-297 */
+void vpo_advance_b(const vpo_field_args_t *a, float frac) {
+  const int nx = a->nx, ny = a->ny, nz = a->nz;
+  const float px = (nx > 1) ? frac * a->cvac * a->dt * a->rdx : 0;
+  const float py = (ny > 1) ? frac * a->cvac * a->dt * a->rdy : 0;
+  const float pz = (nz > 1) ? frac * a->cvac * a->dt * a->rdz : 0;
+  float *F = a->f;
+# define FF(x, y, z, m) F[(size_t)VOX(x, y, z) * F_STRIDE + (m)]
+  for (int z = 1; z <= nz + 1; z++) for (int y = 1; y <= ny + 1; y++) for (int x = 1; x <= nx + 1; x++) {
+    if (y <= ny && z <= nz)
+      FF(x, y, z, F_CBX) -= (py * (FF(x, y + 1, z, F_EZ) - FF(x, y, z, F_EZ)) - pz * (FF(x, y, z + 1, F_EY) - FF(x, y, z, F_EY)));
+    if (z <= nz && x <= nx)
+      FF(x, y, z, F_CBY) -= (pz * (FF(x, y, z + 1, F_EX) - FF(x, y, z, F_EX)) - px * (FF(x + 1, y, z, F_EZ) - FF(x, y, z, F_EZ)));
+    if (x <= nx && y <= ny)
+      FF(x, y, z, F_CBZ) -= (px * (FF(x + 1, y, z, F_EY) - FF(x, y, z, F_EY)) - py * (FF(x, y + 1, z, F_EX) - FF(x, y, z, F_EX)));
+  }
+  /* local_adjust_norm_b: only symmetric_fields (-2) zeroes the normal B on the face */
+  dims_t d = mkdims(a);
+  for (int fc = 0; fc < 6; fc++) {
+    if (a->bc6[fc] != -2) continue;
+    int X = fc % 3, Y = (X + 1) % 3, Z = (X + 2) % 3, face = fc < 3 ? 1 : d.n[X] + 1;
+    PLANE_LOOP(X, face, Y, 1, d.n[Y], Z, 1, d.n[Z], F[(size_t)v * F_STRIDE + F_CBX + X] = 0);
+  }
+# undef FF
+}
+
+/* Tangential-B ghosts: begin/end_remote_ghost_tang_b (remote.cc:61-134) for faces that are periodic onto this
+ * same domain, local_ghost_tang_b (local.cc:50-130) for pec / symmetric / pmc faces. */
+static void ghost_tang_b(const vpo_field_args_t *a) {
+  dims_t d = mkdims(a);
+  float *F = a->f;
+  float *msg[6] = {0};
+  /* pack ("send") first for every periodic face, as the reference does before any ghost is written */
+  for (int fc = 0; fc < 6; fc++) {
+    if (a->bc6[fc] < 0) continue;
+    int X = fc % 3, Y = (X + 1) % 3, Z = (X + 2) % 3, face = fc < 3 ? 1 : d.n[X];
+    float *p = msg[fc] = (float *)malloc(sizeof(float) * (size_t)(1 + d.n[Y] * (d.n[Z] + 1) + d.n[Z] * (d.n[Y] + 1)));
+    *p++ = axis_d(a, X);
+    PLANE_LOOP(X, face, Y, 1, d.n[Y] + 1, Z, 1, d.n[Z], *p++ = F[(size_t)v * F_STRIDE + F_CBX + Y]);   /* ZY edge loop: cbY */
+    PLANE_LOOP(X, face, Y, 1, d.n[Y], Z, 1, d.n[Z] + 1, *p++ = F[(size_t)v * F_STRIDE + F_CBX + Z]);   /* YZ edge loop: cbZ */
+  }
+  /* local boundary conditions */
+  for (int fc = 0; fc < 6; fc++) {
+    int bc = a->bc6[fc];
+    if (bc >= 0) continue;
+    int X = fc % 3, Y = (X + 1) % 3, Z = (X + 2) % 3;
+    int ghost = fc < 3 ? 0 : d.n[X] + 1, step = fc < 3 ? d.s[X] : -d.s[X];   /* f(x-i) = one cell inward */
+    float sgn = (bc == -1) ? 1.0f : -1.0f;                          /* pec copies, symmetric/pmc negate */
+    if (bc != -1 && bc != -2 && bc != -3) abort();                  /* absorbing not restated yet */
+    PLANE_LOOP(X, ghost, Y, 1, d.n[Y] + 1, Z, 1, d.n[Z],
+               F[(size_t)v * F_STRIDE + F_CBX + Y] = (sgn > 0) ? F[(size_t)(v + step) * F_STRIDE + F_CBX + Y] : -F[(size_t)(v + step) * F_STRIDE + F_CBX + Y]);
+    PLANE_LOOP(X, ghost, Y, 1, d.n[Y], Z, 1, d.n[Z] + 1,
+               F[(size_t)v * F_STRIDE + F_CBX + Z] = (sgn > 0) ? F[(size_t)(v + step) * F_STRIDE + F_CBX + Z] : -F[(size_t)(v + step) * F_STRIDE + F_CBX + Z]);
+  }
+  /* unpack ("recv"): the message sent out of port fc lands in the opposite ghost plane */
+  for (int fc = 0; fc < 6; fc++) {
+    if (!msg[fc]) continue;
+    int X = fc % 3, Y = (X + 1) % 3, Z = (X + 2) % 3;
+    int ghost = fc < 3 ? d.n[X] + 1 : 0, step = fc < 3 ? -d.s[X] : d.s[X];   /* field(x+i) with i = sender port dir */
+    float *p = msg[fc];
+    float lw = *p++, dX = axis_d(a, X);
+    float rw = (2. * dX) / (lw + dX);
+    lw = (lw - dX) / (lw + dX);
+    PLANE_LOOP(X, ghost, Y, 1, d.n[Y] + 1, Z, 1, d.n[Z],
+               F[(size_t)v * F_STRIDE + F_CBX + Y] = rw * (*p++) + lw * F[(size_t)(v + step) * F_STRIDE + F_CBX + Y]);
+    PLANE_LOOP(X, ghost, Y, 1, d.n[Y], Z, 1, d.n[Z] + 1,
+               F[(size_t)v * F_STRIDE + F_CBX + Z] = rw * (*p++) + lw * F[(size_t)(v + step) * F_STRIDE + F_CBX + Z]);
+    free(msg[fc]);
+  }
+}
+
+/* vacuum_advance_e: vacuum_advance_e_pipeline.cc:20-332, stencil .h:18-69; local_adjust_tang_e local.cc:224-265 */
+void vpo_vacuum_advance_e(const vpo_field_args_t *a, float frac) {
+  if (frac != 1) abort();                                           /* .cc:58-61 */
+  const int nx = a->nx, ny = a->ny, nz = a->nz;
+  const float damp = a->damp;
+  /* single vacuum material: decay=1, drive=1/eps=1, rmu=1 (sfa.cc:119-136 with eps=mu=1, sigma=0) */
+  const float decayx = 1, drivex = 1, decayy = 1, drivey = 1, decayz = 1, drivez = 1, rmux = 1, rmuy = 1, rmuz = 1;
+  const float px_muz = ((nx > 1) ? (1 + damp) * a->cvac * a->dt * a->rdx : 0) * rmuz;
+  const float px_muy = ((nx > 1) ? (1 + damp) * a->cvac * a->dt * a->rdx : 0) * rmuy;
+  const float py_mux = ((ny > 1) ? (1 + damp) * a->cvac * a->dt * a->rdy : 0) * rmux;
+  const float py_muz = ((ny > 1) ? (1 + damp) * a->cvac * a->dt * a->rdy : 0) * rmuz;
+  const float pz_muy = ((nz > 1) ? (1 + damp) * a->cvac * a->dt * a->rdz : 0) * rmuy;
+  const float pz_mux = ((nz > 1) ? (1 + damp) * a->cvac * a->dt * a->rdz : 0) * rmux;
+  const float cj = a->dt / a->eps0;
+  float *F = a->f;
+
+  ghost_tang_b(a);
+
+# define FF(x, y, z, m) F[(size_t)VOX(x, y, z) * F_STRIDE + (m)]
+  for (int z = 1; z <= nz + 1; z++) for (int y = 1; y <= ny + 1; y++) for (int x = 1; x <= nx + 1; x++) {
+    if (x <= nx) {
+      FF(x, y, z, F_TCAX) = (py_muz * (FF(x, y, z, F_CBZ) - FF(x, y - 1, z, F_CBZ)) -
+                             pz_muy * (FF(x, y, z, F_CBY) - FF(x, y, z - 1, F_CBY))) - damp * FF(x, y, z, F_TCAX);
+      FF(x, y, z, F_EX) = decayx * FF(x, y, z, F_EX) + drivex * (FF(x, y, z, F_TCAX) - cj * FF(x, y, z, F_JFX));
+    }
+    if (y <= ny) {
+      FF(x, y, z, F_TCAY) = (pz_mux * (FF(x, y, z, F_CBX) - FF(x, y, z - 1, F_CBX)) -
+                             px_muz * (FF(x, y, z, F_CBZ) - FF(x - 1, y, z, F_CBZ))) - damp * FF(x, y, z, F_TCAY);
+      FF(x, y, z, F_EY) = decayy * FF(x, y, z, F_EY) + drivey * (FF(x, y, z, F_TCAY) - cj * FF(x, y, z, F_JFY));
+    }
+    if (z <= nz) {
+      FF(x, y, z, F_TCAZ) = (px_muy * (FF(x, y, z, F_CBY) - FF(x - 1, y, z, F_CBY)) -
+                             py_mux * (FF(x, y, z, F_CBX) - FF(x, y - 1, z, F_CBX))) - damp * FF(x, y, z, F_TCAZ);
+      FF(x, y, z, F_EZ) = decayz * FF(x, y, z, F_EZ) + drivez * (FF(x, y, z, F_TCAZ) - cj * FF(x, y, z, F_JFZ));
+    }
+  }
+# undef FF
+  /* local_adjust_tang_e: pec zeroes tangential e and tca on the face */
+  dims_t d = mkdims(a);
+  for (int fc = 0; fc < 6; fc++) {
+    if (a->bc6[fc] != -1) continue;
+    int X = fc % 3, Y = (X + 1) % 3, Z = (X + 2) % 3, face = fc < 3 ? 1 : d.n[X] + 1;
+    PLANE_LOOP(X, face, Y, 1, d.n[Y], Z, 1, d.n[Z] + 1, (F[(size_t)v * F_STRIDE + F_EX + Y] = 0, F[(size_t)v * F_STRIDE + F_TCAX + Y] = 0));
+    PLANE_LOOP(X, face, Y, 1, d.n[Y] + 1, Z, 1, d.n[Z], (F[(size_t)v * F_STRIDE + F_EX + Z] = 0, F[(size_t)v * F_STRIDE + F_TCAX + Z] = 0));
+  }
+}
+
+/* synchronize_jf: remote.cc:417-508 with local_adjust_jf local.cc:335-366 */
+void vpo_synchronize_jf(const vpo_field_args_t *a) {
+  dims_t d = mkdims(a);
+  float *F = a->f;
+  for (int fc = 0; fc < 6; fc++) {                                  /* local_adjust_jf, order -x,-y,-z,+x,+y,+z */
+    int bc = a->bc6[fc];
+    if (bc >= 0) continue;
+    int X = fc % 3, Y = (X + 1) % 3, Z = (X + 2) % 3, face = fc < 3 ? 1 : d.n[X] + 1;
+    if (bc == -1) {
+      PLANE_LOOP(X, face, Y, 1, d.n[Y], Z, 1, d.n[Z] + 1, F[(size_t)v * F_STRIDE + F_JFX + Y] = 0);
+      PLANE_LOOP(X, face, Y, 1, d.n[Y] + 1, Z, 1, d.n[Z], F[(size_t)v * F_STRIDE + F_JFX + Z] = 0);
+    } else {
+      PLANE_LOOP(X, face, Y, 1, d.n[Y], Z, 1, d.n[Z] + 1, F[(size_t)v * F_STRIDE + F_JFX + Y] *= 2.);
+      PLANE_LOOP(X, face, Y, 1, d.n[Y] + 1, Z, 1, d.n[Z], F[(size_t)v * F_STRIDE + F_JFX + Z] *= 2.);
+    }
+  }
+  for (int X = 0; X < 3; X++) {                                     /* exchange one axis at a time */
+    int Y = (X + 1) % 3, Z = (X + 2) % 3;
+    float *msg[2] = {0, 0};
+    for (int side = 0; side < 2; side++) {                          /* pack both before either is applied */
+      int fc = X + 3 * side;
+      if (a->bc6[fc] < 0) continue;
+      int face = side == 0 ? 1 : d.n[X] + 1;
+      float *p = msg[side] = (float *)malloc(sizeof(float) * (size_t)(1 + d.n[Y] * (d.n[Z] + 1) + d.n[Z] * (d.n[Y] + 1)));
+      *p++ = axis_d(a, X);
+      PLANE_LOOP(X, face, Y, 1, d.n[Y], Z, 1, d.n[Z] + 1, *p++ = F[(size_t)v * F_STRIDE + F_JFX + Y]);
+      PLANE_LOOP(X, face, Y, 1, d.n[Y] + 1, Z, 1, d.n[Z], *p++ = F[(size_t)v * F_STRIDE + F_JFX + Z]);
+    }
+    for (int side = 0; side < 2; side++) {
+      if (!msg[side]) continue;
+      float *p = msg[side];
+      float rw = *p++, dX = axis_d(a, X), lw = rw + dX;
+      rw /= lw; lw = dX / lw; lw += lw; rw += rw;
+      int face = side == 0 ? d.n[X] + 1 : 1;                        /* lands on the opposite shared plane */
+      PLANE_LOOP(X, face, Y, 1, d.n[Y], Z, 1, d.n[Z] + 1,
+                 F[(size_t)v * F_STRIDE + F_JFX + Y] = lw * F[(size_t)v * F_STRIDE + F_JFX + Y] + rw * (*p++));
+      PLANE_LOOP(X, face, Y, 1, d.n[Y] + 1, Z, 1, d.n[Z],
+                 F[(size_t)v * F_STRIDE + F_JFX + Z] = lw * F[(size_t)v * F_STRIDE + F_JFX + Z] + rw * (*p++));
+      free(msg[side]);
+    }
+  }
+  (void)axis_rd;
+}
+
+/* vacuum_energy_f: vacuum_energy_f_pipeline.cc:12-97, stencil .h:24-75 (single pipeline order) */
+void vpo_vacuum_energy_f(const vpo_field_args_t *a, double en[6]) {
+  const int nx = a->nx, ny = a->ny, nz = a->nz;
+  const float qeps = 0.25 * 1.0f, hrmu = 0.50 * 1.0f;
+  double e0 = 0, e1 = 0, e2 = 0, b0 = 0, b1 = 0, b2 = 0;
+  const float *F = a->f;
+# define FF(x, y, z, m) F[(size_t)VOX(x, y, z) * F_STRIDE + (m)]
+  for (int z = 1; z <= nz; z++) for (int y = 1; y <= ny; y++) for (int x = 1; x <= nx; x++) {
+    e0 += qeps * (FF(x, y, z, F_EX) * FF(x, y, z, F_EX) + FF(x, y + 1, z, F_EX) * FF(x, y + 1, z, F_EX) +
+                  FF(x, y, z + 1, F_EX) * FF(x, y, z + 1, F_EX) + FF(x, y + 1, z + 1, F_EX) * FF(x, y + 1, z + 1, F_EX));
+    e1 += qeps * (FF(x, y, z, F_EY) * FF(x, y, z, F_EY) + FF(x, y, z + 1, F_EY) * FF(x, y, z + 1, F_EY) +
+                  FF(x + 1, y, z, F_EY) * FF(x + 1, y, z, F_EY) + FF(x + 1, y, z + 1, F_EY) * FF(x + 1, y, z + 1, F_EY));
+    e2 += qeps * (FF(x, y, z, F_EZ) * FF(x, y, z, F_EZ) + FF(x + 1, y, z, F_EZ) * FF(x + 1, y, z, F_EZ) +
+                  FF(x, y + 1, z, F_EZ) * FF(x, y + 1, z, F_EZ) + FF(x + 1, y + 1, z, F_EZ) * FF(x + 1, y + 1, z, F_EZ));
+    b0 += hrmu * (FF(x, y, z, F_CBX) * FF(x, y, z, F_CBX) + FF(x + 1, y, z, F_CBX) * FF(x + 1, y, z, F_CBX));
+    b1 += hrmu * (FF(x, y, z, F_CBY) * FF(x, y, z, F_CBY) + FF(x, y + 1, z, F_CBY) * FF(x, y + 1, z, F_CBY));
+    b2 += hrmu * (FF(x, y, z, F_CBZ) * FF(x, y, z, F_CBZ) + FF(x, y, z + 1, F_CBZ) * FF(x, y, z + 1, F_CBZ));
+  }
+# undef FF
+  double v0 = 0.5 * a->eps0 * a->dV;                            /* .cc:84 */
+  en[0] = e0 * v0; en[1] = e1 * v0; en[2] = e2 * v0; en[3] = b0 * v0; en[4] = b1 * v0; en[5] = b2 * v0;
+}

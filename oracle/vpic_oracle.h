@@ -1,0 +1,95 @@
+/* TEST INFRASTRUCTURE ONLY — CPU restatement ("port") of the reference hot path.
+ *
+ * Plain C, single-threaded, written from the reference's scalar pipelines
+ * (the bit-reproducible numerics reference, SURVEY.md §7 hard part 3).  Each
+ * function cites the reference file:line it follows.  Compiled with
+ * -ffp-contract=off so no FMA is formed, like the reference's scalar build.
+ *
+ * PARITY PINNED: tests/test_oracle_vs_ref.py checks every function here
+ * bit-for-bit against the UNMODIFIED reference compiled into
+ * oracle/_ref/libvpic_ref_scalar.so (recipe: oracle/Makefile) on seeded
+ * inputs, and tests/test_oracle_kat.py re-runs the reference's own
+ * known-answer decks (accel, cyclo, interpe, inbndj, outbndj) through it.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may
+ * load this library.  The product (vpic_b200/) never does.
+ *
+ * All arrays use the reference layouts with runtime strides so every SIMD
+ * padding variant is covered: interpolator stride 20/24/32 floats,
+ * accumulator stride 12/16 floats (sf_interface.h:27-53).
+ */
+#ifndef VPIC_ORACLE_H
+#define VPIC_ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vpo_particle { float dx, dy, dz; int32_t i; float ux, uy, uz, w; } vpo_particle_t;
+typedef struct vpo_mover    { float dispx, dispy, dispz; int32_t i; } vpo_mover_t;
+
+typedef struct vpo_push_args {
+  vpo_particle_t *p;   int32_t np;
+  vpo_mover_t    *pm;  int32_t max_nm;
+  const float    *interp; int32_t interp_stride;   /* floats per voxel */
+  float          *accum;  int32_t accum_stride;    /* floats per voxel */
+  const int64_t  *neighbor;                        /* [6*nv] */
+  int64_t         rangel, rangeh;
+  float           qdt_2mc, cdt_dx, cdt_dy, cdt_dz, qsp;
+} vpo_push_args_t;
+
+/* advance_p_pipeline_scalar, advance_p_pipeline.cc:20-245.  Returns nm (movers kept); *n_ignored = lost movers. */
+int32_t vpo_advance_p(const vpo_push_args_t *a, int32_t *n_ignored);
+
+/* move_p scalar variant, move_p.cc:216-378.  Returns 1 if the mover is still in use. */
+int vpo_move_p(vpo_particle_t *p0, vpo_mover_t *pm, float *accum, int32_t accum_stride,
+               const int64_t *neighbor, int64_t rangel, int64_t rangeh, float qsp);
+
+/* sort_p_pipeline, sort_p_pipeline.cc:220-371: stable counting sort by p.i; partition[0..nv) filled, incl. ghosts. */
+void vpo_sort_p(vpo_particle_t *p, int32_t np, vpo_particle_t *aux, int32_t *partition,
+                int32_t nx, int32_t ny, int32_t nz);
+
+/* load_interpolator_pipeline_scalar, interpolator_array_pipeline.cc:21-135.  fields: 20 floats (80 B) per voxel. */
+void vpo_load_interpolator(float *interp, int32_t interp_stride, const float *fields,
+                           int32_t nx, int32_t ny, int32_t nz);
+
+/* clear_accumulator_array_pipeline, clear_array_pipeline.cc:40-67 (block 0 only). */
+void vpo_clear_accumulator(float *accum, int32_t accum_stride, int32_t nx, int32_t ny, int32_t nz);
+
+/* unload_accumulator_pipeline_scalar, unload_accumulator_pipeline.cc:18-82,137-139. */
+void vpo_unload_accumulator(float *fields, const float *accum, int32_t accum_stride,
+                            int32_t nx, int32_t ny, int32_t nz,
+                            float rdx, float rdy, float rdz, float dt);
+
+/* energy_p_pipeline_scalar + driver, energy_p_pipeline.cc:18-115 (without the cross-rank sum). */
+double vpo_energy_p(const vpo_particle_t *p, int32_t np, const float *interp, int32_t interp_stride,
+                    float q, float m, float dt, float cvac);
+
+/* center_p / uncenter_p scalar pipelines, center_p_pipeline.cc:17-96, uncenter_p_pipeline.cc:17-98. */
+void vpo_center_p(vpo_particle_t *p, int32_t np, const float *interp, int32_t interp_stride, float qdt_2mc);
+void vpo_uncenter_p(vpo_particle_t *p, int32_t np, const float *interp, int32_t interp_stride, float qdt_2mc);
+
+/* ---- standard field advance, vacuum material, one local domain whose six faces are either
+ *      periodic onto itself or a local field BC (pec = -1).  bc6[f] for faces -x,-y,-z,+x,+y,+z:
+ *      >=0 periodic-self, -1 pec.  (sfa: advance_b_pipeline.cc:20-125, vacuum_advance_e_pipeline.cc:20-332,
+ *      local.cc:50-444, remote.cc:61-134,417-508) ------------------------------------------------ */
+typedef struct vpo_field_args {
+  float  *f;                 /* [nv*20] field_t array */
+  int32_t nx, ny, nz;
+  float   dt, cvac, eps0, damp;
+  float   dx, dy, dz, dV;    /* as stored in grid_t (partition.cc:55-72) */
+  float   rdx, rdy, rdz;
+  int32_t bc6[6];
+} vpo_field_args_t;
+
+void vpo_advance_b(const vpo_field_args_t *a, float frac);
+void vpo_vacuum_advance_e(const vpo_field_args_t *a, float frac);
+void vpo_clear_jf(const vpo_field_args_t *a);
+void vpo_synchronize_jf(const vpo_field_args_t *a);
+void vpo_vacuum_energy_f(const vpo_field_args_t *a, double en[6]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
