@@ -1,0 +1,161 @@
+/* vpic_b200.h — C-ABI of libvpic_b200.so (hand-written CUDA for sm_100a).
+ *
+ * Two layers, both plain C (pointers and sizes only, no torch or C++ types):
+ *
+ *  1. DEVICE LAYER  vpb_*   — every pointer is a DEVICE pointer; `stream` is a
+ *     cudaStream_t passed as void* (NULL = default stream).  This is what the
+ *     drop-in layer, bench.py and the GPU tests call.  Each entry point names
+ *     the reference routine it replaces (file:line under the reference tree).
+ *
+ *  2. DROP-IN LAYER (vpic_b200_dropin.h) — the reference's own extern "C"
+ *     symbols (advance_p, sort_p, load_interpolator_array, ...) taking the
+ *     reference's host structs; they mirror host arrays on the device and call
+ *     layer 1.  That is the link-time seam described in INTEGRATION.md.
+ *
+ * Every function returns 0 on success, else a negative vpb error or a positive
+ * cudaError_t; vpb_last_error() gives the message.  There is no CPU fallback:
+ * without a usable CUDA device every call fails loudly.
+ *
+ * Array layouts are the reference's (vpic_b200_abi.h) with runtime strides so
+ * one binary serves every SIMD padding of the host build:
+ *   interp_stride  floats per interpolator_t  (20 | 24 | 32)
+ *   accum_stride   floats per accumulator_t   (12 | 16)
+ *   field_t is always 20 floats (80 B).
+ */
+#ifndef VPIC_B200_H
+#define VPIC_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VPB_VERSION 100
+
+/* ---- runtime ------------------------------------------------------------ */
+int         vpb_version(void);
+const char *vpb_last_error(void);
+int         vpb_device_count(int *count);
+int         vpb_set_device(int device);
+int         vpb_device_info(int device, int *sm_count, int *cc_major, int *cc_minor, size_t *total_bytes);
+int         vpb_malloc(void **dptr, size_t bytes);
+int         vpb_free(void *dptr);
+int         vpb_malloc_host(void **hptr, size_t bytes);        /* pinned host memory */
+int         vpb_free_host(void *hptr);
+int         vpb_memset(void *dptr, int value, size_t bytes, void *stream);
+int         vpb_memcpy_h2d(void *dptr, const void *hptr, size_t bytes, void *stream);
+int         vpb_memcpy_d2h(void *hptr, const void *dptr, size_t bytes, void *stream);
+int         vpb_memcpy_d2d(void *dst, const void *src, size_t bytes, void *stream);
+int         vpb_stream_sync(void *stream);
+int         vpb_device_sync(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+int64_t     vpb_launch_count(void);
+
+/* ---- particle advance ----------------------------------------------------
+ * Replaces advance_p_pipeline + advance_p_pipeline_scalar + move_p
+ * (src/species_advance/standard/pipeline/advance_p_pipeline.cc:20-340,
+ *  src/species_advance/standard/move_p.cc:216-378).
+ * Arithmetic follows the reference's SCALAR pipeline operation for operation
+ * (no FMA contraction, IEEE sqrt and divide) so particle state is bit-exact;
+ * accumulator sums differ only by fp32 atomic ordering.
+ */
+typedef struct vpb_push_args {
+  void          *p;              /* particle_t[np], 32 B each, 16 B aligned          */
+  int32_t        np;
+  void          *pm;             /* particle_mover_t[max_nm]: movers that left the domain */
+  int32_t        max_nm;
+  int32_t       *counters;       /* int32[4] device: [0] += movers emitted (may exceed max_nm),
+                                    [1] += movers dropped for lack of room (p.i restored, advance_p_pipeline.cc:223-236) */
+  const float   *interp;  int32_t interp_stride;
+  float         *accum;   int32_t accum_stride;   /* block 0 of the accumulator array */
+  const int64_t *neighbor;       /* grid_t.neighbor, [6*nv]                          */
+  int64_t        rangel, rangeh;
+  float          qdt_2mc, cdt_dx, cdt_dy, cdt_dz, qsp;   /* computed by the caller in float, advance_p_pipeline.cc:279-283 */
+  int32_t        nx, ny, nz;
+  int32_t        variant;        /* deposit strategy, see VPB_DEPOSIT_*              */
+} vpb_push_args_t;
+
+#define VPB_DEPOSIT_DEFAULT      0   /* library's best measured strategy                                  */
+#define VPB_DEPOSIT_RED_V4       1   /* every particle: 3 x red.global.add.v4.f32                         */
+#define VPB_DEPOSIT_WARP_SEG     2   /* warp-level segmented reduction by voxel, then one RED per sum     */
+#define VPB_DEPOSIT_SMEM_TILE    3   /* warp reduction into a shared-memory accumulator tile, tile flush  */
+
+int vpb_advance_p(const vpb_push_args_t *args, void *stream);
+
+/* Sort the emitted movers ascending by particle index (boundary_p needs that order,
+ * src/boundary/boundary_p.cc:248-255).  nm = min(counters[0], max_nm), read back by the caller.
+ * scratch: >= vpb_sort_movers_scratch_bytes(nm). */
+size_t vpb_sort_scratch_bytes(int32_t n_items, int32_t n_keys_hint);
+size_t vpb_sort_movers_scratch_bytes(int32_t nm);
+int    vpb_sort_movers(void *pm, int32_t nm, void *scratch, size_t scratch_bytes, void *stream);
+
+/* ---- sort_p ---------------------------------------------------------------
+ * Replaces sort_p_pipeline (src/species_advance/standard/pipeline/sort_p_pipeline.cc:220-371):
+ * stable counting sort of particles by voxel index p.i; writes partition[0..nv] (partition[nv] = np).
+ * aux: particle_t[np] scratch; scratch: >= vpb_sort_scratch_bytes(np, nv) bytes. */
+int vpb_sort_p(void *p, int32_t np, void *aux, int32_t *partition,
+               int32_t nx, int32_t ny, int32_t nz,
+               void *scratch, size_t scratch_bytes, void *stream);
+
+/* ---- interpolator / accumulator glue ---------------------------------------
+ * load_interpolator_pipeline_scalar  (src/sf_interface/pipeline/interpolator_array_pipeline.cc:21-135)
+ * clear_accumulator_array_pipeline   (src/sf_interface/pipeline/clear_array_pipeline.cc:40-67)
+ * unload_accumulator_pipeline_scalar (src/sf_interface/pipeline/unload_accumulator_pipeline.cc:18-144)
+ * reduce_accumulator_array is the identity here: the device keeps ONE accumulator block. */
+int vpb_load_interpolator(float *interp, int32_t interp_stride, const float *fields,
+                          int32_t nx, int32_t ny, int32_t nz, void *stream);
+int vpb_clear_accumulator(float *accum, int32_t accum_stride, int32_t nx, int32_t ny, int32_t nz, void *stream);
+int vpb_unload_accumulator(float *fields, const float *accum, int32_t accum_stride,
+                           int32_t nx, int32_t ny, int32_t nz,
+                           float rdx, float rdy, float rdz, float dt, void *stream);
+
+/* ---- particle diagnostics / centering --------------------------------------
+ * energy_p_pipeline (src/species_advance/standard/pipeline/energy_p_pipeline.cc:18-115): result (double, already
+ * times cvac^2) is written to *en_dev (device).  center_p / uncenter_p (center_p_pipeline.cc:17-96,
+ * uncenter_p_pipeline.cc:17-98). */
+int vpb_energy_p(const void *p, int32_t np, const float *interp, int32_t interp_stride,
+                 float q, float m, float dt, float cvac, double *en_dev, void *stream);
+int vpb_center_p(void *p, int32_t np, const float *interp, int32_t interp_stride, float qdt_2mc, void *stream);
+int vpb_uncenter_p(void *p, int32_t np, const float *interp, int32_t interp_stride, float qdt_2mc, void *stream);
+
+/* ---- standard field advance, vacuum material -------------------------------
+ * advance_b (src/field_advance/standard/pipeline/advance_b_pipeline.cc:20-125),
+ * vacuum_advance_e (.../vacuum_advance_e_pipeline.cc:20-332), clear_jf (sfa.cc:231-237),
+ * synchronize_jf (remote.cc:417-508), vacuum_energy_f (.../vacuum_energy_f_pipeline.cc:12-97),
+ * with the local boundary conditions of local.cc and the periodic/remote ghost handling of remote.cc.
+ * face[f], f = -x,-y,-z,+x,+y,+z:  VPB_FACE_PERIODIC_SELF  ghost plane copied from the opposite side of this domain,
+ *                                  VPB_FACE_REMOTE         ghost plane filled by the caller (NCCL halo exchange),
+ *                                  <0                      local field BC code (grid.h:20-26): -1 pec, -2 symmetric, -3 pmc. */
+#define VPB_FACE_PERIODIC_SELF 0
+#define VPB_FACE_REMOTE        1
+
+typedef struct vpb_field_args {
+  float  *f;                       /* field_t[nv], 20 floats each */
+  int32_t nx, ny, nz;
+  float   dt, cvac, eps0, damp;
+  float   dx, dy, dz, dV;
+  float   rdx, rdy, rdz;
+  int32_t face[6];
+} vpb_field_args_t;
+
+int vpb_advance_b(const vpb_field_args_t *a, float frac, void *stream);
+int vpb_vacuum_advance_e(const vpb_field_args_t *a, float frac, void *stream);
+int vpb_clear_jf(const vpb_field_args_t *a, void *stream);
+int vpb_synchronize_jf(const vpb_field_args_t *a, void *stream);
+int vpb_vacuum_energy_f(const vpb_field_args_t *a, double *en6_dev, void *stream);
+
+/* Halo planes for VPB_FACE_REMOTE faces (the payload of begin/end_remote_ghost_tang_b, remote.cc:61-134, and of
+ * synchronize_jf, remote.cc:417-508).  pack copies the plane a neighbour needs into buf; unpack applies a received
+ * plane.  floats per plane: vpb_halo_floats(). */
+#define VPB_HALO_TANG_B 0
+#define VPB_HALO_JF     1
+size_t vpb_halo_floats(int32_t nx, int32_t ny, int32_t nz, int axis);
+int vpb_halo_pack(const vpb_field_args_t *a, int kind, int face, float *buf, void *stream);
+int vpb_halo_unpack(const vpb_field_args_t *a, int kind, int face, const float *buf, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VPIC_B200_H */

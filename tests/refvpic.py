@@ -41,6 +41,14 @@ def load_oracle():
                                            C.c_float, C.c_float, C.c_float, C.c_float]
     lib.vpo_center_p.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_float]
     lib.vpo_uncenter_p.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_float]
+    lib.vpo_advance_p.argtypes = [C.c_void_p, C.c_void_p]
+    lib.vpo_move_p.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_float]
+    lib.vpo_sort_p.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
+    lib.vpo_load_interpolator.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
+    lib.vpo_clear_accumulator.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
+    lib.vpo_clear_jf.argtypes = [C.c_void_p]
+    lib.vpo_synchronize_jf.argtypes = [C.c_void_p]
+    lib.vpo_vacuum_energy_f.argtypes = [C.c_void_p, C.c_void_p]
     lib.vpo_advance_b.argtypes = [C.c_void_p, C.c_float]
     lib.vpo_vacuum_advance_e.argtypes = [C.c_void_p, C.c_float]
     return lib

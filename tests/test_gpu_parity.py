@@ -1,0 +1,292 @@
+"""GPU parity: the CUDA path (through the C-ABI, libvpic_b200.so) against the CPU oracle on identical seeded
+inputs.  Integer/index work is bit-exact; particle state after one push is bit-exact (the kernels follow the scalar
+reference operation for operation); sums whose order differs (atomics, parallel reductions) carry a stated tolerance.
+"""
+import ctypes as C
+import numpy as np
+import pytest
+
+import refvpic as R
+from vpic_b200 import abi, grid as G
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint8)
+
+
+@pytest.fixture(scope="module")
+def eng():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from vpic_b200 import engine, lib
+    lib.load()
+    return engine
+
+
+def make_grid(nx, ny, nz, pbc=None, fbc=None, frac=0.98):
+    dt = G.courant_dt(1.0, 1.0, 1.0, nx, ny, nz, frac=frac)
+    g = G.partition_periodic_box(0, 0, 0, nx, ny, nz, nx, ny, nz, 1, 1, 1, dt=dt)
+    for f, c in (pbc or {}).items():
+        g.set_pbc(f, c)
+    for f, c in (fbc or {}).items():
+        g.set_fbc(f, c)
+    return g
+
+
+def oracle_push(orc, g, parts, interp, q, m, max_nm, isf=20, asf=12):
+    p2 = parts.copy()
+    pm2 = np.zeros(max_nm, dtype=abi.mover_dtype)
+    acc2 = np.zeros(((g.nv + 1) // 2 * 2, asf), dtype=np.float32)
+    f32 = np.float32
+    qf, mf, dt, cvac = f32(q), f32(m), f32(g.dt), f32(g.cvac)
+    a = R.OraclePushArgs(p2.ctypes.data, len(p2), pm2.ctypes.data, max_nm, interp.ctypes.data, isf,
+                         acc2.ctypes.data, asf, g.neighbor.ctypes.data, g.rangel, g.rangeh,
+                         f32(f32(qf * dt) / f32(f32(f32(2) * mf) * cvac)),
+                         f32(f32(cvac * dt) * f32(g.rdx)), f32(f32(cvac * dt) * f32(g.rdy)),
+                         f32(f32(cvac * dt) * f32(g.rdz)), qf)
+    ign = C.c_int32(0)
+    nm = orc.vpo_advance_p(C.byref(a), C.byref(ign))
+    return p2, pm2[:nm], acc2, ign.value
+
+
+def accum_close(a_gpu, a_ref, rtol=2e-5):
+    # fp32 sums of O(ppc) terms in a different order: compare against the magnitude of the entries
+    scale = max(np.abs(a_ref).max(), 1e-30)
+    err = np.abs(a_gpu - a_ref).max() / scale
+    assert err < rtol, f"accumulator mismatch {err:.3e}"
+
+
+PUSH_CASES = [
+    ((6, 5, 4), 0.5, None, 20000, True),          # periodic, ~40% crossings, sorted input
+    ((6, 5, 4), 0.5, None, 20000, False),         # same, unsorted input
+    ((16, 1, 16), 0.3, None, 30011, True),        # 2-D deck shape, ragged np
+    ((5, 4, 3), 0.6, {0: -1, 3: -1}, 9000, True),    # reflecting x walls
+    ((5, 4, 3), 0.6, {2: -2, 5: -2}, 9000, True),    # absorbing z walls -> movers
+    ((4, 4, 4), 0.1, None, 1, True),              # single particle
+    ((4, 4, 4), 0.1, None, 0, True),              # empty species
+]
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("dims,uth,pbc,n,sort_first", PUSH_CASES)
+def test_advance_p(eng, oracle, dims, uth, pbc, n, sort_first, variant):
+    rng = np.random.default_rng(17)
+    nx, ny, nz = dims
+    g = make_grid(nx, ny, nz, pbc=pbc)
+    fields = R.random_fields(rng, g.nv)
+    interp = np.zeros((g.nv, 20), dtype=np.float32)
+    oracle.vpo_load_interpolator(interp.ctypes.data, 20, fields.ctypes.data, nx, ny, nz)
+    parts = R.random_particles(rng, n, nx, ny, nz, uth=uth, w=0.7)
+    if sort_first and n:
+        parts = parts[np.argsort(parts["i"], kind="stable")]
+    max_nm = max(16, n)
+    p_ref, pm_ref, acc_ref, _ = oracle_push(oracle, g, parts, interp, -1.0, 1.0, max_nm)
+
+    dg = eng.DeviceGrid(g)
+    ia, aa = eng.InterpolatorArray(dg), eng.AccumulatorArray(dg)
+    ia.i.copy_(torch.from_numpy(interp))
+    sp = eng.Species("electron", -1.0, 1.0, max(n, 1), max_nm, 20, 0, dg)
+    sp.set_particles(parts)
+    eng.clear_accumulator_array(aa)
+    eng.advance_p(sp, aa, ia, variant=variant)
+    eng.reduce_accumulator_array(aa)
+
+    assert sp.nm == len(pm_ref) and sp.n_ignored == 0
+    got = sp.particles_host()
+    assert np.array_equal(bits(got), bits(p_ref)), "particle state must be bit-exact"
+    assert np.array_equal(bits(sp.movers_host()), bits(pm_ref)), "movers must be bit-exact and ascending"
+    accum_close(aa.a.cpu().numpy(), acc_ref)
+    if n > 100:
+        assert (got["i"] != parts["i"]).mean() > 0.05
+
+
+def test_advance_p_mover_overflow(eng, oracle):
+    """More leavers than max_nm: extra movers are dropped, p.i stays a valid voxel (advance_p_pipeline.cc:223-236)."""
+    rng = np.random.default_rng(2)
+    nx, ny, nz = 4, 4, 4
+    g = make_grid(nx, ny, nz, pbc={i: -2 for i in range(6)})
+    interp = np.zeros((g.nv, 20), dtype=np.float32)
+    parts = R.random_particles(rng, 5000, nx, ny, nz, uth=0.8)
+    dg = eng.DeviceGrid(g)
+    ia, aa = eng.InterpolatorArray(dg), eng.AccumulatorArray(dg)
+    sp = eng.Species("e", -1.0, 1.0, 5000, 8, 20, 0, dg)
+    sp.set_particles(parts)
+    with pytest.warns(UserWarning):
+        eng.advance_p(sp, aa, ia)
+    assert sp.nm == 8 and sp.n_ignored > 0
+    got = sp.particles_host()
+    mv = sp.movers_host()
+    waiting = np.zeros(len(got), bool); waiting[mv["i"]] = True
+    assert np.all(got["i"][~waiting] < g.nv) and np.all(got["i"][~waiting] >= 0)
+    assert np.all(got["i"][waiting] >= 8)
+
+
+@pytest.mark.parametrize("dims,n", [((7, 6, 5), 17777), ((32, 32, 32), 300000), ((64, 64, 1), 262144),
+                                    ((3, 3, 3), 1), ((3, 3, 3), 0), ((130, 70, 40), 50000)])
+def test_sort_p(eng, oracle, dims, n):
+    rng = np.random.default_rng(23)
+    nx, ny, nz = dims
+    g = make_grid(nx, ny, nz)
+    parts = R.random_particles(rng, n, nx, ny, nz)
+    parts["w"] = np.arange(n, dtype=np.float32)           # tag to expose any instability
+    p_ref, aux = parts.copy(), np.zeros_like(parts)
+    part_ref = np.zeros(g.nv + 1, dtype=np.int32)
+    oracle.vpo_sort_p(p_ref.ctypes.data, n, aux.ctypes.data, part_ref.ctypes.data, nx, ny, nz)
+    dg = eng.DeviceGrid(g)
+    sp = eng.Species("e", -1.0, 1.0, max(n, 1), 16, 20, 0, dg)
+    sp.set_particles(parts)
+    eng.sort_p(sp)
+    assert np.array_equal(bits(sp.particles_host()), bits(p_ref)), "sort order must be bit-exact (stable)"
+    assert np.array_equal(sp.partition.cpu().numpy()[:g.nv], part_ref[:g.nv])
+    assert sp.last_sorted == g.step
+    # idempotence: sorting sorted data changes nothing
+    eng.sort_p(sp)
+    assert np.array_equal(bits(sp.particles_host()), bits(p_ref))
+
+
+def test_sort_movers(eng):
+    from vpic_b200 import lib
+    L = lib.load()
+    rng = np.random.default_rng(4)
+    n = 70001
+    mv = np.zeros(n, dtype=abi.mover_dtype)
+    mv["i"] = rng.permutation(5_000_000)[:n].astype(np.int32)
+    mv["dispx"] = mv["i"].astype(np.float32)
+    t = torch.from_numpy(mv.view(np.float32).reshape(-1, 4)).cuda()
+    need = L.vpb_sort_movers_scratch_bytes(n)
+    scratch = torch.empty(need, dtype=torch.uint8, device="cuda")
+    lib.check(L.vpb_sort_movers(t.data_ptr(), n, scratch.data_ptr(), need, None))
+    out = t.cpu().numpy().reshape(-1).view(abi.mover_dtype)
+    assert np.array_equal(out["i"], np.sort(mv["i"]))
+    assert np.array_equal(out["dispx"], out["i"].astype(np.float32))
+
+
+@pytest.mark.parametrize("dims", [(6, 4, 5), (64, 64, 1), (33, 17, 9)])
+def test_interpolator_accumulator_glue(eng, oracle, dims):
+    rng = np.random.default_rng(9)
+    nx, ny, nz = dims
+    g = make_grid(nx, ny, nz)
+    dg = eng.DeviceGrid(g)
+    fields = R.random_fields(rng, g.nv)
+    fa, ia, aa = eng.FieldArray(dg), eng.InterpolatorArray(dg), eng.AccumulatorArray(dg)
+    fa.f.copy_(torch.from_numpy(fields))
+    eng.load_interpolator_array(ia, fa)
+    i_ref = np.zeros((g.nv, 20), dtype=np.float32)
+    oracle.vpo_load_interpolator(i_ref.ctypes.data, 20, fields.ctypes.data, nx, ny, nz)
+    assert np.array_equal(bits(ia.i.cpu().numpy()), bits(i_ref))
+
+    acc = np.zeros((aa.stride, 12), dtype=np.float32)
+    x, y, z = np.meshgrid(np.arange(1, nx + 1), np.arange(1, ny + 1), np.arange(1, nz + 1), indexing="ij")
+    v = abi.voxel(x, y, z, nx, ny, nz).ravel()
+    acc[v] = rng.normal(0, 1, (len(v), 12)).astype(np.float32)
+    aa.a.copy_(torch.from_numpy(acc))
+    f_ref = fields.copy()
+    oracle.vpo_unload_accumulator(f_ref.ctypes.data, acc.ctypes.data, 12, nx, ny, nz, g.rdx, g.rdy, g.rdz, g.dt)
+    eng.unload_accumulator_array(fa, aa)
+    assert np.array_equal(bits(fa.f.cpu().numpy()), bits(f_ref))
+
+    a_ref = acc.copy()
+    a_ref[0] = 5.0                                             # ghost voxel below the cleared window stays untouched
+    aa.a.copy_(torch.from_numpy(a_ref))
+    oracle.vpo_clear_accumulator(a_ref.ctypes.data, 12, nx, ny, nz)
+    eng.clear_accumulator_array(aa)
+    assert np.array_equal(bits(aa.a.cpu().numpy()), bits(a_ref))
+
+
+def test_energy_center_uncenter(eng, oracle):
+    rng = np.random.default_rng(31)
+    nx, ny, nz = 8, 6, 5
+    g = make_grid(nx, ny, nz)
+    dg = eng.DeviceGrid(g)
+    fields = R.random_fields(rng, g.nv)
+    interp = np.zeros((g.nv, 20), dtype=np.float32)
+    oracle.vpo_load_interpolator(interp.ctypes.data, 20, fields.ctypes.data, nx, ny, nz)
+    ia = eng.InterpolatorArray(dg)
+    ia.i.copy_(torch.from_numpy(interp))
+    parts = R.random_particles(rng, 40001, nx, ny, nz, uth=0.4, w=0.37)
+    sp = eng.Species("ion", 1.0, 25.0, len(parts), 16, 20, 0, dg)
+    sp.set_particles(parts)
+    e_ref = oracle.vpo_energy_p(parts.ctypes.data, len(parts), interp.ctypes.data, 20, 1.0, 25.0, g.dt, g.cvac)
+    e_gpu = eng.energy_p(sp, ia)
+    assert abs(e_gpu - e_ref) <= 1e-12 * abs(e_ref)            # same fp32 terms, double sums in another order
+    qdt_2mc = sp.push_constants()[0]
+    p_ref = parts.copy()
+    oracle.vpo_uncenter_p(p_ref.ctypes.data, len(p_ref), interp.ctypes.data, 20, qdt_2mc)
+    eng.uncenter_p(sp, ia)
+    assert np.array_equal(bits(sp.particles_host()), bits(p_ref))
+    oracle.vpo_center_p(p_ref.ctypes.data, len(p_ref), interp.ctypes.data, 20, qdt_2mc)
+    eng.center_p(sp, ia)
+    assert np.array_equal(bits(sp.particles_host()), bits(p_ref))
+
+
+@pytest.mark.parametrize("dims,fbc,damp", [
+    ((6, 5, 4), None, 0.0),
+    ((6, 5, 4), None, 0.01),
+    ((64, 64, 1), {0: -1, 3: -1}, 0.0),          # harris: pec x walls, one cell in z
+    ((5, 1, 7), {2: -2, 5: -3}, 0.0),            # symmetric / pmc, one cell in y
+    ((40, 24, 16), None, 0.0),
+])
+def test_field_advance(eng, oracle, dims, fbc, damp):
+    rng = np.random.default_rng(3)
+    nx, ny, nz = dims
+    g = make_grid(nx, ny, nz, fbc=fbc)
+    dg = eng.DeviceGrid(g)
+    f0 = R.random_fields(rng, g.nv)
+    f0[:, 8:11] = rng.normal(0, 0.01, (g.nv, 3))
+    f0[:, 12:15] = rng.normal(0, 0.02, (g.nv, 3))
+    fa = eng.FieldArray(dg, damp=damp)
+    fa.f.copy_(torch.from_numpy(f0))
+    f_ref = f0.copy()
+    a = R.OracleFieldArgs()
+    a.f = f_ref.ctypes.data
+    a.nx, a.ny, a.nz = nx, ny, nz
+    a.dt, a.cvac, a.eps0, a.damp = g.dt, g.cvac, g.eps0, damp
+    a.dx, a.dy, a.dz, a.dV = g.dx, g.dy, g.dz, g.dV
+    a.rdx, a.rdy, a.rdz = g.rdx, g.rdy, g.rdz
+    for i, (fi, fj, fk) in enumerate(G.FACES):
+        a.bc6[i] = g.bc[G.boundary_index(fi, fj, fk)]
+    for _ in range(3):
+        fa.synchronize_jf(); oracle.vpo_synchronize_jf(C.byref(a))
+        assert np.array_equal(bits(fa.f.cpu().numpy()), bits(f_ref)), "synchronize_jf"
+        fa.advance_b(0.5); oracle.vpo_advance_b(C.byref(a), 0.5)
+        assert np.array_equal(bits(fa.f.cpu().numpy()), bits(f_ref)), "advance_b"
+        fa.advance_e(1.0); oracle.vpo_vacuum_advance_e(C.byref(a), 1.0)
+        assert np.array_equal(bits(fa.f.cpu().numpy()), bits(f_ref)), "advance_e"
+        fa.advance_b(0.5); oracle.vpo_advance_b(C.byref(a), 0.5)
+        assert np.array_equal(bits(fa.f.cpu().numpy()), bits(f_ref)), "advance_b"
+    en = (C.c_double * 6)()
+    oracle.vpo_vacuum_energy_f(C.byref(a), en)
+    np.testing.assert_allclose(fa.energy_f(), np.array(en[:]), rtol=1e-12)
+    fa.clear_jf(); oracle.vpo_clear_jf(C.byref(a))
+    assert np.array_equal(bits(fa.f.cpu().numpy()), bits(f_ref))
+
+
+def test_reference_scalar_agrees_when_present(eng, oracle):
+    """If the prebuilt unmodified reference travelled with the repo, check the CUDA push against it directly."""
+    if not R.have_ref("scalar"):
+        pytest.skip("oracle/_ref not present")
+    lib = R.load_ref("scalar", tpp=1)
+    rng = np.random.default_rng(77)
+    nx, ny, nz = 6, 5, 4
+    W = R.RefWorld(lib, nx, ny, nz)
+    W.fields[:] = R.random_fields(rng, W.nv)
+    lib.load_interpolator_array(W.ia, W.fa)
+    rs = W.new_species("e_gpu_ref", -1.0, 1.0, 8192, 8192)
+    parts = R.random_particles(rng, 8000, nx, ny, nz, uth=0.4)
+    rs.set_particles(parts)
+    lib.clear_accumulator_array(W.aa); lib.advance_p(rs.sp, W.aa, W.ia); lib.reduce_accumulator_array(W.aa)
+    gc = W.g.contents
+    g = G.partition_periodic_box(0, 0, 0, nx, ny, nz, nx, ny, nz, 1, 1, 1, dt=gc.dt)
+    assert np.array_equal(g.neighbor, W.neighbor)
+    dg = eng.DeviceGrid(g)
+    ia, aa = eng.InterpolatorArray(dg), eng.AccumulatorArray(dg)
+    ia.i.copy_(torch.from_numpy(W.interp.copy()))
+    sp = eng.Species("e", -1.0, 1.0, 8192, 8192, 20, 0, dg)
+    sp.set_particles(parts)
+    eng.clear_accumulator_array(aa); eng.advance_p(sp, aa, ia)
+    assert np.array_equal(bits(sp.particles_host()), bits(rs.p[:8000]))
+    accum_close(aa.a.cpu().numpy(), W.accum[0])

@@ -1,0 +1,80 @@
+"""Host-side logic and the C-ABI surface, without a GPU."""
+import ctypes as C
+import os
+import re
+import numpy as np
+import pytest
+
+import refvpic as R
+from vpic_b200 import grid as G, lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    L = lib.load()
+    assert L.vpb_version() == 100
+    hdr = open(os.path.join(ROOT, "include", "vpic_b200.h")).read()
+    declared = set(re.findall(r"\b(vpb_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "header parse failed"
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} declared in include/vpic_b200.h but not exported"
+    dh = os.path.join(ROOT, "include", "vpic_b200_dropin.h")
+    if os.path.exists(dh):
+        for name in re.findall(r"^\s*(?:void|int|double)\s+([a-z_0-9]+)\s*\(", open(dh).read(), re.M):
+            assert hasattr(L, name), f"{name} declared in include/vpic_b200_dropin.h but not exported"
+
+
+def test_no_cpu_fallback_without_device():
+    """Without a CUDA device a compute call must fail loudly, not silently run elsewhere."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    L = lib.load()
+    n = C.c_int(0)
+    rc = L.vpb_device_count(C.byref(n))
+    assert rc != 0 or n.value == 0
+    p = C.c_void_p()
+    rc = L.vpb_malloc(C.byref(p), 1024)
+    assert rc != 0 and b"CUDA" in L.vpb_last_error()
+    with pytest.raises(lib.VpbError):
+        lib.check(rc, "vpb_malloc")
+
+
+def test_bad_args_are_rejected():
+    L = lib.load()
+    assert L.vpb_advance_p(None, None) != 0
+    assert b"Bad args" in L.vpb_last_error()
+    assert L.vpb_sort_p(None, 5, None, None, 4, 4, 4, None, 0, None) != 0
+    assert L.vpb_load_interpolator(None, 20, None, 4, 4, 4, None) != 0
+    a = lib.FieldArgs()
+    assert L.vpb_vacuum_advance_e(C.byref(a), 1.0, None) != 0
+
+
+@pytest.mark.parametrize("dims", [(6, 5, 4), (8, 1, 8), (64, 64, 1)])
+def test_grid_matches_reference(ref_scalar, dims):
+    nx, ny, nz = dims
+    W = R.RefWorld(ref_scalar, nx, ny, nz, lx=2.0 * nx, ly=0.5 * ny, lz=1.25 * nz,
+                   pbc={0: -1, 5: -2}, fbc={0: -1})
+    gc = W.g.contents
+    g = G.partition_periodic_box(0, 0, 0, 2.0 * nx, 0.5 * ny, 1.25 * nz, nx, ny, nz, 1, 1, 1, dt=gc.dt)
+    g.set_pbc(0, -1); g.set_pbc(5, -2); g.set_fbc(0, -1)
+    assert np.array_equal(g.neighbor, W.neighbor)
+    for k in ("dx", "dy", "dz", "dV", "rdx", "rdy", "rdz", "r8V", "x0", "x1", "y1", "z1", "dt"):
+        assert np.float32(getattr(g, k)) == np.float32(getattr(gc, k)), k
+    assert g.rangel == gc.rangel and g.rangeh == gc.rangeh and g.nv == gc.nv
+    assert list(g.bc) == list(gc.bc)
+
+
+def test_slab_grid_neighbours():
+    """1 x N x 1 slab decomposition: remote faces carry the neighbour rank's global voxel ids."""
+    N, nx, ny, nz = 4, 6, 8, 5
+    grids = [G.partition_periodic_box(0, 0, 0, nx, ny, nz, nx, ny, nz, 1, N, 1, rank=r, dt=0.1) for r in range(N)]
+    for r, g in enumerate(grids):
+        assert (g.nx, g.ny, g.nz) == (nx, ny // N, nz)
+        up, dn = grids[(r + 1) % N], grids[(r - 1) % N]
+        v = G.voxel(3, g.ny, 2, g.nx, g.ny, g.nz)
+        assert g.neighbor[v, 4] == up.rangel + G.voxel(3, 1, 2, g.nx, g.ny, g.nz)
+        v = G.voxel(3, 1, 2, g.nx, g.ny, g.nz)
+        assert g.neighbor[v, 1] == dn.rangel + G.voxel(3, dn.ny, 2, g.nx, g.ny, g.nz)
+        assert g.face_codes() == [0, 1, 0, 0, 1, 0]

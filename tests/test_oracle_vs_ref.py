@@ -1,0 +1,149 @@
+"""Pins the C restatement (oracle/liboracle.so) bit-for-bit against the UNMODIFIED reference compiled from
+/root/reference (oracle/_ref/libvpic_ref_scalar.so).  CPU only."""
+import ctypes as C
+import numpy as np
+import pytest
+
+import refvpic as R
+from vpic_b200 import abi
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint8)
+
+
+def make_world(lib, rng, nx, ny, nz, **kw):
+    W = R.RefWorld(lib, nx, ny, nz, **kw)
+    W.fields[:] = R.random_fields(rng, W.nv)
+    lib.load_interpolator_array(W.ia, W.fa)
+    return W
+
+
+def port_push(orc, W, sp, parts, max_nm):
+    p2 = parts.copy()
+    pm2 = np.zeros(max_nm, dtype=abi.mover_dtype)
+    acc2 = np.zeros((W.aa.contents.stride, W.asf), dtype=np.float32)
+    k = sp.push_constants()
+    a = R.OraclePushArgs(p2.ctypes.data, len(p2), pm2.ctypes.data, max_nm, W.interp.ctypes.data, W.isf,
+                         acc2.ctypes.data, W.asf, W.neighbor.ctypes.data, W.g.contents.rangel, W.g.contents.rangeh,
+                         k["qdt_2mc"], k["cdt_dx"], k["cdt_dy"], k["cdt_dz"], k["qsp"])
+    ign = C.c_int32(0)
+    nm = orc.vpo_advance_p(C.byref(a), C.byref(ign))
+    return p2, pm2[:nm], acc2, ign.value
+
+
+@pytest.mark.parametrize("dims,uth,pbc", [
+    ((6, 5, 4), 0.5, None),                       # periodic, many crossings
+    ((8, 1, 8), 0.3, None),                       # 2-D deck shape (ny == 1: the +-y neighbour is the voxel itself)
+    ((5, 4, 3), 0.6, {0: -1, 3: -1}),             # reflecting x walls
+    ((5, 4, 3), 0.6, {2: -2, 5: -2}),             # absorbing z walls -> movers handed to boundary_p
+])
+def test_advance_p_bit_exact(ref_scalar, oracle, dims, uth, pbc):
+    rng = np.random.default_rng(11)
+    nx, ny, nz = dims
+    W = make_world(ref_scalar, rng, nx, ny, nz, pbc=pbc)
+    sp = W.new_species("e%d" % rng.integers(1 << 30), -1.0, 1.0, 4096, 4096)
+    n = 3200                                        # multiple of 16: one pipeline block holds every deposit
+    parts = R.random_particles(rng, n, nx, ny, nz, uth=uth)
+    sp.set_particles(parts)
+    ref_scalar.clear_accumulator_array(W.aa)
+    ref_scalar.advance_p(sp.sp, W.aa, W.ia)
+    ref_scalar.reduce_accumulator_array(W.aa)
+    p2, pm2, acc2, ign = port_push(oracle, W, sp, parts, 4096)
+    assert sp.c.nm == len(pm2)
+    if pbc and -2 in pbc.values():
+        assert sp.c.nm > 0
+    assert np.array_equal(bits(p2), bits(sp.p[:n]))
+    assert np.array_equal(bits(pm2), bits(sp.pm[:sp.c.nm]))
+    assert np.array_equal(bits(acc2), bits(W.accum[0]))
+    assert (p2["i"] != parts["i"]).mean() > 0.1     # the move_p path really ran
+
+
+def test_sort_p_bit_exact(ref_scalar, oracle):
+    rng = np.random.default_rng(5)
+    nx, ny, nz = 7, 6, 5
+    W = make_world(ref_scalar, rng, nx, ny, nz)
+    sp = W.new_species("s%d" % rng.integers(1 << 30), -1.0, 1.0, 20000, 16)
+    parts = R.random_particles(rng, 17777, nx, ny, nz)
+    sp.set_particles(parts)
+    ref_scalar.sort_p(sp.sp)
+    p2, aux = parts.copy(), np.zeros_like(parts)
+    part2 = np.full(W.nv + 1, -7, dtype=np.int32)
+    oracle.vpo_sort_p(p2.ctypes.data, len(p2), aux.ctypes.data, part2.ctypes.data, nx, ny, nz)
+    assert np.array_equal(bits(p2), bits(sp.p[:len(p2)]))
+    assert np.array_equal(part2[:W.nv], sp.partition[:W.nv])
+    assert np.all(np.diff(p2["i"]) >= 0)
+
+
+def test_interpolator_unload_energy_center(ref_scalar, oracle):
+    rng = np.random.default_rng(9)
+    nx, ny, nz = 6, 4, 5
+    W = make_world(ref_scalar, rng, nx, ny, nz)
+    lib = ref_scalar
+    i2 = np.zeros_like(W.interp)
+    oracle.vpo_load_interpolator(i2.ctypes.data, W.isf, W.fields.ctypes.data, nx, ny, nz)
+    assert np.array_equal(bits(i2), bits(W.interp))
+
+    # unload: random accumulators in the interior, zero ghosts as the reference requires
+    acc = W.accum[0]
+    acc[:] = 0
+    x, y, z = np.meshgrid(np.arange(1, nx + 1), np.arange(1, ny + 1), np.arange(1, nz + 1), indexing="ij")
+    v = abi.voxel(x, y, z, nx, ny, nz).ravel()
+    acc[v] = rng.normal(0, 1, (len(v), W.asf)).astype(np.float32)
+    f2 = W.fields.copy()
+    g = W.g.contents
+    oracle.vpo_unload_accumulator(f2.ctypes.data, acc.ctypes.data, W.asf, nx, ny, nz, g.rdx, g.rdy, g.rdz, g.dt)
+    lib.unload_accumulator_array(W.fa, W.aa)
+    assert np.array_equal(bits(f2), bits(W.fields))
+    # clear
+    a2 = acc.copy()
+    oracle.vpo_clear_accumulator(a2.ctypes.data, W.asf, nx, ny, nz)
+    lib.clear_accumulator_array(W.aa)
+    assert np.array_equal(bits(a2), bits(W.accum[0]))
+
+    sp = W.new_species("c%d" % rng.integers(1 << 30), -1.0, 1.5, 8192, 16)
+    parts = R.random_particles(rng, 4800, nx, ny, nz, uth=0.4, w=0.37)
+    sp.set_particles(parts)
+    e_ref = lib.energy_p(sp.sp, W.ia)
+    e_port = oracle.vpo_energy_p(parts.ctypes.data, len(parts), W.interp.ctypes.data, W.isf, -1.0, 1.5, g.dt, g.cvac)
+    assert e_ref == e_port
+    k = sp.push_constants()
+    p2 = parts.copy()
+    oracle.vpo_uncenter_p(p2.ctypes.data, len(p2), W.interp.ctypes.data, W.isf, k["qdt_2mc"])
+    lib.uncenter_p(sp.sp, W.ia)
+    assert np.array_equal(bits(p2), bits(sp.p[:len(p2)]))
+    oracle.vpo_center_p(p2.ctypes.data, len(p2), W.interp.ctypes.data, W.isf, k["qdt_2mc"])
+    lib.center_p(sp.sp, W.ia)
+    assert np.array_equal(bits(p2), bits(sp.p[:len(p2)]))
+
+
+@pytest.mark.parametrize("dims,fbc,damp", [
+    ((6, 5, 4), None, 0.0),
+    ((6, 5, 4), None, 0.01),
+    ((8, 8, 1), {0: -1, 3: -1}, 0.0),             # harris-like: pec x walls, degenerate z
+    ((5, 1, 7), {2: -2, 5: -3}, 0.0),             # symmetric / pmc walls, degenerate y
+])
+def test_field_advance_bit_exact(ref_scalar, oracle, dims, fbc, damp):
+    rng = np.random.default_rng(3)
+    nx, ny, nz = dims
+    W = R.RefWorld(ref_scalar, nx, ny, nz, fbc=fbc, damp=damp)
+    f0 = R.random_fields(rng, W.nv)
+    f0[:, 8:11] = rng.normal(0, 0.01, (W.nv, 3))       # tca
+    f0[:, 12:15] = rng.normal(0, 0.02, (W.nv, 3))      # jf
+    W.fields[:] = f0
+    f2 = f0.copy()
+    a = W.field_args(f2)
+    for _ in range(3):
+        W.synchronize_jf(); oracle.vpo_synchronize_jf(C.byref(a))
+        assert np.array_equal(bits(f2), bits(W.fields))
+        W.advance_b(0.5); oracle.vpo_advance_b(C.byref(a), 0.5)
+        assert np.array_equal(bits(f2), bits(W.fields))
+        W.advance_e(1.0); oracle.vpo_vacuum_advance_e(C.byref(a), 1.0)
+        assert np.array_equal(bits(f2), bits(W.fields))
+        W.advance_b(0.5); oracle.vpo_advance_b(C.byref(a), 0.5)
+        assert np.array_equal(bits(f2), bits(W.fields))
+    en = (C.c_double * 6)()
+    oracle.vpo_vacuum_energy_f(C.byref(a), en)
+    assert np.array_equal(np.array(en[:]), W.energy_f())
+    W.clear_jf(); oracle.vpo_clear_jf(C.byref(a))
+    assert np.array_equal(bits(f2), bits(W.fields))

@@ -1,0 +1,273 @@
+// sort_p for sm_100a: stable counting sort of particles by voxel index, and of movers by particle index.
+//
+// Replaces src/species_advance/standard/pipeline/sort_p_pipeline.cc:30-371 (coarse_count / coarse_sort / subsort
+// over pthread pipelines).  The reference's two stable passes give exactly "stable sort by p.i"; so does this:
+// a least-significant-digit radix sort with 8-bit digits over only the bits nv needs, each pass a stable split
+//   (1) per-CTA digit histogram over the CTA's contiguous chunk,
+//   (2) exclusive scan of the [digit][CTA] matrix (digit-major),
+//   (3) stable scatter: inside a CTA, items are ranked warp by warp with __match_any_sync against per-warp digit
+//       counters in shared memory, so equal keys keep their input order.
+// Whole 32-byte particles (one DRAM sector each) move in every pass as two 128-bit halves; there is no separate
+// key/index array and no gather pass.  partition[] falls out of the sorted keys (lower bounds).
+#include "vpb_common.cuh"
+
+namespace vpb {
+
+constexpr int kRadixBits = 8;
+constexpr int kRadix = 1 << kRadixBits;
+constexpr int kSortBlock = 256;
+constexpr int kSortWarps = kSortBlock / 32;
+constexpr int kIPT = 4;                                 // items per thread per sub-tile
+constexpr int kSubTile = kSortBlock * kIPT;
+constexpr int kMaxSortBlocks = 4096;
+
+// ---- exclusive scan of int32 (in place), n up to 8192 * 8192 ----------------------------------------------
+constexpr int kScanBlock = 1024;
+constexpr int kScanIPT = 8;
+constexpr int kScanTile = kScanBlock * kScanIPT;
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int *s_warp, int &total) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  int x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+  if (lane == 31) s_warp[w] = x;
+  __syncthreads();
+  if (w == 0) {
+    int s = lane < nw ? s_warp[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
+    if (lane < nw) s_warp[lane] = s;
+  }
+  __syncthreads();
+  const int woff = w ? s_warp[w - 1] : 0;
+  total = s_warp[nw - 1];
+  __syncthreads();
+  return woff + x - v;
+}
+
+__global__ void __launch_bounds__(kScanBlock) scan_reduce_kernel(const int *in, int n, int *block_sums) {
+  __shared__ int s_warp[32];
+  const int base = blockIdx.x * kScanTile + threadIdx.x * kScanIPT;
+  int s = 0;
+#pragma unroll
+  for (int k = 0; k < kScanIPT; k++) if (base + k < n) s += in[base + k];
+  int total;
+  block_exclusive_scan(s, s_warp, total);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+// single CTA: exclusive scan of up to kScanTile block sums
+__global__ void __launch_bounds__(kScanBlock) scan_top_kernel(int *sums, int n) {
+  __shared__ int s_warp[32];
+  const int base = threadIdx.x * kScanIPT;
+  int v[kScanIPT], s = 0;
+#pragma unroll
+  for (int k = 0; k < kScanIPT; k++) { v[k] = (base + k < n) ? sums[base + k] : 0; s += v[k]; }
+  int total;
+  int off = block_exclusive_scan(s, s_warp, total);
+#pragma unroll
+  for (int k = 0; k < kScanIPT; k++) { if (base + k < n) sums[base + k] = off; off += v[k]; }
+}
+
+__global__ void __launch_bounds__(kScanBlock) scan_apply_kernel(int *data, int n, const int *block_offs) {
+  __shared__ int s_warp[32];
+  const int base = blockIdx.x * kScanTile + threadIdx.x * kScanIPT;
+  int v[kScanIPT], s = 0;
+#pragma unroll
+  for (int k = 0; k < kScanIPT; k++) { v[k] = (base + k < n) ? data[base + k] : 0; s += v[k]; }
+  int total;
+  int off = block_exclusive_scan(s, s_warp, total) + block_offs[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < kScanIPT; k++) { if (base + k < n) data[base + k] = off; off += v[k]; }
+}
+
+static int exclusive_scan_inplace(int *data, int n, int *tmp /* >= ceil(n/kScanTile) ints */, cudaStream_t st) {
+  const int nb = (n + kScanTile - 1) / kScanTile;
+  VPB_REQUIRE(nb <= kScanTile, "scan: %d elements exceed the two-level scan", n);
+  scan_reduce_kernel<<<nb, kScanBlock, 0, st>>>(data, n, tmp);  VPB_LAUNCH_CHECK();
+  scan_top_kernel<<<1, kScanBlock, 0, st>>>(tmp, nb);           VPB_LAUNCH_CHECK();
+  scan_apply_kernel<<<nb, kScanBlock, 0, st>>>(data, n, tmp);   VPB_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- radix passes ----------------------------------------------------------------------------------------
+// Items are VEC int4 words; the key is word 0's .w (particle_t.i and particle_mover_t.i both sit there).
+
+template <int VEC>
+__global__ void __launch_bounds__(kSortBlock) radix_hist_kernel(const int4 *items, int n, int per_block, int shift,
+                                                                int *hist /* [kRadix][gridDim.x] */) {
+  __shared__ int s_hist[kRadix];
+  for (int d = threadIdx.x; d < kRadix; d += kSortBlock) s_hist[d] = 0;
+  __syncthreads();
+  const int lo = blockIdx.x * per_block;
+  const int hi = min(n, lo + per_block);
+  const int lane = threadIdx.x & 31;
+  for (int i0 = lo; i0 < hi; i0 += kSortBlock) {
+    const int i = i0 + threadIdx.x;
+    const bool valid = i < hi;
+    const int d = valid ? ((items[(size_t)i * VEC].w >> shift) & (kRadix - 1)) : (kRadix + lane);
+    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    if (valid && lane == __ffs(peers) - 1) atomicAdd(&s_hist[d], __popc(peers));
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < kRadix; d += kSortBlock) hist[d * gridDim.x + blockIdx.x] = s_hist[d];
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(kSortBlock) radix_scatter_kernel(const int4 *src, int4 *dst, int n, int per_block,
+                                                                   int shift, const int *offs /* scanned hist */) {
+  __shared__ int s_base[kRadix];                       // next output slot of each digit for this CTA
+  __shared__ int s_wcount[kSortWarps][kRadix];         // per-warp digit counts of the current sub-tile
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  for (int d = tid; d < kRadix; d += kSortBlock) s_base[d] = offs[d * gridDim.x + blockIdx.x];
+  const int lo = blockIdx.x * per_block;
+  const int hi = min(n, lo + per_block);
+
+  for (int t0 = lo; t0 < hi; t0 += kSubTile) {
+    for (int d = tid; d < kRadix * kSortWarps; d += kSortBlock) (&s_wcount[0][0])[d] = 0;
+    __syncthreads();
+
+    int4 it[kIPT][VEC];
+    int digit[kIPT], rank[kIPT];
+    // warp-striped: warp w owns items [t0 + w*32*kIPT, +32*kIPT); step j covers 32 consecutive items
+#pragma unroll
+    for (int j = 0; j < kIPT; j++) {
+      const int i = t0 + w * 32 * kIPT + j * 32 + lane;
+      const bool valid = i < hi;
+      if (valid) {
+#pragma unroll
+        for (int v = 0; v < VEC; v++) it[j][v] = src[(size_t)i * VEC + v];
+      }
+      const int d = valid ? ((it[j][0].w >> shift) & (kRadix - 1)) : (kRadix + lane);
+      digit[j] = valid ? d : -1;
+      const unsigned peers = __match_any_sync(0xffffffffu, d);
+      int before = 0;
+      if (valid) before = s_wcount[w][d];
+      __syncwarp();
+      if (valid && lane == __ffs(peers) - 1) s_wcount[w][d] = before + __popc(peers);
+      __syncwarp();
+      rank[j] = before + __popc(peers & lt_mask);
+    }
+    __syncthreads();
+    // digit-wise exclusive prefix over warps; thread d owns digit d (kSortBlock == kRadix)
+    {
+      int run = 0;
+#pragma unroll
+      for (int ww = 0; ww < kSortWarps; ww++) { const int c = s_wcount[ww][tid]; s_wcount[ww][tid] = run; run += c; }
+      const int b = s_base[tid];
+      s_base[tid] = b + run;
+#pragma unroll
+      for (int ww = 0; ww < kSortWarps; ww++) s_wcount[ww][tid] += b;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kIPT; j++) {
+      if (digit[j] >= 0) {
+        const int o = s_wcount[w][digit[j]] + rank[j];
+#pragma unroll
+        for (int v = 0; v < VEC; v++) dst[(size_t)o * VEC + v] = it[j][v];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// partition[v] = number of particles with p.i < v, for v in [0, nv]  (sort_p_pipeline.cc:183-193,335-340)
+__global__ void partition_kernel(const int4 *p, int np, int nv, int *partition) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > np) return;
+  int lo = (i == 0) ? 0 : p[2 * (size_t)(i - 1)].w + 1;
+  int hi = (i == np) ? nv : p[2 * (size_t)i].w;
+  if (lo < 0) lo = 0;
+  if (hi > nv) hi = nv;
+  for (int v = lo; v <= hi; v++) partition[v] = i;
+}
+
+static int ceil_log2(int64_t x) { int b = 0; while (((int64_t)1 << b) < x) b++; return b; }
+
+struct SortPlan { int nblocks, per_block, scan_tmp; size_t hist_bytes, total_bytes; };
+
+static SortPlan plan_sort(int n) {
+  SortPlan s;
+  int nb = (n + kSubTile - 1) / kSubTile;
+  if (nb < 1) nb = 1;
+  if (nb > kMaxSortBlocks) nb = kMaxSortBlocks;
+  int per = (n + nb - 1) / nb;
+  per = ((per + kSubTile - 1) / kSubTile) * kSubTile;          // whole sub-tiles per CTA
+  if (per < kSubTile) per = kSubTile;
+  nb = (n + per - 1) / per; if (nb < 1) nb = 1;
+  s.nblocks = nb; s.per_block = per;
+  s.scan_tmp = (kRadix * nb + kScanTile - 1) / kScanTile;
+  s.hist_bytes = (size_t)kRadix * nb * sizeof(int);
+  s.total_bytes = ((s.hist_bytes + 255) / 256) * 256 + (size_t)s.scan_tmp * sizeof(int) + 256;
+  return s;
+}
+
+template <int VEC>
+static int radix_sort(int4 *a, int4 *b, int n, int key_bits, void *scratch, size_t scratch_bytes, cudaStream_t st,
+                      bool *result_in_b) {
+  const SortPlan pl = plan_sort(n);
+  VPB_REQUIRE(scratch && scratch_bytes >= pl.total_bytes, "sort: scratch too small (%zu < %zu)", scratch_bytes, pl.total_bytes);
+  int *hist = (int *)scratch;
+  int *tmp = (int *)((char *)scratch + ((pl.hist_bytes + 255) / 256) * 256);
+  int4 *src = a, *dst = b;
+  for (int shift = 0; shift < key_bits; shift += kRadixBits) {
+    radix_hist_kernel<VEC><<<pl.nblocks, kSortBlock, 0, st>>>(src, n, pl.per_block, shift, hist);  VPB_LAUNCH_CHECK();
+    int r = exclusive_scan_inplace(hist, kRadix * pl.nblocks, tmp, st); if (r) return r;
+    radix_scatter_kernel<VEC><<<pl.nblocks, kSortBlock, 0, st>>>(src, dst, n, pl.per_block, shift, hist);  VPB_LAUNCH_CHECK();
+    int4 *t = src; src = dst; dst = t;
+  }
+  *result_in_b = (src == b);
+  return 0;
+}
+
+}  // namespace vpb
+
+using namespace vpb;
+
+extern "C" size_t vpb_sort_scratch_bytes(int32_t n_items, int32_t /*n_keys_hint*/) {
+  return plan_sort(n_items > 0 ? n_items : 1).total_bytes;
+}
+
+extern "C" int vpb_sort_p(void *p, int32_t np, void *aux, int32_t *partition, int32_t nx, int32_t ny, int32_t nz,
+                          void *scratch, size_t scratch_bytes, void *stream) {
+  VPB_REQUIRE(p && partition && (aux || np == 0), "vpb_sort_p: Bad args");
+  VPB_REQUIRE(np >= 0 && nx > 0 && ny > 0 && nz > 0, "vpb_sort_p: Bad args");
+  cudaStream_t st = as_stream(stream);
+  const int64_t nv64 = (int64_t)(nx + 2) * (ny + 2) * (nz + 2);
+  VPB_REQUIRE(nv64 < (1ll << 31), "vpb_sort_p: too many voxels");
+  const int nv = (int)nv64;
+  if (np > 1) {
+    bool in_aux = false;
+    int r = radix_sort<2>((int4 *)p, (int4 *)aux, np, ceil_log2(nv), scratch, scratch_bytes, st, &in_aux);
+    if (r) return r;
+    if (in_aux) VPB_CUDA(cudaMemcpyAsync(p, aux, (size_t)np * 32, cudaMemcpyDeviceToDevice, st));
+  }
+  const int threads = 256;
+  partition_kernel<<<(np + 1 + threads - 1) / threads, threads, 0, st>>>((const int4 *)p, np, nv, partition);
+  VPB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" size_t vpb_sort_movers_scratch_bytes(int32_t nm) {
+  if (nm < 1) nm = 1;
+  return (((size_t)nm * 16 + 255) / 256) * 256 + plan_sort(nm).total_bytes;
+}
+
+// Movers: sort ascending by particle index (unique keys).  nm is a host value here; the drop-in layer reads the
+// device counter first (it has to report sp->nm to the host anyway).
+extern "C" int vpb_sort_movers(void *pm, int32_t nm, void *scratch, size_t scratch_bytes, void *stream) {
+  if (nm <= 1) return 0;
+  VPB_REQUIRE(pm && scratch, "vpb_sort_movers: Bad args");
+  cudaStream_t st = as_stream(stream);
+  // scratch = [aux movers | sort scratch]
+  const size_t aux_bytes = (((size_t)nm * 16 + 255) / 256) * 256;
+  VPB_REQUIRE(scratch_bytes > aux_bytes, "vpb_sort_movers: scratch too small");
+  bool in_aux = false;
+  int r = radix_sort<1>((int4 *)pm, (int4 *)scratch, nm, 31, (char *)scratch + aux_bytes, scratch_bytes - aux_bytes, st, &in_aux);
+  if (r) return r;
+  if (in_aux) VPB_CUDA(cudaMemcpyAsync(pm, scratch, (size_t)nm * 16, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}

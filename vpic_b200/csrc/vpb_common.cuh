@@ -1,0 +1,52 @@
+// Shared helpers for libvpic_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/vpic_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libvpic_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace vpb {
+
+constexpr int kSMs = 148;                  // B200: 2 dies x 74 SMs
+
+void set_error(const char *fmt, ...);
+int  check_cuda(cudaError_t e, const char *what, const char *file, int line);
+void count_launch(int n = 1);
+
+#define VPB_CUDA(call) do { int _r = vpb::check_cuda((call), #call, __FILE__, __LINE__); if (_r) return _r; } while (0)
+#define VPB_LAUNCH_CHECK() do { vpb::count_launch(); VPB_CUDA(cudaGetLastError()); } while (0)
+#define VPB_REQUIRE(cond, ...) do { if (!(cond)) { vpb::set_error(__VA_ARGS__); return -1; } } while (0)
+
+static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// VOXEL macro of the reference (src/grid/grid.h:136)
+__host__ __device__ __forceinline__ int voxel(int x, int y, int z, int nx, int ny) {
+  return x + (nx + 2) * (y + (ny + 2) * z);
+}
+
+// red.global.add.v4.f32 (sm_90+): one 16-byte reduction instead of four scalar ones
+__device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+               :: "l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void red_add(float *addr, float a) {
+  asm volatile("red.global.add.f32 [%0], %1;" :: "l"(addr), "f"(a) : "memory");
+}
+
+// streaming 128-bit accesses that do not allocate in L1
+__device__ __forceinline__ float4 ld_stream(const float4 *p) {
+  float4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream(float4 *p, const float4 &v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};"
+               :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+}  // namespace vpb

@@ -1,0 +1,245 @@
+"""Host-side mirror of the reference's operator interface for the hot path, over device-resident arrays.
+
+Names, argument meaning and error behaviour follow the reference's C API
+(src/species_advance/species_advance.h:27-159, src/sf_interface/sf_interface.h:82-174): `advance_p(sp, aa, ia)`,
+`sort_p(sp)`, `load_interpolator_array(ia, fa)`, `clear/reduce/unload_accumulator_array`, `energy_p`, ...
+Objects hold torch CUDA tensors in the reference's exact layouts (particle_t 32 B, interpolator_t 80 B,
+accumulator_t 48 B, field_t 80 B); every operator is one call into libvpic_b200.so through the C-ABI.
+torch is plumbing only (device memory, streams, torch.distributed) — there is no torch math on this path and no
+CPU fallback: without the CUDA library these calls raise.
+"""
+import ctypes as C
+import numpy as np
+import torch
+
+from . import abi, lib as _lib
+from .grid import Grid
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(None)
+
+
+def _bad_args(cond, who):
+    if cond:
+        raise ValueError(f"{who}: Bad args.")   # the reference ERROR()s and exits; a library raises instead
+
+
+class DeviceGrid:
+    """Device copy of the read-only parts of grid_t."""
+
+    def __init__(self, g: Grid, device="cuda"):
+        self.g = g
+        self.device = torch.device(device)
+        self.neighbor = torch.from_numpy(np.ascontiguousarray(g.neighbor)).to(self.device)
+        for k in ("nx", "ny", "nz", "nv", "dt", "cvac", "eps0", "dx", "dy", "dz", "dV", "rdx", "rdy", "rdz",
+                  "rangel", "rangeh", "rank", "world_size"):
+            setattr(self, k, getattr(g, k))
+
+    @property
+    def step(self):
+        return self.g.step
+
+
+class InterpolatorArray:
+    def __init__(self, g: DeviceGrid, simd_width=4):
+        self.g = g
+        self.stride = abi.interpolator_floats(simd_width)
+        self.i = torch.zeros((g.nv, self.stride), dtype=torch.float32, device=g.device)
+
+
+class AccumulatorArray:
+    """One accumulator block on the device (reduce_accumulator_array is the identity)."""
+
+    def __init__(self, g: DeviceGrid, simd_width=4):
+        self.g = g
+        self.stride_floats = abi.accumulator_floats(simd_width)
+        self.stride = (g.nv + 1) // 2 * 2                      # POW2_CEIL(nv,2), accumulator_array.cc:78
+        self.n_pipeline = 0
+        self.a = torch.zeros((self.stride, self.stride_floats), dtype=torch.float32, device=g.device)
+
+
+class FieldArray:
+    def __init__(self, g: DeviceGrid, damp=0.0):
+        self.g = g
+        self.damp = float(damp)
+        self.f = torch.zeros((g.nv, abi.FIELD_FLOATS), dtype=torch.float32, device=g.device)
+        self._en = torch.zeros(6, dtype=torch.float64, device=g.device)
+
+    def args(self):
+        g = self.g
+        a = _lib.FieldArgs()
+        a.f = self.f.data_ptr()
+        a.nx, a.ny, a.nz = g.nx, g.ny, g.nz
+        a.dt, a.cvac, a.eps0, a.damp = g.dt, g.cvac, g.eps0, self.damp
+        a.dx, a.dy, a.dz, a.dV = g.dx, g.dy, g.dz, g.dV
+        a.rdx, a.rdy, a.rdz = g.rdx, g.rdy, g.rdz
+        for i, c in enumerate(g.g.face_codes()):
+            a.face[i] = c
+        return a
+
+    # field_advance_kernels_t entries on the path (field_advance.h:170-218)
+    def advance_b(self, frac):
+        _lib.check(_lib.load().vpb_advance_b(C.byref(self.args()), frac, _stream()), "advance_b")
+
+    def advance_e(self, frac=1.0):
+        _lib.check(_lib.load().vpb_vacuum_advance_e(C.byref(self.args()), frac, _stream()), "advance_e")
+
+    def clear_jf(self):
+        _lib.check(_lib.load().vpb_clear_jf(C.byref(self.args()), _stream()), "clear_jf")
+
+    def synchronize_jf(self):
+        _lib.check(_lib.load().vpb_synchronize_jf(C.byref(self.args()), _stream()), "synchronize_jf")
+
+    def energy_f(self):
+        _lib.check(_lib.load().vpb_vacuum_energy_f(C.byref(self.args()), _ptr(self._en), _stream()), "energy_f")
+        return self._en.cpu().numpy().copy()
+
+
+class Species:
+    """species_t (species_advance_aos.h:54-94) with device arrays."""
+
+    def __init__(self, name, q, m, max_np, max_nm, sort_interval, sort_out_of_place, g: DeviceGrid):
+        _bad_args(not name or g is None, "species")
+        self.name, self.q, self.m = name, float(np.float32(q)), float(np.float32(m))
+        self.max_np, self.max_nm = max(1, int(max_np)), max(1, int(max_nm))
+        self.np, self.nm = 0, 0
+        self.g = g
+        self.sort_interval, self.sort_out_of_place = sort_interval, sort_out_of_place
+        self.last_sorted = -(2 ** 63)
+        dev = g.device
+        self.p = torch.zeros((self.max_np, 8), dtype=torch.float32, device=dev)
+        self.pm = torch.zeros((self.max_nm, 4), dtype=torch.float32, device=dev)
+        self.partition = torch.zeros(g.nv + 1, dtype=torch.int32, device=dev)
+        self.counters = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.n_ignored = 0
+        self._aux = None
+        self._scratch = None
+        self._en = torch.zeros(1, dtype=torch.float64, device=dev)
+
+    def set_particles(self, arr):
+        """arr: numpy structured array (abi.particle_dtype) or float32 [n,8] tensor."""
+        if isinstance(arr, np.ndarray):
+            t = torch.from_numpy(arr.view(np.float32).reshape(-1, 8))
+        else:
+            t = arr
+        n = t.shape[0]
+        _bad_args(n > self.max_np, "set_particles")
+        self.p[:n].copy_(t)
+        self.np, self.nm = n, 0
+
+    def particles_host(self):
+        return self.p[:self.np].cpu().numpy().reshape(-1).view(abi.particle_dtype)
+
+    def movers_host(self):
+        return self.pm[:self.nm].cpu().numpy().reshape(-1).view(abi.mover_dtype)
+
+    def push_constants(self):
+        """advance_p_pipeline.cc:279-283, evaluated in float like the reference does."""
+        f32, g = np.float32, self.g
+        q, m, dt, cvac = f32(self.q), f32(self.m), f32(g.dt), f32(g.cvac)
+        return (f32(f32(q * dt) / f32(f32(f32(2) * m) * cvac)),
+                f32(f32(cvac * dt) * f32(g.rdx)), f32(f32(cvac * dt) * f32(g.rdy)), f32(f32(cvac * dt) * f32(g.rdz)), q)
+
+
+# ---- operators (same names as the reference's C API) ---------------------------------------------------------
+
+def advance_p(sp: Species, aa: AccumulatorArray, ia: InterpolatorArray, variant=_lib.DEPOSIT_DEFAULT, sync=True):
+    """advance_p(species_t*, accumulator_array_t*, const interpolator_array_t*), species_advance.h:73-76."""
+    _bad_args(sp is None or aa is None or ia is None or sp.g is not aa.g or sp.g is not ia.g, "advance_p")
+    g = sp.g
+    sp.counters.zero_()
+    a = _lib.PushArgs()
+    a.p, a.np = sp.p.data_ptr(), sp.np
+    a.pm, a.max_nm = sp.pm.data_ptr(), sp.max_nm
+    a.counters = sp.counters.data_ptr()
+    a.interp, a.interp_stride = ia.i.data_ptr(), ia.stride
+    a.accum, a.accum_stride = aa.a.data_ptr(), aa.stride_floats
+    a.neighbor, a.rangel, a.rangeh = g.neighbor.data_ptr(), g.rangel, g.rangeh
+    a.qdt_2mc, a.cdt_dx, a.cdt_dy, a.cdt_dz, a.qsp = sp.push_constants()
+    a.nx, a.ny, a.nz = g.nx, g.ny, g.nz
+    a.variant = variant
+    L = _lib.load()
+    _lib.check(L.vpb_advance_p(C.byref(a), _stream()), "advance_p")
+    if sync:
+        finish_advance_p(sp)
+
+
+def finish_advance_p(sp: Species):
+    """Read back the mover count (sp->nm) and put the movers in ascending particle order for boundary_p."""
+    L = _lib.load()
+    c = sp.counters.cpu()
+    sp.nm = min(int(c[0]), sp.max_nm)
+    sp.n_ignored = int(c[1])
+    if sp.n_ignored:
+        import warnings
+        warnings.warn(f"species {sp.name} ran out of storage for {sp.n_ignored} movers")   # advance_p_pipeline.cc:313-329
+    if sp.nm > 1:
+        need = L.vpb_sort_movers_scratch_bytes(sp.nm)
+        scratch = torch.empty(need, dtype=torch.uint8, device=sp.g.device)
+        _lib.check(L.vpb_sort_movers(_ptr(sp.pm), sp.nm, _ptr(scratch), need, _stream()), "sort_movers")
+
+
+def sort_p(sp: Species):
+    """sort_p(species_t*), species_advance.h:65-66."""
+    _bad_args(sp is None, "sort_p")
+    L = _lib.load()
+    g = sp.g
+    sp.last_sorted = g.step
+    if sp._aux is None or sp._aux.shape[0] < sp.np:
+        sp._aux = torch.empty((sp.max_np, 8), dtype=torch.float32, device=g.device)
+    need = L.vpb_sort_scratch_bytes(max(sp.np, 1), g.nv)
+    if sp._scratch is None or sp._scratch.numel() < need:
+        sp._scratch = torch.empty(need, dtype=torch.uint8, device=g.device)
+    _lib.check(L.vpb_sort_p(_ptr(sp.p), sp.np, _ptr(sp._aux), _ptr(sp.partition), g.nx, g.ny, g.nz,
+                            _ptr(sp._scratch), sp._scratch.numel(), _stream()), "sort_p")
+
+
+def load_interpolator_array(ia: InterpolatorArray, fa: FieldArray):
+    _bad_args(ia is None or fa is None or ia.g is not fa.g, "load_interpolator_array")
+    g = ia.g
+    _lib.check(_lib.load().vpb_load_interpolator(_ptr(ia.i), ia.stride, _ptr(fa.f), g.nx, g.ny, g.nz, _stream()),
+               "load_interpolator_array")
+
+
+def clear_accumulator_array(aa: AccumulatorArray):
+    _bad_args(aa is None, "clear_accumulator_array")
+    g = aa.g
+    _lib.check(_lib.load().vpb_clear_accumulator(_ptr(aa.a), aa.stride_floats, g.nx, g.ny, g.nz, _stream()),
+               "clear_accumulator_array")
+
+
+def reduce_accumulator_array(aa: AccumulatorArray):
+    """Identity on the device: there is a single accumulator block (the reference sums n_pipeline+1 blocks)."""
+    _bad_args(aa is None, "reduce_accumulator_array")
+
+
+def unload_accumulator_array(fa: FieldArray, aa: AccumulatorArray):
+    _bad_args(fa is None or aa is None or fa.g is not aa.g, "unload_accumulator_array")
+    g = fa.g
+    _lib.check(_lib.load().vpb_unload_accumulator(_ptr(fa.f), _ptr(aa.a), aa.stride_floats, g.nx, g.ny, g.nz,
+                                                  g.rdx, g.rdy, g.rdz, g.dt, _stream()), "unload_accumulator_array")
+
+
+def energy_p(sp: Species, ia: InterpolatorArray):
+    _bad_args(sp is None or ia is None or sp.g is not ia.g, "energy_p")
+    g = sp.g
+    _lib.check(_lib.load().vpb_energy_p(_ptr(sp.p), sp.np, _ptr(ia.i), ia.stride, sp.q, sp.m, g.dt, g.cvac,
+                                        _ptr(sp._en), _stream()), "energy_p")
+    return float(sp._en.cpu()[0])
+
+
+def center_p(sp: Species, ia: InterpolatorArray):
+    _bad_args(sp is None or ia is None or sp.g is not ia.g, "center_p")
+    _lib.check(_lib.load().vpb_center_p(_ptr(sp.p), sp.np, _ptr(ia.i), ia.stride, sp.push_constants()[0], _stream()),
+               "center_p")
+
+
+def uncenter_p(sp: Species, ia: InterpolatorArray):
+    _bad_args(sp is None or ia is None or sp.g is not ia.g, "uncenter_p")
+    _lib.check(_lib.load().vpb_uncenter_p(_ptr(sp.p), sp.np, _ptr(ia.i), ia.stride, sp.push_constants()[0], _stream()),
+               "uncenter_p")
