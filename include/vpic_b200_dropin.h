@@ -1,0 +1,57 @@
+/* vpic_b200_dropin.h — the link-time seam: the reference's own extern "C" hot-path symbols, re-implemented over
+ * the device layer (vpic_b200.h).  Signatures are the reference's (file:line below, under the reference tree); the
+ * struct types are the layout-compatible restatements in vpic_b200_abi.h.  A host program built from the unmodified
+ * reference sources gets the GPU path by linking libvpic_b200.so in place of the seven source files listed in
+ * INTEGRATION.md (or, for a shared-library build of the reference, by LD_PRELOADing it).
+ *
+ * Ownership stays with the host: every array is allocated, resized and checkpointed by the reference host code.
+ * This layer keeps a device mirror per host array, looked up by the CURRENT host pointer and size on every call.
+ *
+ * Coherence modes (vpic_b200_set_mode, or env VPIC_B200_MODE=coherent|resident):
+ *   VPB_MODE_COHERENT (default)  every call copies its inputs host->device and its outputs device->host, so host
+ *                                code may read or write any array between calls — decks and tests run unchanged.
+ *   VPB_MODE_RESIDENT            arrays stay on the device between calls; host copies go stale until
+ *                                vpic_b200_sync_to_host(ptr) and host writes need vpic_b200_invalidate(ptr).
+ *
+ * Errors follow the reference's convention (src/util/util_base.h:267-273): message on stderr as
+ * "Error at file(line)[rank]:", then exit(1).  There is no CPU fallback.
+ */
+#ifndef VPIC_B200_DROPIN_H
+#define VPIC_B200_DROPIN_H
+
+#include "vpic_b200_abi.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VPB_MODE_COHERENT 0
+#define VPB_MODE_RESIDENT 1
+
+/* src/species_advance/species_advance.h:73-76 */
+void advance_p(vpb_species_t *sp, vpb_accumulator_array_t *aa, const vpb_interpolator_array_t *ia);
+/* src/species_advance/species_advance.h:65-66 */
+void sort_p(vpb_species_t *sp);
+/* src/species_advance/species_advance.h:90-107 */
+void center_p(vpb_species_t *sp, const vpb_interpolator_array_t *ia);
+void uncenter_p(vpb_species_t *sp, const vpb_interpolator_array_t *ia);
+double energy_p(const vpb_species_t *sp, const vpb_interpolator_array_t *ia);
+/* src/sf_interface/sf_interface.h:99-101 */
+void load_interpolator_array(vpb_interpolator_array_t *ia, const vpb_field_array_t *fa);
+/* src/sf_interface/sf_interface.h:147-148,158-159,172-174 */
+void clear_accumulator_array(vpb_accumulator_array_t *aa);
+void reduce_accumulator_array(vpb_accumulator_array_t *aa);
+void unload_accumulator_array(vpb_field_array_t *fa, const vpb_accumulator_array_t *aa);
+
+/* coherence control (new; no reference counterpart) */
+void vpic_b200_set_mode(int mode);
+void vpic_b200_sync_to_host(const void *host_ptr);     /* device -> host for the mirror of host_ptr (NULL: all) */
+void vpic_b200_invalidate(const void *host_ptr);       /* host copy was modified: re-upload on next use (NULL: all) */
+void vpic_b200_release(const void *host_ptr);          /* drop the mirror (call before the host frees/reallocs) */
+/* bytes moved by the drop-in layer since load: [0] host->device, [1] device->host */
+void vpic_b200_transfer_bytes(uint64_t out[2]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,299 @@
+// Drop-in layer: the reference's extern "C" hot-path entry points over the device layer.
+// See include/vpic_b200_dropin.h for the contract and INTEGRATION.md for how a host build links it.
+//
+// Host code only (no kernels): argument checks in the reference's convention, the host<->device mirror registry,
+// and one call into the vpb_* device layer per entry point.
+#include "vpb_common.cuh"
+#include "../../include/vpic_b200_dropin.h"
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+#include <unordered_map>
+
+// Symbols of the reference host program, present when this library is linked into (or preloaded under) it.
+extern "C" {
+extern int _world_rank __attribute__((weak));                                  // src/util/mp/DMPPolicy.h:32
+void mp_allsum_d(double *local, double *global, int n) __attribute__((weak));  // src/util/mp/mp.h
+}
+
+namespace {
+
+constexpr int kInterpFloats = (int)(sizeof(vpb_interpolator_t) / sizeof(float));
+constexpr int kAccumFloats = (int)(sizeof(vpb_accumulator_t) / sizeof(float));
+static_assert(sizeof(vpb_particle_t) == 32 && sizeof(vpb_particle_mover_t) == 16 && sizeof(vpb_field_t) == 80, "ABI");
+
+int rank_for_log() { return &_world_rank ? _world_rank : 0; }
+
+// ERROR(()) of the reference: log, let the message out, exit(1)   (src/util/util_base.h:267-273)
+#define DROPIN_ERROR(...) do {                                                        \
+    fprintf(stderr, "Error at %s(%d)[%d]:\n\t", __FILE__, __LINE__, rank_for_log());  \
+    fprintf(stderr, __VA_ARGS__); fprintf(stderr, "\n"); fflush(stderr);              \
+    sleep(1); exit(1); } while (0)
+#define DROPIN_WARNING(...) do {                                                       \
+    fprintf(stderr, "Warning at %s(%d)[%d]:\n\t", __FILE__, __LINE__, rank_for_log()); \
+    fprintf(stderr, __VA_ARGS__); fprintf(stderr, "\n"); } while (0)
+#define DEV(call) do { int _r = (call); if (_r) DROPIN_ERROR("%s failed (%d): %s", #call, _r, vpb_last_error()); } while (0)
+
+struct Mirror {
+  void *d = nullptr; size_t cap = 0;
+  bool device_valid = false;      // device copy holds the current data
+  bool host_stale = false;        // device copy is newer than the host copy
+  size_t live_bytes = 0;          // extent last written on the device
+  bool pinned = false; size_t pinned_bytes = 0;
+};
+
+std::unordered_map<const void *, Mirror> g_mirrors;
+std::unordered_map<int, Mirror> g_scratch;
+int g_mode = -1;
+bool g_pin = false;
+uint64_t g_h2d = 0, g_d2h = 0;
+int *g_counters = nullptr;
+
+int mode() {
+  if (g_mode < 0) {
+    const char *e = getenv("VPIC_B200_MODE");
+    g_mode = (e && !strcmp(e, "resident")) ? VPB_MODE_RESIDENT : VPB_MODE_COHERENT;
+    const char *p = getenv("VPIC_B200_PIN");
+    g_pin = p && atoi(p) != 0;
+  }
+  return g_mode;
+}
+
+Mirror &mirror(const void *h, size_t bytes) {
+  Mirror &m = g_mirrors[h];
+  if (m.cap < bytes) {
+    if (m.d) { if (m.host_stale) DROPIN_ERROR("host array %p grew while its device copy was newer; sync_to_host first", h); DEV(vpb_free(m.d)); }
+    DEV(vpb_malloc(&m.d, bytes));
+    m.cap = bytes; m.device_valid = false; m.host_stale = false; m.live_bytes = 0;
+  }
+  if (g_pin && bytes >= (1u << 20) && (!m.pinned || m.pinned_bytes < bytes)) {
+    if (m.pinned) cudaHostUnregister(const_cast<void *>(h));
+    m.pinned = cudaHostRegister(const_cast<void *>(h), bytes, cudaHostRegisterDefault) == cudaSuccess;
+    m.pinned_bytes = m.pinned ? bytes : 0;
+    if (!m.pinned) cudaGetLastError();
+  }
+  return m;
+}
+
+// device pointer holding the CURRENT contents of host array h[0..bytes)
+void *dev_in(const void *h, size_t bytes, size_t cap_bytes = 0) {
+  mode();
+  Mirror &m = mirror(h, cap_bytes > bytes ? cap_bytes : bytes);
+  if (g_mode == VPB_MODE_COHERENT || !m.device_valid || m.live_bytes < bytes) {
+    if (bytes) { DEV(vpb_memcpy_h2d(m.d, h, bytes, nullptr)); g_h2d += bytes; }
+    m.device_valid = true; m.host_stale = false; m.live_bytes = bytes;
+  }
+  return m.d;
+}
+// device buffer for an output-only host array
+void *dev_out_only(const void *h, size_t cap_bytes) { mode(); return mirror(h, cap_bytes).d; }
+
+// the device wrote h[0..bytes): copy back now (coherent) or remember that the host copy is stale (resident)
+void dev_written(const void *h, size_t bytes) {
+  Mirror &m = g_mirrors[h];
+  m.device_valid = true; if (bytes > m.live_bytes) m.live_bytes = bytes;
+  if (g_mode == VPB_MODE_COHERENT) {
+    if (bytes) { DEV(vpb_memcpy_d2h(const_cast<void *>(h), m.d, bytes, nullptr)); g_d2h += bytes; }
+    m.host_stale = false;
+  } else {
+    m.host_stale = true;
+  }
+}
+
+void *scratch(int id, size_t bytes) {
+  Mirror &m = g_scratch[id];
+  if (m.cap < bytes) { if (m.d) DEV(vpb_free(m.d)); DEV(vpb_malloc(&m.d, bytes)); m.cap = bytes; }
+  return m.d;
+}
+
+int *counters() { if (!g_counters) DEV(vpb_malloc((void **)&g_counters, 4 * sizeof(int))); return g_counters; }
+
+void sync_one(const void *h, Mirror &m) {
+  if (m.host_stale && m.live_bytes) {
+    DEV(vpb_memcpy_d2h(const_cast<void *>(h), m.d, m.live_bytes, nullptr)); g_d2h += m.live_bytes;
+    DEV(vpb_stream_sync(nullptr));
+  }
+  m.host_stale = false;
+}
+
+float qdt_2mc_of(const vpb_species_t *sp) { return (sp->q * sp->g->dt) / (2 * sp->m * sp->g->cvac); }
+
+}  // namespace
+
+extern "C" {
+
+void vpic_b200_set_mode(int m) {
+  mode();
+  if (m != VPB_MODE_COHERENT && m != VPB_MODE_RESIDENT) DROPIN_ERROR("Bad args");
+  if (m == VPB_MODE_COHERENT) vpic_b200_sync_to_host(nullptr);
+  g_mode = m;
+}
+
+void vpic_b200_sync_to_host(const void *h) {
+  if (h) { auto it = g_mirrors.find(h); if (it != g_mirrors.end()) sync_one(h, it->second); return; }
+  for (auto &kv : g_mirrors) sync_one(kv.first, kv.second);
+}
+
+void vpic_b200_invalidate(const void *h) {
+  if (h) { auto it = g_mirrors.find(h); if (it != g_mirrors.end()) { it->second.device_valid = false; it->second.host_stale = false; } return; }
+  for (auto &kv : g_mirrors) { kv.second.device_valid = false; kv.second.host_stale = false; }
+}
+
+void vpic_b200_release(const void *h) {
+  auto it = g_mirrors.find(h);
+  if (it == g_mirrors.end()) return;
+  if (it->second.pinned) cudaHostUnregister(const_cast<void *>(h));
+  if (it->second.d) vpb_free(it->second.d);
+  g_mirrors.erase(it);
+}
+
+void vpic_b200_transfer_bytes(uint64_t out[2]) { out[0] = g_h2d; out[1] = g_d2h; }
+
+// ---- advance_p: species_advance.h:73-76, advance_p_pipeline.cc:252-340 ------------------------------------
+void advance_p(vpb_species_t *sp, vpb_accumulator_array_t *aa, const vpb_interpolator_array_t *ia) {
+  if (!sp || !aa || !ia || sp->g != aa->g || sp->g != ia->g) DROPIN_ERROR("Bad args.");
+  const vpb_grid_t *g = sp->g;
+  const size_t nv = (size_t)g->nv;
+  vpb_push_args_t a;
+  memset(&a, 0, sizeof a);
+  a.neighbor = (const int64_t *)dev_in(g->neighbor, 6 * nv * sizeof(int64_t));
+  a.interp = (const float *)dev_in(ia->i, nv * sizeof(vpb_interpolator_t));
+  a.interp_stride = kInterpFloats;
+  a.accum = (float *)dev_in(aa->a, (size_t)aa->stride * sizeof(vpb_accumulator_t));      // block 0 only
+  a.accum_stride = kAccumFloats;
+  a.p = dev_in(sp->p, (size_t)sp->np * sizeof(vpb_particle_t), (size_t)sp->max_np * sizeof(vpb_particle_t));
+  a.np = sp->np;
+  a.pm = dev_out_only(sp->pm, (size_t)sp->max_nm * sizeof(vpb_particle_mover_t));
+  a.max_nm = sp->max_nm;
+  a.counters = counters();
+  DEV(vpb_memset(a.counters, 0, 4 * sizeof(int), nullptr));
+  a.rangel = g->rangel; a.rangeh = g->rangeh;
+  a.qdt_2mc = qdt_2mc_of(sp);                              // all in float, as advance_p_pipeline.cc:279-283
+  a.cdt_dx = g->cvac * g->dt * g->rdx;
+  a.cdt_dy = g->cvac * g->dt * g->rdy;
+  a.cdt_dz = g->cvac * g->dt * g->rdz;
+  a.qsp = sp->q;
+  a.nx = g->nx; a.ny = g->ny; a.nz = g->nz;
+  a.variant = VPB_DEPOSIT_DEFAULT;
+  DEV(vpb_advance_p(&a, nullptr));
+
+  int c[4];
+  DEV(vpb_memcpy_d2h(c, a.counters, sizeof c, nullptr));
+  DEV(vpb_stream_sync(nullptr));
+  g_d2h += sizeof c;
+  const int nm = c[0] < sp->max_nm ? c[0] : sp->max_nm;
+  if (c[1]) {
+#ifdef EXIT_ON_LOST_MOVER
+    DROPIN_ERROR("Species = %s ran out of storage for %i movers.  This is an extremely serious problem that affects the physics of your run.", sp->name, c[1]);
+#else
+    DROPIN_WARNING("Species = %s ran out of storage for %i movers.  This is an extremely serious problem that affects the physics of your run.", sp->name, c[1]);
+#endif
+  }
+  if (nm > 1) {   // boundary_p back-fills assuming ascending particle indices (boundary_p.cc:248-255)
+    const size_t need = vpb_sort_movers_scratch_bytes(nm);
+    DEV(vpb_sort_movers(a.pm, nm, scratch(0, need), need, nullptr));
+  }
+  sp->nm = nm;
+  dev_written(sp->p, (size_t)sp->np * sizeof(vpb_particle_t));
+  dev_written(sp->pm, (size_t)nm * sizeof(vpb_particle_mover_t));
+  dev_written(aa->a, (size_t)aa->stride * sizeof(vpb_accumulator_t));
+  if (g_mode == VPB_MODE_COHERENT) DEV(vpb_stream_sync(nullptr));
+}
+
+// ---- sort_p: species_advance.h:65-66, sort_p_pipeline.cc:220-371 ------------------------------------------
+void sort_p(vpb_species_t *sp) {
+  if (!sp) DROPIN_ERROR("Bad args.");
+  const vpb_grid_t *g = sp->g;
+  sp->last_sorted = g->step;
+  void *p = dev_in(sp->p, (size_t)sp->np * sizeof(vpb_particle_t), (size_t)sp->max_np * sizeof(vpb_particle_t));
+  int32_t *part = (int32_t *)dev_out_only(sp->partition, ((size_t)g->nv + 1) * sizeof(int32_t));
+  void *aux = scratch(1, (size_t)(sp->np > 0 ? sp->np : 1) * sizeof(vpb_particle_t));
+  const size_t need = vpb_sort_scratch_bytes(sp->np > 0 ? sp->np : 1, g->nv);
+  DEV(vpb_sort_p(p, sp->np, aux, part, g->nx, g->ny, g->nz, scratch(2, need), need, nullptr));
+  dev_written(sp->p, (size_t)sp->np * sizeof(vpb_particle_t));
+  dev_written(sp->partition, ((size_t)g->nv + 1) * sizeof(int32_t));
+  if (g_mode == VPB_MODE_COHERENT) DEV(vpb_stream_sync(nullptr));
+}
+
+// ---- center_p / uncenter_p / energy_p: species_advance.h:90-107 --------------------------------------------
+static void center_common(vpb_species_t *sp, const vpb_interpolator_array_t *ia, bool center) {
+  if (!sp || !ia || sp->g != ia->g) DROPIN_ERROR("Bad args.");
+  const vpb_grid_t *g = sp->g;
+  const float *di = (const float *)dev_in(ia->i, (size_t)g->nv * sizeof(vpb_interpolator_t));
+  void *p = dev_in(sp->p, (size_t)sp->np * sizeof(vpb_particle_t), (size_t)sp->max_np * sizeof(vpb_particle_t));
+  if (center) DEV(vpb_center_p(p, sp->np, di, kInterpFloats, qdt_2mc_of(sp), nullptr));
+  else        DEV(vpb_uncenter_p(p, sp->np, di, kInterpFloats, qdt_2mc_of(sp), nullptr));
+  dev_written(sp->p, (size_t)sp->np * sizeof(vpb_particle_t));
+  if (g_mode == VPB_MODE_COHERENT) DEV(vpb_stream_sync(nullptr));
+}
+void center_p(vpb_species_t *sp, const vpb_interpolator_array_t *ia) { center_common(sp, ia, true); }
+void uncenter_p(vpb_species_t *sp, const vpb_interpolator_array_t *ia) { center_common(sp, ia, false); }
+
+double energy_p(const vpb_species_t *sp, const vpb_interpolator_array_t *ia) {
+  if (!sp || !ia || sp->g != ia->g) DROPIN_ERROR("Bad args");
+  const vpb_grid_t *g = sp->g;
+  const float *di = (const float *)dev_in(ia->i, (size_t)g->nv * sizeof(vpb_interpolator_t));
+  void *p = dev_in(sp->p, (size_t)sp->np * sizeof(vpb_particle_t), (size_t)sp->max_np * sizeof(vpb_particle_t));
+  double *en = (double *)scratch(3, sizeof(double));
+  DEV(vpb_energy_p(p, sp->np, di, kInterpFloats, sp->q, sp->m, g->dt, g->cvac, en, nullptr));
+  double local = 0, global = 0;
+  DEV(vpb_memcpy_d2h(&local, en, sizeof local, nullptr));
+  DEV(vpb_stream_sync(nullptr));
+  g_d2h += sizeof local;
+  // the reference sums over ranks before scaling by cvac^2 (energy_p_pipeline.cc:111-114); scaling commutes
+  if (mp_allsum_d) { mp_allsum_d(&local, &global, 1); return global; }
+  return local;
+}
+
+// ---- interpolator / accumulator glue: sf_interface.h:99-174 ------------------------------------------------
+void load_interpolator_array(vpb_interpolator_array_t *ia, const vpb_field_array_t *fa) {
+  if (!ia || !fa || ia->g != fa->g) DROPIN_ERROR("Bad args");
+  const vpb_grid_t *g = ia->g;
+  const size_t ibytes = (size_t)g->nv * sizeof(vpb_interpolator_t);
+  const float *df = (const float *)dev_in(fa->f, (size_t)g->nv * sizeof(vpb_field_t));
+  // interpolators of ghost voxels and the struct padding are never written: keep whatever the host has there
+  float *di = (float *)dev_in(ia->i, ibytes);
+  DEV(vpb_load_interpolator(di, kInterpFloats, df, g->nx, g->ny, g->nz, nullptr));
+  dev_written(ia->i, ibytes);
+  if (g_mode == VPB_MODE_COHERENT) DEV(vpb_stream_sync(nullptr));
+}
+
+void clear_accumulator_array(vpb_accumulator_array_t *aa) {
+  if (!aa) DROPIN_ERROR("Bad args.");
+  const vpb_grid_t *g = aa->g;
+  const size_t abytes = (size_t)aa->stride * sizeof(vpb_accumulator_t);
+  // host: zero the same voxel window in every block, exactly like clear_array_pipeline.cc:40-67
+  const int nx = g->nx, ny = g->ny, nz = g->nz;
+  const int i0 = (vpb::voxel(1, 1, 1, nx, ny) / 2) * 2;
+  const int na = (((vpb::voxel(nx, ny, nz, nx, ny) - i0 + 1) + 1) / 2) * 2;
+  if (mode() == VPB_MODE_COHERENT) {
+    // the host arrays are the truth in this mode: clear them; the next consumer uploads block 0 again
+    for (int b = 0; b <= aa->n_pipeline; b++)
+      memset(aa->a + (size_t)b * aa->stride + i0, 0, (size_t)na * sizeof(vpb_accumulator_t));
+    auto it = g_mirrors.find(aa->a);
+    if (it != g_mirrors.end()) { it->second.device_valid = false; it->second.host_stale = false; }
+  } else {
+    float *da = (float *)dev_in(aa->a, abytes);
+    DEV(vpb_clear_accumulator(da, kAccumFloats, nx, ny, nz, nullptr));
+    g_mirrors[aa->a].host_stale = true;
+  }
+}
+
+void reduce_accumulator_array(vpb_accumulator_array_t *aa) {
+  if (!aa) DROPIN_ERROR("Bad args.");
+  // The device deposits every particle into block 0, so there is nothing to fold in from blocks 1..n_pipeline
+  // (they stay zero).  Host-side deposits between advance_p and here (emitters, injection) already go to block 0.
+}
+
+void unload_accumulator_array(vpb_field_array_t *fa, const vpb_accumulator_array_t *aa) {
+  if (!fa || !aa || fa->g != aa->g) DROPIN_ERROR("Bad args");
+  const vpb_grid_t *g = fa->g;
+  const size_t fbytes = (size_t)g->nv * sizeof(vpb_field_t);
+  const float *da = (const float *)dev_in(aa->a, (size_t)aa->stride * sizeof(vpb_accumulator_t));
+  float *df = (float *)dev_in(fa->f, fbytes);
+  DEV(vpb_unload_accumulator(df, da, kAccumFloats, g->nx, g->ny, g->nz, g->rdx, g->rdy, g->rdz, g->dt, nullptr));
+  dev_written(fa->f, fbytes);
+  if (g_mode == VPB_MODE_COHERENT) DEV(vpb_stream_sync(nullptr));
+}
+
+}  // extern "C"

@@ -90,19 +90,20 @@ __global__ void __launch_bounds__(256) ghost_tang_b_kernel(FieldK k) {
   } else {
     src = inward; rw = 1.0f; lw = 0.0f; negate = (bc != -1);
   }
-  float4 g = FQ(v, 1);
+  // Scalar stores: the corner line (X ghost, Y = nY+1) also belongs to the Y face's ghost plane, which writes
+  // a different component of the same field_t — a float4 read-modify-write would lose one of the two.
+  float *gs = reinterpret_cast<float *>(&FQ(v, 1));
   const float4 sv = FQ(src, 1), iv = FQ(inward, 1);
   if (cz <= n[Z]) {                                             // cbY over Y in 1..nY+1, Z in 1..nZ
     float val = comp(sv, Y);
     val = (bc == VPB_FACE_PERIODIC_SELF) ? (rw * val + lw * comp(iv, Y)) : (negate ? -val : val);
-    set_comp(g, Y, val);
+    gs[Y] = val;
   }
   if (cy <= n[Y]) {                                             // cbZ over Y in 1..nY, Z in 1..nZ+1
     float val = comp(sv, Z);
     val = (bc == VPB_FACE_PERIODIC_SELF) ? (rw * val + lw * comp(iv, Z)) : (negate ? -val : val);
-    set_comp(g, Z, val);
+    gs[Z] = val;
   }
-  FQ(v, 1) = g;
 }
 
 // ---- vacuum_advance_e --------------------------------------------------------------------------------------
@@ -151,21 +152,29 @@ __global__ void __launch_bounds__(256) clear_jf_kernel(float4 *f, int nv) {
   float4 j = FQ(v, 3); j.x = 0; j.y = 0; j.z = 0; FQ(v, 3) = j;
 }
 
-// local_adjust_jf (local.cc:335-366): pec zeroes tangential jf on the wall, symmetric/pmc/absorbing double it
+// local_adjust_jf (local.cc:335-366): pec zeroes tangential jf on the wall, symmetric/pmc/absorbing double it.
+// One thread per node applies the six faces in the reference's order (-x,-y,-z,+x,+y,+z): an edge shared by two
+// walls is adjusted twice, exactly as the sequential reference does.
 __global__ void __launch_bounds__(256) adjust_jf_kernel(FieldK k) {
-  const int fc = blockIdx.z;
-  const int bc = k.face[fc];
-  if (bc >= 0) return;
-  const int n[3] = {k.nx, k.ny, k.nz};
-  const int s[3] = {1, k.nx + 2, (k.nx + 2) * (k.ny + 2)};
-  const int X = fc % 3, Y = (X + 1) % 3, Z = (X + 2) % 3;
-  const int cy = blockIdx.x * blockDim.x + threadIdx.x + 1, cz = blockIdx.y + 1;
-  if (cy > n[Y] + 1 || cz > n[Z] + 1) return;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x + 1, y = blockIdx.y + 1, z = blockIdx.z + 1;
+  const int nx = k.nx, ny = k.ny, nz = k.nz;
+  if (x > nx + 1) return;
+  const int n[3] = {nx, ny, nz}; const int cc[3] = {x, y, z};
+  bool on = false;
+#pragma unroll
+  for (int fc = 0; fc < 6; fc++) on |= (k.face[fc] < 0) && (cc[fc % 3] == (fc < 3 ? 1 : n[fc % 3] + 1));
+  if (!on) return;
   float4 *f = k.f;
-  const int v = (fc < 3 ? 1 : n[X] + 1) * s[X] + cy * s[Y] + cz * s[Z];
+  const int v = voxel(x, y, z, nx, ny);
   float4 j = FQ(v, 3);
-  if (cy <= n[Y]) set_comp(j, Y, bc == -1 ? 0.0f : comp(j, Y) * 2.0f);
-  if (cz <= n[Z]) set_comp(j, Z, bc == -1 ? 0.0f : comp(j, Z) * 2.0f);
+#pragma unroll
+  for (int fc = 0; fc < 6; fc++) {
+    const int bc = k.face[fc];
+    const int X = fc % 3, Y = (X + 1) % 3, Z = (X + 2) % 3;
+    if (bc >= 0 || cc[X] != (fc < 3 ? 1 : n[X] + 1)) continue;
+    if (cc[Y] <= n[Y]) set_comp(j, Y, bc == -1 ? 0.0f : comp(j, Y) * 2.0f);     // jfY over Y 1..nY, Z 1..nZ+1
+    if (cc[Z] <= n[Z]) set_comp(j, Z, bc == -1 ? 0.0f : comp(j, Z) * 2.0f);     // jfZ over Y 1..nY+1, Z 1..nZ
+  }
   FQ(v, 3) = j;
 }
 
@@ -333,7 +342,10 @@ extern "C" int vpb_synchronize_jf(const vpb_field_args_t *a, void *stream) {
   cudaStream_t st = as_stream(stream);
   bool any_local = false;
   for (int i = 0; i < 6; i++) any_local |= a->face[i] < 0;
-  if (any_local) { adjust_jf_kernel<<<max_plane_grid(a, 6), 256, 0, st>>>(to_k(a)); VPB_LAUNCH_CHECK(); }
+  if (any_local) {
+    dim3 grid((a->nx + 1 + 255) / 256, a->ny + 1, a->nz + 1);
+    adjust_jf_kernel<<<grid, 256, 0, st>>>(to_k(a)); VPB_LAUNCH_CHECK();
+  }
   for (int X = 0; X < 3; X++) {
     if (a->face[X] == VPB_FACE_PERIODIC_SELF && a->face[X + 3] == VPB_FACE_PERIODIC_SELF) {
       sync_jf_self_kernel<<<plane_grid(a, X, 1), 256, 0, st>>>(to_k(a), X);
