@@ -1,0 +1,522 @@
+#!/usr/bin/env python
+"""bench.py — particle pushes/sec of the hot path (advance_p + deposit and its glue) on B200.
+
+    python bench.py --gpus N --steps K --warmup W            our arm (CUDA path through the C-ABI)
+    python bench.py --impl reference --gpus N --steps K ...  the reference's own CPU path on the host cores
+
+Workload (BASELINE.json configs[1]): 3-D uniform thermal electron-ion plasma, 128^3 cells per GPU, 64 ppc/species,
+periodic, sort_p every 20 steps; synthetic particles, fields start at zero.  A "step" is one pass of the hot-path
+block of vpic_simulation::advance (vpic_b200/simulation.py) over every particle.  N > 1: weak scaling, one slab of
+128^3 cells per GPU (1 x N x 1 decomposition) with particle migration and halo exchange over NCCL.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def build_sim(args, rank, world, device):
+    import torch
+    from vpic_b200 import engine as E, grid as G, simulation as S
+    n = args.grid
+    nx, ny, nz = n, n, n
+    dt = G.courant_dt(1.0, 1.0, 1.0, nx, ny * world, nz, frac=0.99)
+    g = G.partition_periodic_box(0, 0, 0, nx, ny * world, nz, nx, ny * world, nz, 1, world, 1, rank=rank, dt=dt)
+    dg = E.DeviceGrid(g, device)
+    exchange = None
+    if world > 1:
+        from vpic_b200 import parallel
+        exchange = parallel.SlabExchange(dg, axis=1)
+    sim = S.Simulation(dg, exchange=exchange)
+    sim.deposit_variant = args.variant
+    npart = nx * ny * nz * args.ppc
+    gen = torch.Generator(device=device)
+    gen.manual_seed(1234 + rank)
+    for name, q, m, uth in (("electron", -1.0, 1.0, args.uth), ("ion", 1.0, 25.0, args.uth / 5.0)):
+        max_np = int(npart * (1.25 if world > 1 else 1.0)) + 1024
+        sp = sim.define_species(name, q, m, max_np, max(int(npart * 0.05), 1 << 16), args.sort_interval)
+        # synthetic load, in random order like the reference's inject_particle loop; sort_p at step 0 orders it
+        p = sp.p[:npart]
+        p[:, 0:3] = torch.rand((npart, 3), generator=gen, device=device) * 2 - 1
+        ix = torch.randint(1, nx + 1, (npart,), generator=gen, device=device, dtype=torch.int32)
+        iy = torch.randint(1, ny + 1, (npart,), generator=gen, device=device, dtype=torch.int32)
+        iz = torch.randint(1, nz + 1, (npart,), generator=gen, device=device, dtype=torch.int32)
+        sp.p.view(torch.int32)[:npart, 3] = ix + (nx + 2) * (iy + (ny + 2) * iz)
+        p[:, 4:7] = torch.randn((npart, 3), generator=gen, device=device) * uth
+        p[:, 7] = 1.0 / args.ppc
+        sp.np = npart
+        del ix, iy, iz
+    sim.initialize()
+    return sim
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from vpic_b200 import lib
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun for --gpus > 1")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    L = lib.load()
+    sim = build_sim(args, rank, world, device)
+    np_total_local = sum(sp.np for sp in sim.species_list)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        sim.advance()
+    barrier()
+    launches0 = L.vpb_launch_count()
+    sim.push_events = []
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    pushes = 0
+    for _ in range(args.steps):
+        pushes += sum(sp.np for sp in sim.species_list)
+        sim.advance()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = L.vpb_launch_count() - launches0
+    push_ms = [a.elapsed_time(b) for a, b, _ in sim.push_events]
+    push_np = [n for _, _, n in sim.push_events]
+    sim.push_events = None
+    if args.verbose and rank == 0:
+        print("advance_p ms per launch:", " ".join(f"{x:.2f}" for x in push_ms), file=sys.stderr)
+    t = torch.tensor([ms, float(pushes)], dtype=torch.float64, device=device)
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, pushes = float(tmax[0]), float(tsum[1])
+    value = pushes / (ms * 1e-3)
+
+    # roofline of the dominant kernel (advance_p): algorithmic bytes per push = 64 + 176/ppc
+    peak, peak_src = peaks()
+    bytes_per_push = 64.0 + 176.0 / args.ppc
+    avg_push_ms = float(np.mean(push_ms))
+    achieved = bytes_per_push * float(np.mean(push_np)) / (avg_push_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "advance_p_kernel", "achieved": round(achieved, 1), "peak": peak,
+                "peak_source": peak_src, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                "traffic": load_traffic(), "algorithmic_bytes_per_push": bytes_per_push,
+                "avg_launch_ms": round(avg_push_ms, 4), "share_of_step": round(sum(push_ms) / ms, 4)}
+
+    out = None
+    if rank == 0:
+        out = {"metric": "particle pushes/sec (advance_p+deposit)", "value": value, "unit": "pushes/s",
+               "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "config": {"workload": f"uniform thermal e-/ion plasma, {args.grid}^3 cells per GPU, {args.ppc} ppc/species, "
+                                      f"periodic, sort_p every {args.sort_interval} steps (BASELINE.json configs[1])",
+                          "particles_per_gpu": np_total_local, "decomposition": f"1x{world}x1 slabs",
+                          "l2": "particle arrays (8.6 GB per GPU) exceed the 126 MB L2; no flush needed",
+                          "deposit_variant": args.variant},
+               "roofline": roofline, "gpu_launches": int(launches), "clocks": clocks}
+    if args.e2e and world == 1:
+        e2e = run_e2e(args, device)
+        if out is not None:
+            out["e2e"] = e2e
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(args, budget_s=args.cpu_seconds)
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def load_traffic():
+    """dram bytes per advance_p launch from the committed ncu capture (profiles/), if any."""
+    p = os.path.join(ROOT, "profiles", "advance_p_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))["dram_bytes_per_launch"]
+        except Exception:
+            return None
+    return None
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_e2e(args, device):
+    """Same step through the reference-facing drop-in symbols (advance_p(species_t*, ...), sort_p, ...) with HOST
+    arrays: every call copies its inputs host->device and its results device->host inside the timed region."""
+    import torch
+    from vpic_b200 import abi, grid as G, lib
+    L = lib.load()
+    n = args.grid
+    nx = ny = nz = n
+    dt = G.courant_dt(1.0, 1.0, 1.0, nx, ny, nz, frac=0.99)
+    g = G.partition_periodic_box(0, 0, 0, nx, ny, nz, nx, ny, nz, 1, 1, 1, dt=dt)
+    H = HostWorld(L, g, pinned=True)
+    npart = nx * ny * nz * args.ppc
+    rng = np.random.default_rng(7)
+    species = []
+    for name, q, m, uth in (("electron", -1.0, 1.0, args.uth), ("ion", 1.0, 25.0, args.uth / 5.0)):
+        sp = H.new_species(name, q, m, npart, max(int(npart * 0.05), 1 << 16), args.sort_interval)
+        H.fill_uniform(sp, npart, rng, uth, 1.0 / args.ppc)
+        species.append(sp)
+    H.load_interpolator()
+    steps = args.e2e_steps
+    tb0 = H.transfer_bytes()
+    # warm-up step (allocates mirrors, first sort)
+    H.advance(species)
+    tb1 = H.transfer_bytes()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    pushes = 0
+    for _ in range(steps):
+        pushes += sum(sp.c.np for sp in species)
+        H.advance(species)
+    torch.cuda.synchronize()
+    dt_s = time.perf_counter() - t0
+    tb2 = H.transfer_bytes()
+    return {"value": pushes / dt_s, "unit": "pushes/s", "steps": steps,
+            "h2d_bytes_per_step": int((tb2[0] - tb1[0]) / steps), "d2h_bytes_per_step": int((tb2[1] - tb1[1]) / steps),
+            "api": "drop-in extern C symbols (advance_p(species_t*,accumulator_array_t*,interpolator_array_t*), sort_p, "
+                   "clear/reduce/unload_accumulator_array, field kernels, load_interpolator_array) on pinned host arrays, "
+                   "VPB_MODE_COHERENT"}
+
+
+class HostWorld:
+    """Host-side reference structs (vpic_b200/abi.py) over pinned numpy arrays, driven through the drop-in symbols."""
+
+    def __init__(self, L, g, pinned=True):
+        import torch
+        from vpic_b200 import abi
+        self.L, self.g, self.abi, self.torch = L, g, abi, torch
+        self.keep = []
+        G = abi.Grid()
+        for k in ("dt", "cvac", "eps0", "x0", "y0", "z0", "x1", "y1", "z1", "nx", "ny", "nz", "dx", "dy", "dz", "dV",
+                  "rdx", "rdy", "rdz", "r8V"):
+            setattr(G, k, getattr(g, k))
+        G.sx, G.sy, G.sz, G.nv = 1, g.nx + 2, (g.nx + 2) * (g.ny + 2), g.nv
+        for i, b in enumerate(g.bc):
+            G.bc[i] = b
+        self.range_arr = np.ascontiguousarray(g.range)
+        self.nb = self.host_array((g.nv, 6), np.int64, pinned)
+        self.nb[:] = g.neighbor
+        G.range = self.range_arr.ctypes.data_as(C.POINTER(C.c_int64))
+        G.neighbor = self.nb.ctypes.data_as(C.POINTER(C.c_int64))
+        G.rangel, G.rangeh = g.rangel, g.rangeh
+        self.G = G
+        self.fields = self.host_array((g.nv, 20), np.float32, pinned)
+        self.interp = self.host_array((g.nv, 20), np.float32, pinned)
+        stride = (g.nv + 1) // 2 * 2
+        self.accum = self.host_array((stride, 12), np.float32, pinned)
+        self.mc = abi.MaterialCoefficient(1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1)
+        self.prm = abi.SfaParams(C.pointer(self.mc), 1, 0.0)
+        self.fa = abi.FieldArray(self.fields.ctypes.data_as(C.POINTER(C.c_float)), C.pointer(G),
+                                 C.cast(C.pointer(self.prm), C.c_void_p))
+        self.ia = abi.InterpolatorArray(self.interp.ctypes.data_as(C.POINTER(C.c_float)), C.pointer(G))
+        self.aa = abi.AccumulatorArray(self.accum.ctypes.data_as(C.POINTER(C.c_float)), 0, stride, C.pointer(G))
+        for fn, argt in (("advance_p", [C.c_void_p] * 3), ("sort_p", [C.c_void_p]), ("load_interpolator_array", [C.c_void_p] * 2),
+                         ("clear_accumulator_array", [C.c_void_p]), ("reduce_accumulator_array", [C.c_void_p]),
+                         ("unload_accumulator_array", [C.c_void_p] * 2), ("vpic_b200_clear_jf", [C.c_void_p]),
+                         ("vpic_b200_synchronize_jf", [C.c_void_p]), ("vpic_b200_advance_b", [C.c_void_p, C.c_float]),
+                         ("vpic_b200_advance_e", [C.c_void_p, C.c_float]), ("vpic_b200_transfer_bytes", [C.c_void_p]),
+                         ("vpic_b200_set_mode", [C.c_int])):
+            f = getattr(L, fn); f.argtypes = argt; f.restype = None
+        L.energy_p.restype = C.c_double
+        L.energy_p.argtypes = [C.c_void_p, C.c_void_p]
+
+    def host_array(self, shape, dtype, pinned):
+        if pinned:
+            t = self.torch.empty(shape, dtype={np.float32: self.torch.float32, np.int64: self.torch.int64,
+                                               np.int32: self.torch.int32}[dtype]).pin_memory()
+            self.keep.append(t)
+            a = t.numpy()
+            a[...] = 0
+            return a
+        return np.zeros(shape, dtype)
+
+    def new_species(self, name, q, m, max_np, max_nm, sort_interval):
+        abi = self.abi
+        p = self.host_array((max_np, 8), np.float32, True)
+        pm = self.host_array((max_nm, 4), np.float32, True)
+        part = self.host_array((self.g.nv + 1,), np.int32, True)
+        sp = abi.Species()
+        sp.name = name.encode(); sp.q, sp.m = q, m
+        sp.np, sp.max_np, sp.nm, sp.max_nm = 0, max_np, 0, max_nm
+        sp.p = p.ctypes.data_as(C.POINTER(abi.Particle)); sp.pm = pm.ctypes.data_as(C.POINTER(abi.ParticleMover))
+        sp.last_sorted = -(2 ** 63); sp.sort_interval = sort_interval; sp.sort_out_of_place = 0
+        sp.partition = part.ctypes.data_as(C.POINTER(C.c_int32)); sp.g = C.pointer(self.G)
+
+        class W:
+            pass
+        w = W(); w.c = sp; w.p = p; w.pm = pm; w.partition = part
+        return w
+
+    def fill_uniform(self, sp, n, rng, uth, w):
+        g = self.g
+        t = self.torch
+        gen = t.Generator().manual_seed(int(rng.integers(1 << 31)))
+        p = t.from_numpy(sp.p)[:n]
+        p[:, 0:3] = t.rand((n, 3), generator=gen) * 2 - 1
+        ix = t.randint(1, g.nx + 1, (n,), generator=gen, dtype=t.int32)
+        iy = t.randint(1, g.ny + 1, (n,), generator=gen, dtype=t.int32)
+        iz = t.randint(1, g.nz + 1, (n,), generator=gen, dtype=t.int32)
+        t.from_numpy(sp.p).view(t.int32)[:n, 3] = ix + (g.nx + 2) * (iy + (g.ny + 2) * iz)
+        p[:, 4:7] = t.randn((n, 3), generator=gen) * uth
+        p[:, 7] = w
+        sp.c.np = n
+
+    def load_interpolator(self):
+        self.L.load_interpolator_array(C.byref(self.ia), C.byref(self.fa))
+
+    def transfer_bytes(self):
+        out = (C.c_uint64 * 2)()
+        self.L.vpic_b200_transfer_bytes(out)
+        return int(out[0]), int(out[1])
+
+    def advance(self, species):
+        L, fa, ia, aa = self.L, C.byref(self.fa), C.byref(self.ia), C.byref(self.aa)
+        step = self.G.step
+        for sp in species:
+            if step % sp.c.sort_interval == 0:
+                L.sort_p(C.byref(sp.c))
+        L.clear_accumulator_array(aa)
+        for sp in species:
+            L.advance_p(C.byref(sp.c), aa, ia)
+        L.reduce_accumulator_array(aa)
+        L.vpic_b200_clear_jf(fa)
+        L.unload_accumulator_array(fa, aa)
+        L.vpic_b200_synchronize_jf(fa)
+        L.vpic_b200_advance_b(fa, 0.5)
+        L.vpic_b200_advance_e(fa, 1.0)
+        L.vpic_b200_advance_b(fa, 0.5)
+        L.load_interpolator_array(ia, fa)
+        self.G.step += 1
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def pick_ref_variant():
+    """Strongest reference build the host CPU can run: V8 AVX2+FMA if the CPU has it, else V4 SSE, else scalar."""
+    flags = ""
+    try:
+        flags = open("/proc/cpuinfo").read()
+    except Exception:
+        pass
+    order = (["v8"] if (" avx2" in flags and " fma" in flags) else []) + ["v4", "scalar"]
+    for v in order:
+        if os.path.exists(os.path.join(ROOT, "oracle", "_ref", f"libvpic_ref_{v}.so")):
+            return v
+    return None
+
+
+def reference_sample(args, n_steps, grid_n, warm=1):
+    """Time the reference's own CPU hot path (unmodified sources, oracle/_ref) on a bounded sample of the workload."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import refvpic as R
+    variant = pick_ref_variant()
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    if variant is None:
+        return port_sample(args, grid_n)
+    lib = R.load_ref(variant, tpp=cores)
+    nx = ny = nz = grid_n
+    W = R.RefWorld(lib, nx, ny, nz, dt=None)
+    W.g.contents.dt = float(np.float32(0.99 / np.sqrt(3.0)))
+    npart = nx * ny * nz * args.ppc
+    rng = np.random.default_rng(5)
+    species = []
+    for name, q, m, uth in (("electron", -1.0, 1.0, args.uth), ("ion", 1.0, 25.0, args.uth / 5.0)):
+        sp = W.new_species(name, q, m, npart, max(int(npart * 0.05), 1 << 16), args.sort_interval)
+        parts = R.random_particles(rng, npart, nx, ny, nz, uth=uth, w=1.0 / args.ppc)
+        sp.set_particles(parts)
+        del parts
+        species.append(sp)
+    lib.load_interpolator_array(W.ia, W.fa)
+
+    def step(k):
+        for sp in species:
+            if k % args.sort_interval == 0:
+                lib.sort_p(sp.sp)
+        lib.clear_accumulator_array(W.aa)
+        for sp in species:
+            lib.advance_p(sp.sp, W.aa, W.ia)
+        lib.reduce_accumulator_array(W.aa)
+        W.clear_jf()
+        lib.unload_accumulator_array(W.fa, W.aa)
+        W.synchronize_jf()
+        W.advance_b(0.5); W.advance_e(1.0); W.advance_b(0.5)
+        lib.load_interpolator_array(W.ia, W.fa)
+
+    k = 0
+    for _ in range(warm):
+        step(k); k += 1
+    times = []
+    for _ in range(n_steps):
+        t0 = time.perf_counter()
+        step(k); k += 1
+        times.append(time.perf_counter() - t0)
+    total = sum(times)
+    pushes = 2 * npart * n_steps
+    return {"value": pushes / total, "unit": "pushes/s", "cores": cores, "kind": "reference",
+            "sample": f"unmodified reference ({variant} build, pthreads --tpp {cores}), same plasma on a {grid_n}^3-cell box, "
+                      f"{args.ppc} ppc/species, {n_steps} timed steps after {warm} warm-up (first step sorts)",
+            "ms_per_step": 1e3 * total / n_steps, "steps": n_steps}
+
+
+def port_sample(args, grid_n):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import refvpic as R
+    from vpic_b200 import grid as G, abi
+    orc = R.load_oracle()
+    nx = ny = nz = min(grid_n, 32)
+    g = G.partition_periodic_box(0, 0, 0, nx, ny, nz, nx, ny, nz, 1, 1, 1, dt=G.courant_dt(1, 1, 1, nx, ny, nz, frac=0.99))
+    n = nx * ny * nz * args.ppc
+    rng = np.random.default_rng(5)
+    parts = R.random_particles(rng, n, nx, ny, nz, uth=args.uth, w=1.0 / args.ppc)
+    interp = np.zeros((g.nv, 20), np.float32)
+    acc = np.zeros(((g.nv + 1) // 2 * 2, 12), np.float32)
+    pm = np.zeros(1024, dtype=abi.mover_dtype)
+    f32 = np.float32
+    a = R.OraclePushArgs(parts.ctypes.data, n, pm.ctypes.data, 1024, interp.ctypes.data, 20, acc.ctypes.data, 12,
+                         g.neighbor.ctypes.data, g.rangel, g.rangeh, f32(-0.5 * g.dt), f32(g.dt), f32(g.dt), f32(g.dt), f32(-1))
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        orc.vpo_advance_p(C.byref(a), None)
+    dt_s = time.perf_counter() - t0
+    return {"value": n * reps / dt_s, "unit": "pushes/s", "cores": 1, "kind": "port",
+            "sample": f"oracle C port, advance_p only, {nx}^3 cells x {args.ppc} ppc, {reps} passes"}
+
+
+def cpu_baseline(args, budget_s=15.0):
+    # one probing step on a small box, then size the sample to ~budget_s of CPU work
+    try:
+        probe = reference_sample(args, 1, 32, warm=1)
+        if probe["kind"] != "reference":
+            return probe
+        rate = probe["value"]
+        grid_n = 64
+        per_step = 2 * grid_n ** 3 * args.ppc / rate
+        n_steps = int(max(2, min(20, budget_s / max(per_step, 1e-3))))
+        return reference_sample(args, n_steps, grid_n, warm=1)
+    except Exception as e:   # report, never fake
+        return {"value": None, "unit": "pushes/s", "cores": None, "kind": "reference", "sample": f"failed: {e!r}"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    grid_n = args.ref_grid
+    res = reference_sample(args, args.steps, grid_n, warm=max(1, args.warmup))
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    out = {"impl": "reference", "metric": "particle pushes/sec (advance_p+deposit)", "value": res["value"],
+           "unit": "pushes/s", "n_gpus": world, "steps": args.steps, "warmup": max(1, args.warmup),
+           "ms_per_step": res.get("ms_per_step"), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic",
+           "config": {"workload": f"uniform thermal e-/ion plasma, {args.grid}^3 cells per GPU, {args.ppc} ppc/species, "
+                                  f"periodic, sort_p every {args.sort_interval} steps (BASELINE.json configs[1]); each step "
+                                  f"a bounded sample of it: {grid_n}^3 cells on the host cores"},
+           "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+           "e2e": {"value": res["value"], "unit": "pushes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--grid", type=int, default=128)
+    ap.add_argument("--ppc", type=int, default=64)
+    ap.add_argument("--uth", type=float, default=0.18)
+    ap.add_argument("--sort-interval", type=int, default=20)
+    ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--e2e", type=int, default=1)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--ref-grid", type=int, default=64)
+    ap.add_argument("--verbose", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

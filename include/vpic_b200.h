@@ -75,6 +75,8 @@ typedef struct vpb_push_args {
   float          qdt_2mc, cdt_dx, cdt_dy, cdt_dz, qsp;   /* computed by the caller in float, advance_p_pipeline.cc:279-283 */
   int32_t        nx, ny, nz;
   int32_t        variant;        /* deposit strategy, see VPB_DEPOSIT_*              */
+  int32_t        debug_skip;     /* must be 0.  Profiling only (results become INVALID): bit0 skip deposits,
+                                    bit1 skip the mover phase, bit2 skip particle stores, bit3 skip the interpolator gather */
 } vpb_push_args_t;
 
 #define VPB_DEPOSIT_DEFAULT      0   /* library's best measured strategy                                  */
@@ -90,6 +92,29 @@ int vpb_advance_p(const vpb_push_args_t *args, void *stream);
 size_t vpb_sort_scratch_bytes(int32_t n_items, int32_t n_keys_hint);
 size_t vpb_sort_movers_scratch_bytes(int32_t nm);
 int    vpb_sort_movers(void *pm, int32_t nm, void *scratch, size_t scratch_bytes, void *stream);
+
+/* ---- boundary_p (particle side) ---------------------------------------------
+ * Replaces the mover walk, back-fill and injection of src/boundary/boundary_p.cc:257-371,595-711 for runs that are
+ * decomposed over several GPUs; the message exchange between them is NCCL send/recv in the host layer.
+ * vpb_boundary_p_pack: every one of the nm movers' particles leaves the array (np becomes np - nm): particles bound
+ * for a neighbour become particle_injector_t records in `inj`, grouped by destination class in ascending particle
+ * order; class_offsets[c]..[c+1] delimits class c: 0..5 = face -x,-y,-z,+x,+y,+z, 6 = absorbed, 7 = no device handler.
+ * vpb_boundary_p_inject: appends n received injectors at p[push->np ...) (last record first, like the reference),
+ * gives each a mover and finishes its move_p; movers still in use are appended through push->counters. */
+typedef struct vpb_boundary_args {
+  void          *p;   int32_t np;
+  const void    *pm;  int32_t nm;        /* movers, ascending by particle index */
+  const int64_t *neighbor;
+  int64_t        rangel, rangeh, rangem; /* rangem = range[world_size] */
+  int64_t        face_range[6];          /* range[rank behind face] for faces shared with another rank, else -1 */
+  int32_t        sp_id;
+  void          *inj;                    /* out: particle_injector_t[nm] */
+  int32_t       *class_offsets;          /* out: int32[9], device */
+  void          *scratch; size_t scratch_bytes;   /* >= vpb_boundary_scratch_bytes(nm) */
+} vpb_boundary_args_t;
+size_t vpb_boundary_scratch_bytes(int32_t nm);
+int    vpb_boundary_p_pack(const vpb_boundary_args_t *args, void *stream);
+int    vpb_boundary_p_inject(const vpb_push_args_t *push, const void *inj, int32_t n, void *stream);
 
 /* ---- sort_p ---------------------------------------------------------------
  * Replaces sort_p_pipeline (src/species_advance/standard/pipeline/sort_p_pipeline.cc:220-371):

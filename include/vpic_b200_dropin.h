@@ -43,6 +43,15 @@ void clear_accumulator_array(vpb_accumulator_array_t *aa);
 void reduce_accumulator_array(vpb_accumulator_array_t *aa);
 void unload_accumulator_array(vpb_field_array_t *fa, const vpb_accumulator_array_t *aa);
 
+/* Device-backed entries for the field_advance_kernels_t table (src/field_advance/field_advance.h:170-218);
+ * vpic_b200_install_field_kernels(fa) repoints fa->kernel[0] at them (single vacuum material, single rank). */
+void vpic_b200_advance_b(vpb_field_array_t *fa, float frac);
+void vpic_b200_advance_e(vpb_field_array_t *fa, float frac);
+void vpic_b200_clear_jf(vpb_field_array_t *fa);
+void vpic_b200_synchronize_jf(vpb_field_array_t *fa);
+void vpic_b200_energy_f(double *en6, const vpb_field_array_t *fa);
+void vpic_b200_install_field_kernels(vpb_field_array_t *fa);
+
 /* coherence control (new; no reference counterpart) */
 void vpic_b200_set_mode(int mode);
 void vpic_b200_sync_to_host(const void *host_ptr);     /* device -> host for the mirror of host_ptr (NULL: all) */

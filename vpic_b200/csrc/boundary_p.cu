@@ -1,0 +1,150 @@
+// boundary_p on the device: what happens to particles whose move_p ended on a face of the local domain.
+//
+// Replaces the particle-side work of src/boundary/boundary_p.cc:41-750 for slab-decomposed multi-GPU runs:
+//   :257-371  walk the movers, turn particles bound for a neighbouring rank into particle_injector_t records
+//             (coordinate on the crossed axis forced to -/+1, voxel made relative to the receiver's range),
+//             drop absorbed ones, and back-fill the holes they leave in the particle array;
+//   :595-711  append received injectors, give each a mover and finish its move_p.
+// The message exchange itself (boundary_p.cc:392-446, MPI there) is NCCL send/recv in vpic_b200/parallel.py.
+// Custom particle-boundary handlers (host callbacks, boundary_p.cc:332-346) are out of scope on the device.
+//
+// Determinism: movers arrive sorted by particle index (vpb_sort_movers); injectors are grouped per destination
+// face by a STABLE split, so every buffer is in ascending particle order and the back-fill reproduces the
+// reference's sequential "p[i] = p[--np]" result exactly.
+#include "push_common.cuh"
+
+namespace vpb {
+
+int radix_split_injectors(int4 *a, int4 *b, int n, void *scratch, size_t scratch_bytes, cudaStream_t st,
+                          int *class_offsets_dev);
+size_t radix_split_scratch_bytes(int n);
+
+struct BoundK {
+  float4 *p; int np;
+  const int4 *pm; int nm;
+  const long long *neighbor;
+  long long rangel, rangeh, rangem;
+  long long face_range[6];
+  int sp_id;
+};
+
+// class of a mover: 0..5 = send through that face, 6 = absorbed, 7 = no device handler (dropped with a count)
+__global__ void __launch_bounds__(256) bp_build_injectors_kernel(BoundK k, int4 *inj /* 3 words per record */) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= k.nm) return;
+  const int4 mv = k.pm[m];
+  const int i = mv.w;
+  float4 r = k.p[2 * (size_t)i];
+  const float4 u = k.p[2 * (size_t)i + 1];
+  int voxel = __float_as_int(r.w);
+  const int face = voxel & 7;
+  voxel >>= 3;
+  const long long nn = __ldg(k.neighbor + 6ll * voxel + face);
+  int cls = 7;
+  int dst_voxel = voxel;
+  if (nn == -2 /* absorb_particles, grid.h:30 */) cls = 6;
+  else if (((nn >= 0) && (nn < k.rangel)) || ((nn > k.rangeh) && (nn <= k.rangem))) {
+    if (face < 6 && k.face_range[face] >= 0) {
+      cls = face;
+      dst_voxel = (int)(nn - k.face_range[face]);
+      const float dir = face < 3 ? 1.0f : -1.0f;                  // where the sending face sits on the receiver
+      const int axis = face % 3;
+      if (axis == 0) r.x = dir; else if (axis == 1) r.y = dir; else r.z = dir;
+    }
+  }
+  inj[3 * (size_t)m + 0] = make_int4(__float_as_int(r.x), __float_as_int(r.y), __float_as_int(r.z), dst_voxel);
+  inj[3 * (size_t)m + 1] = make_int4(__float_as_int(u.x), __float_as_int(u.y), __float_as_int(u.z), __float_as_int(u.w));
+  inj[3 * (size_t)m + 2] = make_int4(mv.x, mv.y, mv.z, cls);      // class rides in the sp_id slot until the split
+}
+
+__global__ void __launch_bounds__(256) bp_set_sp_id_kernel(int4 *inj, int n, int sp_id) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m < n) inj[3 * (size_t)m + 2].w = sp_id;
+}
+
+__device__ __forceinline__ int lower_bound_mover(const int4 *pm, int n, int key) {   // first m with pm[m].i >= key
+  int lo = 0, hi = n;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (pm[mid].w < key) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+
+// Back-fill: all nm mover particles leave the array.  Sequentially the reference does, for movers in DEscending
+// index order, p[i] = p[--np].  Equivalent closed form: with np' = np - nm, the holes below np' taken in descending
+// order receive the surviving tail particles (index >= np', not a mover) taken in descending order.
+__global__ void __launch_bounds__(256) bp_backfill_kernel(BoundK k) {
+  const int t_rel = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t_rel >= k.nm) return;
+  const int np_new = k.np - k.nm;
+  const int t = np_new + t_rel;                                  // a tail position
+  const int lb = lower_bound_mover(k.pm, k.nm, t);
+  if (lb < k.nm && k.pm[lb].w == t) return;                      // the tail particle itself leaves
+  const int k0 = lower_bound_mover(k.pm, k.nm, np_new);          // movers below np' = holes to fill
+  const int removed_above = k.nm - lb;                           // movers with index > t
+  const int r = (k.np - 1 - t) - removed_above;                  // rank among survivors, from the top
+  const int hole = k.pm[k0 - 1 - r].w;
+  k.p[2 * (size_t)hole] = k.p[2 * (size_t)t];
+  k.p[2 * (size_t)hole + 1] = k.p[2 * (size_t)t + 1];
+}
+
+// Injection: record n_f - 1 - j of a face buffer lands at p[base + j'] in the reference's reverse walk, i.e. the
+// LAST record is appended first (boundary_p.cc:640-644).  Each new particle gets a mover and finishes its move.
+__global__ void __launch_bounds__(128) bp_inject_kernel(PushK a, const int4 *inj, int n, int base) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const int4 w0 = inj[3 * (size_t)(n - 1 - j)], w1 = inj[3 * (size_t)(n - 1 - j) + 1], w2 = inj[3 * (size_t)(n - 1 - j) + 2];
+  const int i = base + j;
+  float4 r = make_float4(__int_as_float(w0.x), __int_as_float(w0.y), __int_as_float(w0.z), __int_as_float(w0.w));
+  float4 u = make_float4(__int_as_float(w1.x), __int_as_float(w1.y), __int_as_float(w1.z), __int_as_float(w1.w));
+  float dispx = __int_as_float(w2.x), dispy = __int_as_float(w2.y), dispz = __int_as_float(w2.z);
+  const int left = move_p_dev(a, r, u, dispx, dispy, dispz);
+  if (left) {
+    const int slot = atomicAdd(a.counters, 1);
+    if (slot < a.max_nm) a.pm[slot] = make_int4(__float_as_int(dispx), __float_as_int(dispy), __float_as_int(dispz), i);
+    else { atomicAdd(a.counters + 1, 1); r.w = __int_as_float(__float_as_int(r.w) >> 3); }
+  }
+  a.p[2 * (size_t)i] = r;
+  a.p[2 * (size_t)i + 1] = u;
+}
+
+}  // namespace vpb
+
+using namespace vpb;
+
+extern "C" size_t vpb_boundary_scratch_bytes(int32_t nm) {
+  if (nm < 1) nm = 1;
+  return (((size_t)nm * 48 + 255) / 256) * 256 + radix_split_scratch_bytes(nm);
+}
+
+extern "C" int vpb_boundary_p_pack(const vpb_boundary_args_t *b, void *stream) {
+  VPB_REQUIRE(b && b->p && b->neighbor && b->class_offsets && (b->nm == 0 || (b->pm && b->inj && b->scratch)),
+              "vpb_boundary_p_pack: Bad args.");
+  VPB_REQUIRE(b->nm >= 0 && b->nm <= b->np, "vpb_boundary_p_pack: nm out of range");
+  cudaStream_t st = as_stream(stream);
+  if (b->nm == 0) { VPB_CUDA(cudaMemsetAsync(b->class_offsets, 0, 9 * sizeof(int), st)); return 0; }
+  VPB_REQUIRE(b->scratch_bytes >= vpb_boundary_scratch_bytes(b->nm), "vpb_boundary_p_pack: scratch too small");
+  BoundK k;
+  k.p = (float4 *)b->p; k.np = b->np; k.pm = (const int4 *)b->pm; k.nm = b->nm;
+  k.neighbor = (const long long *)b->neighbor; k.rangel = b->rangel; k.rangeh = b->rangeh; k.rangem = b->rangem;
+  for (int f = 0; f < 6; f++) k.face_range[f] = b->face_range[f];
+  k.sp_id = b->sp_id;
+  int4 *tmp = (int4 *)b->scratch;
+  void *sort_scratch = (char *)b->scratch + (((size_t)b->nm * 48 + 255) / 256) * 256;
+  const int blocks = (b->nm + 255) / 256;
+  bp_build_injectors_kernel<<<blocks, 256, 0, st>>>(k, tmp);                        VPB_LAUNCH_CHECK();
+  int r = radix_split_injectors(tmp, (int4 *)b->inj, b->nm, sort_scratch, b->scratch_bytes - ((char *)sort_scratch - (char *)b->scratch),
+                                st, b->class_offsets);
+  if (r) return r;
+  bp_set_sp_id_kernel<<<blocks, 256, 0, st>>>((int4 *)b->inj, b->nm, b->sp_id);     VPB_LAUNCH_CHECK();
+  bp_backfill_kernel<<<blocks, 256, 0, st>>>(k);                                    VPB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vpb_boundary_p_inject(const vpb_push_args_t *push, const void *inj, int32_t n, void *stream) {
+  VPB_REQUIRE(push && push->p && push->accum && push->neighbor && push->counters && (inj || n == 0),
+              "vpb_boundary_p_inject: Bad args.");
+  if (n <= 0) return 0;
+  const PushK k = to_push_k(push);
+  bp_inject_kernel<<<(n + 127) / 128, 128, 0, as_stream(stream)>>>(k, (const int4 *)inj, n, push->np);
+  VPB_LAUNCH_CHECK();
+  return 0;
+}

@@ -296,4 +296,59 @@ void unload_accumulator_array(vpb_field_array_t *fa, const vpb_accumulator_array
   if (g_mode == VPB_MODE_COHERENT) DEV(vpb_stream_sync(nullptr));
 }
 
+// ---- standard field advance through the field_advance_kernels_t seam (field_advance.h:170-229) -----------------
+// vpic_b200_install_field_kernels(fa) repoints the time-stepping entries of fa->kernel[0] at the functions below,
+// the same way new_standard_field_array swaps in its vacuum_* variants (sfa.cc:202-211).  They are global symbols
+// because the reference's checkpointing stores the table by symbol name (field_advance.cc:16-58).
+static void field_args_of(const vpb_field_array_t *fa, float *df, vpb_field_args_t *a) {
+  const vpb_grid_t *g = fa->g;
+  const vpb_sfa_params_t *prm = (const vpb_sfa_params_t *)fa->params;
+  a->f = df; a->nx = g->nx; a->ny = g->ny; a->nz = g->nz;
+  a->dt = g->dt; a->cvac = g->cvac; a->eps0 = g->eps0; a->damp = prm ? prm->damp : 0.0f;
+  a->dx = g->dx; a->dy = g->dy; a->dz = g->dz; a->dV = g->dV; a->rdx = g->rdx; a->rdy = g->rdy; a->rdz = g->rdz;
+  static const int off[6][3] = {{-1,0,0},{0,-1,0},{0,0,-1},{1,0,0},{0,1,0},{0,0,1}};
+  const int self = g->bc[13];
+  for (int f = 0; f < 6; f++) {
+    const int b = g->bc[13 + off[f][0] + 3 * off[f][1] + 9 * off[f][2]];          // BOUNDARY(i,j,k), grid.h:16
+    if (b < 0) a->face[f] = b;
+    else if (b == self) a->face[f] = VPB_FACE_PERIODIC_SELF;
+    else DROPIN_ERROR("face %d is shared with rank %d: multi-rank halo exchange runs through the NCCL path, not this seam", f, b);
+  }
+  if (prm && prm->n_mc != 1) DROPIN_ERROR("the device field advance supports a single (vacuum) material; this deck has %d", prm->n_mc);
+}
+
+#define FIELD_ENTRY(name, call)                                                            \
+  if (!fa) DROPIN_ERROR("Bad args");                                                        \
+  const size_t fbytes = (size_t)fa->g->nv * sizeof(vpb_field_t);                            \
+  float *df = (float *)dev_in(fa->f, fbytes);                                               \
+  vpb_field_args_t a; field_args_of(fa, df, &a);                                            \
+  DEV(call);                                                                                \
+  dev_written(fa->f, fbytes);                                                               \
+  if (g_mode == VPB_MODE_COHERENT) DEV(vpb_stream_sync(nullptr));
+
+void vpic_b200_advance_b(vpb_field_array_t *fa, float frac) { FIELD_ENTRY(advance_b, vpb_advance_b(&a, frac, nullptr)) }
+void vpic_b200_advance_e(vpb_field_array_t *fa, float frac) { FIELD_ENTRY(advance_e, vpb_vacuum_advance_e(&a, frac, nullptr)) }
+void vpic_b200_clear_jf(vpb_field_array_t *fa) { FIELD_ENTRY(clear_jf, vpb_clear_jf(&a, nullptr)) }
+void vpic_b200_synchronize_jf(vpb_field_array_t *fa) { FIELD_ENTRY(synchronize_jf, vpb_synchronize_jf(&a, nullptr)) }
+void vpic_b200_energy_f(double *en, const vpb_field_array_t *fa) {
+  if (!en || !fa) DROPIN_ERROR("Bad args");
+  float *df = (float *)dev_in(fa->f, (size_t)fa->g->nv * sizeof(vpb_field_t));
+  vpb_field_args_t a; field_args_of(fa, df, &a);
+  double *den = (double *)scratch(4, 6 * sizeof(double));
+  DEV(vpb_vacuum_energy_f(&a, den, nullptr));
+  double local[6];
+  DEV(vpb_memcpy_d2h(local, den, sizeof local, nullptr));
+  DEV(vpb_stream_sync(nullptr));
+  g_d2h += sizeof local;
+  if (mp_allsum_d) mp_allsum_d(local, en, 6); else memcpy(en, local, sizeof local);
+}
+void vpic_b200_install_field_kernels(vpb_field_array_t *fa) {
+  if (!fa) DROPIN_ERROR("Bad args");
+  fa->kernel->advance_b = vpic_b200_advance_b;
+  fa->kernel->advance_e = vpic_b200_advance_e;
+  fa->kernel->energy_f = vpic_b200_energy_f;
+  fa->kernel->clear_jf = vpic_b200_clear_jf;
+  fa->kernel->synchronize_jf = vpic_b200_synchronize_jf;
+}
+
 }  // extern "C"

@@ -1,0 +1,202 @@
+// Device functions shared by the particle kernels (advance_p.cu, boundary_p.cu).  Every translation unit that
+// includes this is compiled with -fmad=false: the arithmetic follows the reference's scalar code exactly.
+#pragma once
+#include "vpb_common.cuh"
+
+namespace vpb {
+
+struct PushK {
+  float4 *p; int np;
+  int4 *pm; int max_nm; int *counters;
+  const float *interp; int istride;
+  float *accum; int astride;
+  const long long *neighbor; long long rangel, rangeh;
+  float qdt_2mc, cdt_dx, cdt_dy, cdt_dz, qsp;
+  int dbg;
+};
+
+// The 12 accumulator increments of one straight streak inside one voxel (advance_p_pipeline.cc:172-208,
+// move_p.cc:277-305).  q = charge*weight, (ux,uy,uz) = half displacement, (dx,dy,dz) = streak midpoint.
+__device__ __forceinline__ void streak_currents(float q, float ux, float uy, float uz,
+                                                float dx, float dy, float dz, float v5, float (&j)[12]) {
+  float v0, v1, v2, v3, v4;
+#define VPB_ACC(uX, dY, dZ, o)                                     \
+  v4 = q * uX; v1 = v4 * dY; v0 = v4 - v1; v1 += v4;               \
+  v4 = 1.0f + dZ; v2 = v0 * v4; v3 = v1 * v4;                      \
+  v4 = 1.0f - dZ; v0 *= v4; v1 *= v4;                              \
+  v0 += v5; v1 -= v5; v2 -= v5; v3 += v5;                          \
+  j[o] = v0; j[o + 1] = v1; j[o + 2] = v2; j[o + 3] = v3;
+  VPB_ACC(ux, dy, dz, 0)
+  VPB_ACC(uy, dz, dx, 4)
+  VPB_ACC(uz, dx, dy, 8)
+#undef VPB_ACC
+}
+
+__device__ __forceinline__ void deposit_red_v4(float *a, const float (&j)[12]) {
+  red_add_v4(a, j[0], j[1], j[2], j[3]);
+  red_add_v4(a + 4, j[4], j[5], j[6], j[7]);
+  red_add_v4(a + 8, j[8], j[9], j[10], j[11]);
+}
+
+// Warp-level segmented reduction by voxel.  Lanes whose voxel is shared by >= kMinGroup lanes are summed with a
+// reduce-scatter butterfly (15 shuffles for 12 values, not 60) and one lane per component issues the RED;
+// stragglers (drifted particles) go straight to 3 vector REDs.
+constexpr int kMinGroup = 6;
+
+__device__ __forceinline__ void deposit_warp_segmented(float *accum, int astride, int vox, bool active,
+                                                       const float (&j)[12]) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int key = active ? vox : (-1 - lane);
+  const unsigned peers = __match_any_sync(full, key);
+  const bool grouped = active && (__popc(peers) >= kMinGroup);
+  if (active && !grouped) deposit_red_v4(accum + (size_t)vox * astride, j);
+  unsigned big = __ballot_sync(full, grouped);
+  while (big) {
+    const int leader = __ffs(big) - 1;
+    const unsigned grp = __shfl_sync(full, peers, leader);
+    const int gv = __shfl_sync(full, vox, leader);
+    const bool mine = grouped && (peers == grp);
+    float v[16];
+#pragma unroll
+    for (int c = 0; c < 12; c++) v[c] = mine ? j[c] : 0.0f;
+#pragma unroll
+    for (int c = 12; c < 16; c++) v[c] = 0.0f;
+    // reduce-scatter: after the step with lane-bit b, each lane keeps the half of its values selected by bit b
+#pragma unroll
+    for (int half = 8, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
+      const bool hi = (lane & bit) != 0;
+#pragma unroll
+      for (int c = 0; c < half; c++) {
+        const float keep = hi ? v[c + half] : v[c];
+        const float send = hi ? v[c] : v[c + half];
+        v[c] = keep + __shfl_xor_sync(full, send, bit);
+      }
+    }
+    float tot = v[0] + __shfl_xor_sync(full, v[0], 1);
+    const int comp = lane >> 1;
+    if (!(lane & 1) && comp < 12) red_add(accum + (size_t)gv * astride + comp, tot);
+    big &= ~grp;
+  }
+}
+
+// move_p, scalar variant of the reference (move_p.cc:216-378), on registers.
+// r = {dx,dy,dz,i}, u = {ux,uy,uz,w}; returns 1 when the particle left the local domain (r.w = 8*voxel+face).
+__device__ __forceinline__ int move_p_dev(const PushK &a, float4 &r, float4 &u, float &dispx, float &dispy, float &dispz) {
+  const float q = a.qsp * u.w;
+  int vox = __float_as_int(r.w);
+  int ret = 0;
+  for (;;) {
+    float s_midx = r.x, s_midy = r.y, s_midz = r.z;
+    float s_dispx = dispx, s_dispy = dispy, s_dispz = dispz;
+    const float dirx = (s_dispx > 0.0f) ? 1.0f : -1.0f;
+    const float diry = (s_dispy > 0.0f) ? 1.0f : -1.0f;
+    const float dirz = (s_dispz > 0.0f) ? 1.0f : -1.0f;
+    const float v0 = (s_dispx == 0.0f) ? 3.4e38f : __fdiv_rn(dirx - s_midx, s_dispx);
+    const float v1 = (s_dispy == 0.0f) ? 3.4e38f : __fdiv_rn(diry - s_midy, s_dispy);
+    const float v2 = (s_dispz == 0.0f) ? 3.4e38f : __fdiv_rn(dirz - s_midz, s_dispz);
+    float v3 = 2.0f; int axis = 3;
+    if (v0 < v3) { v3 = v0; axis = 0; }
+    if (v1 < v3) { v3 = v1; axis = 1; }
+    if (v2 < v3) { v3 = v2; axis = 2; }
+    v3 *= 0.5f;
+    s_dispx *= v3; s_dispy *= v3; s_dispz *= v3;
+    s_midx += s_dispx; s_midy += s_dispy; s_midz += s_dispz;
+    // the reference multiplies by the double constant 1.0/3.0 here (move_p.cc:277)
+    const float v5 = (float)((double)(((q * s_dispx) * s_dispy) * s_dispz) * (1.0 / 3.0));
+    float j[12];
+    streak_currents(q, s_dispx, s_dispy, s_dispz, s_midx, s_midy, s_midz, v5, j);
+    deposit_red_v4(a.accum + (size_t)vox * a.astride, j);
+    dispx -= s_dispx; dispy -= s_dispy; dispz -= s_dispz;
+    r.x += s_dispx + s_dispx; r.y += s_dispy + s_dispy; r.z += s_dispz + s_dispz;
+    if (axis == 3) break;
+    const float dir = (axis == 0) ? dirx : (axis == 1) ? diry : dirz;
+    if (axis == 0) r.x = dir; else if (axis == 1) r.y = dir; else r.z = dir;   // exactly on the face
+    const int face = axis + ((dir > 0.0f) ? 3 : 0);
+    const long long nb = __ldg(a.neighbor + 6ll * vox + face);
+    if (nb == -1) {                                        // reflect_particles
+      if (axis == 0) { u.x = -u.x; dispx = -dispx; }
+      else if (axis == 1) { u.y = -u.y; dispy = -dispy; }
+      else { u.z = -u.z; dispz = -dispz; }
+      continue;
+    }
+    if (nb < a.rangel || nb > a.rangeh) { vox = 8 * vox + face; ret = 1; break; }
+    vox = (int)(nb - a.rangel);
+    if (axis == 0) r.x = -dir; else if (axis == 1) r.y = -dir; else r.z = -dir;
+  }
+  r.w = __int_as_float(vox);
+  return ret;
+}
+
+
+// Warp-synchronous move_p: all 32 lanes call it together (lanes without a mover pass active = false) and walk the
+// streak loop in lock step, so each round's deposits can be summed across the warp by voxel before they reach
+// memory.  Movers of one tile come from a handful of neighbouring voxels, so most rounds collapse into a few REDs.
+__device__ __forceinline__ int move_p_warp(const PushK &a, bool active, float4 &r, float4 &u,
+                                           float &dispx, float &dispy, float &dispz) {
+  const float q = a.qsp * u.w;
+  int vox = __float_as_int(r.w);
+  int ret = 0;
+  bool live = active;
+  while (__any_sync(0xffffffffu, live)) {
+    float j[12];
+    const int dep_vox = vox;
+    const bool dep = live;
+    if (live) {
+      float s_midx = r.x, s_midy = r.y, s_midz = r.z;
+      float s_dispx = dispx, s_dispy = dispy, s_dispz = dispz;
+      const float dirx = (s_dispx > 0.0f) ? 1.0f : -1.0f;
+      const float diry = (s_dispy > 0.0f) ? 1.0f : -1.0f;
+      const float dirz = (s_dispz > 0.0f) ? 1.0f : -1.0f;
+      const float v0 = (s_dispx == 0.0f) ? 3.4e38f : __fdiv_rn(dirx - s_midx, s_dispx);
+      const float v1 = (s_dispy == 0.0f) ? 3.4e38f : __fdiv_rn(diry - s_midy, s_dispy);
+      const float v2 = (s_dispz == 0.0f) ? 3.4e38f : __fdiv_rn(dirz - s_midz, s_dispz);
+      float v3 = 2.0f; int axis = 3;
+      if (v0 < v3) { v3 = v0; axis = 0; }
+      if (v1 < v3) { v3 = v1; axis = 1; }
+      if (v2 < v3) { v3 = v2; axis = 2; }
+      v3 *= 0.5f;
+      s_dispx *= v3; s_dispy *= v3; s_dispz *= v3;
+      s_midx += s_dispx; s_midy += s_dispy; s_midz += s_dispz;
+      const float v5 = (float)((double)(((q * s_dispx) * s_dispy) * s_dispz) * (1.0 / 3.0));   // move_p.cc:277
+      streak_currents(q, s_dispx, s_dispy, s_dispz, s_midx, s_midy, s_midz, v5, j);
+      dispx -= s_dispx; dispy -= s_dispy; dispz -= s_dispz;
+      r.x += s_dispx + s_dispx; r.y += s_dispy + s_dispy; r.z += s_dispz + s_dispz;
+      if (axis == 3) {
+        live = false;
+      } else {
+        const float dir = (axis == 0) ? dirx : (axis == 1) ? diry : dirz;
+        if (axis == 0) r.x = dir; else if (axis == 1) r.y = dir; else r.z = dir;
+        const int face = axis + ((dir > 0.0f) ? 3 : 0);
+        const long long nb = __ldg(a.neighbor + 6ll * vox + face);
+        if (nb == -1) {
+          if (axis == 0) { u.x = -u.x; dispx = -dispx; }
+          else if (axis == 1) { u.y = -u.y; dispy = -dispy; }
+          else { u.z = -u.z; dispz = -dispz; }
+        } else if (nb < a.rangel || nb > a.rangeh) {
+          vox = 8 * vox + face; ret = 1; live = false;
+        } else {
+          vox = (int)(nb - a.rangel);
+          if (axis == 0) r.x = -dir; else if (axis == 1) r.y = -dir; else r.z = -dir;
+        }
+      }
+    }
+    deposit_warp_segmented(a.accum, a.astride, dep_vox, dep, j);
+  }
+  r.w = __int_as_float(vox);
+  return ret;
+}
+
+static inline PushK to_push_k(const vpb_push_args_t *args) {
+  PushK k;
+  k.p = (float4 *)args->p; k.np = args->np;
+  k.pm = (int4 *)args->pm; k.max_nm = args->max_nm; k.counters = args->counters;
+  k.interp = args->interp; k.istride = args->interp_stride;
+  k.accum = args->accum; k.astride = args->accum_stride;
+  k.neighbor = (const long long *)args->neighbor; k.rangel = args->rangel; k.rangeh = args->rangeh;
+  k.qdt_2mc = args->qdt_2mc; k.cdt_dx = args->cdt_dx; k.cdt_dy = args->cdt_dy; k.cdt_dz = args->cdt_dz; k.qsp = args->qsp;
+  k.dbg = args->debug_skip;
+  return k;
+}
+
+}  // namespace vpb

@@ -13,7 +13,6 @@
 
 namespace vpb {
 
-constexpr int kFieldFloats = 20;
 
 // ---- load_interpolator -----------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) load_interpolator_kernel(float *__restrict__ interp, int istride,

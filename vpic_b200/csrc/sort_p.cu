@@ -92,9 +92,10 @@ static int exclusive_scan_inplace(int *data, int n, int *tmp /* >= ceil(n/kScanT
 }
 
 // ---- radix passes ----------------------------------------------------------------------------------------
-// Items are VEC int4 words; the key is word 0's .w (particle_t.i and particle_mover_t.i both sit there).
+// Items are VEC int4 words; the key is word KEYW's .w (particle_t.i and particle_mover_t.i sit in word 0,
+// the destination class of a particle_injector_t rides in word 2).
 
-template <int VEC>
+template <int VEC, int KEYW>
 __global__ void __launch_bounds__(kSortBlock) radix_hist_kernel(const int4 *items, int n, int per_block, int shift,
                                                                 int *hist /* [kRadix][gridDim.x] */) {
   __shared__ int s_hist[kRadix];
@@ -106,7 +107,7 @@ __global__ void __launch_bounds__(kSortBlock) radix_hist_kernel(const int4 *item
   for (int i0 = lo; i0 < hi; i0 += kSortBlock) {
     const int i = i0 + threadIdx.x;
     const bool valid = i < hi;
-    const int d = valid ? ((items[(size_t)i * VEC].w >> shift) & (kRadix - 1)) : (kRadix + lane);
+    const int d = valid ? ((items[(size_t)i * VEC + KEYW].w >> shift) & (kRadix - 1)) : (kRadix + lane);
     const unsigned peers = __match_any_sync(0xffffffffu, d);
     if (valid && lane == __ffs(peers) - 1) atomicAdd(&s_hist[d], __popc(peers));
   }
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(kSortBlock) radix_hist_kernel(const int4 *item
   for (int d = threadIdx.x; d < kRadix; d += kSortBlock) hist[d * gridDim.x + blockIdx.x] = s_hist[d];
 }
 
-template <int VEC>
+template <int VEC, int KEYW>
 __global__ void __launch_bounds__(kSortBlock) radix_scatter_kernel(const int4 *src, int4 *dst, int n, int per_block,
                                                                    int shift, const int *offs /* scanned hist */) {
   __shared__ int s_base[kRadix];                       // next output slot of each digit for this CTA
@@ -140,7 +141,7 @@ __global__ void __launch_bounds__(kSortBlock) radix_scatter_kernel(const int4 *s
 #pragma unroll
         for (int v = 0; v < VEC; v++) it[j][v] = src[(size_t)i * VEC + v];
       }
-      const int d = valid ? ((it[j][0].w >> shift) & (kRadix - 1)) : (kRadix + lane);
+      const int d = valid ? ((it[j][KEYW].w >> shift) & (kRadix - 1)) : (kRadix + lane);
       digit[j] = valid ? d : -1;
       const unsigned peers = __match_any_sync(0xffffffffu, d);
       int before = 0;
@@ -205,7 +206,7 @@ static SortPlan plan_sort(int n) {
   return s;
 }
 
-template <int VEC>
+template <int VEC, int KEYW = 0>
 static int radix_sort(int4 *a, int4 *b, int n, int key_bits, void *scratch, size_t scratch_bytes, cudaStream_t st,
                       bool *result_in_b) {
   const SortPlan pl = plan_sort(n);
@@ -214,12 +215,33 @@ static int radix_sort(int4 *a, int4 *b, int n, int key_bits, void *scratch, size
   int *tmp = (int *)((char *)scratch + ((pl.hist_bytes + 255) / 256) * 256);
   int4 *src = a, *dst = b;
   for (int shift = 0; shift < key_bits; shift += kRadixBits) {
-    radix_hist_kernel<VEC><<<pl.nblocks, kSortBlock, 0, st>>>(src, n, pl.per_block, shift, hist);  VPB_LAUNCH_CHECK();
+    radix_hist_kernel<VEC, KEYW><<<pl.nblocks, kSortBlock, 0, st>>>(src, n, pl.per_block, shift, hist);  VPB_LAUNCH_CHECK();
     int r = exclusive_scan_inplace(hist, kRadix * pl.nblocks, tmp, st); if (r) return r;
-    radix_scatter_kernel<VEC><<<pl.nblocks, kSortBlock, 0, st>>>(src, dst, n, pl.per_block, shift, hist);  VPB_LAUNCH_CHECK();
+    radix_scatter_kernel<VEC, KEYW><<<pl.nblocks, kSortBlock, 0, st>>>(src, dst, n, pl.per_block, shift, hist);  VPB_LAUNCH_CHECK();
     int4 *t = src; src = dst; dst = t;
   }
   *result_in_b = (src == b);
+  return 0;
+}
+
+// class start offsets of a one-pass split: scanned hist[c * nblocks] is where class c begins
+__global__ void split_offsets_kernel(const int *hist, int nblocks, int n, int *offs9) {
+  const int c = threadIdx.x;
+  if (c < 8) offs9[c] = hist[c * nblocks];
+  if (c == 8) offs9[8] = n;
+}
+
+size_t radix_split_scratch_bytes(int n) { return plan_sort(n > 0 ? n : 1).total_bytes; }
+
+// Stable split of particle_injector_t records (3 words) by the class in word 2 .w (0..7): one radix pass a -> b.
+int radix_split_injectors(int4 *a, int4 *b, int n, void *scratch, size_t scratch_bytes, cudaStream_t st,
+                          int *class_offsets_dev) {
+  bool in_b = false;
+  int r = radix_sort<3, 2>(a, b, n, 3, scratch, scratch_bytes, st, &in_b);
+  if (r) return r;
+  const SortPlan pl = plan_sort(n);
+  split_offsets_kernel<<<1, 32, 0, st>>>((const int *)scratch, pl.nblocks, n, class_offsets_dev);
+  VPB_LAUNCH_CHECK();
   return 0;
 }
 

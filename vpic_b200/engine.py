@@ -9,6 +9,7 @@ torch is plumbing only (device memory, streams, torch.distributed) — there is 
 CPU fallback: without the CUDA library these calls raise.
 """
 import ctypes as C
+import os
 import numpy as np
 import torch
 
@@ -163,6 +164,7 @@ def advance_p(sp: Species, aa: AccumulatorArray, ia: InterpolatorArray, variant=
     a.qdt_2mc, a.cdt_dx, a.cdt_dy, a.cdt_dz, a.qsp = sp.push_constants()
     a.nx, a.ny, a.nz = g.nx, g.ny, g.nz
     a.variant = variant
+    a.debug_skip = int(os.environ.get("VPB_DEBUG_SKIP", "0"))
     L = _lib.load()
     _lib.check(L.vpb_advance_p(C.byref(a), _stream()), "advance_p")
     if sync:
@@ -243,3 +245,57 @@ def uncenter_p(sp: Species, ia: InterpolatorArray):
     _bad_args(sp is None or ia is None or sp.g is not ia.g, "uncenter_p")
     _lib.check(_lib.load().vpb_uncenter_p(_ptr(sp.p), sp.np, _ptr(ia.i), ia.stride, sp.push_constants()[0], _stream()),
                "uncenter_p")
+
+
+# ---- boundary_p, particle side (src/boundary/boundary_p.cc:257-371,595-711) ----------------------------------
+
+def boundary_pack(sp: Species, face_range):
+    """Turn this species' movers into per-face injector buffers and back-fill the holes they leave.
+
+    Returns (inj, offsets_dev): inj is a [nm, 12] float32 view of particle_injector_t records grouped by class,
+    offsets_dev an int32[9] device tensor (class c occupies [offsets[c], offsets[c+1]); 0..5 faces, 6 absorbed,
+    7 no handler).  sp.np and sp.nm are updated (every mover's particle leaves the array)."""
+    L = _lib.load()
+    g = sp.g
+    offs = torch.zeros(9, dtype=torch.int32, device=g.device)
+    nm = sp.nm
+    if nm == 0:
+        return None, offs
+    inj = torch.empty((nm, 12), dtype=torch.float32, device=g.device)
+    need = L.vpb_boundary_scratch_bytes(nm)
+    scratch = torch.empty(need, dtype=torch.uint8, device=g.device)
+    b = _lib.BoundaryArgs()
+    b.p, b.np, b.pm, b.nm = sp.p.data_ptr(), sp.np, sp.pm.data_ptr(), nm
+    b.neighbor = g.neighbor.data_ptr()
+    b.rangel, b.rangeh, b.rangem = g.rangel, g.rangeh, int(g.g.range[g.world_size])
+    for f in range(6):
+        b.face_range[f] = face_range[f]
+    b.sp_id = getattr(sp, "id", 0)
+    b.inj, b.class_offsets = inj.data_ptr(), offs.data_ptr()
+    b.scratch, b.scratch_bytes = scratch.data_ptr(), need
+    _lib.check(L.vpb_boundary_p_pack(C.byref(b), _stream()), "boundary_p_pack")
+    sp.np -= nm
+    sp.nm = 0
+    sp._bp_keep = (inj, scratch)          # keep alive until the stream has consumed them
+    return inj, offs
+
+
+def boundary_inject(sp: Species, aa: AccumulatorArray, ia: InterpolatorArray, inj, n):
+    """Append n received injectors (device tensor [n,12]) and finish their moves; new movers accumulate in sp.pm
+    through sp.counters (call finish_advance_p afterwards to read sp.nm)."""
+    if n == 0:
+        return
+    if sp.np + n > sp.max_np:
+        raise RuntimeError(f"species {sp.name}: {sp.np}+{n} particles exceed max_np={sp.max_np}")
+    g = sp.g
+    a = _lib.PushArgs()
+    a.p, a.np = sp.p.data_ptr(), sp.np
+    a.pm, a.max_nm = sp.pm.data_ptr(), sp.max_nm
+    a.counters = sp.counters.data_ptr()
+    a.interp, a.interp_stride = ia.i.data_ptr(), ia.stride
+    a.accum, a.accum_stride = aa.a.data_ptr(), aa.stride_floats
+    a.neighbor, a.rangel, a.rangeh = g.neighbor.data_ptr(), g.rangel, g.rangeh
+    a.qdt_2mc, a.cdt_dx, a.cdt_dy, a.cdt_dz, a.qsp = sp.push_constants()
+    a.nx, a.ny, a.nz = g.nx, g.ny, g.nz
+    _lib.check(_lib.load().vpb_boundary_p_inject(C.byref(a), _ptr(inj), n, _stream()), "boundary_p_inject")
+    sp.np += n

@@ -25,7 +25,14 @@ class PushArgs(C.Structure):
                 ("neighbor", c_vp), ("rangel", c_i64), ("rangeh", c_i64),
                 ("qdt_2mc", c_f), ("cdt_dx", c_f), ("cdt_dy", c_f), ("cdt_dz", c_f), ("qsp", c_f),
                 ("nx", c_i32), ("ny", c_i32), ("nz", c_i32),
-                ("variant", c_i32)]
+                ("variant", c_i32), ("debug_skip", c_i32)]
+
+
+class BoundaryArgs(C.Structure):
+    """vpb_boundary_args_t"""
+    _fields_ = [("p", c_vp), ("np", c_i32), ("pm", c_vp), ("nm", c_i32), ("neighbor", c_vp),
+                ("rangel", c_i64), ("rangeh", c_i64), ("rangem", c_i64), ("face_range", c_i64 * 6),
+                ("sp_id", c_i32), ("inj", c_vp), ("class_offsets", c_vp), ("scratch", c_vp), ("scratch_bytes", C.c_size_t)]
 
 
 class FieldArgs(C.Structure):
@@ -60,6 +67,9 @@ _PROTOS = {
     "vpb_device_sync": (C.c_int, []),
     "vpb_launch_count": (c_i64, []),
     "vpb_advance_p": (C.c_int, [C.POINTER(PushArgs), c_vp]),
+    "vpb_boundary_scratch_bytes": (C.c_size_t, [c_i32]),
+    "vpb_boundary_p_pack": (C.c_int, [C.POINTER(BoundaryArgs), c_vp]),
+    "vpb_boundary_p_inject": (C.c_int, [C.POINTER(PushArgs), c_vp, c_i32, c_vp]),
     "vpb_sort_scratch_bytes": (C.c_size_t, [c_i32, c_i32]),
     "vpb_sort_movers_scratch_bytes": (C.c_size_t, [c_i32]),
     "vpb_sort_movers": (C.c_int, [c_vp, c_i32, c_vp, C.c_size_t, c_vp]),

@@ -1,0 +1,91 @@
+"""The hot-path block of vpic_simulation::advance() (src/vpic/advance.cc:25-185) over device-resident arrays.
+
+Order of operations is the reference's:
+  sort_p (per species, every sort_interval)            advance.cc:25-29
+  clear_accumulator_array                              :36-37
+  advance_p (per species)                              :49-50
+  reduce_accumulator_array                             :65-66
+  boundary_p x num_comm_round                          :73-77   (slab-decomposed runs: NCCL, see parallel.py)
+  clear_jf ; unload_accumulator_array ; synchronize_jf :107-110
+  advance_b(1/2) ; advance_e(1) ; advance_b(1/2)       :123-137
+  load_interpolator_array                              :185
+Host hooks of the reference (user_* injections, collisions, emitters, dumps) are outside the hot path and are not
+called here.
+"""
+import torch
+
+from . import engine as E
+
+
+class Simulation:
+    def __init__(self, dgrid: E.DeviceGrid, damp=0.0, simd_width=4, num_comm_round=3, exchange=None):
+        self.g = dgrid
+        self.field_array = E.FieldArray(dgrid, damp=damp)
+        self.interpolator_array = E.InterpolatorArray(dgrid, simd_width)
+        self.accumulator_array = E.AccumulatorArray(dgrid, simd_width)
+        self.species_list = []
+        self.num_comm_round = num_comm_round
+        self.exchange = exchange          # parallel.SlabExchange for multi-GPU runs, None on one GPU
+        self.deposit_variant = 0
+        self.push_events = None           # list of (start, end) CUDA events around each advance_p when profiling
+
+    def define_species(self, name, q, m, max_np, max_nm, sort_interval=20, sort_out_of_place=0):
+        sp = E.Species(name, q, m, max_np, max_nm, sort_interval, sort_out_of_place, self.g)
+        sp.id = len(self.species_list)
+        self.species_list.append(sp)
+        return sp
+
+    @property
+    def step(self):
+        return self.g.g.step
+
+    def initialize(self):
+        """The part of vpic_simulation::initialize on the path (initialize.cc:52): interpolators from the fields."""
+        if self.exchange is not None:
+            self.exchange.begin_step(self)
+        E.load_interpolator_array(self.interpolator_array, self.field_array)
+
+    def advance(self):
+        fa, ia, aa = self.field_array, self.interpolator_array, self.accumulator_array
+        step = self.step
+        for sp in self.species_list:
+            if sp.sort_interval > 0 and step % sp.sort_interval == 0:
+                E.sort_p(sp)
+        E.clear_accumulator_array(aa)
+        for sp in self.species_list:
+            if self.push_events is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            E.advance_p(sp, aa, ia, variant=self.deposit_variant, sync=False)
+            if self.push_events is not None:
+                e1.record()
+                self.push_events.append((e0, e1, sp.np))
+        for sp in self.species_list:
+            E.finish_advance_p(sp)
+        E.reduce_accumulator_array(aa)
+        if self.exchange is not None:
+            for _ in range(self.num_comm_round):
+                self.exchange.boundary_p(self)
+        else:
+            for sp in self.species_list:
+                if sp.nm:
+                    raise RuntimeError(f"species {sp.name}: {sp.nm} movers left the domain but no boundary handler "
+                                       "is installed (absorbing walls need boundary_p)")
+        fa.clear_jf()
+        E.unload_accumulator_array(fa, aa)
+        fa.synchronize_jf()
+        if self.exchange is not None:
+            self.exchange.synchronize_jf(self)
+        fa.advance_b(0.5)
+        if self.exchange is not None:
+            self.exchange.ghost_tang_b(self)
+        fa.advance_e(1.0)
+        fa.advance_b(0.5)
+        E.load_interpolator_array(ia, fa)
+        self.g.g.step += 1
+
+    def energies(self):
+        """dump_energies row (src/vpic/dump.cc:38-77): field energies then one kinetic energy per species."""
+        en_f = self.field_array.energy_f()
+        en_p = [E.energy_p(sp, self.interpolator_array) for sp in self.species_list]
+        return list(en_f) + en_p
