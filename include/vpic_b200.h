@@ -61,6 +61,21 @@ int64_t     vpb_launch_count(void);
  * (no FMA contraction, IEEE sqrt and divide) so particle state is bit-exact;
  * accumulator sums differ only by fp32 atomic ordering.
  */
+/* Closed form of grid_t.neighbor for the regular grids the reference builds (size_grid / join_grid / set_pbc,
+ * src/grid/ops.cc:19-211): inside the domain the neighbour is voxel +- stride; on each of the six walls it is one
+ * action for the whole wall — a negative particle-boundary code, or "this voxel plus a constant" (periodic wrap
+ * onto this rank, or the matching voxel of the rank behind the wall).  vpb_neighbor_rule_derive reads the six
+ * actions out of the table and then CHECKS every interior voxel and face against the table on the device; only if
+ * all 6*nx*ny*nz entries agree is valid set, and only then do the kernels skip the table lookup. */
+typedef struct vpb_neighbor_rule {
+  int32_t valid;
+  int32_t nx, ny, nz;
+  int64_t act[6];      /* < 0: boundary code of the wall; >= 0: the wall leads to another voxel */
+  int64_t delta[6];    /* neighbour (global id) = rangel + voxel + delta[face] for walls with act >= 0 */
+} vpb_neighbor_rule_t;
+int vpb_neighbor_rule_derive(const int64_t *neighbor_dev, int32_t nx, int32_t ny, int32_t nz, int64_t rangel,
+                             vpb_neighbor_rule_t *rule_out, void *stream);
+
 typedef struct vpb_push_args {
   void          *p;              /* particle_t[np], 32 B each, 16 B aligned          */
   int32_t        np;
@@ -75,14 +90,16 @@ typedef struct vpb_push_args {
   float          qdt_2mc, cdt_dx, cdt_dy, cdt_dz, qsp;   /* computed by the caller in float, advance_p_pipeline.cc:279-283 */
   int32_t        nx, ny, nz;
   int32_t        variant;        /* deposit strategy, see VPB_DEPOSIT_*              */
+  const vpb_neighbor_rule_t *neighbor_rule;   /* optional (host pointer): verified closed form of `neighbor` */
   int32_t        debug_skip;     /* must be 0.  Profiling only (results become INVALID): bit0 skip deposits,
                                     bit1 skip the mover phase, bit2 skip particle stores, bit3 skip the interpolator gather */
 } vpb_push_args_t;
 
 #define VPB_DEPOSIT_DEFAULT      0   /* library's best measured strategy                                  */
 #define VPB_DEPOSIT_RED_V4       1   /* every particle: 3 x red.global.add.v4.f32                         */
-#define VPB_DEPOSIT_WARP_SEG     2   /* warp-level segmented reduction by voxel, then one RED per sum     */
-#define VPB_DEPOSIT_SMEM_TILE    3   /* warp reduction into a shared-memory accumulator tile, tile flush  */
+#define VPB_DEPOSIT_WARP_SEG     2   /* in-voxel streaks: warp-level segmented reduction by voxel, one RED per sum;
+                                        crossing streaks (move_p): 3 vector REDs each                     */
+#define VPB_DEPOSIT_WARP_SEG_MOVERS 3 /* as 2, and move_p runs warp-synchronously with the same segmented reduction */
 
 int vpb_advance_p(const vpb_push_args_t *args, void *stream);
 

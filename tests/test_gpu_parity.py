@@ -71,9 +71,10 @@ PUSH_CASES = [
 ]
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("use_rule", [True, False])
+@pytest.mark.parametrize("variant", [1, 2, 3])
 @pytest.mark.parametrize("dims,uth,pbc,n,sort_first", PUSH_CASES)
-def test_advance_p(eng, oracle, dims, uth, pbc, n, sort_first, variant):
+def test_advance_p(eng, oracle, dims, uth, pbc, n, sort_first, variant, use_rule):
     rng = np.random.default_rng(17)
     nx, ny, nz = dims
     g = make_grid(nx, ny, nz, pbc=pbc)
@@ -87,6 +88,9 @@ def test_advance_p(eng, oracle, dims, uth, pbc, n, sort_first, variant):
     p_ref, pm_ref, acc_ref, _ = oracle_push(oracle, g, parts, interp, -1.0, 1.0, max_nm)
 
     dg = eng.DeviceGrid(g)
+    dg.use_neighbor_rule = use_rule                      # closed-form neighbours vs the grid_t.neighbor table
+    if use_rule:
+        assert dg.neighbor_rule() is not None, "the closed form must verify on every grid the reference builds"
     ia, aa = eng.InterpolatorArray(dg), eng.AccumulatorArray(dg)
     ia.i.copy_(torch.from_numpy(interp))
     sp = eng.Species("electron", -1.0, 1.0, max(n, 1), max_nm, 20, 0, dg)
@@ -102,6 +106,14 @@ def test_advance_p(eng, oracle, dims, uth, pbc, n, sort_first, variant):
     accum_close(aa.a.cpu().numpy(), acc_ref)
     if n > 100:
         assert (got["i"] != parts["i"]).mean() > 0.05
+
+
+def test_neighbor_rule_rejects_irregular_table(eng):
+    """A neighbour table that is not the regular structure must fail verification (the kernels then use the table)."""
+    g = make_grid(5, 4, 3)
+    g.neighbor[G.voxel(2, 2, 2, 5, 4, 3), 3] = g.rangel + G.voxel(4, 4, 3, 5, 4, 3)     # a wormhole
+    dg = eng.DeviceGrid(g)
+    assert dg.neighbor_rule() is None
 
 
 def test_advance_p_mover_overflow(eng, oracle):

@@ -19,156 +19,220 @@
 //     after the tile, which keeps both phases convergent;
 //   * deposit strategies (args.variant) — see deposit.cuh.
 #include "push_common.cuh"
+#include <string.h>
 
 namespace vpb {
 
 constexpr int kBlock = 256;
-constexpr int kPPT   = 4;                 // particles per thread per tile
+constexpr int kPPT   = 4;                 // rows per warp used to size the grid
 constexpr int kTile  = kBlock * kPPT;
 constexpr int kMinBlocks = 3;            // resident CTAs per SM the register budget is tuned for
 
 template <int VARIANT>
 __device__ __forceinline__ void deposit(const PushK &a, int vox, bool active, const float (&j)[12]) {
-  if (VARIANT == VPB_DEPOSIT_WARP_SEG) {
+  if (VARIANT == VPB_DEPOSIT_WARP_SEG || VARIANT == VPB_DEPOSIT_WARP_SEG_MOVERS) {
     deposit_warp_segmented(a.accum, a.astride, vox, active, j);
   } else {
     if (active) deposit_red_v4(a.accum + (size_t)vox * a.astride, j);
   }
 }
 
+constexpr int kWarps = kBlock / 32;
+constexpr int kQCap  = 64;                 // a warp's queue holds at most 31 carried-over + 32 new movers
+constexpr size_t kSmemBytes = (size_t)kWarps * 3 * kQCap * sizeof(int4);
+
+// One dense batch of queued movers [start, start+count) of this warp's queue, count <= 32.
+template <int VARIANT>
+__device__ __forceinline__ void run_movers(const PushK &a, const int4 *q0, const int4 *q1, const int4 *q2,
+                                           int start, int count, int lane) {
+  const bool act = lane < count;
+  int i = 0;
+  float4 rr = make_float4(0.f, 0.f, 0.f, 0.f), uu = rr;
+  float dispx = 0.f, dispy = 0.f, dispz = 0.f;
+  if (act) {
+    const int4 w0 = q0[start + lane], w1 = q1[start + lane], w2 = q2[start + lane];
+    rr = make_float4(__int_as_float(w0.x), __int_as_float(w0.y), __int_as_float(w0.z), __int_as_float(w0.w));
+    uu = make_float4(__int_as_float(w1.x), __int_as_float(w1.y), __int_as_float(w1.z), __int_as_float(w1.w));
+    dispx = __int_as_float(w2.x); dispy = __int_as_float(w2.y); dispz = __int_as_float(w2.z);
+    i = w2.w;
+  }
+  int left;
+  if (VARIANT == VPB_DEPOSIT_WARP_SEG_MOVERS) left = move_p_warp(a, act, rr, uu, dispx, dispy, dispz);
+  else left = act ? move_p_dev(a, rr, uu, dispx, dispy, dispz) : 0;
+  if (act) {
+    if (left) {
+      const int slot = atomicAdd(a.counters, 1);
+      if (slot < a.max_nm) {
+        a.pm[slot] = make_int4(__float_as_int(dispx), __float_as_int(dispy), __float_as_int(dispz), i);
+      } else {
+        atomicAdd(a.counters + 1, 1);                             // lost mover: keep p.i a valid voxel
+        rr.w = __int_as_float(__float_as_int(rr.w) >> 3);
+      }
+    }
+    st_particle(a.p + 2 * (size_t)i, rr, uu);
+  }
+}
+
 template <int VARIANT>
 __global__ void __launch_bounds__(kBlock, kMinBlocks) advance_p_kernel(const PushK a) {
-  // Every warp is autonomous: it owns warp-tiles of 32*kPPT consecutive particles, keeps its own mover queue in
-  // shared memory and never meets a block-wide barrier, so a warp waiting on HBM does not hold up its neighbours.
-  __shared__ int4 s_mv[kBlock / 32][32 * kPPT];   // queued movers of the warp-tile: {disp bits x3, particle index}
-
+  // Every warp is autonomous: it walks rows of 32 consecutive particles (rows of one CTA are adjacent, so its
+  // warps share interpolator lines in L1), keeps its own mover queue in shared memory and never meets a block-wide
+  // barrier.  The next row's particles are requested before the current row is processed.  A queued mover carries
+  // its whole state {r, u, disp, index} (three 16-byte planes, conflict-free), so finishing it needs no reload;
+  // movers are finished 32 at a time, leftovers ride along to the warp's next row.
+  extern __shared__ int4 s_q[];
   const float one = 1.0f;
   const float one_third = (float)(1.0 / 3.0);
   const float two_fifteenths = (float)(2.0 / 15.0);
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int wtile = 32 * kPPT;
-  const int n_wtiles = (a.np + wtile - 1) / wtile;
-  const int warps_total = gridDim.x * (kBlock / 32);
-  int4 *q = s_mv[w];
+  const int n_rows = (a.np + 31) / 32;
+  const int warps_total = gridDim.x * kWarps;
+  int4 *q0 = s_q + (size_t)w * 3 * kQCap, *q1 = q0 + kQCap, *q2 = q1 + kQCap;
+  int nq = 0;                                                           // warp-uniform queue length
 
-  for (int wt = blockIdx.x * (kBlock / 32) + w; wt < n_wtiles; wt += warps_total) {
-    const int base = wt * wtile;
-    // issue every particle load of the warp-tile before touching any of them (kPPT 1-KB requests in flight)
-    float4 r[kPPT], u[kPPT];
-#pragma unroll
-    for (int k = 0; k < kPPT; k++) {
-      const int i = base + k * 32 + lane;
-      r[k] = make_float4(0.f, 0.f, 0.f, 0.f); u[k] = r[k];
-      if (i < a.np) ld_particle(a.p + 2 * (size_t)i, r[k], u[k]);
+  int row = blockIdx.x * kWarps + w;
+  float4 rn = make_float4(0.f, 0.f, 0.f, 0.f), un_next = rn;
+  if (row < n_rows && row * 32 + lane < a.np) ld_particle(a.p + 2 * (size_t)(row * 32 + lane), rn, un_next);
+
+#pragma unroll 1
+  for (; row < n_rows; row += warps_total) {
+    const float4 r = rn, u = un_next;
+    const int i = row * 32 + lane;
+    const bool valid = i < a.np;
+    {
+      const int inext = (row + warps_total) * 32 + lane;                 // request the next row now
+      if (row + warps_total < n_rows && inext < a.np) ld_particle(a.p + 2 * (size_t)inext, rn, un_next);
     }
-    int nq = 0;                                                         // warp-uniform queue length
-
-#pragma unroll
-    for (int k = 0; k < kPPT; k++) {
-      const int i = base + k * 32 + lane;
-      const bool valid = i < a.np;
-      const int ii = __float_as_int(r[k].w);
-      bool inb = false;
-      float j[12];
-      float mux = 0.f, muy = 0.f, muz = 0.f;
-      if (valid) {
-        const float4 *f = reinterpret_cast<const float4 *>(a.interp + (size_t)ii * a.istride);
-        float4 fex = make_float4(.01f, .02f, .03f, .04f), fey = fex, fez = fex, fb0 = fex;
-        float2 fb1 = make_float2(.01f, .02f);
-        if (!(a.dbg & 8)) {
-          fex = __ldg(f); fey = __ldg(f + 1); fez = __ldg(f + 2); fb0 = __ldg(f + 3);
-          fb1 = __ldg(reinterpret_cast<const float2 *>(f + 4));
-        }
-        const float dx = r[k].x, dy = r[k].y, dz = r[k].z;
-        const float hax = a.qdt_2mc * ((fex.x + dy * fex.y) + dz * (fex.z + dy * fex.w));
-        const float hay = a.qdt_2mc * ((fey.x + dz * fey.y) + dx * (fey.z + dz * fey.w));
-        const float haz = a.qdt_2mc * ((fez.x + dx * fez.y) + dy * (fez.z + dx * fez.w));
-        const float cbx = fb0.x + dx * fb0.y;
-        const float cby = fb0.z + dy * fb0.w;
-        const float cbz = fb1.x + dz * fb1.y;
-        float ux = u[k].x, uy = u[k].y, uz = u[k].z;
-        ux += hax; uy += hay; uz += haz;
-        float v0 = __fdiv_rn(a.qdt_2mc, __fsqrt_rn(one + (ux * ux + (uy * uy + uz * uz))));
-        float v1 = cbx * cbx + (cby * cby + cbz * cbz);
-        float v2 = (v0 * v0) * v1;
-        float v3 = v0 * (one + v2 * (one_third + v2 * two_fifteenths));
-        float v4 = __fdiv_rn(v3, one + v1 * (v3 * v3));
-        v4 += v4;
-        v0 = ux + v3 * (uy * cbz - uz * cby);
-        v1 = uy + v3 * (uz * cbx - ux * cbz);
-        v2 = uz + v3 * (ux * cby - uy * cbx);
-        ux += v4 * (v1 * cbz - v2 * cby);
-        uy += v4 * (v2 * cbx - v0 * cbz);
-        uz += v4 * (v0 * cby - v1 * cbx);
-        ux += hax; uy += hay; uz += haz;
-        float4 un = u[k];
-        un.x = ux; un.y = uy; un.z = uz;                               // momentum is stored in either case
-        v0 = __fdiv_rn(one, __fsqrt_rn(one + (ux * ux + (uy * uy + uz * uz))));
-        ux *= a.cdt_dx; uy *= a.cdt_dy; uz *= a.cdt_dz;
-        ux *= v0; uy *= v0; uz *= v0;                                 // half displacement in cell units
-        v0 = dx + ux; v1 = dy + uy; v2 = dz + uz;                     // streak midpoint
-        v3 = v0 + ux; v4 = v1 + uy; const float v5n = v2 + uz;        // new position
-        inb = (v3 <= one) && (v4 <= one) && (v5n <= one) && (-v3 <= one) && (-v4 <= one) && (-v5n <= one);
-        if (a.dbg & 2) inb = true;
-        if (inb) {
-          const float qw = un.w * a.qsp;
-          if (!(a.dbg & 4)) st_particle(a.p + 2 * (size_t)i, make_float4(v3, v4, v5n, r[k].w), un);
-          const float v5 = (((qw * ux) * uy) * uz) * one_third;
-          streak_currents(qw, ux, uy, uz, v0, v1, v2, v5, j);
-        } else {
-          a.p[2 * (size_t)i + 1] = un;
-          mux = ux; muy = uy; muz = uz;
-        }
+    const int ii = __float_as_int(r.w);
+    bool inb = false;
+    float j[12];
+    float mux = 0.f, muy = 0.f, muz = 0.f;
+    float4 un = u;
+    if (valid) {
+      const float4 *f = reinterpret_cast<const float4 *>(a.interp + (size_t)ii * a.istride);
+      float4 fex = make_float4(.01f, .02f, .03f, .04f), fey = fex, fez = fex, fb0 = fex;
+      float2 fb1 = make_float2(.01f, .02f);
+      if (!(a.dbg & 8)) {
+        fex = __ldg(f); fey = __ldg(f + 1); fez = __ldg(f + 2); fb0 = __ldg(f + 3);
+        fb1 = __ldg(reinterpret_cast<const float2 *>(f + 4));
       }
-      // queue the leavers of this row behind the ones already queued
-      {
-        const bool leave = valid && !inb;
-        const unsigned lm = __ballot_sync(full, leave);
-        if (leave) q[nq + __popc(lm & ((1u << lane) - 1u))] =
-            make_int4(__float_as_int(mux), __float_as_int(muy), __float_as_int(muz), i);
-        nq += __popc(lm);
-      }
-      deposit<VARIANT>(a, ii, inb && !(a.dbg & 1), j);
-    }
-    __syncwarp();
-
-    // finish the queued movers as dense warp-wide batches
-    for (int m0 = 0; m0 < nq; m0 += 32) {
-      const int m = m0 + lane;
-      const bool act = m < nq;
-      int i = 0;
-      float4 rr = make_float4(0.f, 0.f, 0.f, 0.f), uu = rr;
-      float dispx = 0.f, dispy = 0.f, dispz = 0.f;
-      if (act) {
-        const int4 mv = q[m];
-        i = mv.w;
-        ld_particle(a.p + 2 * (size_t)i, rr, uu);
-        dispx = __int_as_float(mv.x); dispy = __int_as_float(mv.y); dispz = __int_as_float(mv.z);
-      }
-      int left;
-      if (VARIANT == VPB_DEPOSIT_WARP_SEG) left = move_p_warp(a, act, rr, uu, dispx, dispy, dispz);
-      else left = act ? move_p_dev(a, rr, uu, dispx, dispy, dispz) : 0;
-      if (act) {
-        if (left) {
-          const int slot = atomicAdd(a.counters, 1);
-          if (slot < a.max_nm) {
-            a.pm[slot] = make_int4(__float_as_int(dispx), __float_as_int(dispy), __float_as_int(dispz), i);
-          } else {
-            atomicAdd(a.counters + 1, 1);                             // lost mover: keep p.i a valid voxel
-            rr.w = __int_as_float(__float_as_int(rr.w) >> 3);
-          }
-        }
-        st_particle(a.p + 2 * (size_t)i, rr, uu);
+      const float dx = r.x, dy = r.y, dz = r.z;
+      const float hax = a.qdt_2mc * ((fex.x + dy * fex.y) + dz * (fex.z + dy * fex.w));
+      const float hay = a.qdt_2mc * ((fey.x + dz * fey.y) + dx * (fey.z + dz * fey.w));
+      const float haz = a.qdt_2mc * ((fez.x + dx * fez.y) + dy * (fez.z + dx * fez.w));
+      const float cbx = fb0.x + dx * fb0.y;
+      const float cby = fb0.z + dy * fb0.w;
+      const float cbz = fb1.x + dz * fb1.y;
+      float ux = u.x, uy = u.y, uz = u.z;
+      ux += hax; uy += hay; uz += haz;
+      float v0 = __fdiv_rn(a.qdt_2mc, __fsqrt_rn(one + (ux * ux + (uy * uy + uz * uz))));
+      float v1 = cbx * cbx + (cby * cby + cbz * cbz);
+      float v2 = (v0 * v0) * v1;
+      float v3 = v0 * (one + v2 * (one_third + v2 * two_fifteenths));
+      float v4 = __fdiv_rn(v3, one + v1 * (v3 * v3));
+      v4 += v4;
+      v0 = ux + v3 * (uy * cbz - uz * cby);
+      v1 = uy + v3 * (uz * cbx - ux * cbz);
+      v2 = uz + v3 * (ux * cby - uy * cbx);
+      ux += v4 * (v1 * cbz - v2 * cby);
+      uy += v4 * (v2 * cbx - v0 * cbz);
+      uz += v4 * (v0 * cby - v1 * cbx);
+      ux += hax; uy += hay; uz += haz;
+      un.x = ux; un.y = uy; un.z = uz;                               // new momentum, kept in either case
+      v0 = __fdiv_rn(one, __fsqrt_rn(one + (ux * ux + (uy * uy + uz * uz))));
+      ux *= a.cdt_dx; uy *= a.cdt_dy; uz *= a.cdt_dz;
+      ux *= v0; uy *= v0; uz *= v0;                                 // half displacement in cell units
+      v0 = dx + ux; v1 = dy + uy; v2 = dz + uz;                     // streak midpoint
+      v3 = v0 + ux; v4 = v1 + uy; const float v5n = v2 + uz;        // new position
+      inb = (v3 <= one) && (v4 <= one) && (v5n <= one) && (-v3 <= one) && (-v4 <= one) && (-v5n <= one);
+      if (a.dbg & 2) inb = true;
+      if (inb) {
+        const float qw = un.w * a.qsp;
+        if (!(a.dbg & 4)) st_particle(a.p + 2 * (size_t)i, make_float4(v3, v4, v5n, r.w), un);
+        const float v5 = (((qw * ux) * uy) * uz) * one_third;
+        streak_currents(qw, ux, uy, uz, v0, v1, v2, v5, j);
+      } else {
+        mux = ux; muy = uy; muz = uz;
       }
     }
-    __syncwarp();
+    // queue the leavers of this row (old position, new momentum, displacement) behind those already queued
+    {
+      const bool leave = valid && !inb;
+      const unsigned lm = __ballot_sync(full, leave);
+      if (leave) {
+        const int slot = nq + __popc(lm & ((1u << lane) - 1u));
+        q0[slot] = make_int4(__float_as_int(r.x), __float_as_int(r.y), __float_as_int(r.z), ii);
+        q1[slot] = make_int4(__float_as_int(un.x), __float_as_int(un.y), __float_as_int(un.z), __float_as_int(un.w));
+        q2[slot] = make_int4(__float_as_int(mux), __float_as_int(muy), __float_as_int(muz), i);
+      }
+      nq += __popc(lm);
+    }
+    deposit<VARIANT>(a, ii, inb && !(a.dbg & 1), j);
+    if (nq >= 32) {                                                     // a full batch; the rest carries over
+      __syncwarp();
+      nq -= 32;
+      run_movers<VARIANT>(a, q0, q1, q2, nq, 32, lane);
+      __syncwarp();
+    }
   }
+  __syncwarp();
+  if (nq > 0) run_movers<VARIANT>(a, q0, q1, q2, 0, nq, lane);
+}
+
+// Check the closed-form neighbour rule against the table for every interior voxel and face.
+__global__ void __launch_bounds__(256) verify_neighbor_rule_kernel(PushK a, int *mismatch) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x + 1, y = blockIdx.y + 1, z = blockIdx.z + 1;
+  if (x > a.nb.nx) return;
+  const int vox = voxel(x, y, z, a.nb.nx, a.nb.ny);
+  int bad = 0;
+#pragma unroll
+  for (int f = 0; f < 6; f++) bad += (neighbor_of(a, vox, f) != __ldg(a.neighbor + 6ll * vox + f));
+  if (bad) atomicAdd(mismatch, bad);
 }
 
 }  // namespace vpb
 
 using namespace vpb;
+
+extern "C" int vpb_neighbor_rule_derive(const int64_t *neighbor_dev, int32_t nx, int32_t ny, int32_t nz, int64_t rangel,
+                                        vpb_neighbor_rule_t *rule, void *stream) {
+  VPB_REQUIRE(neighbor_dev && rule && nx > 0 && ny > 0 && nz > 0, "vpb_neighbor_rule_derive: Bad args");
+  cudaStream_t st = as_stream(stream);
+  memset(rule, 0, sizeof *rule);
+  rule->nx = nx; rule->ny = ny; rule->nz = nz;
+  const int64_t nv = (int64_t)(nx + 2) * (ny + 2) * (nz + 2);
+  if (nv > (1 << 24)) return 0;                      // float-reciprocal coordinates are exact below 2^24 only
+  const int vlo = voxel(1, 1, 1, nx, ny), vhi = voxel(nx, ny, nz, nx, ny);
+  long long lo[6], hi[6];
+  VPB_CUDA(cudaMemcpyAsync(lo, neighbor_dev + 6ll * vlo, sizeof lo, cudaMemcpyDeviceToHost, st));
+  VPB_CUDA(cudaMemcpyAsync(hi, neighbor_dev + 6ll * vhi, sizeof hi, cudaMemcpyDeviceToHost, st));
+  VPB_CUDA(cudaStreamSynchronize(st));
+  for (int f = 0; f < 6; f++) {
+    const long long act = f < 3 ? lo[f] : hi[f];
+    const int vref = f < 3 ? vlo : vhi;
+    rule->act[f] = act;
+    rule->delta[f] = act < 0 ? 0 : act - (rangel + vref);
+  }
+  rule->valid = 1;                                   // provisional, for the check below
+  vpb_push_args_t pa; memset(&pa, 0, sizeof pa);
+  pa.neighbor = neighbor_dev; pa.rangel = rangel; pa.nx = nx; pa.ny = ny; pa.nz = nz; pa.neighbor_rule = rule;
+  const PushK k = to_push_k(&pa);
+  int *d_bad = nullptr, h_bad = 0;
+  VPB_CUDA(cudaMalloc(&d_bad, sizeof(int)));
+  VPB_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+  dim3 grid((nx + 255) / 256, ny, nz);
+  verify_neighbor_rule_kernel<<<grid, 256, 0, st>>>(k, d_bad);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&h_bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d_bad);
+  VPB_CUDA(e);
+  rule->valid = (h_bad == 0);
+  return 0;
+}
+
 
 extern "C" int vpb_advance_p(const vpb_push_args_t *args, void *stream) {
   VPB_REQUIRE(args && args->p && args->interp && args->accum && args->neighbor && args->counters,
@@ -180,14 +244,23 @@ extern "C" int vpb_advance_p(const vpb_push_args_t *args, void *stream) {
               "vpb_advance_p: arrays must be 16-byte aligned");
   if (args->np <= 0) return 0;
   const PushK k = to_push_k(args);
+  static bool attr_done = false;
+  if (!attr_done) {
+    VPB_CUDA(cudaFuncSetAttribute(advance_p_kernel<VPB_DEPOSIT_RED_V4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    VPB_CUDA(cudaFuncSetAttribute(advance_p_kernel<VPB_DEPOSIT_WARP_SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    VPB_CUDA(cudaFuncSetAttribute(advance_p_kernel<VPB_DEPOSIT_WARP_SEG_MOVERS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    attr_done = true;
+  }
   const int ntiles = (args->np + kTile - 1) / kTile;
   const int grid = ntiles < kSMs * 8 ? ntiles : kSMs * 8;
   int variant = args->variant == VPB_DEPOSIT_DEFAULT ? VPB_DEPOSIT_WARP_SEG : args->variant;
   switch (variant) {
     case VPB_DEPOSIT_RED_V4:
-      advance_p_kernel<VPB_DEPOSIT_RED_V4><<<grid, kBlock, 0, as_stream(stream)>>>(k); break;
+      advance_p_kernel<VPB_DEPOSIT_RED_V4><<<grid, kBlock, kSmemBytes, as_stream(stream)>>>(k); break;
     case VPB_DEPOSIT_WARP_SEG:
-      advance_p_kernel<VPB_DEPOSIT_WARP_SEG><<<grid, kBlock, 0, as_stream(stream)>>>(k); break;
+      advance_p_kernel<VPB_DEPOSIT_WARP_SEG><<<grid, kBlock, kSmemBytes, as_stream(stream)>>>(k); break;
+    case VPB_DEPOSIT_WARP_SEG_MOVERS:
+      advance_p_kernel<VPB_DEPOSIT_WARP_SEG_MOVERS><<<grid, kBlock, kSmemBytes, as_stream(stream)>>>(k); break;
     default:
       VPB_REQUIRE(false, "vpb_advance_p: unknown deposit variant %d", variant);
   }

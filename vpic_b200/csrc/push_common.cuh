@@ -5,6 +5,21 @@
 
 namespace vpb {
 
+// Closed-form neighbour lookup (see vpb_neighbor_rule_t).  Coordinates come from the voxel index by float-reciprocal
+// division with a +-1 fix-up, exact for indices below 2^24 (the rule is only enabled for such grids).
+struct NbRule {
+  int use, sy, sz, nx, ny, nz;
+  float inv_sy, inv_sz;
+  long long act[6], delta[6];
+};
+
+__device__ __forceinline__ int fast_div(int v, int d, float inv_d) {
+  int q = __float2int_rz(__int2float_rn(v) * inv_d);
+  const int r = v - q * d;
+  if (r < 0) q--; else if (r >= d) q++;
+  return q;
+}
+
 struct PushK {
   float4 *p; int np;
   int4 *pm; int max_nm; int *counters;
@@ -13,7 +28,26 @@ struct PushK {
   const long long *neighbor; long long rangel, rangeh;
   float qdt_2mc, cdt_dx, cdt_dy, cdt_dz, qsp;
   int dbg;
+  NbRule nb;
 };
+
+// grid_t.neighbor[6*vox + face] as a global voxel id or a negative boundary code
+__device__ __forceinline__ long long neighbor_of(const PushK &a, int vox, int face) {
+  if (!a.nb.use) return __ldg(a.neighbor + 6ll * vox + face);
+  const int axis = face < 3 ? face : face - 3;
+  const int d = face < 3 ? -1 : 1;
+  int c, n, stride;
+  if (axis == 0) { const int q = fast_div(vox, a.nb.sy, a.nb.inv_sy); c = vox - q * a.nb.sy; n = a.nb.nx; stride = 1; }
+  else if (axis == 1) {
+    const int qz = fast_div(vox, a.nb.sz, a.nb.inv_sz);
+    c = fast_div(vox - qz * a.nb.sz, a.nb.sy, a.nb.inv_sy); n = a.nb.ny; stride = a.nb.sy;
+  } else { c = fast_div(vox, a.nb.sz, a.nb.inv_sz); n = a.nb.nz; stride = a.nb.sz; }
+  const bool inside = d < 0 ? (c > 1) : (c < n);
+  if (inside) return a.rangel + vox + d * stride;
+  const long long act = a.nb.act[face];
+  return act < 0 ? act : a.rangel + vox + a.nb.delta[face];
+}
+
 
 // The 12 accumulator increments of one straight streak inside one voxel (advance_p_pipeline.cc:172-208,
 // move_p.cc:277-305).  q = charge*weight, (ux,uy,uz) = half displacement, (dx,dy,dz) = streak midpoint.
@@ -48,7 +82,13 @@ __device__ __forceinline__ void deposit_warp_segmented(float *accum, int astride
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int key = active ? vox : (-1 - lane);
-  const unsigned peers = __match_any_sync(full, key);
+  // right after a sort most warps sit in a single voxel: one shuffle + vote finds that out, match.any is the
+  // (slow) general case
+  const unsigned amask = __ballot_sync(full, active);
+  if (amask == 0) return;
+  const int v_first = __shfl_sync(full, vox, __ffs(amask) - 1);
+  const bool uniform = __all_sync(full, !active || vox == v_first);
+  const unsigned peers = uniform ? (active ? amask : 0u) : __match_any_sync(full, key);
   const bool grouped = active && (__popc(peers) >= kMinGroup);
   if (active && !grouped) deposit_red_v4(accum + (size_t)vox * astride, j);
   unsigned big = __ballot_sync(full, grouped);
@@ -113,7 +153,7 @@ __device__ __forceinline__ int move_p_dev(const PushK &a, float4 &r, float4 &u, 
     const float dir = (axis == 0) ? dirx : (axis == 1) ? diry : dirz;
     if (axis == 0) r.x = dir; else if (axis == 1) r.y = dir; else r.z = dir;   // exactly on the face
     const int face = axis + ((dir > 0.0f) ? 3 : 0);
-    const long long nb = __ldg(a.neighbor + 6ll * vox + face);
+    const long long nb = neighbor_of(a, vox, face);
     if (nb == -1) {                                        // reflect_particles
       if (axis == 0) { u.x = -u.x; dispx = -dispx; }
       else if (axis == 1) { u.y = -u.y; dispy = -dispy; }
@@ -168,7 +208,7 @@ __device__ __forceinline__ int move_p_warp(const PushK &a, bool active, float4 &
         const float dir = (axis == 0) ? dirx : (axis == 1) ? diry : dirz;
         if (axis == 0) r.x = dir; else if (axis == 1) r.y = dir; else r.z = dir;
         const int face = axis + ((dir > 0.0f) ? 3 : 0);
-        const long long nb = __ldg(a.neighbor + 6ll * vox + face);
+        const long long nb = neighbor_of(a, vox, face);
         if (nb == -1) {
           if (axis == 0) { u.x = -u.x; dispx = -dispx; }
           else if (axis == 1) { u.y = -u.y; dispy = -dispy; }
@@ -196,6 +236,15 @@ static inline PushK to_push_k(const vpb_push_args_t *args) {
   k.neighbor = (const long long *)args->neighbor; k.rangel = args->rangel; k.rangeh = args->rangeh;
   k.qdt_2mc = args->qdt_2mc; k.cdt_dx = args->cdt_dx; k.cdt_dy = args->cdt_dy; k.cdt_dz = args->cdt_dz; k.qsp = args->qsp;
   k.dbg = args->debug_skip;
+  k.nb.use = 0;
+  const vpb_neighbor_rule_t *nr = args->neighbor_rule;
+  if (nr && nr->valid && nr->nx == args->nx && nr->ny == args->ny && nr->nz == args->nz) {
+    k.nb.use = 1;
+    k.nb.nx = nr->nx; k.nb.ny = nr->ny; k.nb.nz = nr->nz;
+    k.nb.sy = nr->nx + 2; k.nb.sz = (nr->nx + 2) * (nr->ny + 2);
+    k.nb.inv_sy = 1.0f / (float)k.nb.sy; k.nb.inv_sz = 1.0f / (float)k.nb.sz;
+    for (int f = 0; f < 6; f++) { k.nb.act[f] = nr->act[f]; k.nb.delta[f] = nr->delta[f]; }
+  }
   return k;
 }
 

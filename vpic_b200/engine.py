@@ -41,9 +41,23 @@ class DeviceGrid:
                   "rangel", "rangeh", "rank", "world_size"):
             setattr(self, k, getattr(g, k))
 
+        self.use_neighbor_rule = os.environ.get("VPB_NO_NEIGHBOR_RULE", "0") != "1"
+        self._rule = None
+
     @property
     def step(self):
         return self.g.step
+
+    def neighbor_rule(self):
+        """Verified closed form of the neighbour table (vpb_neighbor_rule_derive), or None to use the table."""
+        if not self.use_neighbor_rule:
+            return None
+        if self._rule is None:
+            r = _lib.NeighborRule()
+            _lib.check(_lib.load().vpb_neighbor_rule_derive(_ptr(self.neighbor), self.nx, self.ny, self.nz, self.rangel,
+                                                            C.byref(r), _stream()), "neighbor_rule_derive")
+            self._rule = r
+        return C.pointer(self._rule) if self._rule.valid else None
 
 
 class InterpolatorArray:
@@ -164,6 +178,9 @@ def advance_p(sp: Species, aa: AccumulatorArray, ia: InterpolatorArray, variant=
     a.qdt_2mc, a.cdt_dx, a.cdt_dy, a.cdt_dz, a.qsp = sp.push_constants()
     a.nx, a.ny, a.nz = g.nx, g.ny, g.nz
     a.variant = variant
+    rule = g.neighbor_rule()
+    if rule is not None:
+        a.neighbor_rule = rule
     a.debug_skip = int(os.environ.get("VPB_DEBUG_SKIP", "0"))
     L = _lib.load()
     _lib.check(L.vpb_advance_p(C.byref(a), _stream()), "advance_p")
@@ -297,5 +314,8 @@ def boundary_inject(sp: Species, aa: AccumulatorArray, ia: InterpolatorArray, in
     a.neighbor, a.rangel, a.rangeh = g.neighbor.data_ptr(), g.rangel, g.rangeh
     a.qdt_2mc, a.cdt_dx, a.cdt_dy, a.cdt_dz, a.qsp = sp.push_constants()
     a.nx, a.ny, a.nz = g.nx, g.ny, g.nz
+    rule = g.neighbor_rule()
+    if rule is not None:
+        a.neighbor_rule = rule
     _lib.check(_lib.load().vpb_boundary_p_inject(C.byref(a), _ptr(inj), n, _stream()), "boundary_p_inject")
     sp.np += n

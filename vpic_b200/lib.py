@@ -15,6 +15,11 @@ class VpbError(RuntimeError):
     pass
 
 
+class NeighborRule(C.Structure):
+    """vpb_neighbor_rule_t"""
+    _fields_ = [("valid", c_i32), ("nx", c_i32), ("ny", c_i32), ("nz", c_i32), ("act", c_i64 * 6), ("delta", c_i64 * 6)]
+
+
 class PushArgs(C.Structure):
     """vpb_push_args_t"""
     _fields_ = [("p", c_vp), ("np", c_i32),
@@ -25,7 +30,7 @@ class PushArgs(C.Structure):
                 ("neighbor", c_vp), ("rangel", c_i64), ("rangeh", c_i64),
                 ("qdt_2mc", c_f), ("cdt_dx", c_f), ("cdt_dy", c_f), ("cdt_dz", c_f), ("qsp", c_f),
                 ("nx", c_i32), ("ny", c_i32), ("nz", c_i32),
-                ("variant", c_i32), ("debug_skip", c_i32)]
+                ("variant", c_i32), ("neighbor_rule", C.POINTER(NeighborRule)), ("debug_skip", c_i32)]
 
 
 class BoundaryArgs(C.Structure):
@@ -44,7 +49,7 @@ class FieldArgs(C.Structure):
                 ("face", c_i32 * 6)]
 
 
-DEPOSIT_DEFAULT, DEPOSIT_RED_V4, DEPOSIT_WARP_SEG, DEPOSIT_SMEM_TILE = 0, 1, 2, 3
+DEPOSIT_DEFAULT, DEPOSIT_RED_V4, DEPOSIT_WARP_SEG, DEPOSIT_WARP_SEG_MOVERS = 0, 1, 2, 3
 FACE_PERIODIC_SELF, FACE_REMOTE = 0, 1
 HALO_TANG_B, HALO_JF = 0, 1
 
@@ -67,6 +72,7 @@ _PROTOS = {
     "vpb_device_sync": (C.c_int, []),
     "vpb_launch_count": (c_i64, []),
     "vpb_advance_p": (C.c_int, [C.POINTER(PushArgs), c_vp]),
+    "vpb_neighbor_rule_derive": (C.c_int, [c_vp, c_i32, c_i32, c_i32, c_i64, C.POINTER(NeighborRule), c_vp]),
     "vpb_boundary_scratch_bytes": (C.c_size_t, [c_i32]),
     "vpb_boundary_p_pack": (C.c_int, [C.POINTER(BoundaryArgs), c_vp]),
     "vpb_boundary_p_inject": (C.c_int, [C.POINTER(PushArgs), c_vp, c_i32, c_vp]),
