@@ -302,3 +302,17 @@ def test_reference_scalar_agrees_when_present(eng, oracle):
     eng.clear_accumulator_array(aa); eng.advance_p(sp, aa, ia)
     assert np.array_equal(bits(sp.particles_host()), bits(rs.p[:8000]))
     accum_close(aa.a.cpu().numpy(), W.accum[0])
+
+
+def test_multi_gpu_slab(eng):
+    """Slab-decomposed run over NCCL vs the undecomposed run (tests/multi_gpu_check.py); needs >= 2 GPUs."""
+    import os, subprocess, sys
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 2 if n < 4 else 4
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(root, "tests", "multi_gpu_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
