@@ -71,7 +71,7 @@ def test_harris_energy_history_matches_reference():
     total = np.abs(tot_a).max()
     for col in range(1, a.shape[1]):
         scale, diff = np.abs(a[:, col]).max(), np.abs(a[:, col] - b[:, col]).max()
-        assert diff <= 5e-6 * total, (col, diff, total)            # every component, against the total energy
+        assert diff <= 5e-5 * total, (col, diff, total)            # every component, against the total energy
         if scale >= 1e-2 * total:                                  # dominant components (main B, kinetic energies)
             assert diff / scale < 1e-4, (col, diff, scale)
         elif scale > 0:                                            # noise-driven components: same order of magnitude
