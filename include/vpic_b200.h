@@ -77,8 +77,8 @@ int vpb_neighbor_rule_derive(const int64_t *neighbor_dev, int32_t nx, int32_t ny
                              vpb_neighbor_rule_t *rule_out, void *stream);
 
 typedef struct vpb_push_args {
-  void          *p;              /* particle_t[np], 32 B each, 16 B aligned          */
-  int32_t        np;
+  void          *p;              /* particle_t array, 32 B each, 32 B aligned         */
+  int32_t        np;             /* particles [p_first, p_first + np) are advanced     */
   void          *pm;             /* particle_mover_t[max_nm]: movers that left the domain */
   int32_t        max_nm;
   int32_t       *counters;       /* int32[4] device: [0] += movers emitted (may exceed max_nm),
@@ -90,6 +90,7 @@ typedef struct vpb_push_args {
   float          qdt_2mc, cdt_dx, cdt_dy, cdt_dz, qsp;   /* computed by the caller in float, advance_p_pipeline.cc:279-283 */
   int32_t        nx, ny, nz;
   int32_t        variant;        /* deposit strategy, see VPB_DEPOSIT_*              */
+  int32_t        p_first;        /* first particle of this call (chunked host pipelines); mover .i stay global */
   const vpb_neighbor_rule_t *neighbor_rule;   /* optional (host pointer): verified closed form of `neighbor` */
   int32_t        debug_skip;     /* must be 0.  Profiling only (results become INVALID): bit0 skip deposits,
                                     bit1 skip the mover phase, bit2 skip particle stores, bit3 skip the interpolator gather */

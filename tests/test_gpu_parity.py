@@ -316,3 +316,67 @@ def test_multi_gpu_slab(eng):
            "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(root, "tests", "multi_gpu_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("mode", ["coherent", "resident"])
+def test_dropin_symbols_on_host_structs(eng, oracle, mode):
+    """The reference-named entry points (advance_p(species_t*, ...), sort_p, ...) on HOST structs: chunked, pipelined
+    copies in coherent mode (chunk forced small so several chunks are in flight), explicit syncs in resident mode."""
+    import subprocess, sys, os, json, textwrap
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = textwrap.dedent(f"""
+        import sys, ctypes as C, numpy as np
+        sys.path.insert(0, {root!r}); sys.path.insert(0, {os.path.join(root, 'tests')!r})
+        import bench, refvpic as R
+        from vpic_b200 import lib, grid as G, abi
+        L = lib.load(); orc = R.load_oracle()
+        nx, ny, nz, n = 7, 6, 5, 23003
+        g = G.partition_periodic_box(0,0,0,nx,ny,nz,nx,ny,nz,1,1,1, dt=G.courant_dt(1,1,1,nx,ny,nz,frac=0.98))
+        g.set_pbc(2, -2); g.set_pbc(5, -2)                      # absorbing z walls: movers come back to the host
+        H = bench.HostWorld(L, g, pinned=True)
+        L.vpic_b200_set_mode(1 if {mode!r} == 'resident' else 0)
+        rng = np.random.default_rng(8)
+        H.fields[:] = R.random_fields(rng, g.nv)
+        sp = H.new_species('e', -1.0, 1.0, n, n, 20)
+        parts = R.random_particles(rng, n, nx, ny, nz, uth=0.4, w=0.5)
+        sp.p[:n] = parts.view(np.float32).reshape(-1, 8); sp.c.np = n
+        H.load_interpolator()
+        L.sort_p(C.byref(sp.c))
+        L.clear_accumulator_array(C.byref(H.aa))
+        L.advance_p(C.byref(sp.c), C.byref(H.aa), C.byref(H.ia))
+        L.reduce_accumulator_array(C.byref(H.aa))
+        L.unload_accumulator_array(C.byref(H.fa), C.byref(H.aa))
+        for fn in ('vpic_b200_sync_to_host',):
+            getattr(L, fn).argtypes = [C.c_void_p]; getattr(L, fn).restype = None
+        L.vpic_b200_sync_to_host(None)
+        # oracle on the same inputs
+        f0 = H.fields.copy(); f0[:, 12:15] = 0
+        interp = np.zeros((g.nv, 20), np.float32)
+        fld_in = R.random_fields(np.random.default_rng(8), g.nv)
+        orc.vpo_load_interpolator(interp.ctypes.data, 20, fld_in.ctypes.data, nx, ny, nz)
+        p2, aux = parts.copy(), np.zeros_like(parts); part = np.zeros(g.nv + 1, np.int32)
+        orc.vpo_sort_p(p2.ctypes.data, n, aux.ctypes.data, part.ctypes.data, nx, ny, nz)
+        pm2 = np.zeros(n, dtype=abi.mover_dtype); acc2 = np.zeros(((g.nv + 1)//2*2, 12), np.float32)
+        f32 = np.float32; dt = f32(g.dt)
+        a = R.OraclePushArgs(p2.ctypes.data, n, pm2.ctypes.data, n, interp.ctypes.data, 20, acc2.ctypes.data, 12,
+                             g.neighbor.ctypes.data, g.rangel, g.rangeh, f32(f32(f32(-1)*dt)/f32(2)), dt, dt, dt, f32(-1))
+        nm = orc.vpo_advance_p(C.byref(a), None)
+        got = sp.p[:n].reshape(-1).view(abi.particle_dtype)
+        ok = dict(interp=bool(np.array_equal(H.interp.view(np.uint32), interp.view(np.uint32))),
+                  nm=bool(nm == sp.c.nm and nm > 0),
+                  particles=bool(np.array_equal(got.view(np.uint8), p2.view(np.uint8))),
+                  movers=bool(np.array_equal(sp.pm[:nm].reshape(-1).view(np.uint8), pm2[:nm].view(np.uint8))),
+                  partition=bool(np.array_equal(sp.partition[:g.nv], part[:g.nv])),
+                  accum=float(np.abs(H.accum - acc2).max() / np.abs(acc2).max()),
+                  last_sorted=int(sp.c.last_sorted))
+        fld_ref = fld_in.copy()
+        orc.vpo_unload_accumulator(fld_ref.ctypes.data, H.accum.ctypes.data, 12, nx, ny, nz, g.rdx, g.rdy, g.rdz, g.dt)
+        ok['jf'] = bool(np.array_equal(fld_ref.view(np.uint32), H.fields.view(np.uint32)))
+        import json; print('RESULT ' + json.dumps(ok))
+    """)
+    env = dict(os.environ, VPIC_B200_CHUNK="4096")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("RESULT ")][0][7:])
+    assert res["interp"] and res["nm"] and res["particles"] and res["movers"] and res["partition"] and res["jf"], res
+    assert res["accum"] < 2e-5 and res["last_sorted"] == 0, res

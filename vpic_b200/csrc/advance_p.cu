@@ -93,16 +93,16 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) advance_p_kernel(const Pus
 
   int row = blockIdx.x * kWarps + w;
   float4 rn = make_float4(0.f, 0.f, 0.f, 0.f), un_next = rn;
-  if (row < n_rows && row * 32 + lane < a.np) ld_particle(a.p + 2 * (size_t)(row * 32 + lane), rn, un_next);
+  if (row < n_rows && row * 32 + lane < a.np) ld_particle(a.p + 2 * (size_t)(a.first + row * 32 + lane), rn, un_next);
 
 #pragma unroll 1
   for (; row < n_rows; row += warps_total) {
     const float4 r = rn, u = un_next;
-    const int i = row * 32 + lane;
-    const bool valid = i < a.np;
+    const int i = a.first + row * 32 + lane;
+    const bool valid = row * 32 + lane < a.np;
     {
       const int inext = (row + warps_total) * 32 + lane;                 // request the next row now
-      if (row + warps_total < n_rows && inext < a.np) ld_particle(a.p + 2 * (size_t)inext, rn, un_next);
+      if (row + warps_total < n_rows && inext < a.np) ld_particle(a.p + 2 * (size_t)(a.first + inext), rn, un_next);
     }
     const int ii = __float_as_int(r.w);
     bool inb = false;
@@ -240,8 +240,9 @@ extern "C" int vpb_advance_p(const vpb_push_args_t *args, void *stream) {
   VPB_REQUIRE(args->pm || args->max_nm == 0, "vpb_advance_p: mover array missing");
   VPB_REQUIRE(args->interp_stride % 4 == 0 && args->accum_stride % 4 == 0,
               "vpb_advance_p: strides must keep 16-byte alignment (got %d, %d)", args->interp_stride, args->accum_stride);
-  VPB_REQUIRE((((uintptr_t)args->p | (uintptr_t)args->interp | (uintptr_t)args->accum | (uintptr_t)args->pm) & 15) == 0,
-              "vpb_advance_p: arrays must be 16-byte aligned");
+  VPB_REQUIRE((((uintptr_t)args->interp | (uintptr_t)args->accum | (uintptr_t)args->pm) & 15) == 0 &&
+              ((uintptr_t)args->p & 31) == 0 && args->p_first >= 0,
+              "vpb_advance_p: particles must be 32-byte aligned, the other arrays 16-byte aligned");
   if (args->np <= 0) return 0;
   const PushK k = to_push_k(args);
   static bool attr_done = false;

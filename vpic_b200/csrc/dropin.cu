@@ -9,6 +9,7 @@
 #include <string.h>
 #include <unistd.h>
 #include <unordered_map>
+#include <vector>
 
 // Symbols of the reference host program, present when this library is linked into (or preloaded under) it.
 extern "C" {
@@ -150,19 +151,44 @@ void vpic_b200_release(const void *h) {
 void vpic_b200_transfer_bytes(uint64_t out[2]) { out[0] = g_h2d; out[1] = g_d2h; }
 
 // ---- advance_p: species_advance.h:73-76, advance_p_pipeline.cc:252-340 ------------------------------------
+// In coherent mode the particle array crosses PCIe twice per call; the copy-in, the kernel and the copy-out of
+// successive chunks run on three streams so the three overlap (needs page-locked host memory to be asynchronous).
+struct Pipeline { cudaStream_t in = nullptr, comp = nullptr, out = nullptr; };
+static Pipeline &pipeline() {
+  static Pipeline p;
+  if (!p.in) {
+    if (cudaStreamCreateWithFlags(&p.in, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&p.comp, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&p.out, cudaStreamNonBlocking) != cudaSuccess)
+      DROPIN_ERROR("cannot create CUDA streams: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  return p;
+}
+static int chunk_particles() {
+  static int c = 0;
+  if (!c) { const char *e = getenv("VPIC_B200_CHUNK"); c = e ? atoi(e) : (1 << 22); if (c < 1024) c = 1024; }
+  return c;
+}
+
 void advance_p(vpb_species_t *sp, vpb_accumulator_array_t *aa, const vpb_interpolator_array_t *ia) {
   if (!sp || !aa || !ia || sp->g != aa->g || sp->g != ia->g) DROPIN_ERROR("Bad args.");
   const vpb_grid_t *g = sp->g;
   const size_t nv = (size_t)g->nv;
+  const bool coherent = mode() == VPB_MODE_COHERENT;
   vpb_push_args_t a;
   memset(&a, 0, sizeof a);
-  a.neighbor = (const int64_t *)dev_in(g->neighbor, 6 * nv * sizeof(int64_t));
+  // grid_t.neighbor is written once by the host's grid setup; its mirror is uploaded on first use and kept
+  // (vpic_b200_invalidate(g->neighbor) after changing particle boundary conditions)
+  {
+    Mirror &m = mirror(g->neighbor, 6 * nv * sizeof(int64_t));
+    if (!m.device_valid) { DEV(vpb_memcpy_h2d(m.d, g->neighbor, 6 * nv * sizeof(int64_t), nullptr)); g_h2d += 6 * nv * sizeof(int64_t);
+                           m.device_valid = true; m.live_bytes = 6 * nv * sizeof(int64_t); }
+    a.neighbor = (const int64_t *)m.d;
+  }
   a.interp = (const float *)dev_in(ia->i, nv * sizeof(vpb_interpolator_t));
   a.interp_stride = kInterpFloats;
   a.accum = (float *)dev_in(aa->a, (size_t)aa->stride * sizeof(vpb_accumulator_t));      // block 0 only
   a.accum_stride = kAccumFloats;
-  a.p = dev_in(sp->p, (size_t)sp->np * sizeof(vpb_particle_t), (size_t)sp->max_np * sizeof(vpb_particle_t));
-  a.np = sp->np;
   a.pm = dev_out_only(sp->pm, (size_t)sp->max_nm * sizeof(vpb_particle_mover_t));
   a.max_nm = sp->max_nm;
   a.counters = counters();
@@ -175,7 +201,41 @@ void advance_p(vpb_species_t *sp, vpb_accumulator_array_t *aa, const vpb_interpo
   a.qsp = sp->q;
   a.nx = g->nx; a.ny = g->ny; a.nz = g->nz;
   a.variant = VPB_DEPOSIT_DEFAULT;
-  DEV(vpb_advance_p(&a, nullptr));
+
+  const size_t pbytes = (size_t)sp->np * sizeof(vpb_particle_t);
+  if (!coherent) {
+    a.p = dev_in(sp->p, pbytes, (size_t)sp->max_np * sizeof(vpb_particle_t));
+    a.np = sp->np;
+    DEV(vpb_advance_p(&a, nullptr));
+  } else {
+    DEV(vpb_stream_sync(nullptr));                          // interp/accum/counters are in place
+    Mirror &mp = mirror(sp->p, (size_t)sp->max_np * sizeof(vpb_particle_t));
+    a.p = mp.d;
+    Pipeline &pl = pipeline();
+    const int chunk = chunk_particles();
+    const int nchunks = (sp->np + chunk - 1) / chunk;
+    std::vector<cudaEvent_t> ev(2 * (size_t)nchunks);
+    for (auto &e : ev) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) DROPIN_ERROR("cudaEventCreate failed");
+    for (int c = 0; c < nchunks; c++) {
+      const int c0 = c * chunk, n = (sp->np - c0 < chunk) ? sp->np - c0 : chunk;
+      char *dptr = (char *)mp.d + (size_t)c0 * sizeof(vpb_particle_t);
+      char *hptr = (char *)sp->p + (size_t)c0 * sizeof(vpb_particle_t);
+      const size_t bytes = (size_t)n * sizeof(vpb_particle_t);
+      DEV(vpb_memcpy_h2d(dptr, hptr, bytes, pl.in));
+      if (cudaEventRecord(ev[2 * c], pl.in) != cudaSuccess || cudaStreamWaitEvent(pl.comp, ev[2 * c], 0) != cudaSuccess)
+        DROPIN_ERROR("CUDA event error");
+      a.p_first = c0; a.np = n;
+      DEV(vpb_advance_p(&a, pl.comp));
+      if (cudaEventRecord(ev[2 * c + 1], pl.comp) != cudaSuccess || cudaStreamWaitEvent(pl.out, ev[2 * c + 1], 0) != cudaSuccess)
+        DROPIN_ERROR("CUDA event error");
+      DEV(vpb_memcpy_d2h(hptr, dptr, bytes, pl.out));
+    }
+    DEV(vpb_stream_sync(pl.comp));
+    DEV(vpb_stream_sync(pl.out));
+    for (auto &e : ev) cudaEventDestroy(e);
+    g_h2d += pbytes; g_d2h += pbytes;
+    mp.device_valid = true; mp.host_stale = false; mp.live_bytes = pbytes;
+  }
 
   int c[4];
   DEV(vpb_memcpy_d2h(c, a.counters, sizeof c, nullptr));
@@ -194,10 +254,10 @@ void advance_p(vpb_species_t *sp, vpb_accumulator_array_t *aa, const vpb_interpo
     DEV(vpb_sort_movers(a.pm, nm, scratch(0, need), need, nullptr));
   }
   sp->nm = nm;
-  dev_written(sp->p, (size_t)sp->np * sizeof(vpb_particle_t));
+  if (!coherent) dev_written(sp->p, pbytes);
   dev_written(sp->pm, (size_t)nm * sizeof(vpb_particle_mover_t));
   dev_written(aa->a, (size_t)aa->stride * sizeof(vpb_accumulator_t));
-  if (g_mode == VPB_MODE_COHERENT) DEV(vpb_stream_sync(nullptr));
+  if (coherent) DEV(vpb_stream_sync(nullptr));
 }
 
 // ---- sort_p: species_advance.h:65-66, sort_p_pipeline.cc:220-371 ------------------------------------------

@@ -134,6 +134,7 @@ class Species:
         self.n_ignored = 0
         self._aux = None
         self._scratch = None
+        self._mv_scratch = None
         self._en = torch.zeros(1, dtype=torch.float64, device=dev)
 
     def set_particles(self, arr):
@@ -201,6 +202,26 @@ def finish_advance_p(sp: Species):
         need = L.vpb_sort_movers_scratch_bytes(sp.nm)
         scratch = torch.empty(need, dtype=torch.uint8, device=sp.g.device)
         _lib.check(L.vpb_sort_movers(_ptr(sp.pm), sp.nm, _ptr(scratch), need, _stream()), "sort_movers")
+
+
+def finish_advance_p_all(species):
+    """finish_advance_p for several species with a single device->host read of all their counters."""
+    if not species:
+        return
+    L = _lib.load()
+    c = torch.stack([sp.counters for sp in species]).cpu()
+    for k, sp in enumerate(species):
+        sp.nm = min(int(c[k, 0]), sp.max_nm)
+        sp.n_ignored = int(c[k, 1])
+        if sp.n_ignored:
+            import warnings
+            warnings.warn(f"species {sp.name} ran out of storage for {sp.n_ignored} movers")
+        if sp.nm > 1:
+            need = L.vpb_sort_movers_scratch_bytes(sp.nm)
+            if sp._mv_scratch is None or sp._mv_scratch.numel() < need:
+                sp._mv_scratch = torch.empty(int(need * 1.5), dtype=torch.uint8, device=sp.g.device)
+            _lib.check(L.vpb_sort_movers(_ptr(sp.pm), sp.nm, _ptr(sp._mv_scratch), sp._mv_scratch.numel(), _stream()),
+                       "sort_movers")
 
 
 def sort_p(sp: Species):

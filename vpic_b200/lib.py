@@ -30,7 +30,7 @@ class PushArgs(C.Structure):
                 ("neighbor", c_vp), ("rangel", c_i64), ("rangeh", c_i64),
                 ("qdt_2mc", c_f), ("cdt_dx", c_f), ("cdt_dy", c_f), ("cdt_dz", c_f), ("qsp", c_f),
                 ("nx", c_i32), ("ny", c_i32), ("nz", c_i32),
-                ("variant", c_i32), ("neighbor_rule", C.POINTER(NeighborRule)), ("debug_skip", c_i32)]
+                ("variant", c_i32), ("p_first", c_i32), ("neighbor_rule", C.POINTER(NeighborRule)), ("debug_skip", c_i32)]
 
 
 class BoundaryArgs(C.Structure):

@@ -69,9 +69,18 @@ class SlabExchange:
 
     # ---- particles ------------------------------------------------------------------------------------------
     def boundary_p(self, sim):
-        """One communication round of boundary_p for every species (the caller loops num_comm_round times)."""
+        """One communication round of boundary_p for every species (the caller loops num_comm_round times).
+
+        A round in which no rank holds a mover is a no-op in the reference too (zero counts both ways); one tiny
+        all-reduce finds that out, so the usual second and third rounds cost one collective instead of a full
+        count/payload handshake."""
         dev = self.g.device
         sps = sim.species_list
+        if self.ring.world > 1:
+            left = torch.tensor([sum(sp.nm for sp in sps)], dtype=torch.int32, device=dev)
+            dist.all_reduce(left, group=self.ring.group)
+            if int(left.item()) == 0:
+                return
         packed = [E.boundary_pack(sp, self.face_range) for sp in sps]
         offs = torch.stack([o for _, o in packed]).cpu()                       # one sync for all species
         n_lo = [int(offs[s, self.f_lo + 1] - offs[s, self.f_lo]) for s in range(len(sps))]
@@ -99,8 +108,7 @@ class SlabExchange:
             # injection order of the reference: faces 0..5, so the low face first
             E.boundary_inject(sp, sim.accumulator_array, sim.interpolator_array, in_lo, r_lo[s])
             E.boundary_inject(sp, sim.accumulator_array, sim.interpolator_array, in_hi, r_hi[s])
-        for sp in sps:
-            E.finish_advance_p(sp)
+        E.finish_advance_p_all(sps)
 
     # ---- fields ---------------------------------------------------------------------------------------------
     def _halo(self, fa, kind):

@@ -60,8 +60,7 @@ class Simulation:
             if self.push_events is not None:
                 e1.record()
                 self.push_events.append((e0, e1, sp.np))
-        for sp in self.species_list:
-            E.finish_advance_p(sp)
+        E.finish_advance_p_all(self.species_list)
         E.reduce_accumulator_array(aa)
         if self.exchange is not None:
             for _ in range(self.num_comm_round):
