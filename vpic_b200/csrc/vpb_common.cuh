@@ -40,7 +40,8 @@ __device__ __forceinline__ void red_add(float *addr, float a) {
 // 256-bit global accesses (LDG.E.256 / STG.E.256, new on sm_100): one particle_t per instruction, so a warp touches
 // 1 KB of consecutive bytes with every sector fully used.  The address must be 32-byte aligned.
 __device__ __forceinline__ void ld_particle(const float4 *p, float4 &r, float4 &u) {
-  asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+  // particles are touched once per step: do not let them evict the interpolator lines from L1
+  asm volatile("ld.global.L1::no_allocate.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w), "=f"(u.x), "=f"(u.y), "=f"(u.z), "=f"(u.w) : "l"(p));
 }
 __device__ __forceinline__ void st_particle(float4 *p, const float4 &r, const float4 &u) {
