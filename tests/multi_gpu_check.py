@@ -29,23 +29,33 @@ def global_particles(rng, n, nx, ny, nz, uth, w):
     return R.random_particles(rng, n, nx, ny, nz, uth=uth, w=w)
 
 
-def to_local(parts, gny_local, rank, nx, ny, nz):
-    """Particles of the global box that live in this rank's y-slab, re-indexed to local voxels."""
+def to_local(parts, n_local, rank, nx, ny, nz, axis=1):
+    """Particles of the global box that live in this rank's slab along `axis`, re-indexed to local voxels."""
     i = parts["i"].astype(np.int64)
-    x = i % (nx + 2)
-    y = (i // (nx + 2)) % (ny + 2)
-    z = i // ((nx + 2) * (ny + 2))
-    sel = (y - 1) // gny_local == rank
+    c = [i % (nx + 2), (i // (nx + 2)) % (ny + 2), i // ((nx + 2) * (ny + 2))]
+    sel = (c[axis] - 1) // n_local == rank
     out = parts[sel].copy()
-    yl = y[sel] - rank * gny_local
-    out["i"] = (x[sel] + (nx + 2) * (yl + (gny_local + 2) * z[sel])).astype(np.int32)
+    c = [v[sel] for v in c]
+    c[axis] = c[axis] - rank * n_local
+    ln = [nx, ny, nz]
+    ln[axis] = n_local
+    out["i"] = (c[0] + (ln[0] + 2) * (c[1] + (ln[1] + 2) * c[2])).astype(np.int32)
     return out
 
 
-def voxel_table(p, nv, key_of=None):
-    """Order-free view: particles sorted by (voxel, then the 7 state words)."""
-    order = np.lexsort((p["w"], p["uz"], p["uy"], p["ux"], p["dz"], p["dy"], p["dx"], p["i"]))
-    return p[order]
+def by_tag(p):
+    """Order-free view: every particle carries a unique weight (set at load time, never changed by the push), so
+    sorting by it pairs each particle of the slab run with the same particle of the single-domain run."""
+    return p[np.argsort(p["w"], kind="stable")]
+
+
+def tag_weights(parts, base):
+    """Unique, exactly representable weights: base * (1 + k * 2^-22), k < 2^17."""
+    k = np.arange(len(parts), dtype=np.float64)
+    assert len(parts) < (1 << 17)
+    parts["w"] = (base * (1.0 + k * 2.0 ** -22)).astype(np.float32)
+    assert len(np.unique(parts["w"])) == len(parts)
+    return parts
 
 
 def main():
@@ -55,6 +65,9 @@ def main():
     ap.add_argument("--ny-per-rank", type=int, default=6)
     ap.add_argument("--nz", type=int, default=8)
     ap.add_argument("--ppc", type=int, default=24)
+    ap.add_argument("--axis", type=int, default=1, help="slab axis (0 = x as sample/reconnection, 1 = y as sample/harris)")
+    ap.add_argument("--harris", action="store_true",
+                    help="C4-like: conducting (pec) z walls that reflect particles, sheared B field, drifting species")
     args = ap.parse_args()
 
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -63,30 +76,60 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
 
-    nx, nyl, nz = args.nx, args.ny_per_rank, args.nz
-    ny = nyl * world
+    ax = args.axis
+    nloc = args.ny_per_rank                                   # cells per rank along the slab axis
+    gn = [args.nx, args.nx, args.nz]                          # global cells; the slab axis gets nloc * world
+    gn[ax] = nloc * world
+    gn[2] = args.nz
+    if ax != 1:
+        gn[1] = max(4, args.nx // 2)
+    nx, ny, nz = gn
+    ln = list(gn); ln[ax] = nloc
+    topo = [1, 1, 1]; topo[ax] = world
     dt = G.courant_dt(1, 1, 1, nx, ny, nz, frac=0.97)
     rng = np.random.default_rng(99)
-    species = [("electron", -1.0, 1.0, 0.35), ("ion", 1.0, 4.0, 0.12)]
+    species = [("electron", -1.0, 1.0, 0.35, (0.0, 0.2, 0.0)), ("ion", 1.0, 4.0, 0.12, (0.0, -0.05, 0.0))]
+    if not args.harris:
+        species = [(n_, q, m, u, (0, 0, 0)) for n_, q, m, u, _ in species]
     npart = nx * ny * nz * args.ppc
-    loads = [global_particles(rng, npart, nx, ny, nz, uth, 1.0 / args.ppc) for _, _, _, uth in species]
-    seed_fields = np.zeros(((nx + 2) * (ny + 2) * (nz + 2), 20), np.float32)   # fields start at zero
+    import refvpic as R
+    loads = [tag_weights(R.random_particles(rng, npart, nx, ny, nz, uth=uth, w=1.0, drift=dr), 1.0 / args.ppc)
+             for _, _, _, uth, dr in species]
+
+    def setup_walls(g):
+        if args.harris:
+            for f in (2, 5):
+                g.set_fbc(f, G.PEC_FIELDS)
+                g.set_pbc(f, G.REFLECT_PARTICLES)
+
+    def initial_fields(nx_, ny_, nz_, x_off=0):
+        f = np.zeros(((nx_ + 2) * (ny_ + 2) * (nz_ + 2), 20), np.float32)
+        if args.harris:
+            z = np.arange(nz_ + 2, dtype=np.float64) - 0.5 * (nz + 1)
+            bx = 0.3 * np.tanh(z / 2.0)
+            f3 = f.reshape(nz_ + 2, ny_ + 2, nx_ + 2, 20)
+            f3[..., 4] = bx[:, None, None].astype(np.float32)            # cbx(z), uniform in x and y
+        return f
 
     # --- single-domain run (every rank has its own copy) ---
     gg = G.partition_periodic_box(0, 0, 0, nx, ny, nz, nx, ny, nz, 1, 1, 1, dt=dt)
+    setup_walls(gg)
     dgg = E.DeviceGrid(gg, dev)
     ref = S.Simulation(dgg)
-    for (name, q, m, _), load in zip(species, loads):
+    ref.field_array.f.copy_(torch.from_numpy(initial_fields(nx, ny, nz)))
+    for (name, q, m, _, _), load in zip(species, loads):
         sp = ref.define_species(name, q, m, npart, npart, sort_interval=5)
         sp.set_particles(load)
     ref.initialize()
 
     # --- slab run ---
-    gl = G.partition_periodic_box(0, 0, 0, nx, ny, nz, nx, ny, nz, 1, world, 1, rank=rank, dt=dt)
+    gl = G.partition_periodic_box(0, 0, 0, nx, ny, nz, nx, ny, nz, topo[0], topo[1], topo[2], rank=rank, dt=dt)
+    setup_walls(gl)
     dgl = E.DeviceGrid(gl, dev)
-    sim = S.Simulation(dgl, exchange=parallel.SlabExchange(dgl, axis=1))
-    for (name, q, m, _), load in zip(species, loads):
-        mine = to_local(load, nyl, rank, nx, ny, nz)
+    sim = S.Simulation(dgl, exchange=parallel.SlabExchange(dgl, axis=ax))
+    sim.field_array.f.copy_(torch.from_numpy(initial_fields(ln[0], ln[1], ln[2])))
+    for (name, q, m, _, _), load in zip(species, loads):
+        mine = to_local(load, nloc, rank, nx, ny, nz, ax)
         sp = sim.define_species(name, q, m, int(npart / world * 1.6) + 64, npart, sort_interval=5)
         sp.set_particles(mine)
     sim.initialize()
@@ -103,12 +146,14 @@ def main():
             if int(tot) != sref.np:
                 ok = False
                 print(f"[{rank}] step {step}: particle count {int(tot)} != {sref.np}")
-            mine_ref = voxel_table(to_local(sref.particles_host(), nyl, rank, nx, ny, nz), gl.nv)
-            mine = voxel_table(sloc.particles_host(), gl.nv)
-            if len(mine) != len(mine_ref):
+            mine_ref = by_tag(to_local(sref.particles_host(), nloc, rank, nx, ny, nz, ax))
+            mine = by_tag(sloc.particles_host())
+            if len(mine) != len(mine_ref) or not np.array_equal(mine["w"], mine_ref["w"]):
                 # a particle within rounding of a slab face may sit on either side for one step; tolerate a handful
-                worst["count"] = max(worst["count"], abs(len(mine) - len(mine_ref)))
-                continue
+                common = np.intersect1d(mine["w"], mine_ref["w"])
+                worst["count"] = max(worst["count"], max(len(mine), len(mine_ref)) - len(common))
+                mine = mine[np.isin(mine["w"], common)]
+                mine_ref = mine_ref[np.isin(mine_ref["w"], common)]
             same_vox = np.mean(mine["i"] == mine_ref["i"])
             if same_vox < 0.999:
                 ok = False
@@ -118,10 +163,12 @@ def main():
                 d = np.abs(mine[k][sel] - mine_ref[k][sel]).max() if sel.any() else 0.0
                 worst["part"] = max(worst["part"], float(d))
         # fields: my slab's interior nodes vs the same nodes of the single-domain run
-        fl = sim.field_array.f.cpu().numpy().reshape(nz + 2, nyl + 2, nx + 2, 20)
+        fl = sim.field_array.f.cpu().numpy().reshape(ln[2] + 2, ln[1] + 2, ln[0] + 2, 20)
         fg = ref.field_array.f.cpu().numpy().reshape(nz + 2, ny + 2, nx + 2, 20)
-        a = fl[1:nz + 1, 1:nyl + 1, 1:nx + 1, :16]
-        b = fg[1:nz + 1, 1 + rank * nyl:1 + (rank + 1) * nyl, 1:nx + 1, :16]
+        a = fl[1:ln[2] + 1, 1:ln[1] + 1, 1:ln[0] + 1, :16]
+        sl = [slice(1, nx + 1), slice(1, ny + 1), slice(1, nz + 1)]
+        sl[ax] = slice(1 + rank * nloc, 1 + (rank + 1) * nloc)
+        b = fg[sl[2], sl[1], sl[0], :16]
         for lo, hi in ((0, 3), (4, 7), (12, 15)):     # e, cb, jf
             scale = max(np.abs(b[..., lo:hi]).max(), 1e-12)
             worst["field"] = max(worst["field"], float(np.abs(a[..., lo:hi] - b[..., lo:hi]).max() / scale))
@@ -134,10 +181,13 @@ def main():
 
     # tolerances: fp32 accumulation order differs between topologies; values grow slowly over the steps
     ok &= worst["count"] <= 4 and worst["part"] < 5e-4 and worst["field"] < 2e-3 and worst["energy"] < 1e-4
+    if not ok:
+        print(f"[{rank}] FAILED with worst {worst}")
     flag = torch.tensor([0 if ok else 1], device=dev)
     dist.all_reduce(flag)
     if rank == 0:
-        print(f"multi_gpu_check world={world} steps={args.steps}: worst {worst} -> {'PASS' if int(flag) == 0 else 'FAIL'}")
+        print(f"multi_gpu_check world={world} axis={ax} harris={args.harris} steps={args.steps}: worst {worst} -> "
+              f"{'PASS' if int(flag) == 0 else 'FAIL'}")
     dist.destroy_process_group()
     sys.exit(0 if int(flag) == 0 else 1)
 

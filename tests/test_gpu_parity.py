@@ -304,8 +304,10 @@ def test_reference_scalar_agrees_when_present(eng, oracle):
     accum_close(aa.a.cpu().numpy(), W.accum[0])
 
 
-def test_multi_gpu_slab(eng):
-    """Slab-decomposed run over NCCL vs the undecomposed run (tests/multi_gpu_check.py); needs >= 2 GPUs."""
+@pytest.mark.parametrize("extra", [[], ["--axis", "0", "--harris"]])
+def test_multi_gpu_slab(eng, extra):
+    """Slab-decomposed run over NCCL vs the undecomposed run (tests/multi_gpu_check.py); needs >= 2 GPUs.
+    Second case: x slabs with conducting, particle-reflecting z walls and a sheared B field (C4-like)."""
     import os, subprocess, sys
     n = torch.cuda.device_count()
     if n < 2:
@@ -313,7 +315,7 @@ def test_multi_gpu_slab(eng):
     world = 2 if n < 4 else 4
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-           "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(root, "tests", "multi_gpu_check.py")]
+           "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(root, "tests", "multi_gpu_check.py")] + extra
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
 

@@ -38,6 +38,7 @@ __device__ __forceinline__ void deposit(const PushK &a, int vox, bool active, co
 }
 
 constexpr int kWarps = kBlock / 32;
+constexpr int kSpan  = 16;                 // consecutive rows a warp takes before jumping ahead
 constexpr int kQCap  = 64;                 // a warp's queue holds at most 31 carried-over + 32 new movers
 constexpr size_t kSmemBytes = (size_t)kWarps * 3 * kQCap * sizeof(int4);
 
@@ -91,19 +92,24 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) advance_p_kernel(const Pus
   int4 *q0 = s_q + (size_t)w * 3 * kQCap, *q1 = q0 + kQCap, *q2 = q1 + kQCap;
   int nq = 0;                                                           // warp-uniform queue length
 
-  int row = blockIdx.x * kWarps + w;
+  // Rows are dealt to warps in spans of kSpan consecutive rows: consecutive rows of voxel-sorted particles share
+  // their interpolator (64 ppc = 2 rows per voxel), so a warp's next gather usually hits the lines it just used.
+  const int n_spans = (n_rows + kSpan - 1) / kSpan;
+  int span = blockIdx.x * kWarps + w;
+  int row = span * kSpan;
   float4 rn = make_float4(0.f, 0.f, 0.f, 0.f), un_next = rn;
-  if (row < n_rows && row * 32 + lane < a.np) ld_particle(a.p + 2 * (size_t)(a.first + row * 32 + lane), rn, un_next);
+  if (span < n_spans && row * 32 + lane < a.np) ld_particle(a.p + 2 * (size_t)(a.first + row * 32 + lane), rn, un_next);
 
 #pragma unroll 1
-  for (; row < n_rows; row += warps_total) {
+  while (span < n_spans) {
     const float4 r = rn, u = un_next;
     const int i = a.first + row * 32 + lane;
     const bool valid = row * 32 + lane < a.np;
-    {
-      const int inext = (row + warps_total) * 32 + lane;                 // request the next row now
-      if (row + warps_total < n_rows && inext < a.np) ld_particle(a.p + 2 * (size_t)(a.first + inext), rn, un_next);
-    }
+    // advance to the next row of this warp (same span, or the first row of its next span) and request it now
+    int next_row = row + 1, next_span = span;
+    if (next_row == (span + 1) * kSpan || next_row >= n_rows) { next_span = span + warps_total; next_row = next_span * kSpan; }
+    if (next_span < n_spans && next_row * 32 + lane < a.np)
+      ld_particle(a.p + 2 * (size_t)(a.first + next_row * 32 + lane), rn, un_next);
     const int ii = __float_as_int(r.w);
     bool inb = false;
     float j[12];
@@ -175,6 +181,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) advance_p_kernel(const Pus
       run_movers<VARIANT>(a, q0, q1, q2, nq, 32, lane);
       __syncwarp();
     }
+    row = next_row; span = next_span;
   }
   __syncwarp();
   if (nq > 0) run_movers<VARIANT>(a, q0, q1, q2, 0, nq, lane);
@@ -202,7 +209,7 @@ extern "C" int vpb_neighbor_rule_derive(const int64_t *neighbor_dev, int32_t nx,
   memset(rule, 0, sizeof *rule);
   rule->nx = nx; rule->ny = ny; rule->nz = nz;
   const int64_t nv = (int64_t)(nx + 2) * (ny + 2) * (nz + 2);
-  if (nv > (1 << 24)) return 0;                      // float-reciprocal coordinates are exact below 2^24 only
+  if (nv >= (1ll << 31) / 6) return 0;               // beyond the reference's own neighbour-index limit
   const int vlo = voxel(1, 1, 1, nx, ny), vhi = voxel(nx, ny, nz, nx, ny);
   long long lo[6], hi[6];
   VPB_CUDA(cudaMemcpyAsync(lo, neighbor_dev + 6ll * vlo, sizeof lo, cudaMemcpyDeviceToHost, st));

@@ -6,7 +6,7 @@
 namespace vpb {
 
 // Closed-form neighbour lookup (see vpb_neighbor_rule_t).  Coordinates come from the voxel index by float-reciprocal
-// division with a +-1 fix-up, exact for indices below 2^24 (the rule is only enabled for such grids).
+// division with a remainder step and a +-1 fix-up.
 struct NbRule {
   int use, sy, sz, nx, ny, nz;
   float inv_sy, inv_sz;
@@ -14,8 +14,12 @@ struct NbRule {
 };
 
 __device__ __forceinline__ int fast_div(int v, int d, float inv_d) {
+  // two float-reciprocal steps (the second divides the small remainder of the first) and a +-1 fix-up: exact for
+  // every voxel index the reference allows (nv < 2^31 / 6, src/grid/grid.h:98-103)
   int q = __float2int_rz(__int2float_rn(v) * inv_d);
-  const int r = v - q * d;
+  int r = v - q * d;
+  const int q2 = __float2int_rd(__int2float_rn(r) * inv_d);
+  q += q2; r -= q2 * d;
   if (r < 0) q--; else if (r >= d) q++;
   return q;
 }

@@ -138,8 +138,15 @@ __global__ void __launch_bounds__(kSortBlock) radix_scatter_kernel(const int4 *s
       const int i = t0 + w * 32 * kIPT + j * 32 + lane;
       const bool valid = i < hi;
       if (valid) {
+        if (VEC == 2) {                                  // a particle is one 32-byte sector: one 256-bit access
+          float4 lo, hi;
+          ld_particle(reinterpret_cast<const float4 *>(src) + 2 * (size_t)i, lo, hi);
+          it[j][0] = make_int4(__float_as_int(lo.x), __float_as_int(lo.y), __float_as_int(lo.z), __float_as_int(lo.w));
+          it[j][VEC - 1] = make_int4(__float_as_int(hi.x), __float_as_int(hi.y), __float_as_int(hi.z), __float_as_int(hi.w));
+        } else {
 #pragma unroll
-        for (int v = 0; v < VEC; v++) it[j][v] = src[(size_t)i * VEC + v];
+          for (int v = 0; v < VEC; v++) it[j][v] = src[(size_t)i * VEC + v];
+        }
       }
       const int d = valid ? ((it[j][KEYW].w >> shift) & (kRadix - 1)) : (kRadix + lane);
       digit[j] = valid ? d : -1;
@@ -167,8 +174,15 @@ __global__ void __launch_bounds__(kSortBlock) radix_scatter_kernel(const int4 *s
     for (int j = 0; j < kIPT; j++) {
       if (digit[j] >= 0) {
         const int o = s_wcount[w][digit[j]] + rank[j];
+        if (VEC == 2) {
+          const int4 a0 = it[j][0], a1 = it[j][VEC - 1];
+          st_particle(reinterpret_cast<float4 *>(dst) + 2 * (size_t)o,
+                      make_float4(__int_as_float(a0.x), __int_as_float(a0.y), __int_as_float(a0.z), __int_as_float(a0.w)),
+                      make_float4(__int_as_float(a1.x), __int_as_float(a1.y), __int_as_float(a1.z), __int_as_float(a1.w)));
+        } else {
 #pragma unroll
-        for (int v = 0; v < VEC; v++) dst[(size_t)o * VEC + v] = it[j][v];
+          for (int v = 0; v < VEC; v++) dst[(size_t)o * VEC + v] = it[j][v];
+        }
       }
     }
     __syncthreads();
