@@ -170,7 +170,8 @@ int vpb_uncenter_p(void *p, int32_t np, const float *interp, int32_t interp_stri
  * with the local boundary conditions of local.cc and the periodic/remote ghost handling of remote.cc.
  * face[f], f = -x,-y,-z,+x,+y,+z:  VPB_FACE_PERIODIC_SELF  ghost plane copied from the opposite side of this domain,
  *                                  VPB_FACE_REMOTE         ghost plane filled by the caller (NCCL halo exchange),
- *                                  <0                      local field BC code (grid.h:20-26): -1 pec, -2 symmetric, -3 pmc. */
+ *                                  <0                      local field BC code (grid.h:20-26): -1 pec, -2 symmetric, -3 pmc,
+ *                                                          -4 absorbing (Higdon, local.cc:84-112). */
 #define VPB_FACE_PERIODIC_SELF 0
 #define VPB_FACE_REMOTE        1
 

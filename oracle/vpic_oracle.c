@@ -350,13 +350,13 @@ static float axis_rd(const vpo_field_args_t *a, int X) { return X == 0 ? a->rdx 
 /* Loop over plane X=xp with Y in [yl,yh], Z in [zl,zh] (cyclic axis naming as in local.cc/remote.cc macros:
  * the reference's XYZ_LOOP always iterates z outer, y middle, x inner in *physical* axes; message packing
  * order therefore depends on the physical order, reproduced here). */
-#define PLANE_LOOP(X, xp, Y, yl, yh, Z, zl, zh, body) do {                                   \
+#define PLANE_LOOP(X, xp, Y, yl, yh, Z, zl, zh, ...) do {                                   \
     int lo_[3], hi_[3], c_[3];                                                               \
     lo_[X] = hi_[X] = (xp); lo_[Y] = (yl); hi_[Y] = (yh); lo_[Z] = (zl); hi_[Z] = (zh);      \
     for (c_[2] = lo_[2]; c_[2] <= hi_[2]; c_[2]++)                                           \
       for (c_[1] = lo_[1]; c_[1] <= hi_[1]; c_[1]++)                                         \
         for (c_[0] = lo_[0]; c_[0] <= hi_[0]; c_[0]++) {                                     \
-          int v = c_[0] * d.s[0] + c_[1] * d.s[1] + c_[2] * d.s[2]; (void)v; body; } } while (0)
+          int v = c_[0] * d.s[0] + c_[1] * d.s[1] + c_[2] * d.s[2]; (void)v; __VA_ARGS__; } } while (0)
 
 void vpo_clear_jf(const vpo_field_args_t *a) {                       /* sfa.cc:231-237 */
   int nv = (a->nx + 2) * (a->ny + 2) * (a->nz + 2);
@@ -405,13 +405,41 @@ static void ghost_tang_b(const vpo_field_args_t *a) {
     PLANE_LOOP(X, face, Y, 1, d.n[Y], Z, 1, d.n[Z] + 1, *p++ = F[(size_t)v * F_STRIDE + F_CBX + Z]);   /* YZ edge loop: cbZ */
   }
   /* local boundary conditions */
+  const float higend = (a->nx > 1 || a->ny > 1 || a->nz > 1) ? 1.03527618 : 1.;          /* local.cc:66 */
   for (int fc = 0; fc < 6; fc++) {
     int bc = a->bc6[fc];
     if (bc >= 0) continue;
     int X = fc % 3, Y = (X + 1) % 3, Z = (X + 2) % 3;
     int ghost = fc < 3 ? 0 : d.n[X] + 1, step = fc < 3 ? d.s[X] : -d.s[X];   /* f(x-i) = one cell inward */
+    if (bc == -4) {                                                 /* absorb_fields: local.cc:84-112 */
+      const float cdt_dX = a->cvac * a->dt * axis_rd(a, X), cdt_dY = a->cvac * a->dt * axis_rd(a, Y),
+                  cdt_dZ = a->cvac * a->dt * axis_rd(a, Z);
+      float drive = cdt_dX * higend, decay = (1 - drive) / (1 + drive);
+      drive = 2 * drive / (1 + drive);
+      const int face = fc < 3 ? 1 : d.n[X] + 1;
+      const int to_face = (face - ghost) * d.s[X];                  /* ghost voxel -> same (Y,Z) on the face plane */
+      PLANE_LOOP(X, ghost, Y, 1, d.n[Y] + 1, Z, 1, d.n[Z], {
+        float *fg = F + (size_t)v * F_STRIDE, *fh = F + (size_t)(v + step) * F_STRIDE;
+        const float *ff = F + (size_t)(v + to_face) * F_STRIDE, *ffi = F + (size_t)(v + to_face + step) * F_STRIDE;
+        float t1 = cdt_dX * (ffi[F_EX + Z] - ff[F_EX + Z]);
+        t1 = fc < 3 ? t1 : -t1;
+        float t2 = F[(size_t)(v + step + d.s[Z]) * F_STRIDE + F_EX + X];
+        t2 = cdt_dZ * (t2 - fh[F_EX + X]);
+        fg[F_CBX + Y] = decay * fg[F_CBX + Y] + drive * fh[F_CBX + Y] - t1 + t2;
+      });
+      PLANE_LOOP(X, ghost, Y, 1, d.n[Y], Z, 1, d.n[Z] + 1, {
+        float *fg = F + (size_t)v * F_STRIDE, *fh = F + (size_t)(v + step) * F_STRIDE;
+        const float *ff = F + (size_t)(v + to_face) * F_STRIDE, *ffi = F + (size_t)(v + to_face + step) * F_STRIDE;
+        float t1 = cdt_dX * (ffi[F_EX + Y] - ff[F_EX + Y]);
+        t1 = fc < 3 ? t1 : -t1;
+        float t2 = F[(size_t)(v + step + d.s[Y]) * F_STRIDE + F_EX + X];
+        t2 = cdt_dY * (t2 - fh[F_EX + X]);
+        fg[F_CBX + Z] = decay * fg[F_CBX + Z] + drive * fh[F_CBX + Z] + t1 - t2;
+      });
+      continue;
+    }
     float sgn = (bc == -1) ? 1.0f : -1.0f;                          /* pec copies, symmetric/pmc negate */
-    if (bc != -1 && bc != -2 && bc != -3) abort();                  /* absorbing not restated yet */
+    if (bc != -1 && bc != -2 && bc != -3) abort();
     PLANE_LOOP(X, ghost, Y, 1, d.n[Y] + 1, Z, 1, d.n[Z],
                F[(size_t)v * F_STRIDE + F_CBX + Y] = (sgn > 0) ? F[(size_t)(v + step) * F_STRIDE + F_CBX + Y] : -F[(size_t)(v + step) * F_STRIDE + F_CBX + Y]);
     PLANE_LOOP(X, ghost, Y, 1, d.n[Y], Z, 1, d.n[Z] + 1,
@@ -522,7 +550,6 @@ void vpo_synchronize_jf(const vpo_field_args_t *a) {
       free(msg[side]);
     }
   }
-  (void)axis_rd;
 }
 
 /* vacuum_energy_f: vacuum_energy_f_pipeline.cc:12-97, stencil .h:24-75 (single pipeline order) */

@@ -241,6 +241,8 @@ def test_energy_center_uncenter(eng, oracle):
     ((64, 64, 1), {0: -1, 3: -1}, 0.0),          # harris: pec x walls, one cell in z
     ((5, 1, 7), {2: -2, 5: -3}, 0.0),            # symmetric / pmc, one cell in y
     ((40, 24, 16), None, 0.0),
+    ((6, 5, 4), {0: -4, 3: -4, 2: -4, 5: -1}, 0.0),   # absorbing (Higdon) walls
+    ((96, 1, 40), {0: -4, 3: -4}, 0.01),          # lpi-like 2-D box with absorbing x walls
 ])
 def test_field_advance(eng, oracle, dims, fbc, damp):
     rng = np.random.default_rng(3)

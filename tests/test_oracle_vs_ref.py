@@ -122,6 +122,8 @@ def test_interpolator_unload_energy_center(ref_scalar, oracle):
     ((6, 5, 4), None, 0.01),
     ((8, 8, 1), {0: -1, 3: -1}, 0.0),             # harris-like: pec x walls, degenerate z
     ((5, 1, 7), {2: -2, 5: -3}, 0.0),             # symmetric / pmc walls, degenerate y
+    ((6, 5, 4), {0: -4, 3: -4, 2: -4, 5: -1}, 0.0),  # absorbing (Higdon) walls on -x, +x, -z; pec on +z
+    ((9, 1, 6), {0: -4, 3: -4}, 0.01),            # lpi-like: 2-D, absorbing x walls
 ])
 def test_field_advance_bit_exact(ref_scalar, oracle, dims, fbc, damp):
     rng = np.random.default_rng(3)

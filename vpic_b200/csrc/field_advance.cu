@@ -80,6 +80,36 @@ __global__ void __launch_bounds__(256) ghost_tang_b_kernel(FieldK k) {
   const int v = ghost * s[X] + cy * s[Y] + cz * s[Z];
   int src; float rw, lw; bool negate = false;
   const int inward = v + (low ? s[X] : -s[X]);
+  float *gs = reinterpret_cast<float *>(&FQ(v, 1));
+  if (bc == -4) {
+    // absorb_fields: 2nd-order accurate 1st-order Higdon ABC on the ghost tangential B (local.cc:84-112); the ghost
+    // value is a state variable here (decay * previous ghost + drive * interior - dE/dn + dE/dt terms)
+    const float rd[3] = {k.rdx, k.rdy, k.rdz};
+    const float cdt_dX = k.cvac * k.dt * rd[X], cdt_dY = k.cvac * k.dt * rd[Y], cdt_dZ = k.cvac * k.dt * rd[Z];
+    const float higend = (k.nx > 1 || k.ny > 1 || k.nz > 1) ? (float)1.03527618 : 1.0f;
+    float drive = cdt_dX * higend;
+    const float decay = (1 - drive) / (1 + drive);
+    drive = 2 * drive / (1 + drive);
+    const int face = (low ? 1 : n[X] + 1) * s[X] + cy * s[Y] + cz * s[Z];
+    const int face_in = face + (low ? s[X] : -s[X]);
+    const float4 g = FQ(v, 1), h = FQ(inward, 1);
+    const float4 e_f = FQ(face, 0), e_fi = FQ(face_in, 0), e_h = FQ(inward, 0);
+    if (cz <= n[Z]) {                                           // cbY over Y in 1..nY+1, Z in 1..nZ
+      float t1 = cdt_dX * (comp(e_fi, Z) - comp(e_f, Z));
+      t1 = low ? t1 : -t1;
+      float t2 = comp(FQ(inward + s[Z], 0), X);
+      t2 = cdt_dZ * (t2 - comp(e_h, X));
+      gs[Y] = ((decay * comp(g, Y) + drive * comp(h, Y)) - t1) + t2;
+    }
+    if (cy <= n[Y]) {                                           // cbZ over Y in 1..nY, Z in 1..nZ+1
+      float t1 = cdt_dX * (comp(e_fi, Y) - comp(e_f, Y));
+      t1 = low ? t1 : -t1;
+      float t2 = comp(FQ(inward + s[Y], 0), X);
+      t2 = cdt_dY * (t2 - comp(e_h, X));
+      gs[Z] = ((decay * comp(g, Z) + drive * comp(h, Z)) + t1) - t2;
+    }
+    return;
+  }
   if (bc == VPB_FACE_PERIODIC_SELF) {
     // the ghost at X=0 receives the plane X=n sent out of the +X port of this same domain, and vice versa
     src = (low ? n[X] : 1) * s[X] + cy * s[Y] + cz * s[Z];
@@ -92,7 +122,6 @@ __global__ void __launch_bounds__(256) ghost_tang_b_kernel(FieldK k) {
   }
   // Scalar stores: the corner line (X ghost, Y = nY+1) also belongs to the Y face's ghost plane, which writes
   // a different component of the same field_t — a float4 read-modify-write would lose one of the two.
-  float *gs = reinterpret_cast<float *>(&FQ(v, 1));
   const float4 sv = FQ(src, 1), iv = FQ(inward, 1);
   if (cz <= n[Z]) {                                             // cbY over Y in 1..nY+1, Z in 1..nZ
     float val = comp(sv, Y);
@@ -276,8 +305,8 @@ static int check_field_args(const vpb_field_args_t *a, const char *who) {
   VPB_REQUIRE(a && a->f && a->nx > 0 && a->ny > 0 && a->nz > 0, "%s: Bad args", who);
   VPB_REQUIRE(a->ny + 1 <= 65535 && a->nz + 1 <= 65535 && a->nx + 1 <= 65535, "%s: grid too large", who);
   for (int i = 0; i < 6; i++)
-    VPB_REQUIRE(a->face[i] == VPB_FACE_PERIODIC_SELF || a->face[i] == VPB_FACE_REMOTE || (a->face[i] <= -1 && a->face[i] >= -3),
-                "%s: Bad boundary condition encountered (face %d = %d; absorbing walls are not on the device yet)", who, i, a->face[i]);
+    VPB_REQUIRE(a->face[i] == VPB_FACE_PERIODIC_SELF || a->face[i] == VPB_FACE_REMOTE || (a->face[i] <= -1 && a->face[i] >= -4),
+                "%s: Bad boundary condition encountered (face %d = %d)", who, i, a->face[i]);
   return 0;
 }
 
