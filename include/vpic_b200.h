@@ -129,6 +129,10 @@ typedef struct vpb_boundary_args {
   void          *inj;                    /* out: particle_injector_t[nm] */
   int32_t       *class_offsets;          /* out: int32[9], device */
   void          *scratch; size_t scratch_bytes;   /* >= vpb_boundary_scratch_bytes(nm) */
+  float         *fields;                 /* optional: field_t array; absorbed particles leave their charge in rhob
+                                            (accumulate_rhob, rho_p.cc:126-213) */
+  float          q_r8V;                  /* species charge * grid r8V, for rhob */
+  int32_t        nx, ny, nz;
 } vpb_boundary_args_t;
 size_t vpb_boundary_scratch_bytes(int32_t nm);
 int    vpb_boundary_p_pack(const vpb_boundary_args_t *args, void *stream);
@@ -162,6 +166,11 @@ int vpb_energy_p(const void *p, int32_t np, const float *interp, int32_t interp_
                  float q, float m, float dt, float cvac, double *en_dev, void *stream);
 int vpb_center_p(void *p, int32_t np, const float *interp, int32_t interp_stride, float qdt_2mc, void *stream);
 int vpb_uncenter_p(void *p, int32_t np, const float *interp, int32_t interp_stride, float qdt_2mc, void *stream);
+
+/* accumulate_rho_p (src/species_advance/standard/rho_p.cc:22-113): node charge density of a species into
+ * field_t.rhof (used by the divergence cleaning and by rho diagnostics). */
+int vpb_accumulate_rho_p(float *fields, const void *p, int32_t np, float q, float r8V,
+                         int32_t nx, int32_t ny, int32_t nz, void *stream);
 
 /* ---- standard field advance, vacuum material -------------------------------
  * advance_b (src/field_advance/standard/pipeline/advance_b_pipeline.cc:20-125),

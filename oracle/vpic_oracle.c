@@ -334,6 +334,53 @@ void vpo_uncenter_p(vpo_particle_t *p, int32_t np, const float *interp, int32_t 
   }
 }
 
+/* trilinear node weights shared by accumulate_rho_p / accumulate_rhob (rho_p.cc:60-75,140-153) */
+static void trilinear8(float w0, float w1, float dz, float w7, float w[8]) {
+  float w2, w3, w4, w5, w6;
+  w6 = w7 - w0 * w7; w7 = w7 + w0 * w7;
+  w4 = w6 - w1 * w6; w5 = w7 - w1 * w7;
+  w6 = w6 + w1 * w6; w7 = w7 + w1 * w7;
+  w0 = w4 - dz * w4; w1 = w5 - dz * w5; w2 = w6 - dz * w6; w3 = w7 - dz * w7;
+  w4 = w4 + dz * w4; w5 = w5 + dz * w5; w6 = w6 + dz * w6; w7 = w7 + dz * w7;
+  w[0] = w0; w[1] = w1; w[2] = w2; w[3] = w3; w[4] = w4; w[5] = w5; w[6] = w6; w[7] = w7;
+}
+
+void vpo_accumulate_rho_p(float *F, const vpo_particle_t *p, int32_t np, float q, float r8V,
+                          int32_t nx, int32_t ny, int32_t nz) {
+  const float q_8V = q * r8V;                                        /* rho_p.cc:32 */
+  const int sy = nx + 2, sz = (nx + 2) * (ny + 2);
+  (void)nz;
+  for (int32_t n = 0; n < np; n++) {
+    float w[8];
+    const int v = p[n].i;
+    trilinear8(p[n].dx, p[n].dy, p[n].dz, p[n].w * q_8V, w);
+    F[(size_t)(v) * F_STRIDE + F_RHOF] += w[0];           F[(size_t)(v + 1) * F_STRIDE + F_RHOF] += w[1];
+    F[(size_t)(v + sy) * F_STRIDE + F_RHOF] += w[2];      F[(size_t)(v + sy + 1) * F_STRIDE + F_RHOF] += w[3];
+    F[(size_t)(v + sz) * F_STRIDE + F_RHOF] += w[4];      F[(size_t)(v + sz + 1) * F_STRIDE + F_RHOF] += w[5];
+    F[(size_t)(v + sz + sy) * F_STRIDE + F_RHOF] += w[6]; F[(size_t)(v + sz + sy + 1) * F_STRIDE + F_RHOF] += w[7];
+  }
+}
+
+void vpo_accumulate_rhob(float *F, const vpo_particle_t *p, float qsp, float r8V, int32_t nx, int32_t ny, int32_t nz) {
+  const int sy = nx + 2, sz = (nx + 2) * (ny + 2);
+  float w[8];
+  const int v = p->i;
+  trilinear8(p->dx, p->dy, p->dz, (qsp * r8V) * p->w, w);            /* rho_p.cc:139 */
+  int x = v, z = x / sz, y;
+  if (z == 1)  { w[0] += w[0]; w[1] += w[1]; w[2] += w[2]; w[3] += w[3]; }
+  if (z == nz) { w[4] += w[4]; w[5] += w[5]; w[6] += w[6]; w[7] += w[7]; }
+  x -= sz * z; y = x / sy;
+  if (y == 1)  { w[0] += w[0]; w[1] += w[1]; w[4] += w[4]; w[5] += w[5]; }
+  if (y == ny) { w[2] += w[2]; w[3] += w[3]; w[6] += w[6]; w[7] += w[7]; }
+  x -= sy * y;
+  if (x == 1)  { w[0] += w[0]; w[2] += w[2]; w[4] += w[4]; w[6] += w[6]; }
+  if (x == nx) { w[1] += w[1]; w[3] += w[3]; w[5] += w[5]; w[7] += w[7]; }
+  F[(size_t)(v) * F_STRIDE + F_RHOB] += w[0];           F[(size_t)(v + 1) * F_STRIDE + F_RHOB] += w[1];
+  F[(size_t)(v + sy) * F_STRIDE + F_RHOB] += w[2];      F[(size_t)(v + sy + 1) * F_STRIDE + F_RHOB] += w[3];
+  F[(size_t)(v + sz) * F_STRIDE + F_RHOB] += w[4];      F[(size_t)(v + sz + 1) * F_STRIDE + F_RHOB] += w[5];
+  F[(size_t)(v + sz + sy) * F_STRIDE + F_RHOB] += w[6]; F[(size_t)(v + sz + sy + 1) * F_STRIDE + F_RHOB] += w[7];
+}
+
 /* ======================================================================== */
 /* Standard field advance, vacuum material, single local domain.            */
 

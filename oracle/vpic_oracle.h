@@ -70,6 +70,13 @@ double vpo_energy_p(const vpo_particle_t *p, int32_t np, const float *interp, in
 void vpo_center_p(vpo_particle_t *p, int32_t np, const float *interp, int32_t interp_stride, float qdt_2mc);
 void vpo_uncenter_p(vpo_particle_t *p, int32_t np, const float *interp, int32_t interp_stride, float qdt_2mc);
 
+/* accumulate_rho_p (rho_p.cc:22-113): trilinear charge of every particle into field_t.rhof; accumulate_rhob
+ * (rho_p.cc:126-213): one particle into field_t.rhob with doubled weights on domain walls. */
+void vpo_accumulate_rho_p(float *fields, const vpo_particle_t *p, int32_t np, float q, float r8V,
+                          int32_t nx, int32_t ny, int32_t nz);
+void vpo_accumulate_rhob(float *fields, const vpo_particle_t *p, float qsp, float r8V,
+                         int32_t nx, int32_t ny, int32_t nz);
+
 /* ---- standard field advance, vacuum material, one local domain whose six faces are either
  *      periodic onto itself or a local field BC (pec = -1).  bc6[f] for faces -x,-y,-z,+x,+y,+z:
  *      >=0 periodic-self, -1 pec.  (sfa: advance_b_pipeline.cc:20-125, vacuum_advance_e_pipeline.cc:20-332,

@@ -49,6 +49,8 @@ def load_oracle():
     lib.vpo_clear_jf.argtypes = [C.c_void_p]
     lib.vpo_synchronize_jf.argtypes = [C.c_void_p]
     lib.vpo_vacuum_energy_f.argtypes = [C.c_void_p, C.c_void_p]
+    lib.vpo_accumulate_rho_p.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_int32, C.c_int32, C.c_int32]
+    lib.vpo_accumulate_rhob.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int32, C.c_int32, C.c_int32]
     lib.vpo_advance_b.argtypes = [C.c_void_p, C.c_float]
     lib.vpo_vacuum_advance_e.argtypes = [C.c_void_p, C.c_float]
     return lib
@@ -116,6 +118,8 @@ def load_ref(variant="scalar", tpp=1):
     lib.clear_accumulator_array.argtypes = [C.POINTER(abi.AccumulatorArray)]
     lib.reduce_accumulator_array.argtypes = [C.POINTER(abi.AccumulatorArray)]
     lib.unload_accumulator_array.argtypes = [C.POINTER(abi.FieldArray), C.POINTER(abi.AccumulatorArray)]
+    lib.accumulate_rho_p.argtypes = [C.POINTER(abi.FieldArray), C.POINTER(abi.Species)]
+    lib.accumulate_rhob.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(abi.Grid), C.c_float]
     lib.move_p.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(abi.Grid), C.c_float]
     lib.move_p.restype = C.c_int
     lib.variant = variant

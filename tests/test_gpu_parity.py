@@ -384,3 +384,76 @@ def test_dropin_symbols_on_host_structs(eng, oracle, mode):
     res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("RESULT ")][0][7:])
     assert res["interp"] and res["nm"] and res["particles"] and res["movers"] and res["partition"] and res["jf"], res
     assert res["accum"] < 2e-5 and res["last_sorted"] == 0, res
+
+
+def test_accumulate_rho_p(eng, oracle):
+    rng = np.random.default_rng(12)
+    nx, ny, nz = 9, 7, 5
+    g = make_grid(nx, ny, nz)
+    dg = eng.DeviceGrid(g)
+    fields = R.random_fields(rng, g.nv)
+    fa = eng.FieldArray(dg)
+    fa.f.copy_(torch.from_numpy(fields))
+    parts = R.random_particles(rng, 50001, nx, ny, nz, w=0.21)
+    sp = eng.Species("ion", 2.0, 25.0, len(parts), 16, 20, 0, dg)
+    sp.set_particles(parts)
+    eng.accumulate_rho_p(fa, sp)
+    f_ref = fields.copy()
+    oracle.vpo_accumulate_rho_p(f_ref.ctypes.data, parts.ctypes.data, len(parts), 2.0, g.r8V, nx, ny, nz)
+    got = fa.f.cpu().numpy()
+    assert np.array_equal(bits(np.delete(got, 15, axis=1)), bits(np.delete(f_ref, 15, axis=1)))     # only rhof changes
+    assert np.abs(got[:, 15] - f_ref[:, 15]).max() / np.abs(f_ref[:, 15]).max() < 2e-5
+
+
+def test_boundary_p_absorbing_walls_match_reference(eng, oracle):
+    """Absorbing walls on one rank: movers -> device boundary_p (back-fill + rhob) vs the reference's own boundary_p
+    (when the prebuilt reference is present) or its restated semantics (sequential p[i] = p[--np])."""
+    rng = np.random.default_rng(6)
+    nx, ny, nz, n = 6, 5, 4, 12000
+    pbc = {0: -2, 3: -2, 2: -2}
+    g = make_grid(nx, ny, nz, pbc=pbc)
+    fields = R.random_fields(rng, g.nv)
+    interp = np.zeros((g.nv, 20), dtype=np.float32)
+    oracle.vpo_load_interpolator(interp.ctypes.data, 20, fields.ctypes.data, nx, ny, nz)
+    parts = R.random_particles(rng, n, nx, ny, nz, uth=0.5, w=0.7)
+    # expected result from the oracle push followed by the reference's sequential removal
+    p_ref, pm_ref, acc_ref, _ = oracle_push(oracle, g, parts, interp, -1.0, 1.0, n)
+    assert len(pm_ref) > 50
+    f_ref = fields.copy()
+    np_ref = n
+    for m in pm_ref[::-1]:                                  # boundary_p.cc:257-371: reverse walk, back-fill
+        i = int(m["i"])
+        one = p_ref[i:i + 1].copy()
+        one["i"] >>= 3
+        oracle.vpo_accumulate_rhob(f_ref.ctypes.data, one.ctypes.data, -1.0, g.r8V, nx, ny, nz)
+        np_ref -= 1
+        p_ref[i] = p_ref[np_ref]
+    dg = eng.DeviceGrid(g)
+    fa, ia, aa = eng.FieldArray(dg), eng.InterpolatorArray(dg), eng.AccumulatorArray(dg)
+    fa.f.copy_(torch.from_numpy(fields)); ia.i.copy_(torch.from_numpy(interp))
+    sp = eng.Species("e", -1.0, 1.0, n, n, 20, 0, dg)
+    sp.set_particles(parts)
+    eng.advance_p(sp, aa, ia)
+    assert sp.nm == len(pm_ref)
+    inj, offs = eng.boundary_pack(sp, [-1] * 6, fa)
+    o = offs.cpu().numpy()
+    assert o[6] == 0 and o[7] == len(pm_ref) and o[8] == len(pm_ref)          # every mover was absorbed
+    assert sp.np == np_ref and sp.nm == 0
+    assert np.array_equal(bits(sp.particles_host()), bits(p_ref[:np_ref])), "back-fill must equal the sequential one"
+    got = fa.f.cpu().numpy()
+    assert np.abs(got[:, 11] - f_ref[:, 11]).max() <= 2e-5 * np.abs(f_ref[:, 11]).max()
+    assert np.array_equal(bits(np.delete(got, 11, axis=1)), bits(np.delete(f_ref, 11, axis=1)))
+    if R.have_ref("scalar"):                               # and against the unmodified reference's boundary_p itself
+        lib = R.load_ref("scalar", tpp=1)
+        W = R.RefWorld(lib, nx, ny, nz, pbc=pbc)
+        W.g.contents.dt = g.dt
+        W.fields[:] = fields
+        lib.load_interpolator_array(W.ia, W.fa)
+        rs = W.new_species("e_bp", -1.0, 1.0, n, n)
+        rs.set_particles(parts)
+        lib.clear_accumulator_array(W.aa); lib.advance_p(rs.sp, W.aa, W.ia); lib.reduce_accumulator_array(W.aa)
+        lib.boundary_p.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.boundary_p(None, rs.sp, W.fa, W.aa)
+        assert rs.c.np == sp.np
+        assert np.array_equal(bits(rs.p[:rs.c.np]), bits(sp.particles_host()))
+        assert np.abs(got[:, 11] - W.fields[:, 11]).max() <= 2e-5 * np.abs(W.fields[:, 11]).max()

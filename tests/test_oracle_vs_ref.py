@@ -149,3 +149,21 @@ def test_field_advance_bit_exact(ref_scalar, oracle, dims, fbc, damp):
     assert np.array_equal(np.array(en[:]), W.energy_f())
     W.clear_jf(); oracle.vpo_clear_jf(C.byref(a))
     assert np.array_equal(bits(f2), bits(W.fields))
+
+
+def test_rho_p_and_rhob_bit_exact(ref_scalar, oracle):
+    rng = np.random.default_rng(41)
+    nx, ny, nz = 5, 4, 6
+    W = make_world(ref_scalar, rng, nx, ny, nz)
+    g = W.g.contents
+    sp = W.new_species("r%d" % rng.integers(1 << 30), -1.0, 1.0, 8192, 16)
+    parts = R.random_particles(rng, 6000, nx, ny, nz, w=0.3)
+    sp.set_particles(parts)
+    f2 = W.fields.copy()
+    ref_scalar.accumulate_rho_p(W.fa, sp.sp)
+    oracle.vpo_accumulate_rho_p(f2.ctypes.data, parts.ctypes.data, len(parts), -1.0, g.r8V, nx, ny, nz)
+    assert np.array_equal(bits(f2), bits(W.fields))
+    for k in range(200):                                   # includes wall voxels (doubled weights)
+        ref_scalar.accumulate_rhob(W.fa.contents.f, parts[k:k + 1].ctypes.data, W.g, 1.5)
+        oracle.vpo_accumulate_rhob(f2.ctypes.data, parts[k:k + 1].ctypes.data, 1.5, g.r8V, nx, ny, nz)
+    assert np.array_equal(bits(f2), bits(W.fields))

@@ -10,7 +10,8 @@
 //
 // Determinism: movers arrive sorted by particle index (vpb_sort_movers); injectors are grouped per destination
 // face by a STABLE split, so every buffer is in ascending particle order and the back-fill reproduces the
-// reference's sequential "p[i] = p[--np]" result exactly.
+// reference's sequential "p[i] = p[--np]" result exactly (checked against the reference's own boundary_p in
+// tests/test_gpu_parity.py::test_boundary_p_absorbing_walls_match_reference).
 #include "push_common.cuh"
 
 namespace vpb {
@@ -26,6 +27,7 @@ struct BoundK {
   long long rangel, rangeh, rangem;
   long long face_range[6];
   int sp_id;
+  float *fields; float q_r8V; int nx, ny, nz;
 };
 
 // class of a mover: 0..5 = send through that face, 6 = absorbed, 7 = no device handler (dropped with a count)
@@ -42,7 +44,33 @@ __global__ void __launch_bounds__(256) bp_build_injectors_kernel(BoundK k, int4 
   const long long nn = __ldg(k.neighbor + 6ll * voxel + face);
   int cls = 7;
   int dst_voxel = voxel;
-  if (nn == -2 /* absorb_particles, grid.h:30 */) cls = 6;
+  if (nn == -2 /* absorb_particles, grid.h:30 */) {
+    cls = 6;
+    if (k.fields) {                       // accumulate_rhob (rho_p.cc:126-213): the absorbed charge stays on the wall
+      const int sy = k.nx + 2, sz = (k.nx + 2) * (k.ny + 2);
+      float w0 = r.x, w1 = r.y, w2, w3, w4, w5, w6, w7 = k.q_r8V * u.w;
+      const float dz = r.z;
+      w6 = w7 - w0 * w7; w7 = w7 + w0 * w7;
+      w4 = w6 - w1 * w6; w5 = w7 - w1 * w7;
+      w6 = w6 + w1 * w6; w7 = w7 + w1 * w7;
+      w0 = w4 - dz * w4; w1 = w5 - dz * w5; w2 = w6 - dz * w6; w3 = w7 - dz * w7;
+      w4 = w4 + dz * w4; w5 = w5 + dz * w5; w6 = w6 + dz * w6; w7 = w7 + dz * w7;
+      int x = voxel; const int z = x / sz;
+      if (z == 1)    { w0 += w0; w1 += w1; w2 += w2; w3 += w3; }
+      if (z == k.nz) { w4 += w4; w5 += w5; w6 += w6; w7 += w7; }
+      x -= sz * z; const int y = x / sy;
+      if (y == 1)    { w0 += w0; w1 += w1; w4 += w4; w5 += w5; }
+      if (y == k.ny) { w2 += w2; w3 += w3; w6 += w6; w7 += w7; }
+      x -= sy * y;
+      if (x == 1)    { w0 += w0; w2 += w2; w4 += w4; w6 += w6; }
+      if (x == k.nx) { w1 += w1; w3 += w3; w5 += w5; w7 += w7; }
+      float *f = k.fields + 11;           // field_t.rhob
+      red_add(f + 20 * (size_t)(voxel), w0);           red_add(f + 20 * (size_t)(voxel + 1), w1);
+      red_add(f + 20 * (size_t)(voxel + sy), w2);      red_add(f + 20 * (size_t)(voxel + sy + 1), w3);
+      red_add(f + 20 * (size_t)(voxel + sz), w4);      red_add(f + 20 * (size_t)(voxel + sz + 1), w5);
+      red_add(f + 20 * (size_t)(voxel + sz + sy), w6); red_add(f + 20 * (size_t)(voxel + sz + sy + 1), w7);
+    }
+  }
   else if (((nn >= 0) && (nn < k.rangel)) || ((nn > k.rangeh) && (nn <= k.rangem))) {
     if (face < 6 && k.face_range[face] >= 0) {
       cls = face;
@@ -69,21 +97,24 @@ __device__ __forceinline__ int lower_bound_mover(const int4 *pm, int n, int key)
 }
 
 // Back-fill: all nm mover particles leave the array.  Sequentially the reference does, for movers in DEscending
-// index order, p[i] = p[--np].  Equivalent closed form: with np' = np - nm, the holes below np' taken in descending
-// order receive the surviving tail particles (index >= np', not a mover) taken in descending order.
+// index order, p[i] = p[--np] (boundary_p.cc:354-371).  Step j (0-based) therefore reads position L_j = np-1-j and
+// writes the j-th largest mover index.  A position that is itself a mover index was overwritten at its own (earlier)
+// step with the content of ITS L, so the element that finally lands in a hole is found by following that chain
+// upwards until it leaves the mover set; chains are short (a tail position is a mover with probability nm/np).
+// Holes at or above np' = np - nm are dead afterwards and need no write; sources are never written, so every
+// thread can resolve and copy independently.
 __global__ void __launch_bounds__(256) bp_backfill_kernel(BoundK k) {
-  const int t_rel = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t_rel >= k.nm) return;
-  const int np_new = k.np - k.nm;
-  const int t = np_new + t_rel;                                  // a tail position
-  const int lb = lower_bound_mover(k.pm, k.nm, t);
-  if (lb < k.nm && k.pm[lb].w == t) return;                      // the tail particle itself leaves
-  const int k0 = lower_bound_mover(k.pm, k.nm, np_new);          // movers below np' = holes to fill
-  const int removed_above = k.nm - lb;                           // movers with index > t
-  const int r = (k.np - 1 - t) - removed_above;                  // rank among survivors, from the top
-  const int hole = k.pm[k0 - 1 - r].w;
-  k.p[2 * (size_t)hole] = k.p[2 * (size_t)t];
-  k.p[2 * (size_t)hole + 1] = k.p[2 * (size_t)t + 1];
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;          // ascending position in the mover list
+  if (m >= k.nm) return;
+  const int hole = k.pm[m].w;
+  if (hole >= k.np - k.nm) return;
+  int L = k.np - 1 - (k.nm - 1 - m);
+  for (;;) {
+    const int lb = lower_bound_mover(k.pm, k.nm, L);
+    if (lb < k.nm && k.pm[lb].w == L) L = k.np - 1 - (k.nm - 1 - lb); else break;
+  }
+  k.p[2 * (size_t)hole] = k.p[2 * (size_t)L];
+  k.p[2 * (size_t)hole + 1] = k.p[2 * (size_t)L + 1];
 }
 
 // Injection: record n_f - 1 - j of a face buffer lands at p[base + j'] in the reference's reverse walk, i.e. the
@@ -127,6 +158,8 @@ extern "C" int vpb_boundary_p_pack(const vpb_boundary_args_t *b, void *stream) {
   k.neighbor = (const long long *)b->neighbor; k.rangel = b->rangel; k.rangeh = b->rangeh; k.rangem = b->rangem;
   for (int f = 0; f < 6; f++) k.face_range[f] = b->face_range[f];
   k.sp_id = b->sp_id;
+  k.fields = b->fields; k.q_r8V = b->q_r8V; k.nx = b->nx; k.ny = b->ny; k.nz = b->nz;
+  VPB_REQUIRE(!b->fields || (b->nx > 0 && b->ny > 0 && b->nz > 0), "vpb_boundary_p_pack: grid size missing for rhob");
   int4 *tmp = (int4 *)b->scratch;
   void *sort_scratch = (char *)b->scratch + (((size_t)b->nm * 48 + 255) / 256) * 256;
   const int blocks = (b->nm + 255) / 256;

@@ -305,6 +305,18 @@ double energy_p(const vpb_species_t *sp, const vpb_interpolator_array_t *ia) {
   return local;
 }
 
+// ---- accumulate_rho_p: species_advance.h:117-119, rho_p.cc:22-113 -----------------------------------------
+void accumulate_rho_p(vpb_field_array_t *fa, const vpb_species_t *sp) {
+  if (!fa || !sp || fa->g != sp->g) DROPIN_ERROR("Bad args");
+  const vpb_grid_t *g = sp->g;
+  const size_t fbytes = (size_t)g->nv * sizeof(vpb_field_t);
+  float *df = (float *)dev_in(fa->f, fbytes);
+  void *p = dev_in(sp->p, (size_t)sp->np * sizeof(vpb_particle_t), (size_t)sp->max_np * sizeof(vpb_particle_t));
+  DEV(vpb_accumulate_rho_p(df, p, sp->np, sp->q, g->r8V, g->nx, g->ny, g->nz, nullptr));
+  dev_written(fa->f, fbytes);
+  if (g_mode == VPB_MODE_COHERENT) DEV(vpb_stream_sync(nullptr));
+}
+
 // ---- interpolator / accumulator glue: sf_interface.h:99-174 ------------------------------------------------
 void load_interpolator_array(vpb_interpolator_array_t *ia, const vpb_field_array_t *fa) {
   if (!ia || !fa || ia->g != fa->g) DROPIN_ERROR("Bad args");

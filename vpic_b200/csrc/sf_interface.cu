@@ -151,9 +151,44 @@ __global__ void __launch_bounds__(256) center_p_kernel(float4 *__restrict__ p, i
   p[2 * (size_t)n + 1] = u;
 }
 
+// accumulate_rho_p (rho_p.cc:22-113): trilinear node charges of every particle into field_t.rhof (float 15 of the
+// 20-float field record).  One thread per particle, eight scalar REDs.
+__global__ void __launch_bounds__(256) accumulate_rho_p_kernel(float *__restrict__ fld, const float4 *__restrict__ p,
+                                                               int np, float q_8V, int sy, int sz) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= np) return;
+  const float4 r = p[2 * (size_t)n];
+  const float pw = p[2 * (size_t)n + 1].w;
+  float w0 = r.x, w1 = r.y, w2, w3, w4, w5, w6, w7 = pw * q_8V;
+  const float dz = r.z;
+  const int v = __float_as_int(r.w);
+  w6 = w7 - w0 * w7; w7 = w7 + w0 * w7;
+  w4 = w6 - w1 * w6; w5 = w7 - w1 * w7;
+  w6 = w6 + w1 * w6; w7 = w7 + w1 * w7;
+  w0 = w4 - dz * w4; w1 = w5 - dz * w5; w2 = w6 - dz * w6; w3 = w7 - dz * w7;
+  w4 = w4 + dz * w4; w5 = w5 + dz * w5; w6 = w6 + dz * w6; w7 = w7 + dz * w7;
+  float *f = fld + 15;
+  red_add(f + 20 * (size_t)(v), w0);           red_add(f + 20 * (size_t)(v + 1), w1);
+  red_add(f + 20 * (size_t)(v + sy), w2);      red_add(f + 20 * (size_t)(v + sy + 1), w3);
+  red_add(f + 20 * (size_t)(v + sz), w4);      red_add(f + 20 * (size_t)(v + sz + 1), w5);
+  red_add(f + 20 * (size_t)(v + sz + sy), w6); red_add(f + 20 * (size_t)(v + sz + sy + 1), w7);
+}
+
 }  // namespace vpb
 
 using namespace vpb;
+
+extern "C" int vpb_accumulate_rho_p(float *fields, const void *p, int32_t np, float q, float r8V,
+                                    int32_t nx, int32_t ny, int32_t nz, void *stream) {
+  VPB_REQUIRE(fields && (p || np == 0) && nx > 0 && ny > 0 && nz > 0, "vpb_accumulate_rho_p: Bad args");
+  if (np <= 0) return 0;
+  const float q_8V = q * r8V;
+  accumulate_rho_p_kernel<<<(np + 255) / 256, 256, 0, as_stream(stream)>>>(fields, (const float4 *)p, np, q_8V,
+                                                                          nx + 2, (nx + 2) * (ny + 2));
+  VPB_LAUNCH_CHECK();
+  return 0;
+}
+
 
 extern "C" int vpb_load_interpolator(float *interp, int32_t interp_stride, const float *fields,
                                      int32_t nx, int32_t ny, int32_t nz, void *stream) {

@@ -273,6 +273,14 @@ def energy_p(sp: Species, ia: InterpolatorArray):
     return float(sp._en.cpu()[0])
 
 
+def accumulate_rho_p(fa: FieldArray, sp: Species):
+    """accumulate_rho_p(field_array_t*, const species_t*), species_advance.h:117-119."""
+    _bad_args(fa is None or sp is None or fa.g is not sp.g, "accumulate_rho_p")
+    g = sp.g
+    _lib.check(_lib.load().vpb_accumulate_rho_p(_ptr(fa.f), _ptr(sp.p), sp.np, sp.q, g.g.r8V, g.nx, g.ny, g.nz, _stream()),
+               "accumulate_rho_p")
+
+
 def center_p(sp: Species, ia: InterpolatorArray):
     _bad_args(sp is None or ia is None or sp.g is not ia.g, "center_p")
     _lib.check(_lib.load().vpb_center_p(_ptr(sp.p), sp.np, _ptr(ia.i), ia.stride, sp.push_constants()[0], _stream()),
@@ -287,7 +295,7 @@ def uncenter_p(sp: Species, ia: InterpolatorArray):
 
 # ---- boundary_p, particle side (src/boundary/boundary_p.cc:257-371,595-711) ----------------------------------
 
-def boundary_pack(sp: Species, face_range):
+def boundary_pack(sp: Species, face_range, fa: FieldArray = None):
     """Turn this species' movers into per-face injector buffers and back-fill the holes they leave.
 
     Returns (inj, offsets_dev): inj is a [nm, 12] float32 view of particle_injector_t records grouped by class,
@@ -311,6 +319,9 @@ def boundary_pack(sp: Species, face_range):
     b.sp_id = getattr(sp, "id", 0)
     b.inj, b.class_offsets = inj.data_ptr(), offs.data_ptr()
     b.scratch, b.scratch_bytes = scratch.data_ptr(), need
+    if fa is not None:                                   # absorbed particles leave their charge in rhob
+        b.fields, b.q_r8V = fa.f.data_ptr(), float(np.float32(np.float32(sp.q) * np.float32(g.g.r8V)))
+        b.nx, b.ny, b.nz = g.nx, g.ny, g.nz
     _lib.check(L.vpb_boundary_p_pack(C.byref(b), _stream()), "boundary_p_pack")
     sp.np -= nm
     sp.nm = 0

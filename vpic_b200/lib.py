@@ -37,7 +37,8 @@ class BoundaryArgs(C.Structure):
     """vpb_boundary_args_t"""
     _fields_ = [("p", c_vp), ("np", c_i32), ("pm", c_vp), ("nm", c_i32), ("neighbor", c_vp),
                 ("rangel", c_i64), ("rangeh", c_i64), ("rangem", c_i64), ("face_range", c_i64 * 6),
-                ("sp_id", c_i32), ("inj", c_vp), ("class_offsets", c_vp), ("scratch", c_vp), ("scratch_bytes", C.c_size_t)]
+                ("sp_id", c_i32), ("inj", c_vp), ("class_offsets", c_vp), ("scratch", c_vp), ("scratch_bytes", C.c_size_t),
+                ("fields", c_vp), ("q_r8V", c_f), ("nx", c_i32), ("ny", c_i32), ("nz", c_i32)]
 
 
 class FieldArgs(C.Structure):
@@ -83,6 +84,7 @@ _PROTOS = {
     "vpb_load_interpolator": (C.c_int, [c_vp, c_i32, c_vp, c_i32, c_i32, c_i32, c_vp]),
     "vpb_clear_accumulator": (C.c_int, [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "vpb_unload_accumulator": (C.c_int, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_f, c_f, c_f, c_f, c_vp]),
+    "vpb_accumulate_rho_p": (C.c_int, [c_vp, c_vp, c_i32, c_f, c_f, c_i32, c_i32, c_i32, c_vp]),
     "vpb_energy_p": (C.c_int, [c_vp, c_i32, c_vp, c_i32, c_f, c_f, c_f, c_f, c_vp, c_vp]),
     "vpb_center_p": (C.c_int, [c_vp, c_i32, c_vp, c_i32, c_f, c_vp]),
     "vpb_uncenter_p": (C.c_int, [c_vp, c_i32, c_vp, c_i32, c_f, c_vp]),
@@ -99,6 +101,7 @@ _PROTOS = {
 # the reference's own extern "C" symbols that the drop-in layer exports (include/vpic_b200_dropin.h)
 DROPIN_SYMBOLS = ["advance_p", "sort_p", "load_interpolator_array", "clear_accumulator_array",
                   "reduce_accumulator_array", "unload_accumulator_array", "energy_p", "center_p", "uncenter_p",
+                  "accumulate_rho_p",
                   "vpic_b200_sync_to_host", "vpic_b200_invalidate", "vpic_b200_set_mode"]
 
 _lib = None

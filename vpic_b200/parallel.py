@@ -81,7 +81,7 @@ class SlabExchange:
             dist.all_reduce(left, group=self.ring.group)
             if int(left.item()) == 0:
                 return
-        packed = [E.boundary_pack(sp, self.face_range) for sp in sps]
+        packed = [E.boundary_pack(sp, self.face_range, sim.field_array) for sp in sps]
         offs = torch.stack([o for _, o in packed]).cpu()                       # one sync for all species
         n_lo = [int(offs[s, self.f_lo + 1] - offs[s, self.f_lo]) for s in range(len(sps))]
         n_hi = [int(offs[s, self.f_hi + 1] - offs[s, self.f_hi]) for s in range(len(sps))]

@@ -66,10 +66,15 @@ class Simulation:
             for _ in range(self.num_comm_round):
                 self.exchange.boundary_p(self)
         else:
+            # one rank: the only movers are particles that hit an absorbing wall (boundary_p.cc:268-275)
             for sp in self.species_list:
                 if sp.nm:
-                    raise RuntimeError(f"species {sp.name}: {sp.nm} movers left the domain but no boundary handler "
-                                       "is installed (absorbing walls need boundary_p)")
+                    _, offs = E.boundary_pack(sp, [-1] * 6, fa)
+                    o = offs.cpu()
+                    if int(o[8] - o[6]) != int(o[8]):
+                        raise RuntimeError(f"species {sp.name}: particles left through a face that is neither local, "
+                                           "absorbing nor shared with another rank (custom boundary handlers stay on "
+                                           "the host)")
         fa.clear_jf()
         E.unload_accumulator_array(fa, aa)
         fa.synchronize_jf()
