@@ -186,9 +186,10 @@ def run_ours(args):
                "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                "config": {"workload": f"uniform thermal e-/ion plasma, {args.grid}^3 cells per GPU, {args.ppc} ppc/species, "
-                                      f"periodic, sort_p every {args.sort_interval} steps (BASELINE.json configs[1])",
+                                      f"periodic, sort_p every {args.sort_interval} steps"
+                                      + (" (BASELINE.json configs[1])" if (args.grid, args.ppc) == (128, 64) else ""),
                           "particles_per_gpu": np_total_local, "decomposition": f"1x{world}x1 slabs",
-                          "l2": "particle arrays (8.6 GB per GPU) exceed the 126 MB L2; no flush needed",
+                          "l2": f"particle arrays ({np_total_local * 32 / 1e9:.1f} GB per GPU) exceed the 126 MB L2; no flush needed",
                           "deposit_variant": args.variant},
                "roofline": roofline, "gpu_launches": int(launches), "clocks": clocks}
     if args.e2e and world == 1:

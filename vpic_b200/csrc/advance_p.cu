@@ -31,7 +31,7 @@ constexpr int kMinBlocks = 3;            // resident CTAs per SM the register bu
 template <int VARIANT>
 __device__ __forceinline__ void deposit(const PushK &a, int vox, bool active, const float (&j)[12]) {
   if (VARIANT == VPB_DEPOSIT_WARP_SEG || VARIANT == VPB_DEPOSIT_WARP_SEG_MOVERS) {
-    deposit_warp_segmented(a.accum, a.astride, vox, active, j);
+    deposit_warp_segmented(a.accum, a.astride, vox, active, j, (a.dbg >> 8) ? (a.dbg >> 8) : kMinGroup);
   } else {
     if (active) deposit_red_v4(a.accum + (size_t)vox * a.astride, j);
   }

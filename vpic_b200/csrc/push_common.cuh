@@ -82,7 +82,7 @@ __device__ __forceinline__ void deposit_red_v4(float *a, const float (&j)[12]) {
 constexpr int kMinGroup = 6;
 
 __device__ __forceinline__ void deposit_warp_segmented(float *accum, int astride, int vox, bool active,
-                                                       const float (&j)[12]) {
+                                                       const float (&j)[12], int min_group = kMinGroup) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int key = active ? vox : (-1 - lane);
@@ -93,7 +93,7 @@ __device__ __forceinline__ void deposit_warp_segmented(float *accum, int astride
   const int v_first = __shfl_sync(full, vox, __ffs(amask) - 1);
   const bool uniform = __all_sync(full, !active || vox == v_first);
   const unsigned peers = uniform ? (active ? amask : 0u) : __match_any_sync(full, key);
-  const bool grouped = active && (__popc(peers) >= kMinGroup);
+  const bool grouped = active && (__popc(peers) >= min_group);
   if (active && !grouped) deposit_red_v4(accum + (size_t)vox * astride, j);
   unsigned big = __ballot_sync(full, grouped);
   while (big) {
