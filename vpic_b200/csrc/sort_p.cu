@@ -2,7 +2,8 @@
 //
 // Replaces src/species_advance/standard/pipeline/sort_p_pipeline.cc:30-371 (coarse_count / coarse_sort / subsort
 // over pthread pipelines).  The reference's two stable passes give exactly "stable sort by p.i"; so does this:
-// a least-significant-digit radix sort with 8-bit digits over only the bits nv needs, each pass a stable split
+// a least-significant-digit radix sort over only the bits nv needs (11-bit digits when that saves a pass, else
+// 8-bit), each pass a stable split
 //   (1) per-CTA digit histogram over the CTA's contiguous chunk,
 //   (2) exclusive scan of the [digit][CTA] matrix (digit-major),
 //   (3) stable scatter: inside a CTA, items are ranked warp by warp with __match_any_sync against per-warp digit
@@ -13,8 +14,6 @@
 
 namespace vpb {
 
-constexpr int kRadixBits = 8;
-constexpr int kRadix = 1 << kRadixBits;
 constexpr int kSortBlock = 256;
 constexpr int kSortWarps = kSortBlock / 32;
 constexpr int kIPT = 4;                                 // items per thread per sub-tile
@@ -95,11 +94,12 @@ static int exclusive_scan_inplace(int *data, int n, int *tmp /* >= ceil(n/kScanT
 // Items are VEC int4 words; the key is word KEYW's .w (particle_t.i and particle_mover_t.i sit in word 0,
 // the destination class of a particle_injector_t rides in word 2).
 
-template <int VEC, int KEYW>
+template <int VEC, int KEYW, int BITS>
 __global__ void __launch_bounds__(kSortBlock) radix_hist_kernel(const int4 *items, int n, int per_block, int shift,
-                                                                int *hist /* [kRadix][gridDim.x] */) {
-  __shared__ int s_hist[kRadix];
-  for (int d = threadIdx.x; d < kRadix; d += kSortBlock) s_hist[d] = 0;
+                                                                int *hist /* [1<<BITS][gridDim.x] */) {
+  constexpr int R = 1 << BITS;
+  __shared__ int s_hist[R];
+  for (int d = threadIdx.x; d < R; d += kSortBlock) s_hist[d] = 0;
   __syncthreads();
   const int lo = blockIdx.x * per_block;
   const int hi = min(n, lo + per_block);
@@ -107,29 +107,37 @@ __global__ void __launch_bounds__(kSortBlock) radix_hist_kernel(const int4 *item
   for (int i0 = lo; i0 < hi; i0 += kSortBlock) {
     const int i = i0 + threadIdx.x;
     const bool valid = i < hi;
-    const int d = valid ? ((items[(size_t)i * VEC + KEYW].w >> shift) & (kRadix - 1)) : (kRadix + lane);
+    const int d = valid ? ((items[(size_t)i * VEC + KEYW].w >> shift) & (R - 1)) : (R + lane);
     const unsigned peers = __match_any_sync(0xffffffffu, d);
     if (valid && lane == __ffs(peers) - 1) atomicAdd(&s_hist[d], __popc(peers));
   }
   __syncthreads();
-  for (int d = threadIdx.x; d < kRadix; d += kSortBlock) hist[d * gridDim.x + blockIdx.x] = s_hist[d];
+  for (int d = threadIdx.x; d < R; d += kSortBlock) hist[d * gridDim.x + blockIdx.x] = s_hist[d];
 }
 
-template <int VEC, int KEYW>
+// Stable scatter of one digit.  Shared memory: next output slot per digit (s_base), per-warp digit counters of the
+// current sub-tile (s_wcount) and a bitmap of the digits the sub-tile touched.  Only touched digits are prefixed and
+// re-zeroed, so an 11-bit digit (2048 bins x 8 warps) costs no more per sub-tile than an 8-bit one when the input is
+// nearly sorted (a sub-tile of voxel-ordered particles touches a few dozen digits).
+template <int VEC, int KEYW, int BITS>
 __global__ void __launch_bounds__(kSortBlock) radix_scatter_kernel(const int4 *src, int4 *dst, int n, int per_block,
                                                                    int shift, const int *offs /* scanned hist */) {
-  __shared__ int s_base[kRadix];                       // next output slot of each digit for this CTA
-  __shared__ int s_wcount[kSortWarps][kRadix];         // per-warp digit counts of the current sub-tile
+  constexpr int R = 1 << BITS;
+  constexpr int kWords = R / 32;
+  extern __shared__ int s_dyn[];
+  int *s_base = s_dyn;                                  // [R]
+  int *s_wcount = s_dyn + R;                            // [kSortWarps][R]
+  unsigned *s_touched = reinterpret_cast<unsigned *>(s_dyn + R + kSortWarps * R);   // [kWords]
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
-  for (int d = tid; d < kRadix; d += kSortBlock) s_base[d] = offs[d * gridDim.x + blockIdx.x];
+  for (int d = tid; d < R; d += kSortBlock) s_base[d] = offs[d * gridDim.x + blockIdx.x];
+  for (int d = tid; d < R * kSortWarps; d += kSortBlock) s_wcount[d] = 0;
+  for (int d = tid; d < kWords; d += kSortBlock) s_touched[d] = 0u;
   const int lo = blockIdx.x * per_block;
   const int hi = min(n, lo + per_block);
+  __syncthreads();
 
   for (int t0 = lo; t0 < hi; t0 += kSubTile) {
-    for (int d = tid; d < kRadix * kSortWarps; d += kSortBlock) (&s_wcount[0][0])[d] = 0;
-    __syncthreads();
-
     int4 it[kIPT][VEC];
     int digit[kIPT], rank[kIPT];
     // warp-striped: warp w owns items [t0 + w*32*kIPT, +32*kIPT); step j covers 32 consecutive items
@@ -148,32 +156,37 @@ __global__ void __launch_bounds__(kSortBlock) radix_scatter_kernel(const int4 *s
           for (int v = 0; v < VEC; v++) it[j][v] = src[(size_t)i * VEC + v];
         }
       }
-      const int d = valid ? ((it[j][KEYW].w >> shift) & (kRadix - 1)) : (kRadix + lane);
+      const int d = valid ? ((it[j][KEYW].w >> shift) & (R - 1)) : (R + lane);
       digit[j] = valid ? d : -1;
       const unsigned peers = __match_any_sync(0xffffffffu, d);
       int before = 0;
-      if (valid) before = s_wcount[w][d];
+      if (valid) before = s_wcount[w * R + d];
       __syncwarp();
-      if (valid && lane == __ffs(peers) - 1) s_wcount[w][d] = before + __popc(peers);
+      if (valid && lane == __ffs(peers) - 1) {
+        s_wcount[w * R + d] = before + __popc(peers);
+        if (before == 0) atomicOr(&s_touched[d >> 5], 1u << (d & 31));
+      }
       __syncwarp();
       rank[j] = before + __popc(peers & lt_mask);
     }
     __syncthreads();
-    // digit-wise exclusive prefix over warps; thread d owns digit d (kSortBlock == kRadix)
-    {
-      int run = 0;
+    // exclusive prefix over warps for every touched digit; thread t walks bitmap words t, t+256, ...
+    for (int word = tid; word < kWords; word += kSortBlock) {
+      unsigned bitsw = s_touched[word];
+      while (bitsw) {
+        const int d = word * 32 + __ffs(bitsw) - 1;
+        bitsw &= bitsw - 1;
+        int run = s_base[d];
 #pragma unroll
-      for (int ww = 0; ww < kSortWarps; ww++) { const int c = s_wcount[ww][tid]; s_wcount[ww][tid] = run; run += c; }
-      const int b = s_base[tid];
-      s_base[tid] = b + run;
-#pragma unroll
-      for (int ww = 0; ww < kSortWarps; ww++) s_wcount[ww][tid] += b;
+        for (int ww = 0; ww < kSortWarps; ww++) { const int c = s_wcount[ww * R + d]; s_wcount[ww * R + d] = run; run += c; }
+        s_base[d] = run;
+      }
     }
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < kIPT; j++) {
       if (digit[j] >= 0) {
-        const int o = s_wcount[w][digit[j]] + rank[j];
+        const int o = s_wcount[w * R + digit[j]] + rank[j];
         if (VEC == 2) {
           const int4 a0 = it[j][0], a1 = it[j][VEC - 1];
           st_particle(reinterpret_cast<float4 *>(dst) + 2 * (size_t)o,
@@ -183,6 +196,18 @@ __global__ void __launch_bounds__(kSortBlock) radix_scatter_kernel(const int4 *s
 #pragma unroll
           for (int v = 0; v < VEC; v++) dst[(size_t)o * VEC + v] = it[j][v];
         }
+      }
+    }
+    __syncthreads();
+    // re-zero the counters this sub-tile used
+    for (int word = tid; word < kWords; word += kSortBlock) {
+      unsigned bitsw = s_touched[word];
+      if (bitsw) s_touched[word] = 0u;
+      while (bitsw) {
+        const int d = word * 32 + __ffs(bitsw) - 1;
+        bitsw &= bitsw - 1;
+#pragma unroll
+        for (int ww = 0; ww < kSortWarps; ww++) s_wcount[ww * R + d] = 0;
       }
     }
     __syncthreads();
@@ -204,7 +229,8 @@ static int ceil_log2(int64_t x) { int b = 0; while (((int64_t)1 << b) < x) b++; 
 
 struct SortPlan { int nblocks, per_block, scan_tmp; size_t hist_bytes, total_bytes; };
 
-static SortPlan plan_sort(int n) {
+static SortPlan plan_sort(int n, int bits = 11) {
+  const int R = 1 << bits;
   SortPlan s;
   int nb = (n + kSubTile - 1) / kSubTile;
   if (nb < 1) nb = 1;
@@ -214,24 +240,40 @@ static SortPlan plan_sort(int n) {
   if (per < kSubTile) per = kSubTile;
   nb = (n + per - 1) / per; if (nb < 1) nb = 1;
   s.nblocks = nb; s.per_block = per;
-  s.scan_tmp = (kRadix * nb + kScanTile - 1) / kScanTile;
-  s.hist_bytes = (size_t)kRadix * nb * sizeof(int);
+  s.scan_tmp = (R * nb + kScanTile - 1) / kScanTile;
+  s.hist_bytes = (size_t)R * nb * sizeof(int);
   s.total_bytes = ((s.hist_bytes + 255) / 256) * 256 + (size_t)s.scan_tmp * sizeof(int) + 256;
   return s;
 }
 
-template <int VEC, int KEYW = 0>
+template <int VEC, int KEYW, int BITS>
+static int radix_pass(const int4 *src, int4 *dst, int n, int shift, const SortPlan &pl, int *hist, int *tmp, cudaStream_t st) {
+  constexpr int R = 1 << BITS;
+  constexpr size_t smem = ((size_t)R * (1 + kSortWarps) + R / 32) * sizeof(int);
+  static bool attr_done = false;
+  if (!attr_done) {
+    VPB_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<VEC, KEYW, BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  radix_hist_kernel<VEC, KEYW, BITS><<<pl.nblocks, kSortBlock, 0, st>>>(src, n, pl.per_block, shift, hist);  VPB_LAUNCH_CHECK();
+  int r = exclusive_scan_inplace(hist, R * pl.nblocks, tmp, st); if (r) return r;
+  radix_scatter_kernel<VEC, KEYW, BITS><<<pl.nblocks, kSortBlock, smem, st>>>(src, dst, n, pl.per_block, shift, hist);  VPB_LAUNCH_CHECK();
+  return 0;
+}
+
+// LSD radix sort of n items on the low key_bits of the key.  WIDE: 11-bit digits (two passes cover the 22 bits of a
+// 128^3 grid), else 8-bit digits (small arrays: movers, injectors).  The result ends in a or b (*result_in_b).
+template <int VEC, int KEYW, bool WIDE>
 static int radix_sort(int4 *a, int4 *b, int n, int key_bits, void *scratch, size_t scratch_bytes, cudaStream_t st,
                       bool *result_in_b) {
-  const SortPlan pl = plan_sort(n);
+  constexpr int BITS = WIDE ? 11 : 8;
+  const SortPlan pl = plan_sort(n, BITS);
   VPB_REQUIRE(scratch && scratch_bytes >= pl.total_bytes, "sort: scratch too small (%zu < %zu)", scratch_bytes, pl.total_bytes);
   int *hist = (int *)scratch;
   int *tmp = (int *)((char *)scratch + ((pl.hist_bytes + 255) / 256) * 256);
   int4 *src = a, *dst = b;
-  for (int shift = 0; shift < key_bits; shift += kRadixBits) {
-    radix_hist_kernel<VEC, KEYW><<<pl.nblocks, kSortBlock, 0, st>>>(src, n, pl.per_block, shift, hist);  VPB_LAUNCH_CHECK();
-    int r = exclusive_scan_inplace(hist, kRadix * pl.nblocks, tmp, st); if (r) return r;
-    radix_scatter_kernel<VEC, KEYW><<<pl.nblocks, kSortBlock, 0, st>>>(src, dst, n, pl.per_block, shift, hist);  VPB_LAUNCH_CHECK();
+  for (int shift = 0; shift < key_bits; shift += BITS) {
+    int r = radix_pass<VEC, KEYW, BITS>(src, dst, n, shift, pl, hist, tmp, st); if (r) return r;
     int4 *t = src; src = dst; dst = t;
   }
   *result_in_b = (src == b);
@@ -245,15 +287,15 @@ __global__ void split_offsets_kernel(const int *hist, int nblocks, int n, int *o
   if (c == 8) offs9[8] = n;
 }
 
-size_t radix_split_scratch_bytes(int n) { return plan_sort(n > 0 ? n : 1).total_bytes; }
+size_t radix_split_scratch_bytes(int n) { return plan_sort(n > 0 ? n : 1, 8).total_bytes; }
 
 // Stable split of particle_injector_t records (3 words) by the class in word 2 .w (0..7): one radix pass a -> b.
 int radix_split_injectors(int4 *a, int4 *b, int n, void *scratch, size_t scratch_bytes, cudaStream_t st,
                           int *class_offsets_dev) {
   bool in_b = false;
-  int r = radix_sort<3, 2>(a, b, n, 3, scratch, scratch_bytes, st, &in_b);
+  int r = radix_sort<3, 2, false>(a, b, n, 3, scratch, scratch_bytes, st, &in_b);
   if (r) return r;
-  const SortPlan pl = plan_sort(n);
+  const SortPlan pl = plan_sort(n, 8);
   split_offsets_kernel<<<1, 32, 0, st>>>((const int *)scratch, pl.nblocks, n, class_offsets_dev);
   VPB_LAUNCH_CHECK();
   return 0;
@@ -264,7 +306,7 @@ int radix_split_injectors(int4 *a, int4 *b, int n, void *scratch, size_t scratch
 using namespace vpb;
 
 extern "C" size_t vpb_sort_scratch_bytes(int32_t n_items, int32_t /*n_keys_hint*/) {
-  return plan_sort(n_items > 0 ? n_items : 1).total_bytes;
+  return plan_sort(n_items > 0 ? n_items : 1, 11).total_bytes;     // the wider plan covers both digit widths
 }
 
 extern "C" int vpb_sort_p(void *p, int32_t np, void *aux, int32_t *partition, int32_t nx, int32_t ny, int32_t nz,
@@ -277,7 +319,11 @@ extern "C" int vpb_sort_p(void *p, int32_t np, void *aux, int32_t *partition, in
   const int nv = (int)nv64;
   if (np > 1) {
     bool in_aux = false;
-    int r = radix_sort<2>((int4 *)p, (int4 *)aux, np, ceil_log2(nv), scratch, scratch_bytes, st, &in_aux);
+    // 11-bit digits when they save a pass (e.g. 22 key bits: 2 passes instead of 3), else 8-bit digits
+    const int kb = ceil_log2(nv);
+    const bool wide = (kb + 10) / 11 < (kb + 7) / 8;
+    int r = wide ? radix_sort<2, 0, true>((int4 *)p, (int4 *)aux, np, kb, scratch, scratch_bytes, st, &in_aux)
+                 : radix_sort<2, 0, false>((int4 *)p, (int4 *)aux, np, kb, scratch, scratch_bytes, st, &in_aux);
     if (r) return r;
     if (in_aux) VPB_CUDA(cudaMemcpyAsync(p, aux, (size_t)np * 32, cudaMemcpyDeviceToDevice, st));
   }
@@ -289,7 +335,7 @@ extern "C" int vpb_sort_p(void *p, int32_t np, void *aux, int32_t *partition, in
 
 extern "C" size_t vpb_sort_movers_scratch_bytes(int32_t nm) {
   if (nm < 1) nm = 1;
-  return (((size_t)nm * 16 + 255) / 256) * 256 + plan_sort(nm).total_bytes;
+  return (((size_t)nm * 16 + 255) / 256) * 256 + plan_sort(nm, 8).total_bytes;
 }
 
 // Movers: sort ascending by particle index (unique keys).  nm is a host value here; the drop-in layer reads the
@@ -302,7 +348,7 @@ extern "C" int vpb_sort_movers(void *pm, int32_t nm, void *scratch, size_t scrat
   const size_t aux_bytes = (((size_t)nm * 16 + 255) / 256) * 256;
   VPB_REQUIRE(scratch_bytes > aux_bytes, "vpb_sort_movers: scratch too small");
   bool in_aux = false;
-  int r = radix_sort<1>((int4 *)pm, (int4 *)scratch, nm, 31, (char *)scratch + aux_bytes, scratch_bytes - aux_bytes, st, &in_aux);
+  int r = radix_sort<1, 0, false>((int4 *)pm, (int4 *)scratch, nm, 31, (char *)scratch + aux_bytes, scratch_bytes - aux_bytes, st, &in_aux);
   if (r) return r;
   if (in_aux) VPB_CUDA(cudaMemcpyAsync(pm, scratch, (size_t)nm * 16, cudaMemcpyDeviceToDevice, st));
   return 0;
