@@ -260,7 +260,7 @@ extern "C" int vpb_advance_p(const vpb_push_args_t *args, void *stream) {
     attr_done = true;
   }
   const int ntiles = (args->np + kTile - 1) / kTile;
-  const int grid = ntiles < kSMs * 8 ? ntiles : kSMs * 8;
+  const int grid = ntiles < kSMs * 32 ? ntiles : kSMs * 32;   // many short CTAs: side-stream kernels slot in between them
   int variant = args->variant == VPB_DEPOSIT_DEFAULT ? VPB_DEPOSIT_WARP_SEG : args->variant;
   switch (variant) {
     case VPB_DEPOSIT_RED_V4:

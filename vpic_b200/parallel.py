@@ -68,15 +68,16 @@ class SlabExchange:
         pass
 
     # ---- particles ------------------------------------------------------------------------------------------
-    def boundary_p(self, sim):
-        """One communication round of boundary_p for every species (the caller loops num_comm_round times).
+    def boundary_p(self, sim, species=None, check_empty=True):
+        """One communication round of boundary_p for `species` (default: every species; the caller loops
+        num_comm_round times).
 
         A round in which no rank holds a mover is a no-op in the reference too (zero counts both ways); one tiny
         all-reduce finds that out, so the usual second and third rounds cost one collective instead of a full
         count/payload handshake."""
         dev = self.g.device
-        sps = sim.species_list
-        if self.ring.world > 1:
+        sps = sim.species_list if species is None else species
+        if self.ring.world > 1 and check_empty:
             left = torch.tensor([sum(sp.nm for sp in sps)], dtype=torch.int32, device=dev)
             dist.all_reduce(left, group=self.ring.group)
             if int(left.item()) == 0:

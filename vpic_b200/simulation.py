@@ -28,6 +28,8 @@ class Simulation:
         self.exchange = exchange          # parallel.SlabExchange for multi-GPU runs, None on one GPU
         self.deposit_variant = 0
         self.push_events = None           # list of (start, end) CUDA events around each advance_p when profiling
+        self.overlap_exchange = True      # multi-GPU: migrate species k while species k+1 is pushed
+        self._side = None
 
     def define_species(self, name, q, m, max_np, max_nm, sort_interval=20, sort_out_of_place=0):
         sp = E.Species(name, q, m, max_np, max_nm, sort_interval, sort_out_of_place, self.g)
@@ -52,6 +54,7 @@ class Simulation:
             if sp.sort_interval > 0 and step % sp.sort_interval == 0:
                 E.sort_p(sp)
         E.clear_accumulator_array(aa)
+        done = []
         for sp in self.species_list:
             if self.push_events is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -60,12 +63,33 @@ class Simulation:
             if self.push_events is not None:
                 e1.record()
                 self.push_events.append((e0, e1, sp.np))
-        E.finish_advance_p_all(self.species_list)
-        E.reduce_accumulator_array(aa)
-        if self.exchange is not None:
+            if self.exchange is not None:
+                ev = torch.cuda.Event()
+                ev.record()
+                done.append(ev)
+        if self.exchange is not None and self.overlap_exchange:
+            # First migration round per species on a side stream: species k's movers are packed, exchanged over NCCL
+            # and injected while species k+1 is still being pushed (injection deposits are atomics, like the push's).
+            main = torch.cuda.current_stream()
+            if self._side is None:
+                self._side = torch.cuda.Stream(priority=-1)
+            with torch.cuda.stream(self._side):
+                for sp, ev in zip(self.species_list, done):
+                    self._side.wait_event(ev)
+                    E.finish_advance_p_all([sp])
+                    self.exchange.boundary_p(self, species=[sp], check_empty=False)
+            main.wait_stream(self._side)
+            E.reduce_accumulator_array(aa)
+            for _ in range(self.num_comm_round - 1):
+                self.exchange.boundary_p(self)
+        elif self.exchange is not None:
+            E.finish_advance_p_all(self.species_list)
+            E.reduce_accumulator_array(aa)
             for _ in range(self.num_comm_round):
                 self.exchange.boundary_p(self)
         else:
+            E.finish_advance_p_all(self.species_list)
+            E.reduce_accumulator_array(aa)
             # one rank: the only movers are particles that hit an absorbing wall (boundary_p.cc:268-275)
             for sp in self.species_list:
                 if sp.nm:
