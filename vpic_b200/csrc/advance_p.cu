@@ -31,14 +31,14 @@ constexpr int kMinBlocks = 3;            // resident CTAs per SM the register bu
 template <int VARIANT>
 __device__ __forceinline__ void deposit(const PushK &a, int vox, bool active, const float (&j)[12]) {
   if (VARIANT == VPB_DEPOSIT_WARP_SEG || VARIANT == VPB_DEPOSIT_WARP_SEG_MOVERS) {
-    deposit_warp_segmented(a.accum, a.astride, vox, active, j, (a.dbg >> 8) ? (a.dbg >> 8) : kMinGroup);
+    deposit_warp_segmented(a.accum, a.astride, vox, active, j, ((a.dbg >> 8) & 0xff) ? ((a.dbg >> 8) & 0xff) : kMinGroup);
   } else {
     if (active) deposit_red_v4(a.accum + (size_t)vox * a.astride, j);
   }
 }
 
 constexpr int kWarps = kBlock / 32;
-constexpr int kSpan  = 16;                 // consecutive rows a warp takes before jumping ahead
+constexpr int kSpan  = 64;                 // consecutive rows a warp takes before jumping ahead
 constexpr int kQCap  = 64;                 // a warp's queue holds at most 31 carried-over + 32 new movers
 constexpr size_t kSmemBytes = (size_t)kWarps * 3 * kQCap * sizeof(int4);
 
@@ -94,9 +94,10 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) advance_p_kernel(const Pus
 
   // Rows are dealt to warps in spans of kSpan consecutive rows: consecutive rows of voxel-sorted particles share
   // their interpolator (64 ppc = 2 rows per voxel), so a warp's next gather usually hits the lines it just used.
-  const int n_spans = (n_rows + kSpan - 1) / kSpan;
+  const int span_rows = ((a.dbg >> 16) & 0xff) ? ((a.dbg >> 16) & 0xff) : kSpan;    // profiling override
+  const int n_spans = (n_rows + span_rows - 1) / span_rows;
   int span = blockIdx.x * kWarps + w;
-  int row = span * kSpan;
+  int row = span * span_rows;
   float4 rn = make_float4(0.f, 0.f, 0.f, 0.f), un_next = rn;
   if (span < n_spans && row * 32 + lane < a.np) ld_particle(a.p + 2 * (size_t)(a.first + row * 32 + lane), rn, un_next);
 
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) advance_p_kernel(const Pus
     const bool valid = row * 32 + lane < a.np;
     // advance to the next row of this warp (same span, or the first row of its next span) and request it now
     int next_row = row + 1, next_span = span;
-    if (next_row == (span + 1) * kSpan || next_row >= n_rows) { next_span = span + warps_total; next_row = next_span * kSpan; }
+    if (next_row == (span + 1) * span_rows || next_row >= n_rows) { next_span = span + warps_total; next_row = next_span * span_rows; }
     if (next_span < n_spans && next_row * 32 + lane < a.np)
       ld_particle(a.p + 2 * (size_t)(a.first + next_row * 32 + lane), rn, un_next);
     const int ii = __float_as_int(r.w);
@@ -260,7 +261,8 @@ extern "C" int vpb_advance_p(const vpb_push_args_t *args, void *stream) {
     attr_done = true;
   }
   const int ntiles = (args->np + kTile - 1) / kTile;
-  const int grid = ntiles < kSMs * 32 ? ntiles : kSMs * 32;   // many short CTAs: side-stream kernels slot in between them
+  const int gmul = ((args->debug_skip >> 24) & 0xff) ? ((args->debug_skip >> 24) & 0xff) : 32;     // profiling override
+  const int grid = ntiles < kSMs * gmul ? ntiles : kSMs * gmul;   // many short CTAs: side-stream kernels slot in between them
   int variant = args->variant == VPB_DEPOSIT_DEFAULT ? VPB_DEPOSIT_WARP_SEG : args->variant;
   switch (variant) {
     case VPB_DEPOSIT_RED_V4:
