@@ -48,6 +48,31 @@ def test_reference_kat_deck_passes_on_gpu_path(deck):
     assert "pass" in out and "FAIL" not in out and "fail" not in out.replace("fail 0", ""), out[-2000:]
 
 
+@pytest.mark.parametrize("deck", ["simple", "reconnection_test"])
+def test_reference_to_completion_deck_runs_on_gpu_path(deck):
+    """test/integrated/to_completion ("does not die" in the reference's own CTest): whole vpic_simulation::advance loop,
+    two species, sorts, divergence cleaning on the host, dumps — with the hot path on the GPU through LD_PRELOAD.
+    reconnection_test also writes an energies history, which must match the CPU run of the same binary."""
+    path = _need(f"{deck}.scalar")
+    hist = {}
+    for tag, preload in (("cpu", False), ("gpu", True)):
+        d = tempfile.mkdtemp(prefix=f"{deck}_{tag}_")
+        try:
+            rc, out = _run(path, ["--tpp", "1"], preload, d)
+            assert rc == 0 and "normal exit" in out, out[-2000:]
+            en = os.path.join(d, "rundata", "energies")
+            if os.path.exists(en):
+                rows = [ln.split() for ln in open(en) if ln.strip() and not ln.startswith("%")]
+                hist[tag] = np.array([[float(x) for x in r] for r in rows if len(r) > 3])
+        finally:
+            shutil.rmtree(d, ignore_errors=True)
+    if "cpu" in hist:
+        a, b = hist["cpu"], hist["gpu"]
+        assert a.shape == b.shape and len(a) > 0
+        tot_a, tot_b = a[:, 1:].sum(axis=1), b[:, 1:].sum(axis=1)
+        np.testing.assert_allclose(tot_b, tot_a, rtol=1e-4)
+
+
 def test_harris_energy_history_matches_reference():
     path = _need("harris.scalar")
     hist = {}
