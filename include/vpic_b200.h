@@ -101,6 +101,8 @@ typedef struct vpb_push_args {
 #define VPB_DEPOSIT_WARP_SEG     2   /* in-voxel streaks: warp-level segmented reduction by voxel, one RED per sum;
                                         crossing streaks (move_p): 3 vector REDs each                     */
 #define VPB_DEPOSIT_WARP_SEG_MOVERS 3 /* as 2, and move_p runs warp-synchronously with the same segmented reduction */
+#define VPB_DEPOSIT_WARP_SEG_FIRST  4 /* as 2, and the FIRST streak of a mover batch (still in the source voxels) is
+                                        summed across the warp; later streaks go out as vector REDs          */
 
 int vpb_advance_p(const vpb_push_args_t *args, void *stream);
 

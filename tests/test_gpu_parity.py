@@ -72,7 +72,7 @@ PUSH_CASES = [
 
 
 @pytest.mark.parametrize("use_rule", [True, False])
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])
 @pytest.mark.parametrize("dims,uth,pbc,n,sort_first", PUSH_CASES)
 def test_advance_p(eng, oracle, dims, uth, pbc, n, sort_first, variant, use_rule):
     rng = np.random.default_rng(17)

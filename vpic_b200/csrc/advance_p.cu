@@ -30,7 +30,7 @@ constexpr int kMinBlocks = 3;            // resident CTAs per SM the register bu
 
 template <int VARIANT>
 __device__ __forceinline__ void deposit(const PushK &a, int vox, bool active, const float (&j)[12]) {
-  if (VARIANT == VPB_DEPOSIT_WARP_SEG || VARIANT == VPB_DEPOSIT_WARP_SEG_MOVERS) {
+  if (VARIANT == VPB_DEPOSIT_WARP_SEG || VARIANT == VPB_DEPOSIT_WARP_SEG_MOVERS || VARIANT == VPB_DEPOSIT_WARP_SEG_FIRST) {
     deposit_warp_segmented(a.accum, a.astride, vox, active, j, ((a.dbg >> 8) & 0xff) ? ((a.dbg >> 8) & 0xff) : kMinGroup);
   } else {
     if (active) deposit_red_v4(a.accum + (size_t)vox * a.astride, j);
@@ -58,7 +58,8 @@ __device__ __forceinline__ void run_movers(const PushK &a, const int4 *q0, const
     i = w2.w;
   }
   int left;
-  if (VARIANT == VPB_DEPOSIT_WARP_SEG_MOVERS) left = move_p_warp(a, act, rr, uu, dispx, dispy, dispz);
+  if (VARIANT == VPB_DEPOSIT_WARP_SEG_MOVERS) left = move_p_warp<false, true>(a, act, rr, uu, dispx, dispy, dispz);
+  else if (VARIANT == VPB_DEPOSIT_WARP_SEG_FIRST) left = move_p_warp<true, false>(a, act, rr, uu, dispx, dispy, dispz);
   else left = act ? move_p_dev(a, rr, uu, dispx, dispy, dispz) : 0;
   if (act) {
     if (left) {
@@ -258,6 +259,7 @@ extern "C" int vpb_advance_p(const vpb_push_args_t *args, void *stream) {
     VPB_CUDA(cudaFuncSetAttribute(advance_p_kernel<VPB_DEPOSIT_RED_V4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     VPB_CUDA(cudaFuncSetAttribute(advance_p_kernel<VPB_DEPOSIT_WARP_SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     VPB_CUDA(cudaFuncSetAttribute(advance_p_kernel<VPB_DEPOSIT_WARP_SEG_MOVERS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    VPB_CUDA(cudaFuncSetAttribute(advance_p_kernel<VPB_DEPOSIT_WARP_SEG_FIRST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     attr_done = true;
   }
   const int ntiles = (args->np + kTile - 1) / kTile;
@@ -271,6 +273,8 @@ extern "C" int vpb_advance_p(const vpb_push_args_t *args, void *stream) {
       advance_p_kernel<VPB_DEPOSIT_WARP_SEG><<<grid, kBlock, kSmemBytes, as_stream(stream)>>>(k); break;
     case VPB_DEPOSIT_WARP_SEG_MOVERS:
       advance_p_kernel<VPB_DEPOSIT_WARP_SEG_MOVERS><<<grid, kBlock, kSmemBytes, as_stream(stream)>>>(k); break;
+    case VPB_DEPOSIT_WARP_SEG_FIRST:
+      advance_p_kernel<VPB_DEPOSIT_WARP_SEG_FIRST><<<grid, kBlock, kSmemBytes, as_stream(stream)>>>(k); break;
     default:
       VPB_REQUIRE(false, "vpb_advance_p: unknown deposit variant %d", variant);
   }

@@ -124,111 +124,96 @@ __device__ __forceinline__ void deposit_warp_segmented(float *accum, int astride
   }
 }
 
-// move_p, scalar variant of the reference (move_p.cc:216-378), on registers.
-// r = {dx,dy,dz,i}, u = {ux,uy,uz,w}; returns 1 when the particle left the local domain (r.w = 8*voxel+face).
+// One streak of move_p, scalar variant of the reference (move_p.cc:233-375), on registers: advance the particle to
+// the first cell face on its way (or to the end of its displacement), produce the 12 accumulator increments of that
+// streak for voxel dep_vox, and apply the face's boundary action.
+// r = {dx,dy,dz,-}, u = {ux,uy,uz,w}, vox = current voxel.  Returns 0 = displacement used up, 1 = the particle left
+// the local domain (vox = 8*voxel+face), 2 = more streaks to do.
+__device__ __forceinline__ int streak_step(const PushK &a, float q, float4 &r, float4 &u, int &vox,
+                                           float &dispx, float &dispy, float &dispz, float (&j)[12]) {
+  float s_midx = r.x, s_midy = r.y, s_midz = r.z;
+  float s_dispx = dispx, s_dispy = dispy, s_dispz = dispz;
+  const float dirx = (s_dispx > 0.0f) ? 1.0f : -1.0f;
+  const float diry = (s_dispy > 0.0f) ? 1.0f : -1.0f;
+  const float dirz = (s_dispz > 0.0f) ? 1.0f : -1.0f;
+  const float v0 = (s_dispx == 0.0f) ? 3.4e38f : __fdiv_rn(dirx - s_midx, s_dispx);
+  const float v1 = (s_dispy == 0.0f) ? 3.4e38f : __fdiv_rn(diry - s_midy, s_dispy);
+  const float v2 = (s_dispz == 0.0f) ? 3.4e38f : __fdiv_rn(dirz - s_midz, s_dispz);
+  float v3 = 2.0f; int axis = 3;
+  if (v0 < v3) { v3 = v0; axis = 0; }
+  if (v1 < v3) { v3 = v1; axis = 1; }
+  if (v2 < v3) { v3 = v2; axis = 2; }
+  v3 *= 0.5f;
+  s_dispx *= v3; s_dispy *= v3; s_dispz *= v3;
+  s_midx += s_dispx; s_midy += s_dispy; s_midz += s_dispz;
+  // the reference multiplies by the double constant 1.0/3.0 here (move_p.cc:277)
+  const float v5 = (float)((double)(((q * s_dispx) * s_dispy) * s_dispz) * (1.0 / 3.0));
+  streak_currents(q, s_dispx, s_dispy, s_dispz, s_midx, s_midy, s_midz, v5, j);
+  dispx -= s_dispx; dispy -= s_dispy; dispz -= s_dispz;
+  r.x += s_dispx + s_dispx; r.y += s_dispy + s_dispy; r.z += s_dispz + s_dispz;
+  if (axis == 3) return 0;
+  const float dir = (axis == 0) ? dirx : (axis == 1) ? diry : dirz;
+  if (axis == 0) r.x = dir; else if (axis == 1) r.y = dir; else r.z = dir;   // exactly on the face
+  const int face = axis + ((dir > 0.0f) ? 3 : 0);
+  const long long nb = neighbor_of(a, vox, face);
+  if (nb == -1) {                                        // reflect_particles
+    if (axis == 0) { u.x = -u.x; dispx = -dispx; }
+    else if (axis == 1) { u.y = -u.y; dispy = -dispy; }
+    else { u.z = -u.z; dispz = -dispz; }
+    return 2;
+  }
+  if (nb < a.rangel || nb > a.rangeh) { vox = 8 * vox + face; return 1; }
+  vox = (int)(nb - a.rangel);
+  if (axis == 0) r.x = -dir; else if (axis == 1) r.y = -dir; else r.z = -dir;
+  return 2;
+}
+
+// move_p for one particle per thread: every streak goes to memory as three vector REDs.
 __device__ __forceinline__ int move_p_dev(const PushK &a, float4 &r, float4 &u, float &dispx, float &dispy, float &dispz) {
   const float q = a.qsp * u.w;
   int vox = __float_as_int(r.w);
-  int ret = 0;
-  for (;;) {
-    float s_midx = r.x, s_midy = r.y, s_midz = r.z;
-    float s_dispx = dispx, s_dispy = dispy, s_dispz = dispz;
-    const float dirx = (s_dispx > 0.0f) ? 1.0f : -1.0f;
-    const float diry = (s_dispy > 0.0f) ? 1.0f : -1.0f;
-    const float dirz = (s_dispz > 0.0f) ? 1.0f : -1.0f;
-    const float v0 = (s_dispx == 0.0f) ? 3.4e38f : __fdiv_rn(dirx - s_midx, s_dispx);
-    const float v1 = (s_dispy == 0.0f) ? 3.4e38f : __fdiv_rn(diry - s_midy, s_dispy);
-    const float v2 = (s_dispz == 0.0f) ? 3.4e38f : __fdiv_rn(dirz - s_midz, s_dispz);
-    float v3 = 2.0f; int axis = 3;
-    if (v0 < v3) { v3 = v0; axis = 0; }
-    if (v1 < v3) { v3 = v1; axis = 1; }
-    if (v2 < v3) { v3 = v2; axis = 2; }
-    v3 *= 0.5f;
-    s_dispx *= v3; s_dispy *= v3; s_dispz *= v3;
-    s_midx += s_dispx; s_midy += s_dispy; s_midz += s_dispz;
-    // the reference multiplies by the double constant 1.0/3.0 here (move_p.cc:277)
-    const float v5 = (float)((double)(((q * s_dispx) * s_dispy) * s_dispz) * (1.0 / 3.0));
+  int st;
+  do {
     float j[12];
-    streak_currents(q, s_dispx, s_dispy, s_dispz, s_midx, s_midy, s_midz, v5, j);
-    deposit_red_v4(a.accum + (size_t)vox * a.astride, j);
-    dispx -= s_dispx; dispy -= s_dispy; dispz -= s_dispz;
-    r.x += s_dispx + s_dispx; r.y += s_dispy + s_dispy; r.z += s_dispz + s_dispz;
-    if (axis == 3) break;
-    const float dir = (axis == 0) ? dirx : (axis == 1) ? diry : dirz;
-    if (axis == 0) r.x = dir; else if (axis == 1) r.y = dir; else r.z = dir;   // exactly on the face
-    const int face = axis + ((dir > 0.0f) ? 3 : 0);
-    const long long nb = neighbor_of(a, vox, face);
-    if (nb == -1) {                                        // reflect_particles
-      if (axis == 0) { u.x = -u.x; dispx = -dispx; }
-      else if (axis == 1) { u.y = -u.y; dispy = -dispy; }
-      else { u.z = -u.z; dispz = -dispz; }
-      continue;
-    }
-    if (nb < a.rangel || nb > a.rangeh) { vox = 8 * vox + face; ret = 1; break; }
-    vox = (int)(nb - a.rangel);
-    if (axis == 0) r.x = -dir; else if (axis == 1) r.y = -dir; else r.z = -dir;
-  }
+    const int dep_vox = vox;
+    st = streak_step(a, q, r, u, vox, dispx, dispy, dispz, j);
+    deposit_red_v4(a.accum + (size_t)dep_vox * a.astride, j);
+  } while (st == 2);
   r.w = __int_as_float(vox);
-  return ret;
+  return st;
 }
 
-
-// Warp-synchronous move_p: all 32 lanes call it together (lanes without a mover pass active = false) and walk the
-// streak loop in lock step, so each round's deposits can be summed across the warp by voxel before they reach
-// memory.  Movers of one tile come from a handful of neighbouring voxels, so most rounds collapse into a few REDs.
+// move_p for a warp-wide batch.  FIRST_SEG: every mover's first streak lies in the voxel it was queued from, and a
+// batch is queued from two or three neighbouring voxels, so the first streaks are summed across the warp by voxel
+// (one RED per sum) — the later streaks scatter to the face neighbours and go out as per-lane vector REDs.
+// ALL_SEG: every round is summed across the warp (kept for comparison).
+template <bool FIRST_SEG, bool ALL_SEG>
 __device__ __forceinline__ int move_p_warp(const PushK &a, bool active, float4 &r, float4 &u,
                                            float &dispx, float &dispy, float &dispz) {
   const float q = a.qsp * u.w;
   int vox = __float_as_int(r.w);
-  int ret = 0;
-  bool live = active;
-  while (__any_sync(0xffffffffu, live)) {
+  int st = active ? 2 : 0;
+  bool first = true;
+  while (__any_sync(0xffffffffu, st == 2)) {
     float j[12];
     const int dep_vox = vox;
-    const bool dep = live;
-    if (live) {
-      float s_midx = r.x, s_midy = r.y, s_midz = r.z;
-      float s_dispx = dispx, s_dispy = dispy, s_dispz = dispz;
-      const float dirx = (s_dispx > 0.0f) ? 1.0f : -1.0f;
-      const float diry = (s_dispy > 0.0f) ? 1.0f : -1.0f;
-      const float dirz = (s_dispz > 0.0f) ? 1.0f : -1.0f;
-      const float v0 = (s_dispx == 0.0f) ? 3.4e38f : __fdiv_rn(dirx - s_midx, s_dispx);
-      const float v1 = (s_dispy == 0.0f) ? 3.4e38f : __fdiv_rn(diry - s_midy, s_dispy);
-      const float v2 = (s_dispz == 0.0f) ? 3.4e38f : __fdiv_rn(dirz - s_midz, s_dispz);
-      float v3 = 2.0f; int axis = 3;
-      if (v0 < v3) { v3 = v0; axis = 0; }
-      if (v1 < v3) { v3 = v1; axis = 1; }
-      if (v2 < v3) { v3 = v2; axis = 2; }
-      v3 *= 0.5f;
-      s_dispx *= v3; s_dispy *= v3; s_dispz *= v3;
-      s_midx += s_dispx; s_midy += s_dispy; s_midz += s_dispz;
-      const float v5 = (float)((double)(((q * s_dispx) * s_dispy) * s_dispz) * (1.0 / 3.0));   // move_p.cc:277
-      streak_currents(q, s_dispx, s_dispy, s_dispz, s_midx, s_midy, s_midz, v5, j);
-      dispx -= s_dispx; dispy -= s_dispy; dispz -= s_dispz;
-      r.x += s_dispx + s_dispx; r.y += s_dispy + s_dispy; r.z += s_dispz + s_dispz;
-      if (axis == 3) {
-        live = false;
-      } else {
-        const float dir = (axis == 0) ? dirx : (axis == 1) ? diry : dirz;
-        if (axis == 0) r.x = dir; else if (axis == 1) r.y = dir; else r.z = dir;
-        const int face = axis + ((dir > 0.0f) ? 3 : 0);
-        const long long nb = neighbor_of(a, vox, face);
-        if (nb == -1) {
-          if (axis == 0) { u.x = -u.x; dispx = -dispx; }
-          else if (axis == 1) { u.y = -u.y; dispy = -dispy; }
-          else { u.z = -u.z; dispz = -dispz; }
-        } else if (nb < a.rangel || nb > a.rangeh) {
-          vox = 8 * vox + face; ret = 1; live = false;
-        } else {
-          vox = (int)(nb - a.rangel);
-          if (axis == 0) r.x = -dir; else if (axis == 1) r.y = -dir; else r.z = -dir;
-        }
-      }
+    const bool dep = (st == 2);
+    if (dep) st = streak_step(a, q, r, u, vox, dispx, dispy, dispz, j);
+    if (ALL_SEG || (FIRST_SEG && first)) deposit_warp_segmented(a.accum, a.astride, dep_vox, dep, j);
+    else if (dep) deposit_red_v4(a.accum + (size_t)dep_vox * a.astride, j);
+    first = false;
+    if (!ALL_SEG && FIRST_SEG) break;                    // the remaining streaks run per lane below
+  }
+  if (!ALL_SEG && FIRST_SEG) {
+    while (st == 2) {
+      float j[12];
+      const int dep_vox = vox;
+      st = streak_step(a, q, r, u, vox, dispx, dispy, dispz, j);
+      deposit_red_v4(a.accum + (size_t)dep_vox * a.astride, j);
     }
-    deposit_warp_segmented(a.accum, a.astride, dep_vox, dep, j);
   }
   r.w = __int_as_float(vox);
-  return ret;
+  return st;
 }
 
 static inline PushK to_push_k(const vpb_push_args_t *args) {

@@ -50,7 +50,7 @@ class FieldArgs(C.Structure):
                 ("face", c_i32 * 6)]
 
 
-DEPOSIT_DEFAULT, DEPOSIT_RED_V4, DEPOSIT_WARP_SEG, DEPOSIT_WARP_SEG_MOVERS = 0, 1, 2, 3
+DEPOSIT_DEFAULT, DEPOSIT_RED_V4, DEPOSIT_WARP_SEG, DEPOSIT_WARP_SEG_MOVERS, DEPOSIT_WARP_SEG_FIRST = 0, 1, 2, 3, 4
 FACE_PERIODIC_SELF, FACE_REMOTE = 0, 1
 HALO_TANG_B, HALO_JF = 0, 1
 
