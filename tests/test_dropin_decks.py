@@ -48,6 +48,25 @@ def test_reference_kat_deck_passes_on_gpu_path(deck):
     assert "pass" in out and "FAIL" not in out and "fail" not in out.replace("fail 0", ""), out[-2000:]
 
 
+def test_reference_golden_energy_test_passes_on_gpu_path():
+    """test/unit/energy_comparison/3d_test.cc — the reference's own golden-vector test of the whole step loop (16^3
+    cells, 16 ppc, 2 species, 50 steps, dump_energies every step) compares itself against energies_gold.3d_test with
+    the reference's tolerances.  Here the unmodified test binary runs with the hot path on the GPU."""
+    path = _need("3d_test.scalar")
+    gold = os.path.join(REF, "energies_gold.3d_test")
+    for preload in (False, True):
+        with tempfile.TemporaryDirectory() as d:
+            shutil.copy(gold, d)
+            rc, out = _run(path, ["--tpp", "1"], preload, d)
+            assert rc == 0 and "All tests passed" in out, out[-2000:]
+            if preload:
+                mine = np.loadtxt(os.path.join(d, "energies"), comments="%")
+                ref = np.loadtxt(gold, comments="%")
+                n = min(len(mine), len(ref))
+                # much tighter than the reference's own 1 % / 3 % / 30 %: kinetic energies to 1e-5
+                assert np.abs(mine[:n, -2:] - ref[:n, -2:]).max() / np.abs(ref[:n, -2:]).max() < 1e-5
+
+
 @pytest.mark.parametrize("deck", ["simple", "reconnection_test"])
 def test_reference_to_completion_deck_runs_on_gpu_path(deck):
     """test/integrated/to_completion ("does not die" in the reference's own CTest): whole vpic_simulation::advance loop,
