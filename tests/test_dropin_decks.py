@@ -48,20 +48,24 @@ def test_reference_kat_deck_passes_on_gpu_path(deck):
     assert "pass" in out and "FAIL" not in out and "fail" not in out.replace("fail 0", ""), out[-2000:]
 
 
-def test_reference_golden_energy_test_passes_on_gpu_path():
-    """test/unit/energy_comparison/3d_test.cc — the reference's own golden-vector test of the whole step loop (16^3
-    cells, 16 ppc, 2 species, 50 steps, dump_energies every step) compares itself against energies_gold.3d_test with
-    the reference's tolerances.  Here the unmodified test binary runs with the hot path on the GPU."""
-    path = _need("3d_test.scalar")
-    gold = os.path.join(REF, "energies_gold.3d_test")
+@pytest.mark.parametrize("binary,gold,tpp", [("3d_test", "energies_gold.3d_test", 1),
+                                             ("3d_test_threaded", "energies_gold.3d_test_threaded", 8),
+                                             ("weibel_driver", "energies_gold.weibel_driver", 1)])
+def test_reference_golden_energy_test_passes_on_gpu_path(binary, gold, tpp):
+    """test/unit/energy_comparison — the reference's own golden-vector tests of the whole step loop (3d_test: 16^3
+    cells, 16 ppc, 2 species, 50 steps; its --tpp 8 variant, whose particle load differs; weibel_driver: 700 steps)
+    compare themselves against energies_gold.* with the reference's tolerances.  Here the unmodified test binaries
+    run with the hot path on the GPU."""
+    path = _need(f"{binary}.scalar")
+    goldp = os.path.join(REF, gold)
     for preload in (False, True):
         with tempfile.TemporaryDirectory() as d:
-            shutil.copy(gold, d)
-            rc, out = _run(path, ["--tpp", "1"], preload, d)
+            shutil.copy(goldp, d)
+            rc, out = _run(path, ["--tpp", str(tpp)], preload, d)
             assert rc == 0 and "All tests passed" in out, out[-2000:]
             if preload:
                 mine = np.loadtxt(os.path.join(d, "energies"), comments="%")
-                ref = np.loadtxt(gold, comments="%")
+                ref = np.loadtxt(goldp, comments="%")
                 n = min(len(mine), len(ref))
                 # much tighter than the reference's own 1 % / 3 % / 30 %: kinetic energies to 1e-5
                 assert np.abs(mine[:n, -2:] - ref[:n, -2:]).max() / np.abs(ref[:n, -2:]).max() < 1e-5
