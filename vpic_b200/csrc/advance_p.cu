@@ -9,23 +9,23 @@
 // particle state (offsets, voxel index, momentum) is bit-identical to the scalar CPU build.  Deposited currents
 // are the same per-particle values; only the order of the fp32 sums differs (atomics).
 //
-// Mapping to the machine (HBM-bound, no tensor cores — see DESIGN.md):
-//   * one thread per particle, a CTA walks tiles of kTile consecutive particles (voxel-sorted by sort_p), so a
-//     warp's 32 particles sit in one or two voxels: its five 128-bit interpolator loads are L1 broadcasts;
-//   * particles move as two 128-bit halves ({dx,dy,dz,i} and {ux,uy,uz,w}); a warp's two loads cover the same
-//     eight 128-byte lines, so HBM sees each line once;
+// Mapping to the machine (no tensor cores: there is no contraction on this path — see DESIGN.md §3.1):
+//   * one thread per particle; every warp is autonomous (no block-wide barrier) and takes spans of kSpan consecutive
+//     rows of 32 voxel-sorted particles, so its five read-only interpolator loads are mostly L1 broadcasts/hits;
+//   * a particle is one 32-byte sector: one 256-bit load (no L1 allocation) and one 256-bit store each; the next
+//     row is requested before the current one is processed;
+//   * in-voxel streaks are summed across the warp by voxel before any atomic (deposit_warp_segmented);
 //   * particles that leave their voxel are NOT moved inline (one crossing lane would stall its 31 neighbours
-//     through the whole streak loop): they are queued in shared memory and finished by the CTA as a dense batch
-//     after the tile, which keeps both phases convergent;
-//   * deposit strategies (args.variant) — see deposit.cuh.
+//     through the whole streak loop): their full state goes to a per-warp queue in shared memory and is finished
+//     32 at a time by the same warp, which keeps both phases convergent;
+//   * args.variant selects the deposit strategy (VPB_DEPOSIT_*), args.debug_skip the profiling ablations.
 #include "push_common.cuh"
 #include <string.h>
 
 namespace vpb {
 
 constexpr int kBlock = 256;
-constexpr int kPPT   = 4;                 // rows per warp used to size the grid
-constexpr int kTile  = kBlock * kPPT;
+constexpr int kTile  = kBlock * 4;        // particles per CTA used only to size the grid
 constexpr int kMinBlocks = 3;            // resident CTAs per SM the register budget is tuned for
 
 template <int VARIANT>

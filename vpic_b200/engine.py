@@ -191,17 +191,7 @@ def advance_p(sp: Species, aa: AccumulatorArray, ia: InterpolatorArray, variant=
 
 def finish_advance_p(sp: Species):
     """Read back the mover count (sp->nm) and put the movers in ascending particle order for boundary_p."""
-    L = _lib.load()
-    c = sp.counters.cpu()
-    sp.nm = min(int(c[0]), sp.max_nm)
-    sp.n_ignored = int(c[1])
-    if sp.n_ignored:
-        import warnings
-        warnings.warn(f"species {sp.name} ran out of storage for {sp.n_ignored} movers")   # advance_p_pipeline.cc:313-329
-    if sp.nm > 1:
-        need = L.vpb_sort_movers_scratch_bytes(sp.nm)
-        scratch = torch.empty(need, dtype=torch.uint8, device=sp.g.device)
-        _lib.check(L.vpb_sort_movers(_ptr(sp.pm), sp.nm, _ptr(scratch), need, _stream()), "sort_movers")
+    finish_advance_p_all([sp])
 
 
 def finish_advance_p_all(species):
