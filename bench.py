@@ -85,6 +85,10 @@ def build_sim(args, rank, world, device):
     from vpic_b200 import engine as E, grid as G, simulation as S
     n = args.grid
     nx, ny, nz = n, n, n
+    if args.scaling == "strong":                       # fixed global box, y split over the ranks
+        if n % world:
+            raise SystemExit("--scaling strong needs grid divisible by the number of GPUs")
+        ny = n // world
     dt = G.courant_dt(1.0, 1.0, 1.0, nx, ny * world, nz, frac=0.99)
     g = G.partition_periodic_box(0, 0, 0, nx, ny * world, nz, nx, ny * world, nz, 1, world, 1, rank=rank, dt=dt)
     dg = E.DeviceGrid(g, device)
@@ -184,8 +188,9 @@ def run_ours(args):
     if rank == 0:
         out = {"metric": "particle pushes/sec (advance_p+deposit)", "value": value, "unit": "pushes/s",
                "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
-               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-               "config": {"workload": f"uniform thermal e-/ion plasma, {args.grid}^3 cells per GPU, {args.ppc} ppc/species, "
+               "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "config": {"workload": f"uniform thermal e-/ion plasma, {args.grid}^3 cells "
+                                      + ("per GPU" if args.scaling == "weak" else "in total") + f", {args.ppc} ppc/species, "
                                       f"periodic, sort_p every {args.sort_interval} steps"
                                       + (" (BASELINE.json configs[1])" if (args.grid, args.ppc) == (128, 64) else ""),
                           "particles_per_gpu": np_total_local, "decomposition": f"1x{world}x1 slabs",
@@ -512,6 +517,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--ref-grid", type=int, default=64)
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default, the driver's contract): one grid^3 slab per GPU; strong: one grid^3 box split over the GPUs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
