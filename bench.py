@@ -254,7 +254,28 @@ def run_e2e(args, device):
     torch.cuda.synchronize()
     dt_s = time.perf_counter() - t0
     tb2 = H.transfer_bytes()
-    return {"value": pushes / dt_s, "unit": "pushes/s", "steps": steps,
+    # Same calls with the drop-in layer in resident mode (what a deck with sync hooks at its diagnostics gets): arrays
+    # stay in HBM between calls; per step the host only reads sp->nm and the two kinetic energies back.
+    L.vpic_b200_set_mode(1)
+    H.advance(species)                                        # first resident step uploads whatever is stale
+    torch.cuda.synchronize()
+    tb3 = H.transfer_bytes()
+    r_steps = max(steps, 10)
+    t0 = time.perf_counter()
+    r_pushes = 0
+    for _ in range(r_steps):
+        r_pushes += sum(sp.c.np for sp in species)
+        H.advance(species)
+        for sp in species:
+            L.energy_p(C.byref(sp.c), C.byref(H.ia))
+    torch.cuda.synchronize()
+    r_dt = time.perf_counter() - t0
+    tb4 = H.transfer_bytes()
+    L.vpic_b200_set_mode(0)
+    resident = {"value": r_pushes / r_dt, "unit": "pushes/s", "steps": r_steps,
+                "h2d_bytes_per_step": int((tb4[0] - tb3[0]) / r_steps), "d2h_bytes_per_step": int((tb4[1] - tb3[1]) / r_steps),
+                "api": "same drop-in symbols, VPB_MODE_RESIDENT; per step the host reads sp->nm and energy_p of both species"}
+    return {"value": pushes / dt_s, "unit": "pushes/s", "steps": steps, "resident_mode": resident,
             "h2d_bytes_per_step": int((tb2[0] - tb1[0]) / steps), "d2h_bytes_per_step": int((tb2[1] - tb1[1]) / steps),
             "api": "drop-in extern C symbols (advance_p(species_t*,accumulator_array_t*,interpolator_array_t*), sort_p, "
                    "clear/reduce/unload_accumulator_array, field kernels, load_interpolator_array) on pinned host arrays, "
