@@ -222,8 +222,16 @@ def load_traffic():
 
 # ------------------------------------------------------------------------------------------------------------------
 def run_e2e(args, device):
-    """Same step through the reference-facing drop-in symbols (advance_p(species_t*, ...), sort_p, ...) with HOST
-    arrays: every call copies its inputs host->device and its results device->host inside the timed region."""
+    """Same step through the reference-facing drop-in symbols (advance_p(species_t*, ...), sort_p, ...) on HOST
+    arrays, the way an unmodified reference host program drives them.  Three legs over the same host memory:
+
+      auto      VPB_MODE_AUTO (the library's default): the host may touch any array at any time; arrays the host
+                does not touch stay in HBM (page-protection tracking, csrc/lazy_pages.h).  Timed: `--e2e-steps` whole
+                steps, each followed by the host reading the kinetic energy of every species and the six field
+                energies (dump_energies), then one full host read of both particle arrays (a particle dump).
+      coherent  VPB_MODE_COHERENT: every call copies its inputs in and its outputs back (2 timed steps).
+      resident  VPB_MODE_RESIDENT: explicit syncs only.
+    The headline value is the auto leg; bytes per step are what actually crossed PCIe inside the timed region."""
     import torch
     from vpic_b200 import abi, grid as G, lib
     L = lib.load()
@@ -231,7 +239,7 @@ def run_e2e(args, device):
     nx = ny = nz = n
     dt = G.courant_dt(1.0, 1.0, 1.0, nx, ny, nz, frac=0.99)
     g = G.partition_periodic_box(0, 0, 0, nx, ny, nz, nx, ny, nz, 1, 1, 1, dt=dt)
-    H = HostWorld(L, g, pinned=True)
+    H = HostWorld(L, g, pinned="register")
     npart = nx * ny * nz * args.ppc
     rng = np.random.default_rng(7)
     species = []
@@ -239,47 +247,61 @@ def run_e2e(args, device):
         sp = H.new_species(name, q, m, npart, max(int(npart * 0.05), 1 << 16), args.sort_interval)
         H.fill_uniform(sp, npart, rng, uth, 1.0 / args.ppc)
         species.append(sp)
-    H.load_interpolator()
-    steps = args.e2e_steps
-    tb0 = H.transfer_bytes()
-    # warm-up step (allocates mirrors, first sort)
-    H.advance(species)
-    tb1 = H.transfer_bytes()
-    torch.cuda.synchronize()
+    en_f = (C.c_double * 6)()
+    L.vpic_b200_energy_f.argtypes = [C.c_void_p, C.c_void_p]; L.vpic_b200_energy_f.restype = None
+
+    def timed(mode, steps, diagnostics):
+        L.vpic_b200_set_mode(mode)
+        t0 = time.perf_counter()
+        H.load_interpolator()
+        H.advance(species)                                    # first step in a mode: mirrors are (re)filled from the host
+        torch.cuda.synchronize()
+        first = time.perf_counter() - t0
+        tb0 = H.transfer_bytes()
+        t0 = time.perf_counter()
+        pushes = 0
+        energies = None
+        for _ in range(steps):
+            pushes += sum(sp.c.np for sp in species)
+            H.advance(species)
+            if diagnostics:
+                L.vpic_b200_energy_f(en_f, C.byref(H.fa))
+                energies = [float(x) for x in en_f] + [L.energy_p(C.byref(sp.c), C.byref(H.ia)) for sp in species]
+        torch.cuda.synchronize()
+        dt_s = time.perf_counter() - t0
+        tb1 = H.transfer_bytes()
+        return {"value": pushes / dt_s, "unit": "pushes/s", "steps": steps, "ms_per_step": 1e3 * dt_s / steps,
+                "h2d_bytes_per_step": int((tb1[0] - tb0[0]) / steps), "d2h_bytes_per_step": int((tb1[1] - tb0[1]) / steps),
+                "first_step_s": first}, energies
+
+    steps = max(args.e2e_steps, 1)
+    auto, energies = timed(2, steps, True)
+    # a particle dump in auto mode: the host walks both particle arrays; every device-owned chunk faults back once
+    st0 = (C.c_uint64 * 4)(); L.vpic_b200_lazy_stats(st0)
     t0 = time.perf_counter()
-    pushes = 0
-    for _ in range(steps):
-        pushes += sum(sp.c.np for sp in species)
-        H.advance(species)
-    torch.cuda.synchronize()
-    dt_s = time.perf_counter() - t0
-    tb2 = H.transfer_bytes()
-    # Same calls with the drop-in layer in resident mode (what a deck with sync hooks at its diagnostics gets): arrays
-    # stay in HBM between calls; per step the host only reads sp->nm and the two kinetic energies back.
-    L.vpic_b200_set_mode(1)
-    H.advance(species)                                        # first resident step uploads whatever is stale
-    torch.cuda.synchronize()
-    tb3 = H.transfer_bytes()
-    r_steps = max(steps, 10)
+    checksum = 0.0
+    for sp in species:
+        checksum += float(sp.p[:sp.c.np, 7].sum(dtype=np.float64))
+    t_dump = time.perf_counter() - t0
+    st1 = (C.c_uint64 * 4)(); L.vpic_b200_lazy_stats(st1)
+    expect = sum(sp.c.np for sp in species) / args.ppc
+    auto["host_reads_all_particles"] = {"seconds": t_dump, "faults": int(st1[0] - st0[0]), "bytes": int(st1[1] - st0[1]),
+                                        "weight_checksum_rel_err": abs(checksum - expect) / expect}
     t0 = time.perf_counter()
-    r_pushes = 0
-    for _ in range(r_steps):
-        r_pushes += sum(sp.c.np for sp in species)
-        H.advance(species)
-        for sp in species:
-            L.energy_p(C.byref(sp.c), C.byref(H.ia))
+    H.advance(species)                                        # the step after the dump uploads what the host took back
     torch.cuda.synchronize()
-    r_dt = time.perf_counter() - t0
-    tb4 = H.transfer_bytes()
+    auto["step_after_dump_s"] = time.perf_counter() - t0
+    auto["energies_last_step"] = energies
+    coherent, _ = timed(0, 2, False)
+    resident, _ = timed(1, max(steps, 10), True)
     L.vpic_b200_set_mode(0)
-    resident = {"value": r_pushes / r_dt, "unit": "pushes/s", "steps": r_steps,
-                "h2d_bytes_per_step": int((tb4[0] - tb3[0]) / r_steps), "d2h_bytes_per_step": int((tb4[1] - tb3[1]) / r_steps),
-                "api": "same drop-in symbols, VPB_MODE_RESIDENT; per step the host reads sp->nm and energy_p of both species"}
-    return {"value": pushes / dt_s, "unit": "pushes/s", "steps": steps, "resident_mode": resident,
-            "h2d_bytes_per_step": int((tb2[0] - tb1[0]) / steps), "d2h_bytes_per_step": int((tb2[1] - tb1[1]) / steps),
-            "api": "drop-in extern C symbols (advance_p(species_t*,accumulator_array_t*,interpolator_array_t*), sort_p, "
-                   "clear/reduce/unload_accumulator_array, field kernels, load_interpolator_array) on pinned host arrays, "
-                   "VPB_MODE_COHERENT"}
+    auto.update({
+        "coherent_mode": coherent, "resident_mode": resident,
+        "api": "drop-in extern C symbols (advance_p(species_t*,accumulator_array_t*,interpolator_array_t*), sort_p, "
+               "clear/reduce/unload_accumulator_array, field kernels, load_interpolator_array, energy_p, energy_f) on "
+               "page-locked HOST arrays, VPB_MODE_AUTO: host memory stays the program's truth (any host access faults "
+               "the data back); per step the host reads sp->nm, both kinetic energies and the six field energies"})
+    return auto
 
 
 class HostWorld:
@@ -290,6 +312,7 @@ class HostWorld:
         from vpic_b200 import abi
         self.L, self.g, self.abi, self.torch = L, g, abi, torch
         self.keep = []
+        self.pinned = pinned if pinned else True
         G = abi.Grid()
         for k in ("dt", "cvac", "eps0", "x0", "y0", "z0", "x1", "y1", "z1", "nx", "ny", "nz", "dx", "dy", "dz", "dV",
                   "rdx", "rdy", "rdz", "r8V"):
@@ -325,6 +348,21 @@ class HostWorld:
         L.energy_p.argtypes = [C.c_void_p, C.c_void_p]
 
     def host_array(self, shape, dtype, pinned):
+        if pinned == "register":
+            # What a reference host program has: ordinary anonymous memory, 128-byte aligned (MALLOC_ALIGNED,
+            # src/util/util_base.h:150-170) rather than page aligned, page-locked after the fact with cudaHostRegister
+            # (what VPIC_B200_PIN=1 does inside the library).  Unlike cudaHostAlloc memory it can be mprotect'ed, which
+            # VPB_MODE_AUTO relies on.
+            import mmap
+            nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+            length = (nbytes + 128 + 4095) // 4096 * 4096
+            m = mmap.mmap(-1, length)
+            raw = np.frombuffer(m, dtype=np.uint8)
+            rc = self.torch.cuda.cudart().cudaHostRegister(raw.ctypes.data, length, 0)
+            if int(rc) != 0:
+                raise RuntimeError(f"cudaHostRegister failed: {rc}")
+            self.keep.append((m, raw))
+            return raw[128:128 + nbytes].view(dtype).reshape(shape)
         if pinned:
             t = self.torch.empty(shape, dtype={np.float32: self.torch.float32, np.int64: self.torch.int64,
                                                np.int32: self.torch.int32}[dtype]).pin_memory()
@@ -336,9 +374,9 @@ class HostWorld:
 
     def new_species(self, name, q, m, max_np, max_nm, sort_interval):
         abi = self.abi
-        p = self.host_array((max_np, 8), np.float32, True)
-        pm = self.host_array((max_nm, 4), np.float32, True)
-        part = self.host_array((self.g.nv + 1,), np.int32, True)
+        p = self.host_array((max_np, 8), np.float32, self.pinned)
+        pm = self.host_array((max_nm, 4), np.float32, self.pinned)
+        part = self.host_array((self.g.nv + 1,), np.int32, self.pinned)
         sp = abi.Species()
         sp.name = name.encode(); sp.q, sp.m = q, m
         sp.np, sp.max_np, sp.nm, sp.max_nm = 0, max_np, 0, max_nm
@@ -533,7 +571,7 @@ def main():
     ap.add_argument("--sort-interval", type=int, default=20)
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--e2e", type=int, default=1)
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--ref-grid", type=int, default=64)

@@ -7,9 +7,14 @@
  * Ownership stays with the host: every array is allocated, resized and checkpointed by the reference host code.
  * This layer keeps a device mirror per host array, looked up by the CURRENT host pointer and size on every call.
  *
- * Coherence modes (vpic_b200_set_mode, or env VPIC_B200_MODE=coherent|resident):
- *   VPB_MODE_COHERENT (default)  every call copies its inputs host->device and its outputs device->host, so host
- *                                code may read or write any array between calls — decks and tests run unchanged.
+ * Coherence modes (vpic_b200_set_mode, or env VPIC_B200_MODE=auto|coherent|resident):
+ *   VPB_MODE_AUTO (default)      arrays stay on the device between calls AND host code may still read or write any
+ *                                array at any time: the pages of a device-owned array are access-protected, the
+ *                                first host touch of a 2 MB chunk faults and the chunk is copied back before the
+ *                                access is retried (vpic_b200/csrc/lazy_pages.h).  Arrays below VPIC_B200_LAZY_MIN
+ *                                bytes (default 32 MB + 4 KB) are copied on every call as in coherent mode, so small
+ *                                decks and tests behave exactly as VPB_MODE_COHERENT.
+ *   VPB_MODE_COHERENT            every call copies its inputs host->device and its outputs device->host.
  *   VPB_MODE_RESIDENT            arrays stay on the device between calls; host copies go stale until
  *                                vpic_b200_sync_to_host(ptr) and host writes need vpic_b200_invalidate(ptr).
  *
@@ -27,6 +32,7 @@ extern "C" {
 
 #define VPB_MODE_COHERENT 0
 #define VPB_MODE_RESIDENT 1
+#define VPB_MODE_AUTO 2
 
 /* src/species_advance/species_advance.h:73-76 */
 void advance_p(vpb_species_t *sp, vpb_accumulator_array_t *aa, const vpb_interpolator_array_t *ia);
@@ -61,6 +67,17 @@ void vpic_b200_invalidate(const void *host_ptr);       /* host copy was modified
 void vpic_b200_release(const void *host_ptr);          /* drop the mirror (call before the host frees/reallocs) */
 /* bytes moved by the drop-in layer since load: [0] host->device, [1] device->host */
 void vpic_b200_transfer_bytes(uint64_t out[2]);
+/* VPB_MODE_AUTO: make host memory [p, p+bytes) current and host-owned before handing it to code that does not fault
+ * in user space (system calls, RDMA, MPI on registered memory).  fwrite/fread — what the reference's dumps and
+ * checkpoints use, src/util/io/StandardIOPolicy.h:133-145 — are interposed by this library and need no call.
+ * Returns the number of tracked arrays the range overlapped. */
+int vpic_b200_host_access(const void *p, size_t bytes);
+/* VPB_MODE_AUTO counters: [0] page faults served, [1] bytes copied back on host accesses, [2] arrays found remapped
+ * by the host allocator, [3] arrays currently tracked */
+void vpic_b200_lazy_stats(uint64_t out[4]);
+/* VPB_MODE_AUTO: smallest array (bytes) that is tracked by page protection; same as env VPIC_B200_LAZY_MIN.  Applies
+ * to arrays first seen after the call. */
+void vpic_b200_set_lazy_min(size_t bytes);
 
 #ifdef __cplusplus
 }

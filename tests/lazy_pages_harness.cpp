@@ -1,0 +1,187 @@
+// CPU-only self-test of vpic_b200/csrc/lazy_pages.cpp (the page-protection tracker behind VPB_MODE_AUTO).
+// The "device" is a second host buffer and the copies are memcpy, so every state transition, the fault handler,
+// the edge handling, the remap detection and concurrent faulting threads can be exercised without a GPU.
+// Built by `make -C vpic_b200/csrc lazy_test`, run by tests/test_host.py.  Exit code 0 = pass; otherwise the
+// failing line is printed.
+#include "lazy_pages.h"
+
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <unistd.h>
+#include <vector>
+
+static uint64_t g_h2d_calls = 0, g_d2h_calls = 0;
+static int fake_h2d(void *d, const void *h, size_t n) { memcpy(d, h, n); g_h2d_calls++; return 0; }
+static int fake_d2h(void *h, const void *d, size_t n) { memcpy(h, d, n); g_d2h_calls++; return 0; }
+static void fake_fatal(const char *m) { fprintf(stderr, "FATAL: %s\n", m); _exit(3); }
+
+#define CHECK(c) do { if (!(c)) { fprintf(stderr, "lazy_pages_test: line %d: %s\n", __LINE__, #c); return __LINE__; } } while (0)
+
+static const size_t kPage = 4096, kChunk = 4 * 4096;
+
+struct Arr { char *map, *h, *d; size_t cap; };
+// host array at an odd offset inside its mapping (like MALLOC_ALIGNED's 128-byte alignment), ending mid-page
+static Arr make(size_t pages, size_t head, size_t tail_cut) {
+  Arr a;
+  a.map = (char *)mmap(nullptr, pages * kPage, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+  a.h = a.map + head; a.cap = pages * kPage - head - tail_cut;
+  a.d = (char *)malloc(a.cap);
+  memset(a.d, 0xEE, a.cap);
+  return a;
+}
+static void fill(char *p, size_t n, int seed) { for (size_t i = 0; i < n; i++) p[i] = (char)((i * 31 + seed) & 0x7f); }
+static bool same(const char *p, size_t n, int seed, int add) {
+  for (size_t i = 0; i < n; i++) if (p[i] != (char)((((i * 31 + seed) & 0x7f) + add) & 0xff)) return false;
+  return true;
+}
+static void device_kernel(Arr &a, size_t n) { for (size_t i = 0; i < n; i++) a.d[i] = (char)(a.d[i] + 1); }   // "+1 everywhere"
+
+struct Reader { const char *p; size_t n; long sum; };
+static void *reader_main(void *arg) { Reader *r = (Reader *)arg; long s = 0; for (size_t i = 0; i < r->n; i++) s += r->p[i]; r->sum = s; return nullptr; }
+
+static int run() {
+  vpb_lazy::Copier cp = {fake_h2d, fake_d2h, fake_fatal, nullptr, nullptr};
+  vpb_lazy::init(cp, kChunk);
+  uint64_t h2d = 0, d2h = 0;
+
+  // --- 1. upload, device write, host read faults the data back -------------------------------------------------
+  Arr a = make(40, 128, 1000);
+  fill(a.h, a.cap, 1);
+  vpb_lazy::Region *r = vpb_lazy::attach(a.h, a.cap, a.d);
+  CHECK(r != nullptr && vpb_lazy::active() == 1);
+  vpb_lazy::to_device(r, a.cap, &h2d);
+  CHECK(h2d == a.cap);
+  CHECK(memcmp(a.d, a.h, 128) == 0);                         // (only the unprotected head can be compared directly)
+  device_kernel(a, a.cap);
+  vpb_lazy::device_wrote(r, a.cap, &d2h);
+  CHECK(d2h == (kPage - 128) + (kPage - 1000));              // the two edges came back eagerly
+  vpb_lazy::Stats s0 = vpb_lazy::stats();
+  CHECK(same(a.h, a.cap, 1, 1));                             // reads every byte: faults chunk by chunk
+  vpb_lazy::Stats s1 = vpb_lazy::stats();
+  CHECK(s1.faults > s0.faults && s1.faults - s0.faults <= 10);
+  CHECK(s1.fault_bytes - s0.fault_bytes == 38 * kPage);      // exactly the whole pages, once
+  CHECK(same(a.h, a.cap, 1, 1));
+  CHECK(vpb_lazy::stats().faults == s1.faults);              // host-owned now: no more faults
+
+  // --- 2. steady state: nothing host-touched means nothing copied ---------------------------------------------
+  h2d = d2h = 0;
+  vpb_lazy::to_device(r, a.cap, &h2d);                       // everything host-owned after the read: full upload
+  CHECK(h2d == a.cap);
+  for (int step = 0; step < 5; step++) {
+    h2d = d2h = 0;
+    vpb_lazy::to_device(r, a.cap, &h2d);
+    device_kernel(a, a.cap);
+    vpb_lazy::device_wrote(r, a.cap, &d2h);
+    CHECK(h2d == (kPage - 128) + (kPage - 1000) && d2h == h2d);      // edges only
+  }
+  // --- 3. a sparse host write (inject_particle) moves one chunk, and the write survives the next device pass ---
+  s0 = vpb_lazy::stats();
+  a.h[20 * kPage + 7] = 99;
+  s1 = vpb_lazy::stats();
+  CHECK(s1.faults == s0.faults + 1 && s1.fault_bytes - s0.fault_bytes == kChunk);
+  CHECK(a.h[20 * kPage + 8] == (char)(((((20 * kPage + 8) * 31 + 1) & 0x7f) + 6) & 0xff));   // neighbours are current
+  h2d = 0;
+  vpb_lazy::to_device(r, a.cap, &h2d);
+  CHECK(h2d == kChunk + (kPage - 128) + (kPage - 1000));
+  device_kernel(a, a.cap);
+  vpb_lazy::device_wrote(r, a.cap, &d2h);
+  CHECK(a.h[20 * kPage + 7] == 100);
+
+  // --- 4. partial extents: the device only uses the first part; the host's tail is preserved -------------------
+  {
+    Arr b = make(24, 256, 0);
+    fill(b.h, b.cap, 5);
+    vpb_lazy::Region *rb = vpb_lazy::attach(b.h, b.cap, b.d);
+    const size_t live = 9 * kPage + 100;
+    h2d = 0;
+    vpb_lazy::to_device(rb, live, &h2d);
+    device_kernel(b, live);
+    vpb_lazy::device_wrote(rb, live, &d2h);
+    CHECK(same(b.h, live, 5, 1));
+    for (size_t i = live; i < b.cap; i++) CHECK(b.h[i] == (char)((i * 31 + 5) & 0x7f));       // untouched tail
+    // to_host on a sub-range, forget_device, detach with sync
+    vpb_lazy::to_device(rb, b.cap, &h2d);
+    device_kernel(b, b.cap);
+    vpb_lazy::device_wrote(rb, b.cap, &d2h);
+    d2h = 0;
+    vpb_lazy::to_host(rb, 5 * kPage, 2 * kPage, &d2h);
+    CHECK(d2h >= 2 * kPage && d2h <= 2 * kChunk);
+    vpb_lazy::detach(rb, true, &d2h);
+    CHECK(vpb_lazy::active() == 1);
+    for (size_t i = 0; i < live; i++) CHECK(b.h[i] == (char)((((i * 31 + 5) & 0x7f) + 2) & 0xff));
+    for (size_t i = live; i < b.cap; i++) CHECK(b.h[i] == (char)((((i * 31 + 5) & 0x7f) + 1) & 0xff));
+    munmap(b.map, 24 * kPage); free(b.d);
+  }
+
+  // --- 5. host_access (what the fwrite/fread interposers call): no fault, range becomes readable by the kernel --
+  vpb_lazy::to_device(r, a.cap, &h2d);
+  {
+    int fd[2]; CHECK(pipe(fd) == 0);
+    ssize_t w = write(fd[1], a.h + 8 * kPage, 64);
+    CHECK(w < 0);                                            // EFAULT: device-owned pages are invisible to syscalls
+    s0 = vpb_lazy::stats();
+    CHECK(vpb_lazy::host_access(a.h + 8 * kPage, 64) == 1);
+    w = write(fd[1], a.h + 8 * kPage, 64);
+    CHECK(w == 64 && vpb_lazy::stats().faults == s0.faults);
+    close(fd[0]); close(fd[1]);
+  }
+
+  // --- 6. several host threads fault on the same array at once (the reference's pipelines) --------------------
+  vpb_lazy::to_device(r, a.cap, &h2d);
+  device_kernel(a, a.cap);
+  vpb_lazy::device_wrote(r, a.cap, &d2h);
+  {
+    long expect = 0;
+    std::vector<char> copy(a.d, a.d + a.cap);
+    for (size_t i = 0; i < a.cap; i++) expect += copy[i];
+    pthread_t th[4]; Reader rd[4];
+    for (int t = 0; t < 4; t++) { rd[t] = {a.h, a.cap, 0}; pthread_create(&th[t], nullptr, reader_main, &rd[t]); }
+    for (int t = 0; t < 4; t++) { pthread_join(th[t], nullptr); CHECK(rd[t].sum == expect); }
+  }
+
+  // --- 7. the host frees the array and the allocator maps fresh memory at the same address ---------------------
+  vpb_lazy::to_device(r, a.cap, &h2d);
+  munmap(a.map, 40 * kPage);
+  char *again = (char *)mmap(a.map, 40 * kPage, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_FIXED, -1, 0);
+  CHECK(again == a.map);
+  fill(a.h, a.cap, 9);                                       // no faults: fresh pages
+  h2d = 0;
+  vpb_lazy::to_device(r, a.cap, &h2d);
+  CHECK(vpb_lazy::stats().remaps == 1 && h2d == a.cap);      // noticed, everything uploaded again
+  CHECK(memcmp(a.d, a.h, 128) == 0);
+  device_kernel(a, a.cap);
+  vpb_lazy::device_wrote(r, a.cap, &d2h);
+  CHECK(same(a.h, a.cap, 9, 1));
+
+  // --- 8. forget_device (vpic_b200_invalidate): host copy wins without a copy back -----------------------------
+  vpb_lazy::to_device(r, a.cap, &h2d);
+  device_kernel(a, a.cap);
+  vpb_lazy::device_wrote(r, a.cap, &d2h);
+  vpb_lazy::forget_device(r);
+  s0 = vpb_lazy::stats();
+  volatile char c = a.h[10 * kPage]; (void)c;
+  CHECK(vpb_lazy::stats().faults == s0.faults);
+  vpb_lazy::detach(r, false, nullptr);
+  CHECK(vpb_lazy::active() == 0);
+
+  // --- 9. an array with no whole page inside is not tracked -----------------------------------------------------
+  {
+    Arr t = make(2, 100, kPage + 100);
+    CHECK(vpb_lazy::attach(t.h, t.cap, t.d) == nullptr);
+  }
+  printf("lazy_pages_test: ok (%llu faults, %llu h2d calls, %llu d2h calls)\n",
+         (unsigned long long)vpb_lazy::stats().faults, (unsigned long long)g_h2d_calls, (unsigned long long)g_d2h_calls);
+  return 0;
+}
+
+int main(int argc, char **argv) {
+  const int rc = run();
+  if (rc) return 1;
+  if (argc > 1 && !strcmp(argv[1], "--crash")) {             // a genuine wild access must still kill the process
+    volatile int *bad = (volatile int *)16; *bad = 1;
+  }
+  return 0;
+}

@@ -31,27 +31,38 @@ def _need(binary):
     return path
 
 
-def _run(path, args, preload, cwd, timeout=900):
+# VPB_MODE_AUTO with every array of a page or more tracked by page protection (the production threshold is 32 MB):
+# the decks' host code reads and writes particles, fields and accumulators between calls, the reference's field
+# solver and divergence cleaning run on the host, dumps go through fwrite — all of it has to fault the data back.
+AUTO_ENV = {"VPIC_B200_MODE": "auto", "VPIC_B200_LAZY_MIN": "4096", "VPIC_B200_LAZY_CHUNK": "16384"}
+MODES = {"coherent": {"VPIC_B200_MODE": "coherent"}, "auto": AUTO_ENV, "auto_pinned": dict(AUTO_ENV, VPIC_B200_PIN="1")}
+
+
+def _run(path, args, preload, cwd, timeout=900, extra_env=None):
     env = dict(os.environ)
     if preload:
         env["LD_PRELOAD"] = LIB
+        env.update(extra_env or {})
     r = subprocess.run([path] + args, cwd=cwd, env=env, capture_output=True, text=True, timeout=timeout)
     return r.returncode, r.stdout + r.stderr
 
 
+@pytest.mark.parametrize("mode", ["coherent", "auto"])
 @pytest.mark.parametrize("deck", ["accel", "cyclo", "inbndj", "interpe", "outbndj"])
-def test_reference_kat_deck_passes_on_gpu_path(deck):
+def test_reference_kat_deck_passes_on_gpu_path(deck, mode):
     path = _need(f"{deck}.scalar")
     with tempfile.TemporaryDirectory() as d:
-        rc, out = _run(path, ["1", "1"], True, d)
+        rc, out = _run(path, ["1", "1"], True, d, extra_env=MODES[mode])
     assert rc == 0, out[-2000:]
     assert "pass" in out and "FAIL" not in out and "fail" not in out.replace("fail 0", ""), out[-2000:]
 
 
-@pytest.mark.parametrize("binary,gold,tpp", [("3d_test", "energies_gold.3d_test", 1),
-                                             ("3d_test_threaded", "energies_gold.3d_test_threaded", 8),
-                                             ("weibel_driver", "energies_gold.weibel_driver", 1)])
-def test_reference_golden_energy_test_passes_on_gpu_path(binary, gold, tpp):
+@pytest.mark.parametrize("binary,gold,tpp,mode", [("3d_test", "energies_gold.3d_test", 1, "coherent"),
+                                                  ("3d_test_threaded", "energies_gold.3d_test_threaded", 8, "coherent"),
+                                                  ("3d_test_threaded", "energies_gold.3d_test_threaded", 8, "auto"),
+                                                  ("3d_test_threaded", "energies_gold.3d_test_threaded", 8, "auto_pinned"),
+                                                  ("weibel_driver", "energies_gold.weibel_driver", 1, "coherent")])
+def test_reference_golden_energy_test_passes_on_gpu_path(binary, gold, tpp, mode):
     """test/unit/energy_comparison — the reference's own golden-vector tests of the whole step loop (3d_test: 16^3
     cells, 16 ppc, 2 species, 50 steps; its --tpp 8 variant, whose particle load differs; weibel_driver: 700 steps)
     compare themselves against energies_gold.* with the reference's tolerances.  Here the unmodified test binaries
@@ -61,7 +72,9 @@ def test_reference_golden_energy_test_passes_on_gpu_path(binary, gold, tpp):
     for preload in (False, True):
         with tempfile.TemporaryDirectory() as d:
             shutil.copy(goldp, d)
-            rc, out = _run(path, ["--tpp", str(tpp)], preload, d)
+            if not preload and mode != "coherent":
+                continue                                      # the CPU leg is the same for every mode
+            rc, out = _run(path, ["--tpp", str(tpp)], preload, d, extra_env=MODES[mode])
             assert rc == 0 and "All tests passed" in out, out[-2000:]
             if preload:
                 mine = np.loadtxt(os.path.join(d, "energies"), comments="%")
@@ -71,17 +84,25 @@ def test_reference_golden_energy_test_passes_on_gpu_path(binary, gold, tpp):
                 assert np.abs(mine[:n, -2:] - ref[:n, -2:]).max() / np.abs(ref[:n, -2:]).max() < 1e-5
 
 
-@pytest.mark.parametrize("deck", ["simple", "reconnection_test"])
-def test_reference_to_completion_deck_runs_on_gpu_path(deck):
+_cpu_history = {}
+
+
+@pytest.mark.parametrize("deck,mode", [("simple", "coherent"), ("reconnection_test", "coherent"),
+                                       ("simple", "auto"), ("reconnection_test", "auto")])
+def test_reference_to_completion_deck_runs_on_gpu_path(deck, mode):
     """test/integrated/to_completion ("does not die" in the reference's own CTest): whole vpic_simulation::advance loop,
     two species, sorts, divergence cleaning on the host, dumps — with the hot path on the GPU through LD_PRELOAD.
     reconnection_test also writes an energies history, which must match the CPU run of the same binary."""
     path = _need(f"{deck}.scalar")
     hist = {}
+    if deck in _cpu_history:
+        hist["cpu"] = _cpu_history[deck]
     for tag, preload in (("cpu", False), ("gpu", True)):
+        if tag in hist:
+            continue
         d = tempfile.mkdtemp(prefix=f"{deck}_{tag}_")
         try:
-            rc, out = _run(path, ["--tpp", "1"], preload, d)
+            rc, out = _run(path, ["--tpp", "1"], preload, d, extra_env=MODES[mode])
             assert rc == 0 and "normal exit" in out, out[-2000:]
             en = os.path.join(d, "rundata", "energies")
             if os.path.exists(en):
@@ -90,24 +111,31 @@ def test_reference_to_completion_deck_runs_on_gpu_path(deck):
         finally:
             shutil.rmtree(d, ignore_errors=True)
     if "cpu" in hist:
+        _cpu_history[deck] = hist["cpu"]
         a, b = hist["cpu"], hist["gpu"]
         assert a.shape == b.shape and len(a) > 0
         tot_a, tot_b = a[:, 1:].sum(axis=1), b[:, 1:].sum(axis=1)
         np.testing.assert_allclose(tot_b, tot_a, rtol=1e-4)
 
 
-def test_harris_energy_history_matches_reference():
+@pytest.mark.parametrize("mode", ["coherent", "auto_pinned"])
+def test_harris_energy_history_matches_reference(mode):
     path = _need("harris.scalar")
     hist = {}
+    if "harris" in _cpu_history:
+        hist["cpu"] = _cpu_history["harris"]
     for tag, preload in (("cpu", False), ("gpu", True)):
+        if tag in hist:
+            continue
         d = tempfile.mkdtemp(prefix=f"harris_{tag}_")
         try:
-            rc, out = _run(path, ["--tpp", "1"], preload, d, timeout=1800)
+            rc, out = _run(path, ["--tpp", "1"], preload, d, timeout=1800, extra_env=MODES[mode])
             assert rc == 0, out[-3000:]
             rows = [ln.split() for ln in open(os.path.join(d, "energies")) if ln.strip() and not ln.startswith("%")]
             hist[tag] = np.array([[float(x) for x in r] for r in rows if len(r) > 3])
         finally:
             shutil.rmtree(d, ignore_errors=True)
+    _cpu_history["harris"] = hist["cpu"]
     a, b = hist["cpu"], hist["gpu"]
     assert a.shape == b.shape and a.shape[0] >= 5, (a.shape, b.shape)
     assert np.array_equal(a[:, 0], b[:, 0])                        # same steps

@@ -322,10 +322,11 @@ def test_multi_gpu_slab(eng, extra):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
 
 
-@pytest.mark.parametrize("mode", ["coherent", "resident"])
+@pytest.mark.parametrize("mode", ["coherent", "resident", "auto"])
 def test_dropin_symbols_on_host_structs(eng, oracle, mode):
     """The reference-named entry points (advance_p(species_t*, ...), sort_p, ...) on HOST structs: chunked, pipelined
-    copies in coherent mode (chunk forced small so several chunks are in flight), explicit syncs in resident mode."""
+    copies in coherent mode (chunk forced small so several chunks are in flight), explicit syncs in resident mode,
+    and no syncs at all in auto mode — there the host reads below fault the device-owned pages back in."""
     import subprocess, sys, os, json, textwrap
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     code = textwrap.dedent(f"""
@@ -337,8 +338,11 @@ def test_dropin_symbols_on_host_structs(eng, oracle, mode):
         nx, ny, nz, n = 7, 6, 5, 23003
         g = G.partition_periodic_box(0,0,0,nx,ny,nz,nx,ny,nz,1,1,1, dt=G.courant_dt(1,1,1,nx,ny,nz,frac=0.98))
         g.set_pbc(2, -2); g.set_pbc(5, -2)                      # absorbing z walls: movers come back to the host
-        H = bench.HostWorld(L, g, pinned=True)
-        L.vpic_b200_set_mode(1 if {mode!r} == 'resident' else 0)
+        mode = {mode!r}
+        H = bench.HostWorld(L, g, pinned='register' if mode == 'auto' else True)
+        L.vpic_b200_set_lazy_min.argtypes = [C.c_size_t]; L.vpic_b200_set_lazy_min.restype = None
+        L.vpic_b200_set_lazy_min(4096)
+        L.vpic_b200_set_mode(dict(coherent=0, resident=1, auto=2)[mode])
         rng = np.random.default_rng(8)
         H.fields[:] = R.random_fields(rng, g.nv)
         sp = H.new_species('e', -1.0, 1.0, n, n, 20)
@@ -352,7 +356,8 @@ def test_dropin_symbols_on_host_structs(eng, oracle, mode):
         L.unload_accumulator_array(C.byref(H.fa), C.byref(H.aa))
         for fn in ('vpic_b200_sync_to_host',):
             getattr(L, fn).argtypes = [C.c_void_p]; getattr(L, fn).restype = None
-        L.vpic_b200_sync_to_host(None)
+        if mode != 'auto':
+            L.vpic_b200_sync_to_host(None)
         # oracle on the same inputs
         f0 = H.fields.copy(); f0[:, 12:15] = 0
         interp = np.zeros((g.nv, 20), np.float32)
@@ -376,14 +381,107 @@ def test_dropin_symbols_on_host_structs(eng, oracle, mode):
         fld_ref = fld_in.copy()
         orc.vpo_unload_accumulator(fld_ref.ctypes.data, H.accum.ctypes.data, 12, nx, ny, nz, g.rdx, g.rdy, g.rdz, g.dt)
         ok['jf'] = bool(np.array_equal(fld_ref.view(np.uint32), H.fields.view(np.uint32)))
+        st = (C.c_uint64 * 4)(); L.vpic_b200_lazy_stats(st)
+        ok['lazy'] = [int(x) for x in st]
+        L.vpic_b200_set_mode(0)                                  # hands every array back before the buffers are freed
         import json; print('RESULT ' + json.dumps(ok))
     """)
-    env = dict(os.environ, VPIC_B200_CHUNK="4096")
+    env = dict(os.environ, VPIC_B200_CHUNK="4096", VPIC_B200_LAZY_CHUNK="8192")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("RESULT ")][0][7:])
     assert res["interp"] and res["nm"] and res["particles"] and res["movers"] and res["partition"] and res["jf"], res
     assert res["accum"] < 2e-5 and res["last_sorted"] == 0, res
+    if mode == "auto":
+        faults, fault_bytes, remaps, regions = res["lazy"]
+        assert faults > 0 and fault_bytes > 0 and regions >= 4 and remaps == 0, res
+
+
+_AUTO_SCRIPT = """
+import sys, os, ctypes as C, numpy as np
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, 'tests'))
+import bench, refvpic as R
+from vpic_b200 import lib, grid as G, abi
+mode, out = sys.argv[1], sys.argv[2]
+L = lib.load()
+nx, ny, nz, n = 9, 8, 7, 70001
+g = G.partition_periodic_box(0,0,0,nx,ny,nz,nx,ny,nz,1,1,1, dt=G.courant_dt(1,1,1,nx,ny,nz,frac=0.98))
+H = bench.HostWorld(L, g, pinned='register')
+L.vpic_b200_set_lazy_min.argtypes = [C.c_size_t]; L.vpic_b200_set_lazy_min.restype = None
+L.vpic_b200_set_lazy_min(4096)
+L.vpic_b200_set_mode(dict(coherent=0, auto=2)[mode])
+rng = np.random.default_rng(21)
+H.fields[:] = R.random_fields(rng, g.nv) * 0.05
+sp = H.new_species('e', -1.0, 1.0, n + 64, n, 3)
+parts = R.random_particles(rng, n, nx, ny, nz, uth=0.3, w=0.5)
+sp.p[:n] = parts.view(np.float32).reshape(-1, 8); sp.c.np = n
+H.load_interpolator()
+energies = []
+libc = C.CDLL(None)
+libc.fopen.restype = C.c_void_p; libc.fopen.argtypes = [C.c_char_p, C.c_char_p]; libc.fclose.argtypes = [C.c_void_p]
+L.fwrite.restype = C.c_size_t; L.fwrite.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]
+aa, ia, fa = C.byref(H.aa), C.byref(H.ia), C.byref(H.fa)
+for step in range(7):
+    # particle side of the step only: E and B stay what the host set, so both runs push bit-identically
+    if step % 3 == 0:
+        L.sort_p(C.byref(sp.c))
+    L.clear_accumulator_array(aa)
+    L.advance_p(C.byref(sp.c), aa, ia)
+    L.reduce_accumulator_array(aa)
+    L.vpic_b200_clear_jf(fa)
+    L.unload_accumulator_array(fa, aa)
+    energies.append(L.energy_p(C.byref(sp.c), C.byref(H.ia)))
+    # what decks do between steps: poke single particles, read a few, append one (inject_particle), touch a field
+    k = (step * 9973) % n
+    sp.p[k, 4] += np.float32(0.01)                                  # host write into a device-owned chunk
+    energies.append(float(sp.p[(k * 7) % n, 5]))                    # host read
+    if step == 2:
+        sp.p[sp.c.np] = sp.p[0]; sp.p[sp.c.np, 0] = 0.25; sp.c.np += 1    # grow the live extent by one particle
+    if step == 4:
+        H.fields[g.nv // 2, 0] += np.float32(0.125)                 # set_region_field-like
+        H.load_interpolator()
+    if step == 5:                                                   # dump: fwrite of a device-owned array (no fault: syscall)
+        f = libc.fopen(out.encode() + b'.dump', b'wb')
+        wrote = L.fwrite(sp.p.ctypes.data, 32, sp.c.np, f); libc.fclose(f)
+        assert wrote == sp.c.np, wrote
+st = (C.c_uint64 * 4)(); L.vpic_b200_lazy_stats(st)
+tb = H.transfer_bytes()
+np.savez(out, p=sp.p[:sp.c.np].copy(), f=H.fields.copy(), i=H.interp.copy(), a=H.accum.copy(), e=np.array(energies),
+         lazy=np.array([int(x) for x in st]), tb=np.array(tb, dtype=np.float64),
+         dump=np.fromfile(out + '.dump', dtype=np.float32))
+L.vpic_b200_set_mode(0)
+"""
+
+
+def test_dropin_auto_mode_matches_coherent_under_host_interference(eng, tmp_path):
+    """VPB_MODE_AUTO must be indistinguishable from VPB_MODE_COHERENT for a host that reads, writes, grows and dumps
+    its arrays between calls — while moving far fewer bytes.  Same script twice, results compared bit for bit
+    (currents are summed with atomics in no fixed order, so they are compared with a tolerance)."""
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for mode in ("coherent", "auto"):
+        out = str(tmp_path / f"{mode}.npz")
+        env = dict(os.environ, VPIC_B200_LAZY_CHUNK="16384")
+        r = subprocess.run([sys.executable, "-c", _AUTO_SCRIPT.format(root=root), mode, out],
+                           capture_output=True, text=True, timeout=600, env=env)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+        res[mode] = np.load(out)
+    c, a = res["coherent"], res["auto"]
+    assert c["p"].shape == a["p"].shape
+    # E and B are never advanced in the script, so the push is bit-reproducible; only the currents (atomic order) are not
+    assert np.array_equal(c["p"].view(np.uint32), a["p"].view(np.uint32))
+    assert np.array_equal(c["i"].view(np.uint32), a["i"].view(np.uint32))
+    assert np.array_equal(c["f"][:, :12].view(np.uint32), a["f"][:, :12].view(np.uint32))
+    np.testing.assert_allclose(a["f"], c["f"], rtol=0, atol=2e-5 * max(1.0, float(np.abs(c["f"]).max())))
+    np.testing.assert_allclose(a["a"], c["a"], rtol=0, atol=2e-5 * max(1.0, float(np.abs(c["a"]).max())))
+    np.testing.assert_allclose(a["e"], c["e"], rtol=1e-6, atol=0)
+    assert a["dump"].size == c["dump"].size > 0
+    assert np.array_equal(a["dump"].view(np.uint32), c["dump"].view(np.uint32))   # the dump saw current data, not stale pages
+    faults, fault_bytes, remaps, regions = a["lazy"]
+    assert faults >= 10 and regions >= 5 and remaps == 0
+    assert c["lazy"][0] == 0
+    assert a["tb"].sum() < 0.5 * c["tb"].sum(), (a["tb"], c["tb"])             # and it moved much less data
 
 
 def test_accumulate_rho_p(eng, oracle):

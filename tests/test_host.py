@@ -78,3 +78,18 @@ def test_slab_grid_neighbours():
         v = G.voxel(3, 1, 2, g.nx, g.ny, g.nz)
         assert g.neighbor[v, 1] == dn.rangel + G.voxel(3, dn.ny, 2, g.nx, g.ny, g.nz)
         assert g.face_codes() == [0, 1, 0, 0, 1, 0]
+
+
+def test_lazy_pages_state_machine():
+    """VPB_MODE_AUTO's page-protection tracker (vpic_b200/csrc/lazy_pages.cpp) against a fake device: faults bring
+    chunks back, sparse host writes survive, edges are copied eagerly, syscalls are served by host_access, concurrent
+    faulting threads never see a half-filled chunk, remapped arrays are noticed — and a wild access still crashes."""
+    import signal
+    import subprocess
+    csrc = os.path.join(ROOT, "vpic_b200", "csrc")
+    subprocess.check_call(["make", "-s", "-C", csrc, "lazy_test"])
+    exe = os.path.join(csrc, "build", "lazy_pages_test")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "lazy_pages_test: ok" in r.stdout, r.stdout + r.stderr
+    r = subprocess.run([exe, "--crash"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == -signal.SIGSEGV, (r.returncode, r.stdout, r.stderr)

@@ -4,7 +4,9 @@
 // Host code only (no kernels): argument checks in the reference's convention, the host<->device mirror registry,
 // and one call into the vpb_* device layer per entry point.
 #include "vpb_common.cuh"
+#include "lazy_pages.h"
 #include "../../include/vpic_b200_dropin.h"
+#include <dlfcn.h>
 #include <stdlib.h>
 #include <string.h>
 #include <unistd.h>
@@ -41,6 +43,7 @@ struct Mirror {
   bool host_stale = false;        // device copy is newer than the host copy
   size_t live_bytes = 0;          // extent last written on the device
   bool pinned = false; size_t pinned_bytes = 0;
+  vpb_lazy::Region *lazy = nullptr;   // VPB_MODE_AUTO: page-protected lazy coherence (lazy_pages.h)
 };
 
 std::unordered_map<const void *, Mirror> g_mirrors;
@@ -49,23 +52,82 @@ int g_mode = -1;
 bool g_pin = false;
 uint64_t g_h2d = 0, g_d2h = 0;
 int *g_counters = nullptr;
+// VPB_MODE_AUTO: arrays of at least this many bytes are tracked by page protection, smaller ones are copied on every
+// call as in coherent mode.  The default is just above glibc's largest dynamic mmap threshold (32 MB on LP64,
+// malloc/malloc.c DEFAULT_MMAP_THRESHOLD_MAX), so a tracked array is always its own mapping and free() on it is a
+// plain munmap that never touches protected pages.
+size_t g_lazy_min = (32u << 20) + 4096;
+int g_device = 0;
+
+int lazy_h2d(void *d, const void *h, size_t n) { return vpb_memcpy_h2d(d, h, n, nullptr); }
+int lazy_d2h(void *h, const void *d, size_t n) {
+  // may run inside the SIGSEGV handler on any host thread: bind the device, copy on the legacy default stream (which
+  // orders it after every kernel the entry points launched) and return only when the bytes are in host memory
+  cudaSetDevice(g_device);
+  return cudaMemcpy(h, d, n, cudaMemcpyDeviceToHost) != cudaSuccess;
+}
+// Page-locked (cudaHostRegister'ed) destination: the copy engine writes it without going through the CPU's page
+// tables, so the pages can stay PROT_NONE until the data is there.  Pageable destinations are refused (the driver
+// would memcpy through the CPU and fault inside the fault handler).
+bool g_dma_into_protected = true;
+int lazy_d2h_protected(void *h, const void *d, size_t n) {
+  if (!g_dma_into_protected) return 1;
+  cudaSetDevice(g_device);
+  cudaPointerAttributes a0, a1;
+  if (cudaPointerGetAttributes(&a0, h) != cudaSuccess || cudaPointerGetAttributes(&a1, (char *)h + n - 1) != cudaSuccess ||
+      a0.type != cudaMemoryTypeHost || a1.type != cudaMemoryTypeHost) { cudaGetLastError(); return 1; }
+  if (cudaMemcpy(h, d, n, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return 1; }
+  return 0;
+}
+void *lazy_staging(size_t n) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, n, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); p = malloc(n); }
+  return p;
+}
+void lazy_fatal(const char *msg) {
+  fprintf(stderr, "Error at %s[%d]:\n\t%s (%s)\n", __FILE__, rank_for_log(), msg, cudaGetErrorString(cudaGetLastError()));
+  fflush(stderr); _exit(1);
+}
 
 int mode() {
   if (g_mode < 0) {
     const char *e = getenv("VPIC_B200_MODE");
-    g_mode = (e && !strcmp(e, "resident")) ? VPB_MODE_RESIDENT : VPB_MODE_COHERENT;
+    g_mode = !e || !strcmp(e, "auto") ? VPB_MODE_AUTO : !strcmp(e, "resident") ? VPB_MODE_RESIDENT : !strcmp(e, "coherent") ? VPB_MODE_COHERENT : -1;
+    if (g_mode < 0) DROPIN_ERROR("VPIC_B200_MODE=%s: expected auto, coherent or resident", e);
     const char *p = getenv("VPIC_B200_PIN");
     g_pin = p && atoi(p) != 0;
+    if (const char *m = getenv("VPIC_B200_LAZY_MIN")) g_lazy_min = (size_t)atoll(m);
   }
   return g_mode;
 }
 
-Mirror &mirror(const void *h, size_t bytes) {
+void lazy_setup() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+  cudaGetDevice(&g_device);
+  const char *c = getenv("VPIC_B200_LAZY_CHUNK");
+  if (const char *e = getenv("VPIC_B200_LAZY_DMA")) g_dma_into_protected = atoi(e) != 0;
+  vpb_lazy::Copier cp = {lazy_h2d, lazy_d2h, lazy_fatal, lazy_d2h_protected, lazy_staging};
+  vpb_lazy::init(cp, c ? (size_t)atoll(c) : 0);
+}
+
+// copies every call (coherent mode, and the small arrays of auto mode)
+inline bool strict(const Mirror &m) { return g_mode == VPB_MODE_COHERENT || (g_mode == VPB_MODE_AUTO && !m.lazy); }
+bool g_copied_back = false;     // an asynchronous device->host copy is in flight: the entry point must not return yet
+void finish_entry() { if (g_copied_back) { DEV(vpb_stream_sync(nullptr)); g_copied_back = false; } }
+
+Mirror &mirror(const void *h, size_t bytes, bool may_track = true) {
   Mirror &m = g_mirrors[h];
   if (m.cap < bytes) {
+    if (m.lazy) { vpb_lazy::detach(m.lazy, true, &g_d2h); m.lazy = nullptr; }
     if (m.d) { if (m.host_stale) DROPIN_ERROR("host array %p grew while its device copy was newer; sync_to_host first", h); DEV(vpb_free(m.d)); }
     DEV(vpb_malloc(&m.d, bytes));
     m.cap = bytes; m.device_valid = false; m.host_stale = false; m.live_bytes = 0;
+  }
+  if (g_mode == VPB_MODE_AUTO && may_track && !m.lazy && m.cap >= g_lazy_min) {
+    lazy_setup();
+    m.lazy = vpb_lazy::attach(const_cast<void *>(h), m.cap, m.d);
   }
   if (g_pin && bytes >= (1u << 20) && (!m.pinned || m.pinned_bytes < bytes)) {
     if (m.pinned) cudaHostUnregister(const_cast<void *>(h));
@@ -80,21 +142,31 @@ Mirror &mirror(const void *h, size_t bytes) {
 void *dev_in(const void *h, size_t bytes, size_t cap_bytes = 0) {
   mode();
   Mirror &m = mirror(h, cap_bytes > bytes ? cap_bytes : bytes);
-  if (g_mode == VPB_MODE_COHERENT || !m.device_valid || m.live_bytes < bytes) {
+  if (m.lazy) { vpb_lazy::to_device(m.lazy, bytes, &g_h2d); m.device_valid = true; if (bytes > m.live_bytes) m.live_bytes = bytes; return m.d; }
+  if (strict(m) || !m.device_valid || m.live_bytes < bytes) {
     if (bytes) { DEV(vpb_memcpy_h2d(m.d, h, bytes, nullptr)); g_h2d += bytes; }
     m.device_valid = true; m.host_stale = false; m.live_bytes = bytes;
   }
   return m.d;
 }
 // device buffer for an output-only host array
-void *dev_out_only(const void *h, size_t cap_bytes) { mode(); return mirror(h, cap_bytes).d; }
+void *dev_out_only(const void *h, size_t cap_bytes) {
+  mode();
+  Mirror &m = mirror(h, cap_bytes);
+  // tracked arrays: chunks are handed over whole, so what the host holds past the part the device will write has to
+  // be on the device before the chunk can come back; after the first call there is nothing left to upload
+  if (m.lazy) vpb_lazy::to_device(m.lazy, cap_bytes, &g_h2d);
+  return m.d;
+}
 
 // the device wrote h[0..bytes): copy back now (coherent) or remember that the host copy is stale (resident)
 void dev_written(const void *h, size_t bytes) {
   Mirror &m = g_mirrors[h];
   m.device_valid = true; if (bytes > m.live_bytes) m.live_bytes = bytes;
-  if (g_mode == VPB_MODE_COHERENT) {
-    if (bytes) { DEV(vpb_memcpy_d2h(const_cast<void *>(h), m.d, bytes, nullptr)); g_d2h += bytes; }
+  if (m.lazy) {
+    vpb_lazy::device_wrote(m.lazy, bytes, &g_d2h);
+  } else if (strict(m)) {
+    if (bytes) { DEV(vpb_memcpy_d2h(const_cast<void *>(h), m.d, bytes, nullptr)); g_d2h += bytes; g_copied_back = true; }
     m.host_stale = false;
   } else {
     m.host_stale = true;
@@ -110,6 +182,7 @@ void *scratch(int id, size_t bytes) {
 int *counters() { if (!g_counters) DEV(vpb_malloc((void **)&g_counters, 4 * sizeof(int))); return g_counters; }
 
 void sync_one(const void *h, Mirror &m) {
+  if (m.lazy) { vpb_lazy::to_host(m.lazy, 0, m.cap, &g_d2h); return; }
   if (m.host_stale && m.live_bytes) {
     DEV(vpb_memcpy_d2h(const_cast<void *>(h), m.d, m.live_bytes, nullptr)); g_d2h += m.live_bytes;
     DEV(vpb_stream_sync(nullptr));
@@ -125,8 +198,15 @@ extern "C" {
 
 void vpic_b200_set_mode(int m) {
   mode();
-  if (m != VPB_MODE_COHERENT && m != VPB_MODE_RESIDENT) DROPIN_ERROR("Bad args");
-  if (m == VPB_MODE_COHERENT) vpic_b200_sync_to_host(nullptr);
+  if (m != VPB_MODE_COHERENT && m != VPB_MODE_RESIDENT && m != VPB_MODE_AUTO) DROPIN_ERROR("Bad args");
+  if (m == g_mode) return;
+  // leaving a mode hands every array back to the host; the new mode starts from the host copies
+  vpic_b200_sync_to_host(nullptr);
+  for (auto &kv : g_mirrors) {
+    Mirror &mm = kv.second;
+    if (mm.lazy) { vpb_lazy::detach(mm.lazy, true, &g_d2h); mm.lazy = nullptr; }
+    mm.device_valid = false; mm.host_stale = false;
+  }
   g_mode = m;
 }
 
@@ -136,19 +216,54 @@ void vpic_b200_sync_to_host(const void *h) {
 }
 
 void vpic_b200_invalidate(const void *h) {
-  if (h) { auto it = g_mirrors.find(h); if (it != g_mirrors.end()) { it->second.device_valid = false; it->second.host_stale = false; } return; }
-  for (auto &kv : g_mirrors) { kv.second.device_valid = false; kv.second.host_stale = false; }
+  auto drop = [](Mirror &m) { if (m.lazy) vpb_lazy::forget_device(m.lazy); m.device_valid = false; m.host_stale = false; };
+  if (h) { auto it = g_mirrors.find(h); if (it != g_mirrors.end()) drop(it->second); return; }
+  for (auto &kv : g_mirrors) drop(kv.second);
 }
 
 void vpic_b200_release(const void *h) {
   auto it = g_mirrors.find(h);
   if (it == g_mirrors.end()) return;
+  if (it->second.lazy) vpb_lazy::detach(it->second.lazy, false, nullptr);
   if (it->second.pinned) cudaHostUnregister(const_cast<void *>(h));
   if (it->second.d) vpb_free(it->second.d);
   g_mirrors.erase(it);
 }
 
-void vpic_b200_transfer_bytes(uint64_t out[2]) { out[0] = g_h2d; out[1] = g_d2h; }
+void vpic_b200_transfer_bytes(uint64_t out[2]) {
+  const vpb_lazy::Stats st = vpb_lazy::stats();
+  out[0] = g_h2d; out[1] = g_d2h + st.fault_bytes;
+}
+
+void vpic_b200_lazy_stats(uint64_t out[4]) {
+  const vpb_lazy::Stats st = vpb_lazy::stats();
+  out[0] = st.faults; out[1] = st.fault_bytes; out[2] = st.remaps; out[3] = st.regions;
+}
+
+void vpic_b200_set_lazy_min(size_t bytes) { mode(); g_lazy_min = bytes; }
+
+int vpic_b200_host_access(const void *p, size_t bytes) { return vpb_lazy::host_access(p, bytes); }
+
+// The reference's dumps and checkpoints hand whole arrays to fwrite/fread (src/util/io/StandardIOPolicy.h:133-145).
+// Large requests bypass the stdio buffer and reach write(2)/read(2), which fail with EFAULT on device-owned pages
+// instead of faulting, so both calls make the range host-owned first.  They take effect when this library precedes
+// libc in symbol resolution (LD_PRELOAD, or linked into the host program).
+static void *next_symbol(const char *name) {
+  void *f = dlsym(RTLD_NEXT, name);
+  if (!f) { void *libc = dlopen("libc.so.6", RTLD_LAZY | RTLD_NOLOAD); if (libc) f = dlsym(libc, name); }
+  if (!f) { fprintf(stderr, "vpic_b200: cannot resolve %s\n", name); _exit(1); }
+  return f;
+}
+size_t fwrite(const void *ptr, size_t size, size_t n, FILE *stream) {
+  static size_t (*real)(const void *, size_t, size_t, FILE *) = (size_t (*)(const void *, size_t, size_t, FILE *))next_symbol("fwrite");
+  if (vpb_lazy::active()) vpb_lazy::host_access(ptr, size * n);
+  return real(ptr, size, n, stream);
+}
+size_t fread(void *ptr, size_t size, size_t n, FILE *stream) {
+  static size_t (*real)(void *, size_t, size_t, FILE *) = (size_t (*)(void *, size_t, size_t, FILE *))next_symbol("fread");
+  if (vpb_lazy::active()) vpb_lazy::host_access(ptr, size * n);
+  return real(ptr, size, n, stream);
+}
 
 // ---- advance_p: species_advance.h:73-76, advance_p_pipeline.cc:252-340 ------------------------------------
 // In coherent mode the particle array crosses PCIe twice per call; the copy-in, the kernel and the copy-out of
@@ -174,13 +289,16 @@ void advance_p(vpb_species_t *sp, vpb_accumulator_array_t *aa, const vpb_interpo
   if (!sp || !aa || !ia || sp->g != aa->g || sp->g != ia->g) DROPIN_ERROR("Bad args.");
   const vpb_grid_t *g = sp->g;
   const size_t nv = (size_t)g->nv;
-  const bool coherent = mode() == VPB_MODE_COHERENT;
+  mode();
+  // coherent mode, and particle arrays too small to be worth tracking in auto mode, stream through the device
+  const bool coherent = g_mode == VPB_MODE_COHERENT ||
+                        (g_mode == VPB_MODE_AUTO && (size_t)sp->max_np * sizeof(vpb_particle_t) < g_lazy_min);
   vpb_push_args_t a;
   memset(&a, 0, sizeof a);
   // grid_t.neighbor is written once by the host's grid setup; its mirror is uploaded on first use and kept
   // (vpic_b200_invalidate(g->neighbor) after changing particle boundary conditions)
   {
-    Mirror &m = mirror(g->neighbor, 6 * nv * sizeof(int64_t));
+    Mirror &m = mirror(g->neighbor, 6 * nv * sizeof(int64_t), false);
     if (!m.device_valid) { DEV(vpb_memcpy_h2d(m.d, g->neighbor, 6 * nv * sizeof(int64_t), nullptr)); g_h2d += 6 * nv * sizeof(int64_t);
                            m.device_valid = true; m.live_bytes = 6 * nv * sizeof(int64_t); }
     a.neighbor = (const int64_t *)m.d;
@@ -257,7 +375,7 @@ void advance_p(vpb_species_t *sp, vpb_accumulator_array_t *aa, const vpb_interpo
   if (!coherent) dev_written(sp->p, pbytes);
   dev_written(sp->pm, (size_t)nm * sizeof(vpb_particle_mover_t));
   dev_written(aa->a, (size_t)aa->stride * sizeof(vpb_accumulator_t));
-  if (coherent) DEV(vpb_stream_sync(nullptr));
+  finish_entry();
 }
 
 // ---- sort_p: species_advance.h:65-66, sort_p_pipeline.cc:220-371 ------------------------------------------
@@ -272,7 +390,7 @@ void sort_p(vpb_species_t *sp) {
   DEV(vpb_sort_p(p, sp->np, aux, part, g->nx, g->ny, g->nz, scratch(2, need), need, nullptr));
   dev_written(sp->p, (size_t)sp->np * sizeof(vpb_particle_t));
   dev_written(sp->partition, ((size_t)g->nv + 1) * sizeof(int32_t));
-  if (g_mode == VPB_MODE_COHERENT) DEV(vpb_stream_sync(nullptr));
+  finish_entry();
 }
 
 // ---- center_p / uncenter_p / energy_p: species_advance.h:90-107 --------------------------------------------
@@ -284,7 +402,7 @@ static void center_common(vpb_species_t *sp, const vpb_interpolator_array_t *ia,
   if (center) DEV(vpb_center_p(p, sp->np, di, kInterpFloats, qdt_2mc_of(sp), nullptr));
   else        DEV(vpb_uncenter_p(p, sp->np, di, kInterpFloats, qdt_2mc_of(sp), nullptr));
   dev_written(sp->p, (size_t)sp->np * sizeof(vpb_particle_t));
-  if (g_mode == VPB_MODE_COHERENT) DEV(vpb_stream_sync(nullptr));
+  finish_entry();
 }
 void center_p(vpb_species_t *sp, const vpb_interpolator_array_t *ia) { center_common(sp, ia, true); }
 void uncenter_p(vpb_species_t *sp, const vpb_interpolator_array_t *ia) { center_common(sp, ia, false); }
@@ -314,7 +432,7 @@ void accumulate_rho_p(vpb_field_array_t *fa, const vpb_species_t *sp) {
   void *p = dev_in(sp->p, (size_t)sp->np * sizeof(vpb_particle_t), (size_t)sp->max_np * sizeof(vpb_particle_t));
   DEV(vpb_accumulate_rho_p(df, p, sp->np, sp->q, g->r8V, g->nx, g->ny, g->nz, nullptr));
   dev_written(fa->f, fbytes);
-  if (g_mode == VPB_MODE_COHERENT) DEV(vpb_stream_sync(nullptr));
+  finish_entry();
 }
 
 // ---- interpolator / accumulator glue: sf_interface.h:99-174 ------------------------------------------------
@@ -327,7 +445,7 @@ void load_interpolator_array(vpb_interpolator_array_t *ia, const vpb_field_array
   float *di = (float *)dev_in(ia->i, ibytes);
   DEV(vpb_load_interpolator(di, kInterpFloats, df, g->nx, g->ny, g->nz, nullptr));
   dev_written(ia->i, ibytes);
-  if (g_mode == VPB_MODE_COHERENT) DEV(vpb_stream_sync(nullptr));
+  finish_entry();
 }
 
 void clear_accumulator_array(vpb_accumulator_array_t *aa) {
@@ -338,7 +456,8 @@ void clear_accumulator_array(vpb_accumulator_array_t *aa) {
   const int nx = g->nx, ny = g->ny, nz = g->nz;
   const int i0 = (vpb::voxel(1, 1, 1, nx, ny) / 2) * 2;
   const int na = (((vpb::voxel(nx, ny, nz, nx, ny) - i0 + 1) + 1) / 2) * 2;
-  if (mode() == VPB_MODE_COHERENT) {
+  mode();
+  if (strict(mirror(aa->a, abytes))) {
     // the host arrays are the truth in this mode: clear them; the next consumer uploads block 0 again
     for (int b = 0; b <= aa->n_pipeline; b++)
       memset(aa->a + (size_t)b * aa->stride + i0, 0, (size_t)na * sizeof(vpb_accumulator_t));
@@ -347,7 +466,8 @@ void clear_accumulator_array(vpb_accumulator_array_t *aa) {
   } else {
     float *da = (float *)dev_in(aa->a, abytes);
     DEV(vpb_clear_accumulator(da, kAccumFloats, nx, ny, nz, nullptr));
-    g_mirrors[aa->a].host_stale = true;
+    dev_written(aa->a, abytes);
+    finish_entry();
   }
 }
 
@@ -365,7 +485,7 @@ void unload_accumulator_array(vpb_field_array_t *fa, const vpb_accumulator_array
   float *df = (float *)dev_in(fa->f, fbytes);
   DEV(vpb_unload_accumulator(df, da, kAccumFloats, g->nx, g->ny, g->nz, g->rdx, g->rdy, g->rdz, g->dt, nullptr));
   dev_written(fa->f, fbytes);
-  if (g_mode == VPB_MODE_COHERENT) DEV(vpb_stream_sync(nullptr));
+  finish_entry();
 }
 
 // ---- standard field advance through the field_advance_kernels_t seam (field_advance.h:170-229) -----------------
@@ -396,7 +516,7 @@ static void field_args_of(const vpb_field_array_t *fa, float *df, vpb_field_args
   vpb_field_args_t a; field_args_of(fa, df, &a);                                            \
   DEV(call);                                                                                \
   dev_written(fa->f, fbytes);                                                               \
-  if (g_mode == VPB_MODE_COHERENT) DEV(vpb_stream_sync(nullptr));
+  finish_entry();
 
 void vpic_b200_advance_b(vpb_field_array_t *fa, float frac) { FIELD_ENTRY(advance_b, vpb_advance_b(&a, frac, nullptr)) }
 void vpic_b200_advance_e(vpb_field_array_t *fa, float frac) { FIELD_ENTRY(advance_e, vpb_vacuum_advance_e(&a, frac, nullptr)) }

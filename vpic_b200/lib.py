@@ -102,7 +102,10 @@ _PROTOS = {
 DROPIN_SYMBOLS = ["advance_p", "sort_p", "load_interpolator_array", "clear_accumulator_array",
                   "reduce_accumulator_array", "unload_accumulator_array", "energy_p", "center_p", "uncenter_p",
                   "accumulate_rho_p",
-                  "vpic_b200_sync_to_host", "vpic_b200_invalidate", "vpic_b200_set_mode"]
+                  "vpic_b200_advance_b", "vpic_b200_advance_e", "vpic_b200_clear_jf", "vpic_b200_synchronize_jf",
+                  "vpic_b200_energy_f", "vpic_b200_install_field_kernels",
+                  "vpic_b200_sync_to_host", "vpic_b200_invalidate", "vpic_b200_release", "vpic_b200_set_mode",
+                  "vpic_b200_transfer_bytes", "vpic_b200_host_access", "vpic_b200_lazy_stats", "vpic_b200_set_lazy_min"]
 
 _lib = None
 
