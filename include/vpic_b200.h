@@ -193,6 +193,12 @@ typedef struct vpb_field_args {
   float   dx, dy, dz, dV;
   float   rdx, rdy, rdz;
   int32_t face[6];
+  /* The single material that fills space (the reference's vacuum_* kernels are used whenever the material list has
+   * one entry, whatever its coefficients — sfa.cc:202-211): material_coefficient_t order (sfa_private.h:14-25)
+   * decayx drivex decayy drivey decayz drivez rmux rmuy rmuz nonconductive epsx epsy epsz.  has_material == 0 means
+   * true vacuum (all ones). */
+  int32_t has_material;
+  float   material[13];
 } vpb_field_args_t;
 
 int vpb_advance_b(const vpb_field_args_t *a, float frac, void *stream);

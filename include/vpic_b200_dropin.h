@@ -51,8 +51,19 @@ void clear_accumulator_array(vpb_accumulator_array_t *aa);
 void reduce_accumulator_array(vpb_accumulator_array_t *aa);
 void unload_accumulator_array(vpb_field_array_t *fa, const vpb_accumulator_array_t *aa);
 
+/* The reference's own field kernels (src/field_advance/standard/sfa_private.h:40,51-53,86-88,117-119,383): its
+ * kernel table is filled from these C symbols (sfa.cc:27-64,202-211), so under LD_PRELOAD they take over without a
+ * deck change.  Served on the device when the field array has one material and no face shared with another rank;
+ * otherwise (or with VPIC_B200_FIELDS=0) the call falls through to the reference's definition (dlsym RTLD_NEXT). */
+void advance_b(vpb_field_array_t *fa, float frac);
+void vacuum_advance_e(vpb_field_array_t *fa, float frac);
+void clear_jf(vpb_field_array_t *fa);
+void synchronize_jf(vpb_field_array_t *fa);
+void vacuum_energy_f(double *en6, const vpb_field_array_t *fa);
+
 /* Device-backed entries for the field_advance_kernels_t table (src/field_advance/field_advance.h:170-218);
- * vpic_b200_install_field_kernels(fa) repoints fa->kernel[0] at them (single vacuum material, single rank). */
+ * vpic_b200_install_field_kernels(fa) repoints fa->kernel[0] at them (one material, single rank) — for host builds
+ * where the symbols above cannot be interposed (static linking with the reference's field sources kept). */
 void vpic_b200_advance_b(vpb_field_array_t *fa, float frac);
 void vpic_b200_advance_e(vpb_field_array_t *fa, float frac);
 void vpic_b200_clear_jf(vpb_field_array_t *fa);

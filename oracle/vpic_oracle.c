@@ -514,8 +514,12 @@ void vpo_vacuum_advance_e(const vpo_field_args_t *a, float frac) {
   if (frac != 1) abort();                                           /* .cc:58-61 */
   const int nx = a->nx, ny = a->ny, nz = a->nz;
   const float damp = a->damp;
-  /* single vacuum material: decay=1, drive=1/eps=1, rmu=1 (sfa.cc:119-136 with eps=mu=1, sigma=0) */
-  const float decayx = 1, drivex = 1, decayy = 1, drivey = 1, decayz = 1, drivez = 1, rmux = 1, rmuy = 1, rmuz = 1;
+  /* the single material's coefficients (vacuum_advance_e_pipeline.h:18-26); true vacuum: decay=1, drive=1/eps=1,
+     rmu=1 (sfa.cc:119-136 with eps=mu=1, sigma=0) */
+  const float *m = a->material;
+  const int hm = a->has_material;
+  const float decayx = hm ? m[0] : 1, drivex = hm ? m[1] : 1, decayy = hm ? m[2] : 1, drivey = hm ? m[3] : 1;
+  const float decayz = hm ? m[4] : 1, drivez = hm ? m[5] : 1, rmux = hm ? m[6] : 1, rmuy = hm ? m[7] : 1, rmuz = hm ? m[8] : 1;
   const float px_muz = ((nx > 1) ? (1 + damp) * a->cvac * a->dt * a->rdx : 0) * rmuz;
   const float px_muy = ((nx > 1) ? (1 + damp) * a->cvac * a->dt * a->rdx : 0) * rmuy;
   const float py_mux = ((ny > 1) ? (1 + damp) * a->cvac * a->dt * a->rdy : 0) * rmux;
@@ -602,20 +606,23 @@ void vpo_synchronize_jf(const vpo_field_args_t *a) {
 /* vacuum_energy_f: vacuum_energy_f_pipeline.cc:12-97, stencil .h:24-75 (single pipeline order) */
 void vpo_vacuum_energy_f(const vpo_field_args_t *a, double en[6]) {
   const int nx = a->nx, ny = a->ny, nz = a->nz;
-  const float qeps = 0.25 * 1.0f, hrmu = 0.50 * 1.0f;
+  const float *m = a->material;
+  const int hm = a->has_material;                              /* .h:24-29: 0.25*eps, 0.50*rmu of the single material */
+  const float qepsx = 0.25 * (hm ? m[10] : 1.0f), qepsy = 0.25 * (hm ? m[11] : 1.0f), qepsz = 0.25 * (hm ? m[12] : 1.0f);
+  const float hrmux = 0.50 * (hm ? m[6] : 1.0f), hrmuy = 0.50 * (hm ? m[7] : 1.0f), hrmuz = 0.50 * (hm ? m[8] : 1.0f);
   double e0 = 0, e1 = 0, e2 = 0, b0 = 0, b1 = 0, b2 = 0;
   const float *F = a->f;
 # define FF(x, y, z, m) F[(size_t)VOX(x, y, z) * F_STRIDE + (m)]
   for (int z = 1; z <= nz; z++) for (int y = 1; y <= ny; y++) for (int x = 1; x <= nx; x++) {
-    e0 += qeps * (FF(x, y, z, F_EX) * FF(x, y, z, F_EX) + FF(x, y + 1, z, F_EX) * FF(x, y + 1, z, F_EX) +
+    e0 += qepsx * (FF(x, y, z, F_EX) * FF(x, y, z, F_EX) + FF(x, y + 1, z, F_EX) * FF(x, y + 1, z, F_EX) +
                   FF(x, y, z + 1, F_EX) * FF(x, y, z + 1, F_EX) + FF(x, y + 1, z + 1, F_EX) * FF(x, y + 1, z + 1, F_EX));
-    e1 += qeps * (FF(x, y, z, F_EY) * FF(x, y, z, F_EY) + FF(x, y, z + 1, F_EY) * FF(x, y, z + 1, F_EY) +
+    e1 += qepsy * (FF(x, y, z, F_EY) * FF(x, y, z, F_EY) + FF(x, y, z + 1, F_EY) * FF(x, y, z + 1, F_EY) +
                   FF(x + 1, y, z, F_EY) * FF(x + 1, y, z, F_EY) + FF(x + 1, y, z + 1, F_EY) * FF(x + 1, y, z + 1, F_EY));
-    e2 += qeps * (FF(x, y, z, F_EZ) * FF(x, y, z, F_EZ) + FF(x + 1, y, z, F_EZ) * FF(x + 1, y, z, F_EZ) +
+    e2 += qepsz * (FF(x, y, z, F_EZ) * FF(x, y, z, F_EZ) + FF(x + 1, y, z, F_EZ) * FF(x + 1, y, z, F_EZ) +
                   FF(x, y + 1, z, F_EZ) * FF(x, y + 1, z, F_EZ) + FF(x + 1, y + 1, z, F_EZ) * FF(x + 1, y + 1, z, F_EZ));
-    b0 += hrmu * (FF(x, y, z, F_CBX) * FF(x, y, z, F_CBX) + FF(x + 1, y, z, F_CBX) * FF(x + 1, y, z, F_CBX));
-    b1 += hrmu * (FF(x, y, z, F_CBY) * FF(x, y, z, F_CBY) + FF(x, y + 1, z, F_CBY) * FF(x, y + 1, z, F_CBY));
-    b2 += hrmu * (FF(x, y, z, F_CBZ) * FF(x, y, z, F_CBZ) + FF(x, y, z + 1, F_CBZ) * FF(x, y, z + 1, F_CBZ));
+    b0 += hrmux * (FF(x, y, z, F_CBX) * FF(x, y, z, F_CBX) + FF(x + 1, y, z, F_CBX) * FF(x + 1, y, z, F_CBX));
+    b1 += hrmuy * (FF(x, y, z, F_CBY) * FF(x, y, z, F_CBY) + FF(x, y + 1, z, F_CBY) * FF(x, y + 1, z, F_CBY));
+    b2 += hrmuz * (FF(x, y, z, F_CBZ) * FF(x, y, z, F_CBZ) + FF(x, y, z + 1, F_CBZ) * FF(x, y, z + 1, F_CBZ));
   }
 # undef FF
   double v0 = 0.5 * a->eps0 * a->dV;                            /* .cc:84 */

@@ -88,6 +88,11 @@ typedef struct vpo_field_args {
   float   dx, dy, dz, dV;    /* as stored in grid_t (partition.cc:55-72) */
   float   rdx, rdy, rdz;
   int32_t bc6[6];
+  /* coefficients of the single material that fills space, in material_coefficient_t order (sfa_private.h:14-25):
+   * decayx drivex decayy drivey decayz drivez rmux rmuy rmuz nonconductive epsx epsy epsz.  Used when has_material
+   * is nonzero; otherwise true vacuum (all ones). */
+  int32_t has_material;
+  float   material[13];
 } vpo_field_args_t;
 
 void vpo_advance_b(const vpo_field_args_t *a, float frac);

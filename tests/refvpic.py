@@ -72,7 +72,7 @@ class OracleFieldArgs(C.Structure):
                 ("dt", C.c_float), ("cvac", C.c_float), ("eps0", C.c_float), ("damp", C.c_float),
                 ("dx", C.c_float), ("dy", C.c_float), ("dz", C.c_float), ("dV", C.c_float),
                 ("rdx", C.c_float), ("rdy", C.c_float), ("rdz", C.c_float),
-                ("bc6", C.c_int32 * 6)]
+                ("bc6", C.c_int32 * 6), ("has_material", C.c_int32), ("material", C.c_float * 13)]
 
 
 def load_ref(variant="scalar", tpp=1):
@@ -139,7 +139,9 @@ class RefWorld:
     """A reference grid + field/interpolator/accumulator arrays, with numpy views of the host arrays."""
 
     def __init__(self, lib, nx, ny, nz, lx=None, ly=None, lz=None, dt=None, cvac=1.0, eps0=1.0, damp=0.0,
-                 fbc=None, pbc=None):
+                 fbc=None, pbc=None, material=None):
+        """material: 12 floats eps(x,y,z), mu(x,y,z), sigma(x,y,z), zeta(x,y,z) of the single material that fills
+        space (material.h); default vacuum."""
         self.lib = lib
         g = lib.new_grid()
         self.g = g
@@ -159,7 +161,7 @@ class RefWorld:
         for f, code in (pbc or {}).items():
             lib.set_pbc(g, BOUNDARY(*FACES[f]), code)
         m_list = C.c_void_p(None)
-        m = lib.material(b"vacuum", *([1.0] * 6 + [0.0] * 6))
+        m = lib.material(b"vacuum", *(list(material) if material is not None else [1.0] * 6 + [0.0] * 6))
         lib.append_material(m, C.byref(m_list))
         self.fa = lib.new_standard_field_array(g, m_list, damp)
         self.ia = lib.new_interpolator_array(g)
@@ -223,7 +225,16 @@ class RefWorld:
         a.rdx, a.rdy, a.rdz = g.rdx, g.rdy, g.rdz
         for f in range(6):
             a.bc6[f] = g.bc[BOUNDARY(*FACES[f])]
+        a.has_material = 1
+        for k, v in enumerate(self.material_coefficients()):
+            a.material[k] = v
         return a
+
+    def material_coefficients(self):
+        """The 13 material_coefficient_t floats the reference derived for the single material (sfa.cc:108-148)."""
+        prm = C.cast(self.fa.contents.params, C.POINTER(abi.SfaParams)).contents
+        mc = C.cast(prm.mc, C.POINTER(C.c_float * 13)).contents
+        return [float(x) for x in mc]
 
 
 class RefSpecies:

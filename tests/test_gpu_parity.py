@@ -235,16 +235,21 @@ def test_energy_center_uncenter(eng, oracle):
     assert np.array_equal(bits(sp.particles_host()), bits(p_ref))
 
 
-@pytest.mark.parametrize("dims,fbc,damp", [
-    ((6, 5, 4), None, 0.0),
-    ((6, 5, 4), None, 0.01),
-    ((64, 64, 1), {0: -1, 3: -1}, 0.0),          # harris: pec x walls, one cell in z
-    ((5, 1, 7), {2: -2, 5: -3}, 0.0),            # symmetric / pmc, one cell in y
-    ((40, 24, 16), None, 0.0),
-    ((6, 5, 4), {0: -4, 3: -4, 2: -4, 5: -1}, 0.0),   # absorbing (Higdon) walls
-    ((96, 1, 40), {0: -4, 3: -4}, 0.01),          # lpi-like 2-D box with absorbing x walls
+# material_coefficient_t of one anisotropic conducting material (decay/drive x,y,z; rmu x,y,z; nonconductive; eps x,y,z)
+MATERIAL = [0.93, 0.64, 0.88, 0.47, 0.97, 0.39, 0.83, 0.91, 0.77, 0.0, 1.5, 2.0, 2.5]
+
+
+@pytest.mark.parametrize("dims,fbc,damp,material", [
+    ((6, 5, 4), None, 0.0, None),
+    ((6, 5, 4), None, 0.01, None),
+    ((64, 64, 1), {0: -1, 3: -1}, 0.0, None),          # harris: pec x walls, one cell in z
+    ((5, 1, 7), {2: -2, 5: -3}, 0.0, None),            # symmetric / pmc, one cell in y
+    ((40, 24, 16), None, 0.0, None),
+    ((6, 5, 4), {0: -4, 3: -4, 2: -4, 5: -1}, 0.0, None),   # absorbing (Higdon) walls
+    ((96, 1, 40), {0: -4, 3: -4}, 0.01, None),          # lpi-like 2-D box with absorbing x walls
+    ((33, 9, 12), {0: -1, 3: -4}, 0.01, MATERIAL),      # one non-vacuum material filling space (sfa.cc:202-211)
 ])
-def test_field_advance(eng, oracle, dims, fbc, damp):
+def test_field_advance(eng, oracle, dims, fbc, damp, material):
     rng = np.random.default_rng(3)
     nx, ny, nz = dims
     g = make_grid(nx, ny, nz, fbc=fbc)
@@ -252,10 +257,14 @@ def test_field_advance(eng, oracle, dims, fbc, damp):
     f0 = R.random_fields(rng, g.nv)
     f0[:, 8:11] = rng.normal(0, 0.01, (g.nv, 3))
     f0[:, 12:15] = rng.normal(0, 0.02, (g.nv, 3))
-    fa = eng.FieldArray(dg, damp=damp)
+    fa = eng.FieldArray(dg, damp=damp, material=material)
     fa.f.copy_(torch.from_numpy(f0))
     f_ref = f0.copy()
     a = R.OracleFieldArgs()
+    if material is not None:
+        a.has_material = 1
+        for i, v in enumerate(material):
+            a.material[i] = v
     a.f = f_ref.ctypes.data
     a.nx, a.ny, a.nz = nx, ny, nz
     a.dt, a.cvac, a.eps0, a.damp = g.dt, g.cvac, g.eps0, damp

@@ -117,18 +117,27 @@ def test_interpolator_unload_energy_center(ref_scalar, oracle):
     assert np.array_equal(bits(p2), bits(sp.p[:len(p2)]))
 
 
-@pytest.mark.parametrize("dims,fbc,damp", [
-    ((6, 5, 4), None, 0.0),
-    ((6, 5, 4), None, 0.01),
-    ((8, 8, 1), {0: -1, 3: -1}, 0.0),             # harris-like: pec x walls, degenerate z
-    ((5, 1, 7), {2: -2, 5: -3}, 0.0),             # symmetric / pmc walls, degenerate y
-    ((6, 5, 4), {0: -4, 3: -4, 2: -4, 5: -1}, 0.0),  # absorbing (Higdon) walls on -x, +x, -z; pec on +z
-    ((9, 1, 6), {0: -4, 3: -4}, 0.01),            # lpi-like: 2-D, absorbing x walls
+# one anisotropic, conducting material filling space: the reference still uses its vacuum_* kernels (sfa.cc:202-211)
+DIELECTRIC = (1.5, 2.0, 2.5, 1.2, 1.1, 1.3, 0.1, 0.2, 0.05, 0.0, 0.0, 0.0)
+
+
+@pytest.mark.parametrize("dims,fbc,damp,material", [
+    ((6, 5, 4), None, 0.0, None),
+    ((6, 5, 4), None, 0.01, None),
+    ((8, 8, 1), {0: -1, 3: -1}, 0.0, None),             # harris-like: pec x walls, degenerate z
+    ((5, 1, 7), {2: -2, 5: -3}, 0.0, None),             # symmetric / pmc walls, degenerate y
+    ((6, 5, 4), {0: -4, 3: -4, 2: -4, 5: -1}, 0.0, None),  # absorbing (Higdon) walls on -x, +x, -z; pec on +z
+    ((9, 1, 6), {0: -4, 3: -4}, 0.01, None),            # lpi-like: 2-D, absorbing x walls
+    ((6, 5, 4), None, 0.01, DIELECTRIC),
+    ((7, 4, 5), {0: -1, 3: -4}, 0.0, DIELECTRIC),
 ])
-def test_field_advance_bit_exact(ref_scalar, oracle, dims, fbc, damp):
+def test_field_advance_bit_exact(ref_scalar, oracle, dims, fbc, damp, material):
     rng = np.random.default_rng(3)
     nx, ny, nz = dims
-    W = R.RefWorld(ref_scalar, nx, ny, nz, fbc=fbc, damp=damp)
+    W = R.RefWorld(ref_scalar, nx, ny, nz, fbc=fbc, damp=damp, material=material)
+    if material is not None:
+        mc = W.material_coefficients()
+        assert mc[0] != 1.0 and mc[1] != 1.0 and mc[6] != 1.0 and mc[10] == 1.5
     f0 = R.random_fields(rng, W.nv)
     f0[:, 8:11] = rng.normal(0, 0.01, (W.nv, 3))       # tca
     f0[:, 12:15] = rng.normal(0, 0.02, (W.nv, 3))      # jf

@@ -492,21 +492,38 @@ void unload_accumulator_array(vpb_field_array_t *fa, const vpb_accumulator_array
 // vpic_b200_install_field_kernels(fa) repoints the time-stepping entries of fa->kernel[0] at the functions below,
 // the same way new_standard_field_array swaps in its vacuum_* variants (sfa.cc:202-211).  They are global symbols
 // because the reference's checkpointing stores the table by symbol name (field_advance.cc:16-58).
-static void field_args_of(const vpb_field_array_t *fa, float *df, vpb_field_args_t *a) {
+// Why the device field kernels cannot serve this field array, or nullptr when they can: one material filling space
+// (exactly when the reference itself picks its vacuum_* kernels, sfa.cc:202-211) and no face shared with another rank.
+static const char *device_fields_obstacle(const vpb_field_array_t *fa) {
   const vpb_grid_t *g = fa->g;
   const vpb_sfa_params_t *prm = (const vpb_sfa_params_t *)fa->params;
-  a->f = df; a->nx = g->nx; a->ny = g->ny; a->nz = g->nz;
-  a->dt = g->dt; a->cvac = g->cvac; a->eps0 = g->eps0; a->damp = prm ? prm->damp : 0.0f;
-  a->dx = g->dx; a->dy = g->dy; a->dz = g->dz; a->dV = g->dV; a->rdx = g->rdx; a->rdy = g->rdy; a->rdz = g->rdz;
+  if (!prm || !prm->mc) return "the field array has no standard-field-advance parameters";
+  if (prm->n_mc != 1) return "more than one material";
   static const int off[6][3] = {{-1,0,0},{0,-1,0},{0,0,-1},{1,0,0},{0,1,0},{0,0,1}};
   const int self = g->bc[13];
   for (int f = 0; f < 6; f++) {
     const int b = g->bc[13 + off[f][0] + 3 * off[f][1] + 9 * off[f][2]];          // BOUNDARY(i,j,k), grid.h:16
-    if (b < 0) a->face[f] = b;
-    else if (b == self) a->face[f] = VPB_FACE_PERIODIC_SELF;
-    else DROPIN_ERROR("face %d is shared with rank %d: multi-rank halo exchange runs through the NCCL path, not this seam", f, b);
+    if (b >= 0 && b != self) return "a face is shared with another rank (multi-rank halo exchange runs through the NCCL path)";
+    if (b < -4) return "a field boundary condition the device kernels do not know";
   }
-  if (prm && prm->n_mc != 1) DROPIN_ERROR("the device field advance supports a single (vacuum) material; this deck has %d", prm->n_mc);
+  return nullptr;
+}
+
+static void field_args_of(const vpb_field_array_t *fa, float *df, vpb_field_args_t *a) {
+  if (const char *why = device_fields_obstacle(fa)) DROPIN_ERROR("the device field advance cannot serve this field array: %s", why);
+  const vpb_grid_t *g = fa->g;
+  const vpb_sfa_params_t *prm = (const vpb_sfa_params_t *)fa->params;
+  memset(a, 0, sizeof *a);
+  a->f = df; a->nx = g->nx; a->ny = g->ny; a->nz = g->nz;
+  a->dt = g->dt; a->cvac = g->cvac; a->eps0 = g->eps0; a->damp = prm->damp;
+  a->dx = g->dx; a->dy = g->dy; a->dz = g->dz; a->dV = g->dV; a->rdx = g->rdx; a->rdy = g->rdy; a->rdz = g->rdz;
+  static const int off[6][3] = {{-1,0,0},{0,-1,0},{0,0,-1},{1,0,0},{0,1,0},{0,0,1}};
+  for (int f = 0; f < 6; f++) {
+    const int b = g->bc[13 + off[f][0] + 3 * off[f][1] + 9 * off[f][2]];
+    a->face[f] = b < 0 ? b : VPB_FACE_PERIODIC_SELF;
+  }
+  a->has_material = 1;                                       // material_coefficient_t, sfa_private.h:14-25
+  memcpy(a->material, prm->mc, 13 * sizeof(float));
 }
 
 #define FIELD_ENTRY(name, call)                                                            \
@@ -534,8 +551,51 @@ void vpic_b200_energy_f(double *en, const vpb_field_array_t *fa) {
   g_d2h += sizeof local;
   if (mp_allsum_d) mp_allsum_d(local, en, 6); else memcpy(en, local, sizeof local);
 }
+
+// The reference's own field kernels are C-linkage symbols too (sfa_private.h:32-452) and its kernel table is filled
+// from them through the GOT (sfa.cc:27-64,202-211), so when this library precedes the reference in symbol resolution
+// (LD_PRELOAD under a shared-library build) the five entries below take over without touching the deck.  A field
+// array the device kernels cannot serve (several materials, faces shared with other ranks) and VPIC_B200_FIELDS=0
+// fall through to the reference's definition, found with dlsym(RTLD_NEXT).
+static bool fields_on_device(const vpb_field_array_t *fa) {
+  static int enabled = -1;
+  if (enabled < 0) { const char *e = getenv("VPIC_B200_FIELDS"); enabled = !(e && atoi(e) == 0 && e[0] == '0'); }
+  return enabled && fa && fa->g && !device_fields_obstacle(fa);
+}
+static void *reference_kernel(const char *name) {
+  void *f = dlsym(RTLD_NEXT, name);
+  if (!f) DROPIN_ERROR("%s: this field array needs the reference's own kernel, which is not linked in", name);
+  return f;
+}
+void advance_b(vpb_field_array_t *fa, float frac) {
+  if (fields_on_device(fa)) { vpic_b200_advance_b(fa, frac); return; }
+  static auto ref = (void (*)(vpb_field_array_t *, float))reference_kernel("advance_b");
+  ref(fa, frac);
+}
+void vacuum_advance_e(vpb_field_array_t *fa, float frac) {
+  if (fields_on_device(fa)) { vpic_b200_advance_e(fa, frac); return; }
+  static auto ref = (void (*)(vpb_field_array_t *, float))reference_kernel("vacuum_advance_e");
+  ref(fa, frac);
+}
+void clear_jf(vpb_field_array_t *fa) {
+  if (fields_on_device(fa)) { vpic_b200_clear_jf(fa); return; }
+  static auto ref = (void (*)(vpb_field_array_t *))reference_kernel("clear_jf");
+  ref(fa);
+}
+void synchronize_jf(vpb_field_array_t *fa) {
+  if (fields_on_device(fa)) { vpic_b200_synchronize_jf(fa); return; }
+  static auto ref = (void (*)(vpb_field_array_t *))reference_kernel("synchronize_jf");
+  ref(fa);
+}
+void vacuum_energy_f(double *en, const vpb_field_array_t *fa) {
+  if (fields_on_device(fa)) { vpic_b200_energy_f(en, fa); return; }
+  static auto ref = (void (*)(double *, const vpb_field_array_t *))reference_kernel("vacuum_energy_f");
+  ref(en, fa);
+}
+
 void vpic_b200_install_field_kernels(vpb_field_array_t *fa) {
   if (!fa) DROPIN_ERROR("Bad args");
+  if (const char *why = device_fields_obstacle(fa)) DROPIN_ERROR("the device field advance cannot serve this field array: %s", why);
   fa->kernel->advance_b = vpic_b200_advance_b;
   fa->kernel->advance_e = vpic_b200_advance_e;
   fa->kernel->energy_f = vpic_b200_energy_f;

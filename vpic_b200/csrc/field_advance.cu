@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(256) ghost_tang_b_kernel(FieldK k) {
 }
 
 // ---- vacuum_advance_e --------------------------------------------------------------------------------------
-struct ECoef { float px_muz, px_muy, py_mux, py_muz, pz_muy, pz_mux, cj, damp; };
+struct ECoef { float px_muz, px_muy, py_mux, py_muz, pz_muy, pz_mux, cj, damp, decayx, drivex, decayy, drivey, decayz, drivez; };
 
 __global__ void __launch_bounds__(256) vacuum_advance_e_kernel(FieldK k, ECoef c) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x + 1, y = blockIdx.y + 1, z = blockIdx.z + 1;
@@ -147,19 +147,18 @@ __global__ void __launch_bounds__(256) vacuum_advance_e_kernel(FieldK k, ECoef c
   float4 e = FQ(v, 0), t = FQ(v, 2);
   const float4 b0 = FQ(v, 1), j = FQ(v, 3);
   const float4 bx = FQ(v - 1, 1), by = FQ(v - sy, 1), bz = FQ(v - sz, 1);
-  // vacuum: decay = 1, drive = 1 (sfa.cc:119-136 with eps = mu = 1, sigma = 0); kept as explicit multiplies
-  const float decay = 1.0f, drive = 1.0f;
+  // decay/drive of the single material (sfa.cc:119-136); 1 and 1 in true vacuum, kept as explicit multiplies
   if (x <= nx) {
     t.x = (c.py_muz * (b0.z - by.z) - c.pz_muy * (b0.y - bz.y)) - c.damp * t.x;
-    e.x = decay * e.x + drive * (t.x - c.cj * j.x);
+    e.x = c.decayx * e.x + c.drivex * (t.x - c.cj * j.x);
   }
   if (y <= ny) {
     t.y = (c.pz_mux * (b0.x - bz.x) - c.px_muz * (b0.z - bx.z)) - c.damp * t.y;
-    e.y = decay * e.y + drive * (t.y - c.cj * j.y);
+    e.y = c.decayy * e.y + c.drivey * (t.y - c.cj * j.y);
   }
   if (z <= nz) {
     t.z = (c.px_muy * (b0.y - bx.y) - c.py_mux * (b0.x - by.x)) - c.damp * t.z;
-    e.z = decay * e.z + drive * (t.z - c.cj * j.z);
+    e.z = c.decayz * e.z + c.drivez * (t.z - c.cj * j.z);
   }
   // local_adjust_tang_e: a pec (-1) wall zeroes tangential E and TCA on its face plane (local.cc:236-247)
   const int n[3] = {nx, ny, nz}; const int cc[3] = {x, y, z};
@@ -266,13 +265,14 @@ __global__ void __launch_bounds__(256) halo_kernel(FieldK k, int kind, int fc, f
 }
 
 // ---- vacuum_energy_f ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) energy_f_kernel(FieldK k, double *en6) {
+struct EnCoef { float qepsx, qepsy, qepsz, hrmux, hrmuy, hrmuz; };
+
+__global__ void __launch_bounds__(256) energy_f_kernel(FieldK k, EnCoef m, double *en6) {
   __shared__ double s_part[8][6];
   const int nx = k.nx, ny = k.ny, nz = k.nz;
   const float4 *f = k.f;
   const int sy = nx + 2, sz = (nx + 2) * (ny + 2);
   double acc[6] = {0, 0, 0, 0, 0, 0};
-  const float qeps = 0.25f, hrmu = 0.5f;
   const long long total = (long long)nx * ny * nz;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
     const int x = (int)(t % nx) + 1, y = (int)((t / nx) % ny) + 1, z = (int)(t / ((long long)nx * ny)) + 1;
@@ -280,12 +280,12 @@ __global__ void __launch_bounds__(256) energy_f_kernel(FieldK k, double *en6) {
     const float4 e0 = FQ(v, 0), ex = FQ(v + 1, 0), ey = FQ(v + sy, 0), ez = FQ(v + sz, 0);
     const float4 eyz = FQ(v + sy + sz, 0), ezx = FQ(v + sz + 1, 0), exy = FQ(v + 1 + sy, 0);
     const float4 b0 = FQ(v, 1), bx = FQ(v + 1, 1), by = FQ(v + sy, 1), bz = FQ(v + sz, 1);
-    acc[0] += (double)(qeps * (((e0.x * e0.x + ey.x * ey.x) + ez.x * ez.x) + eyz.x * eyz.x));
-    acc[1] += (double)(qeps * (((e0.y * e0.y + ez.y * ez.y) + ex.y * ex.y) + ezx.y * ezx.y));
-    acc[2] += (double)(qeps * (((e0.z * e0.z + ex.z * ex.z) + ey.z * ey.z) + exy.z * exy.z));
-    acc[3] += (double)(hrmu * (b0.x * b0.x + bx.x * bx.x));
-    acc[4] += (double)(hrmu * (b0.y * b0.y + by.y * by.y));
-    acc[5] += (double)(hrmu * (b0.z * b0.z + bz.z * bz.z));
+    acc[0] += (double)(m.qepsx * (((e0.x * e0.x + ey.x * ey.x) + ez.x * ez.x) + eyz.x * eyz.x));
+    acc[1] += (double)(m.qepsy * (((e0.y * e0.y + ez.y * ez.y) + ex.y * ex.y) + ezx.y * ezx.y));
+    acc[2] += (double)(m.qepsz * (((e0.z * e0.z + ex.z * ex.z) + ey.z * ey.z) + exy.z * exy.z));
+    acc[3] += (double)(m.hrmux * (b0.x * b0.x + bx.x * bx.x));
+    acc[4] += (double)(m.hrmuy * (b0.y * b0.y + by.y * by.y));
+    acc[5] += (double)(m.hrmuz * (b0.z * b0.z + bz.z * bz.z));
   }
 #pragma unroll
   for (int c = 0; c < 6; c++) {
@@ -343,15 +343,21 @@ extern "C" int vpb_vacuum_advance_e(const vpb_field_args_t *a, float frac, void 
   ghost_tang_b_kernel<<<max_plane_grid(a, 6), 256, 0, st>>>(to_k(a));
   VPB_LAUNCH_CHECK();
   ECoef c;
-  const float damp = a->damp, rmu = 1.0f;
-  c.px_muz = ((a->nx > 1) ? (1 + damp) * a->cvac * a->dt * a->rdx : 0) * rmu;    // vacuum_advance_e_pipeline.h:27-33
-  c.px_muy = c.px_muz;
-  c.py_mux = ((a->ny > 1) ? (1 + damp) * a->cvac * a->dt * a->rdy : 0) * rmu;
-  c.py_muz = c.py_mux;
-  c.pz_muy = ((a->nz > 1) ? (1 + damp) * a->cvac * a->dt * a->rdz : 0) * rmu;
-  c.pz_mux = c.pz_muy;
+  const float damp = a->damp;
+  const bool hm = a->has_material != 0;
+  const float *m = a->material;
+  const float rmux = hm ? m[6] : 1.0f, rmuy = hm ? m[7] : 1.0f, rmuz = hm ? m[8] : 1.0f;
+  c.px_muz = ((a->nx > 1) ? (1 + damp) * a->cvac * a->dt * a->rdx : 0) * rmuz;   // vacuum_advance_e_pipeline.h:18-33
+  c.px_muy = ((a->nx > 1) ? (1 + damp) * a->cvac * a->dt * a->rdx : 0) * rmuy;
+  c.py_mux = ((a->ny > 1) ? (1 + damp) * a->cvac * a->dt * a->rdy : 0) * rmux;
+  c.py_muz = ((a->ny > 1) ? (1 + damp) * a->cvac * a->dt * a->rdy : 0) * rmuz;
+  c.pz_muy = ((a->nz > 1) ? (1 + damp) * a->cvac * a->dt * a->rdz : 0) * rmuy;
+  c.pz_mux = ((a->nz > 1) ? (1 + damp) * a->cvac * a->dt * a->rdz : 0) * rmux;
   c.cj = a->dt / a->eps0;
   c.damp = damp;
+  c.decayx = hm ? m[0] : 1.0f; c.drivex = hm ? m[1] : 1.0f;
+  c.decayy = hm ? m[2] : 1.0f; c.drivey = hm ? m[3] : 1.0f;
+  c.decayz = hm ? m[4] : 1.0f; c.drivez = hm ? m[5] : 1.0f;
   dim3 grid((a->nx + 1 + 255) / 256, a->ny + 1, a->nz + 1);
   vacuum_advance_e_kernel<<<grid, 256, 0, st>>>(to_k(a), c);
   VPB_LAUNCH_CHECK();
@@ -395,7 +401,13 @@ extern "C" int vpb_vacuum_energy_f(const vpb_field_args_t *a, double *en6_dev, v
   VPB_CUDA(cudaMemsetAsync(en6_dev, 0, 6 * sizeof(double), st));
   long long total = (long long)a->nx * a->ny * a->nz;
   int grid = (int)((total + 255) / 256); if (grid > kSMs * 4) grid = kSMs * 4;
-  energy_f_kernel<<<grid, 256, 0, st>>>(to_k(a), en6_dev);
+  const bool hm = a->has_material != 0;                       // vacuum_energy_f_pipeline.h:24-29
+  EnCoef m;
+  m.qepsx = 0.25f * (hm ? a->material[10] : 1.0f); m.qepsy = 0.25f * (hm ? a->material[11] : 1.0f);
+  m.qepsz = 0.25f * (hm ? a->material[12] : 1.0f);
+  m.hrmux = 0.5f * (hm ? a->material[6] : 1.0f); m.hrmuy = 0.5f * (hm ? a->material[7] : 1.0f);
+  m.hrmuz = 0.5f * (hm ? a->material[8] : 1.0f);
+  energy_f_kernel<<<grid, 256, 0, st>>>(to_k(a), m, en6_dev);
   VPB_LAUNCH_CHECK();
   scale6_kernel<<<1, 32, 0, st>>>(en6_dev, 0.5 * (double)a->eps0 * (double)a->dV);
   VPB_LAUNCH_CHECK();

@@ -79,9 +79,13 @@ class AccumulatorArray:
 
 
 class FieldArray:
-    def __init__(self, g: DeviceGrid, damp=0.0):
+    def __init__(self, g: DeviceGrid, damp=0.0, material=None):
+        """material: the 13 material_coefficient_t floats (sfa_private.h:14-25) of the single material that fills
+        space, or None for true vacuum."""
         self.g = g
         self.damp = float(damp)
+        self.material = None if material is None else [float(x) for x in material]
+        assert self.material is None or len(self.material) == 13
         self.f = torch.zeros((g.nv, abi.FIELD_FLOATS), dtype=torch.float32, device=g.device)
         self._en = torch.zeros(6, dtype=torch.float64, device=g.device)
 
@@ -95,6 +99,10 @@ class FieldArray:
         a.rdx, a.rdy, a.rdz = g.rdx, g.rdy, g.rdz
         for i, c in enumerate(g.g.face_codes()):
             a.face[i] = c
+        if self.material is not None:
+            a.has_material = 1
+            for i, v in enumerate(self.material):
+                a.material[i] = v
         return a
 
     # field_advance_kernels_t entries on the path (field_advance.h:170-218)

@@ -47,7 +47,7 @@ class FieldArgs(C.Structure):
                 ("dt", c_f), ("cvac", c_f), ("eps0", c_f), ("damp", c_f),
                 ("dx", c_f), ("dy", c_f), ("dz", c_f), ("dV", c_f),
                 ("rdx", c_f), ("rdy", c_f), ("rdz", c_f),
-                ("face", c_i32 * 6)]
+                ("face", c_i32 * 6), ("has_material", c_i32), ("material", c_f * 13)]
 
 
 DEPOSIT_DEFAULT, DEPOSIT_RED_V4, DEPOSIT_WARP_SEG, DEPOSIT_WARP_SEG_MOVERS, DEPOSIT_WARP_SEG_FIRST = 0, 1, 2, 3, 4
@@ -101,7 +101,7 @@ _PROTOS = {
 # the reference's own extern "C" symbols that the drop-in layer exports (include/vpic_b200_dropin.h)
 DROPIN_SYMBOLS = ["advance_p", "sort_p", "load_interpolator_array", "clear_accumulator_array",
                   "reduce_accumulator_array", "unload_accumulator_array", "energy_p", "center_p", "uncenter_p",
-                  "accumulate_rho_p",
+                  "accumulate_rho_p", "advance_b", "vacuum_advance_e", "clear_jf", "synchronize_jf", "vacuum_energy_f",
                   "vpic_b200_advance_b", "vpic_b200_advance_e", "vpic_b200_clear_jf", "vpic_b200_synchronize_jf",
                   "vpic_b200_energy_f", "vpic_b200_install_field_kernels",
                   "vpic_b200_sync_to_host", "vpic_b200_invalidate", "vpic_b200_release", "vpic_b200_set_mode",
