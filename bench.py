@@ -91,6 +91,11 @@ def build_sim(args, rank, world, device):
         ny = n // world
     dt = G.courant_dt(1.0, 1.0, 1.0, nx, ny * world, nz, frac=0.99)
     g = G.partition_periodic_box(0, 0, 0, nx, ny * world, nz, nx, ny * world, nz, 1, world, 1, rank=rank, dt=dt)
+    harris = args.workload == "harris"
+    if harris:                                         # sample/harris: conducting z walls that reflect particles
+        for f in (2, 5):
+            g.set_fbc(f, G.PEC_FIELDS)
+            g.set_pbc(f, G.REFLECT_PARTICLES)
     dg = E.DeviceGrid(g, device)
     exchange = None
     if world > 1:
@@ -101,6 +106,14 @@ def build_sim(args, rank, world, device):
     npart = nx * ny * nz * args.ppc
     gen = torch.Generator(device=device)
     gen.manual_seed(1234 + rank)
+    # Harris sheet (sample/harris:117-131,216-250 scaled to this box): B_x = b0 tanh((z-zc)/L), two thirds of every
+    # species in the sech^2 sheet drifting along +-y, one third as uniform background; same particle count as the
+    # uniform load, so the sheet cells hold several times the mean ppc and the lobes a third of it.
+    L_sheet, b0, drift = nz / 16.0, 0.15, 0.05
+    if harris:
+        z = torch.arange(nz + 2, device=device, dtype=torch.float64) - 0.5 - 0.5 * nz     # cell-centred distance from zc
+        f3 = sim.field_array.f.view(nz + 2, ny + 2, nx + 2, -1)
+        f3[..., 4] = (b0 * torch.tanh(z / L_sheet)).to(torch.float32)[:, None, None]       # cbx(z)
     for name, q, m, uth in (("electron", -1.0, 1.0, args.uth), ("ion", 1.0, 25.0, args.uth / 5.0)):
         max_np = int(npart * (1.25 if world > 1 else 1.0)) + 1024
         sp = sim.define_species(name, q, m, max_np, max(int(npart * 0.05), 1 << 16), args.sort_interval)
@@ -110,8 +123,17 @@ def build_sim(args, rank, world, device):
         ix = torch.randint(1, nx + 1, (npart,), generator=gen, device=device, dtype=torch.int32)
         iy = torch.randint(1, ny + 1, (npart,), generator=gen, device=device, dtype=torch.int32)
         iz = torch.randint(1, nz + 1, (npart,), generator=gen, device=device, dtype=torch.int32)
-        sp.p.view(torch.int32)[:npart, 3] = ix + (nx + 2) * (iy + (ny + 2) * iz)
         p[:, 4:7] = torch.randn((npart, 3), generator=gen, device=device) * uth
+        if harris:
+            n_sheet = (2 * npart) // 3
+            u01 = torch.rand((n_sheet,), generator=gen, device=device, dtype=torch.float64).clamp_(1e-9, 1 - 1e-9)
+            zs = (0.5 * nz + L_sheet * torch.atanh(2 * u01 - 1)).clamp_(1e-3, nz - 1e-3)   # sech^2 profile, inside the walls
+            cell = torch.floor(zs)
+            iz[:n_sheet] = cell.to(torch.int32) + 1
+            p[:n_sheet, 2] = (2 * (zs - cell) - 1).to(torch.float32)
+            p[:n_sheet, 5] += drift if q > 0 else -drift
+            del u01, zs, cell
+        sp.p.view(torch.int32)[:npart, 3] = ix + (nx + 2) * (iy + (ny + 2) * iz)
         p[:, 7] = 1.0 / args.ppc
         sp.np = npart
         del ix, iy, iz
@@ -189,10 +211,14 @@ def run_ours(args):
         out = {"metric": "particle pushes/sec (advance_p+deposit)", "value": value, "unit": "pushes/s",
                "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
                "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-               "config": {"workload": f"uniform thermal e-/ion plasma, {args.grid}^3 cells "
-                                      + ("per GPU" if args.scaling == "weak" else "in total") + f", {args.ppc} ppc/species, "
-                                      f"periodic, sort_p every {args.sort_interval} steps"
-                                      + (" (BASELINE.json configs[1])" if (args.grid, args.ppc) == (128, 64) else ""),
+               "config": {"workload": (f"uniform thermal e-/ion plasma, {args.grid}^3 cells " if args.workload == "uniform" else
+                                       f"Harris current sheet (sech^2 sheet + background, B_x = b0 tanh(z/L), drifting e-/ion, "
+                                       f"conducting reflecting z walls), {args.grid}^3 cells ")
+                                      + ("per GPU" if args.scaling == "weak" else "in total")
+                                      + f", {args.ppc} ppc/species" + (" on average" if args.workload == "harris" else "")
+                                      + f", periodic{' in x and y' if args.workload == 'harris' else ''}, "
+                                      f"sort_p every {args.sort_interval} steps"
+                                      + (" (BASELINE.json configs[1])" if (args.grid, args.ppc, args.workload) == (128, 64, "uniform") else ""),
                           "particles_per_gpu": np_total_local, "decomposition": f"1x{world}x1 slabs",
                           "l2": f"particle arrays ({np_total_local * 32 / 1e9:.1f} GB per GPU) exceed the 126 MB L2; no flush needed",
                           "deposit_variant": args.variant},
@@ -576,9 +602,13 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--ref-grid", type=int, default=64)
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--workload", default="uniform", choices=["uniform", "harris"],
+                    help="uniform thermal plasma (BASELINE.json configs[1], the default) or a Harris current sheet")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (default, the driver's contract): one grid^3 slab per GPU; strong: one grid^3 box split over the GPUs")
     args = ap.parse_args()
+    if args.workload == "harris":        # the end-to-end and CPU legs are defined on the uniform workload only
+        args.e2e, args.no_cpu_baseline = 0, True
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -628,3 +628,299 @@ void vpo_vacuum_energy_f(const vpo_field_args_t *a, double en[6]) {
   double v0 = 0.5 * a->eps0 * a->dV;                            /* .cc:84 */
   en[0] = e0 * v0; en[1] = e1 * v0; en[2] = e2 * v0; en[3] = b0 * v0; en[4] = b1 * v0; en[5] = b2 * v0;
 }
+
+
+/* ======================================================================== */
+/* Divergence cleaning (Marder passes) and shared-face synchronisation.     */
+
+#define FV(v, m) F[(size_t)(v) * F_STRIDE + (m)]
+
+static void adjust_tang_e(const vpo_field_args_t *a) {             /* local_adjust_tang_e, local.cc:224-265 */
+  dims_t d = mkdims(a);
+  float *F = a->f;
+  for (int fc = 0; fc < 6; fc++) {
+    if (a->bc6[fc] != -1) continue;
+    int X = fc % 3, Y = (X + 1) % 3, Z = (X + 2) % 3, face = fc < 3 ? 1 : d.n[X] + 1;
+    PLANE_LOOP(X, face, Y, 1, d.n[Y], Z, 1, d.n[Z] + 1, (FV(v, F_EX + Y) = 0, FV(v, F_TCAX + Y) = 0));
+    PLANE_LOOP(X, face, Y, 1, d.n[Y] + 1, Z, 1, d.n[Z], (FV(v, F_EX + Z) = 0, FV(v, F_TCAX + Z) = 0));
+  }
+}
+
+static void adjust_norm_b(const vpo_field_args_t *a) {             /* local_adjust_norm_b, local.cc:266-297 */
+  dims_t d = mkdims(a);
+  float *F = a->f;
+  for (int fc = 0; fc < 6; fc++) {
+    if (a->bc6[fc] != -2) continue;
+    int X = fc % 3, Y = (X + 1) % 3, Z = (X + 2) % 3, face = fc < 3 ? 1 : d.n[X] + 1;
+    PLANE_LOOP(X, face, Y, 1, d.n[Y], Z, 1, d.n[Z], FV(v, F_CBX + X) = 0);
+  }
+}
+
+void vpo_clear_rhof(const vpo_field_args_t *a) {
+  int nv = (a->nx + 2) * (a->ny + 2) * (a->nz + 2);
+  for (int v = 0; v < nv; v++) a->f[(size_t)v * F_STRIDE + F_RHOF] = 0;
+}
+
+void vpo_synchronize_rho(const vpo_field_args_t *a) {
+  dims_t d = mkdims(a);
+  float *F = a->f;
+  for (int fc = 0; fc < 6; fc++) {                                  /* local_adjust_rhof: pec zeroes, others double */
+    int bc = a->bc6[fc];
+    if (bc >= 0) continue;
+    int X = fc % 3, Y = (X + 1) % 3, Z = (X + 2) % 3, face = fc < 3 ? 1 : d.n[X] + 1;
+    if (bc == -1) PLANE_LOOP(X, face, Y, 1, d.n[Y] + 1, Z, 1, d.n[Z] + 1, FV(v, F_RHOF) = 0);
+    else          PLANE_LOOP(X, face, Y, 1, d.n[Y] + 1, Z, 1, d.n[Z] + 1, FV(v, F_RHOF) *= 2);
+  }
+  for (int fc = 0; fc < 6; fc++) {                                  /* local_adjust_rhob: pec zeroes */
+    if (a->bc6[fc] != -1) continue;
+    int X = fc % 3, Y = (X + 1) % 3, Z = (X + 2) % 3, face = fc < 3 ? 1 : d.n[X] + 1;
+    PLANE_LOOP(X, face, Y, 1, d.n[Y] + 1, Z, 1, d.n[Z] + 1, FV(v, F_RHOB) = 0);
+  }
+  for (int X = 0; X < 3; X++) {                                     /* one axis at a time; both sides packed first */
+    int Y = (X + 1) % 3, Z = (X + 2) % 3;
+    float *msg[2] = {0, 0};
+    for (int side = 0; side < 2; side++) {
+      if (a->bc6[X + 3 * side] < 0) continue;
+      int face = side == 0 ? 1 : d.n[X] + 1;
+      float *p = msg[side] = (float *)malloc(sizeof(float) * (size_t)(1 + 2 * (d.n[Y] + 1) * (d.n[Z] + 1)));
+      *p++ = axis_d(a, X);
+      PLANE_LOOP(X, face, Y, 1, d.n[Y] + 1, Z, 1, d.n[Z] + 1, (*p++ = FV(v, F_RHOF), *p++ = FV(v, F_RHOB)));
+    }
+    for (int side = 0; side < 2; side++) {
+      if (!msg[side]) continue;
+      float *p = msg[side];
+      float hrw = *p++, dX = axis_d(a, X), hlw = hrw + dX;
+      hrw /= hlw; hlw = dX / hlw;
+      float lw = hlw + hlw, rw = hrw + hrw;
+      int face = side == 0 ? d.n[X] + 1 : 1;
+      PLANE_LOOP(X, face, Y, 1, d.n[Y] + 1, Z, 1, d.n[Z] + 1, {
+        float rf = *p++, rb = *p++;
+        FV(v, F_RHOF) = lw * FV(v, F_RHOF) + rw * rf;
+        FV(v, F_RHOB) = hlw * FV(v, F_RHOB) + hrw * rb;
+      });
+      free(msg[side]);
+    }
+  }
+}
+
+/* Normal-E ghosts: begin/end_remote_ghost_norm_e (remote.cc:136-206) for periodic-self faces, local_ghost_norm_e
+ * (local.cc:128-179) for local walls. */
+static void ghost_norm_e(const vpo_field_args_t *a) {
+  dims_t d = mkdims(a);
+  float *F = a->f;
+  float *msg[6] = {0};
+  for (int fc = 0; fc < 6; fc++) {
+    if (a->bc6[fc] < 0) continue;
+    int X = fc % 3, Y = (X + 1) % 3, Z = (X + 2) % 3, face = fc < 3 ? 1 : d.n[X];
+    float *p = msg[fc] = (float *)malloc(sizeof(float) * (size_t)(1 + (d.n[Y] + 1) * (d.n[Z] + 1)));
+    *p++ = axis_d(a, X);
+    PLANE_LOOP(X, face, Y, 1, d.n[Y] + 1, Z, 1, d.n[Z] + 1, *p++ = FV(v, F_EX + X));
+  }
+  for (int fc = 0; fc < 6; fc++) {
+    int bc = a->bc6[fc];
+    if (bc >= 0) continue;
+    int X = fc % 3, Y = (X + 1) % 3, Z = (X + 2) % 3;
+    int ghost = fc < 3 ? 0 : d.n[X] + 1, in1 = fc < 3 ? d.s[X] : -d.s[X];
+    if (bc == -1)
+      PLANE_LOOP(X, ghost, Y, 1, d.n[Y] + 1, Z, 1, d.n[Z] + 1,
+                 (FV(v, F_EX + X) = FV(v + in1, F_EX + X), FV(v, F_TCAX + X) = FV(v + in1, F_TCAX + X)));
+    else if (bc == -2 || bc == -3)
+      PLANE_LOOP(X, ghost, Y, 1, d.n[Y] + 1, Z, 1, d.n[Z] + 1,
+                 (FV(v, F_EX + X) = -FV(v + in1, F_EX + X), FV(v, F_TCAX + X) = -FV(v + in1, F_TCAX + X)));
+    else if (bc == -4)
+      PLANE_LOOP(X, ghost, Y, 1, d.n[Y] + 1, Z, 1, d.n[Z] + 1,
+                 (FV(v, F_EX + X) = 2 * FV(v + in1, F_EX + X) - FV(v + 2 * in1, F_EX + X),
+                  FV(v, F_TCAX + X) = 2 * FV(v + in1, F_TCAX + X) - FV(v + 2 * in1, F_TCAX + X)));
+    else abort();
+  }
+  for (int fc = 0; fc < 6; fc++) {
+    if (!msg[fc]) continue;
+    int X = fc % 3, Y = (X + 1) % 3, Z = (X + 2) % 3;
+    int ghost = fc < 3 ? d.n[X] + 1 : 0, step = fc < 3 ? -d.s[X] : d.s[X];
+    float *p = msg[fc];
+    float lw = *p++, dX = axis_d(a, X);
+    float rw = (2. * dX) / (lw + dX);
+    lw = (lw - dX) / (lw + dX);
+    PLANE_LOOP(X, ghost, Y, 1, d.n[Y] + 1, Z, 1, d.n[Z] + 1, FV(v, F_EX + X) = rw * (*p++) + lw * FV(v + step, F_EX + X));
+    free(msg[fc]);
+  }
+}
+
+void vpo_vacuum_compute_div_e_err(const vpo_field_args_t *a) {
+  const int nx = a->nx, ny = a->ny, nz = a->nz;
+  const int hm = a->has_material;
+  const float *m = a->material;
+  const float nc = hm ? m[9] : 1.0f;
+  const float px = ((nx > 1) ? a->rdx : 0) * (hm ? m[10] : 1.0f);
+  const float py = ((ny > 1) ? a->rdy : 0) * (hm ? m[11] : 1.0f);
+  const float pz = ((nz > 1) ? a->rdz : 0) * (hm ? m[12] : 1.0f);
+  const float cj = 1. / a->eps0;
+  float *F = a->f;
+  ghost_norm_e(a);
+# define FF(x, y, z, m) F[(size_t)VOX(x, y, z) * F_STRIDE + (m)]
+  for (int z = 1; z <= nz + 1; z++) for (int y = 1; y <= ny + 1; y++) for (int x = 1; x <= nx + 1; x++)
+    FF(x, y, z, F_DIVE) = nc * (px * (FF(x, y, z, F_EX) - FF(x - 1, y, z, F_EX)) +
+                                py * (FF(x, y, z, F_EY) - FF(x, y - 1, z, F_EY)) +
+                                pz * (FF(x, y, z, F_EZ) - FF(x, y, z - 1, F_EZ)) -
+                                cj * (FF(x, y, z, F_RHOF) + FF(x, y, z, F_RHOB)));
+# undef FF
+  dims_t d = mkdims(a);                                              /* local_adjust_div_e, local.cc:298-330 */
+  for (int fc = 0; fc < 6; fc++) {
+    int bc = a->bc6[fc];
+    if (bc != -1 && bc != -4) continue;
+    int X = fc % 3, Y = (X + 1) % 3, Z = (X + 2) % 3, face = fc < 3 ? 1 : d.n[X] + 1;
+    PLANE_LOOP(X, face, Y, 1, d.n[Y] + 1, Z, 1, d.n[Z] + 1, FV(v, F_DIVE) = 0);
+  }
+}
+
+double vpo_compute_rms_div_e_err(const vpo_field_args_t *a) {
+  const int nx = a->nx, ny = a->ny, nz = a->nz;
+  const float *F = a->f;
+  double err = 0;
+# define D(x, y, z) F[(size_t)VOX(x, y, z) * F_STRIDE + F_DIVE]
+  /* interior nodes: float product summed in double (pipeline :38); walls, edges and corners weigh 1/2, 1/4, 1/8 and
+     multiply in double (:96-160) */
+  for (int z = 1; z <= nz + 1; z++) for (int y = 1; y <= ny + 1; y++) for (int x = 1; x <= nx + 1; x++) {
+    int on = (x == 1 || x == nx + 1) + (y == 1 || y == ny + 1) + (z == 1 || z == nz + 1);
+    float e = D(x, y, z);
+    if (on == 0) err += e * e;
+    else err += (on == 1 ? 0.5 : on == 2 ? 0.25 : 0.125) * (double)e * (double)e;
+  }
+# undef D
+  double l0 = err * a->dV, l1 = (nx * ny * nz) * a->dV;
+  return a->eps0 * sqrt(l0 / l1);
+}
+
+void vpo_vacuum_clean_div_e(const vpo_field_args_t *a) {
+  const int nx = a->nx, ny = a->ny, nz = a->nz;
+  const int hm = a->has_material;
+  const float *m = a->material;
+  const float rdx = (nx > 1) ? a->rdx : 0, rdy = (ny > 1) ? a->rdy : 0, rdz = (nz > 1) ? a->rdz : 0;
+  const float alphadt = 0.3888889 / (rdx * rdx + rdy * rdy + rdz * rdz);
+  const float px = (alphadt * rdx) * (hm ? m[1] : 1.0f);
+  const float py = (alphadt * rdy) * (hm ? m[3] : 1.0f);
+  const float pz = (alphadt * rdz) * (hm ? m[5] : 1.0f);
+  float *F = a->f;
+# define FF(x, y, z, m) F[(size_t)VOX(x, y, z) * F_STRIDE + (m)]
+  for (int z = 1; z <= nz + 1; z++) for (int y = 1; y <= ny + 1; y++) for (int x = 1; x <= nx + 1; x++) {
+    if (x <= nx) FF(x, y, z, F_EX) += px * (FF(x + 1, y, z, F_DIVE) - FF(x, y, z, F_DIVE));
+    if (y <= ny) FF(x, y, z, F_EY) += py * (FF(x, y + 1, z, F_DIVE) - FF(x, y, z, F_DIVE));
+    if (z <= nz) FF(x, y, z, F_EZ) += pz * (FF(x, y, z + 1, F_DIVE) - FF(x, y, z, F_DIVE));
+  }
+# undef FF
+  adjust_tang_e(a);
+}
+
+void vpo_compute_div_b_err(const vpo_field_args_t *a) {
+  const int nx = a->nx, ny = a->ny, nz = a->nz;
+  const float px = (nx > 1) ? a->rdx : 0, py = (ny > 1) ? a->rdy : 0, pz = (nz > 1) ? a->rdz : 0;
+  float *F = a->f;
+# define FF(x, y, z, m) F[(size_t)VOX(x, y, z) * F_STRIDE + (m)]
+  for (int z = 1; z <= nz; z++) for (int y = 1; y <= ny; y++) for (int x = 1; x <= nx; x++)
+    FF(x, y, z, F_DIVB) = px * (FF(x + 1, y, z, F_CBX) - FF(x, y, z, F_CBX)) +
+                          py * (FF(x, y + 1, z, F_CBY) - FF(x, y, z, F_CBY)) +
+                          pz * (FF(x, y, z + 1, F_CBZ) - FF(x, y, z, F_CBZ));
+# undef FF
+}
+
+double vpo_compute_rms_div_b_err(const vpo_field_args_t *a) {
+  const int nx = a->nx, ny = a->ny, nz = a->nz;
+  const float *F = a->f;
+  double err = 0;
+  for (int z = 1; z <= nz; z++) for (int y = 1; y <= ny; y++) for (int x = 1; x <= nx; x++) {
+    float e = F[(size_t)VOX(x, y, z) * F_STRIDE + F_DIVB];
+    err += e * e;
+  }
+  double l0 = err * a->dV, l1 = (nx * ny * nz) * a->dV;
+  return a->eps0 * sqrt(l0 / l1);
+}
+
+/* div-B-error ghosts: begin/end_remote_ghost_div_b (remote.cc:208-282), local_ghost_div_b (local.cc:181-217) */
+static void ghost_div_b(const vpo_field_args_t *a) {
+  dims_t d = mkdims(a);
+  float *F = a->f;
+  float *msg[6] = {0};
+  for (int fc = 0; fc < 6; fc++) {
+    if (a->bc6[fc] < 0) continue;
+    int X = fc % 3, Y = (X + 1) % 3, Z = (X + 2) % 3, face = fc < 3 ? 1 : d.n[X];
+    float *p = msg[fc] = (float *)malloc(sizeof(float) * (size_t)(1 + d.n[Y] * d.n[Z]));
+    *p++ = axis_d(a, X);
+    PLANE_LOOP(X, face, Y, 1, d.n[Y], Z, 1, d.n[Z], *p++ = FV(v, F_DIVB));
+  }
+  for (int fc = 0; fc < 6; fc++) {
+    int bc = a->bc6[fc];
+    if (bc >= 0) continue;
+    int X = fc % 3, Y = (X + 1) % 3, Z = (X + 2) % 3;
+    int ghost = fc < 3 ? 0 : d.n[X] + 1, in1 = fc < 3 ? d.s[X] : -d.s[X];
+    if (bc == -1)                  PLANE_LOOP(X, ghost, Y, 1, d.n[Y], Z, 1, d.n[Z], FV(v, F_DIVB) = FV(v + in1, F_DIVB));
+    else if (bc == -2 || bc == -3) PLANE_LOOP(X, ghost, Y, 1, d.n[Y], Z, 1, d.n[Z], FV(v, F_DIVB) = -FV(v + in1, F_DIVB));
+    else if (bc == -4)             PLANE_LOOP(X, ghost, Y, 1, d.n[Y], Z, 1, d.n[Z], FV(v, F_DIVB) = 0);
+    else abort();
+  }
+  for (int fc = 0; fc < 6; fc++) {
+    if (!msg[fc]) continue;
+    int X = fc % 3, Y = (X + 1) % 3, Z = (X + 2) % 3;
+    int ghost = fc < 3 ? d.n[X] + 1 : 0, step = fc < 3 ? -d.s[X] : d.s[X];
+    float *p = msg[fc];
+    float lw = *p++, dX = axis_d(a, X);
+    float rw = (2. * dX) / (lw + dX);
+    lw = (lw - dX) / (lw + dX);
+    PLANE_LOOP(X, ghost, Y, 1, d.n[Y], Z, 1, d.n[Z], FV(v, F_DIVB) = rw * (*p++) + lw * FV(v + step, F_DIVB));
+    free(msg[fc]);
+  }
+}
+
+void vpo_clean_div_b(const vpo_field_args_t *a) {
+  const int nx = a->nx, ny = a->ny, nz = a->nz;
+  float px = (nx > 1) ? a->rdx : 0, py = (ny > 1) ? a->rdy : 0, pz = (nz > 1) ? a->rdz : 0;
+  float alphadt = 0.3888889 / (px * px + py * py + pz * pz);
+  px *= alphadt; py *= alphadt; pz *= alphadt;
+  float *F = a->f;
+  ghost_div_b(a);
+# define FF(x, y, z, m) F[(size_t)VOX(x, y, z) * F_STRIDE + (m)]
+  for (int z = 1; z <= nz + 1; z++) for (int y = 1; y <= ny + 1; y++) for (int x = 1; x <= nx + 1; x++) {
+    if (y <= ny && z <= nz) FF(x, y, z, F_CBX) += px * (FF(x, y, z, F_DIVB) - FF(x - 1, y, z, F_DIVB));
+    if (z <= nz && x <= nx) FF(x, y, z, F_CBY) += py * (FF(x, y, z, F_DIVB) - FF(x, y - 1, z, F_DIVB));
+    if (x <= nx && y <= ny) FF(x, y, z, F_CBZ) += pz * (FF(x, y, z, F_DIVB) - FF(x, y, z - 1, F_DIVB));
+  }
+# undef FF
+  adjust_norm_b(a);
+}
+
+double vpo_synchronize_tang_e_norm_b(const vpo_field_args_t *a) {
+  dims_t d = mkdims(a);
+  float *F = a->f;
+  double err = 0;
+  adjust_tang_e(a);
+  adjust_norm_b(a);
+  for (int X = 0; X < 3; X++) {
+    int Y = (X + 1) % 3, Z = (X + 2) % 3;
+    float *msg[2] = {0, 0};
+    for (int side = 0; side < 2; side++) {
+      if (a->bc6[X + 3 * side] < 0) continue;
+      int face = side == 0 ? 1 : d.n[X] + 1;
+      float *p = msg[side] = (float *)malloc(sizeof(float) *
+          (size_t)(2 * d.n[Y] * (d.n[Z] + 1) + 2 * d.n[Z] * (d.n[Y] + 1) + d.n[Y] * d.n[Z]));
+      PLANE_LOOP(X, face, Y, 1, d.n[Y], Z, 1, d.n[Z], *p++ = FV(v, F_CBX + X));
+      PLANE_LOOP(X, face, Y, 1, d.n[Y], Z, 1, d.n[Z] + 1, (*p++ = FV(v, F_EX + Y), *p++ = FV(v, F_TCAX + Y)));
+      PLANE_LOOP(X, face, Y, 1, d.n[Y] + 1, Z, 1, d.n[Z], (*p++ = FV(v, F_EX + Z), *p++ = FV(v, F_TCAX + Z)));
+    }
+    /* the reference receives the -X message first, then +X (remote.cc:376-383); the error sum follows that order */
+    for (int side = 0; side < 2; side++) {
+      if (!msg[side]) continue;
+      float *p = msg[side];
+      int face = side == 0 ? d.n[X] + 1 : 1;
+      double w1, w2;
+      PLANE_LOOP(X, face, Y, 1, d.n[Y], Z, 1, d.n[Z],
+                 (w1 = *p++, w2 = FV(v, F_CBX + X), FV(v, F_CBX + X) = 0.5 * (w1 + w2), err += (w1 - w2) * (w1 - w2)));
+      PLANE_LOOP(X, face, Y, 1, d.n[Y], Z, 1, d.n[Z] + 1,
+                 (w1 = *p++, w2 = FV(v, F_EX + Y), FV(v, F_EX + Y) = 0.5 * (w1 + w2), err += (w1 - w2) * (w1 - w2),
+                  w1 = *p++, w2 = FV(v, F_TCAX + Y), FV(v, F_TCAX + Y) = 0.5 * (w1 + w2)));
+      PLANE_LOOP(X, face, Y, 1, d.n[Y] + 1, Z, 1, d.n[Z],
+                 (w1 = *p++, w2 = FV(v, F_EX + Z), FV(v, F_EX + Z) = 0.5 * (w1 + w2), err += (w1 - w2) * (w1 - w2),
+                  w1 = *p++, w2 = FV(v, F_TCAX + Z), FV(v, F_TCAX + Z) = 0.5 * (w1 + w2)));
+      free(msg[side]);
+    }
+  }
+  return err;
+}

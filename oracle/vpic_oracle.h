@@ -101,6 +101,17 @@ void vpo_clear_jf(const vpo_field_args_t *a);
 void vpo_synchronize_jf(const vpo_field_args_t *a);
 void vpo_vacuum_energy_f(const vpo_field_args_t *a, double en[6]);
 
+/* ---- divergence cleaning and shared-face synchronisation (advance.cc:138-176), same single-domain setting ---- */
+void   vpo_clear_rhof(const vpo_field_args_t *a);                 /* sfa.cc:239-256 */
+void   vpo_synchronize_rho(const vpo_field_args_t *a);            /* remote.cc:534-620, local.cc:376-444 */
+void   vpo_vacuum_compute_div_e_err(const vpo_field_args_t *a);   /* vacuum_compute_div_e_err_pipeline.{h,cc} */
+double vpo_compute_rms_div_e_err(const vpo_field_args_t *a);      /* compute_rms_div_e_err_pipeline.cc */
+void   vpo_vacuum_clean_div_e(const vpo_field_args_t *a);         /* vacuum_clean_div_e_pipeline.{h,cc} */
+void   vpo_compute_div_b_err(const vpo_field_args_t *a);          /* compute_div_b_err_pipeline.cc */
+double vpo_compute_rms_div_b_err(const vpo_field_args_t *a);      /* compute_rms_div_b_err_pipeline.cc */
+void   vpo_clean_div_b(const vpo_field_args_t *a);                /* clean_div_b_pipeline.cc */
+double vpo_synchronize_tang_e_norm_b(const vpo_field_args_t *a);  /* remote.cc:298-416 */
+
 #ifdef __cplusplus
 }
 #endif

@@ -49,6 +49,13 @@ def load_oracle():
     lib.vpo_clear_jf.argtypes = [C.c_void_p]
     lib.vpo_synchronize_jf.argtypes = [C.c_void_p]
     lib.vpo_vacuum_energy_f.argtypes = [C.c_void_p, C.c_void_p]
+    for name in ("vpo_clear_rhof", "vpo_synchronize_rho", "vpo_vacuum_compute_div_e_err", "vpo_vacuum_clean_div_e",
+                 "vpo_compute_div_b_err", "vpo_clean_div_b"):
+        getattr(lib, name).argtypes = [C.c_void_p]
+        getattr(lib, name).restype = None
+    for name in ("vpo_compute_rms_div_e_err", "vpo_compute_rms_div_b_err", "vpo_synchronize_tang_e_norm_b"):
+        getattr(lib, name).argtypes = [C.c_void_p]
+        getattr(lib, name).restype = C.c_double
     lib.vpo_accumulate_rho_p.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_int32, C.c_int32, C.c_int32]
     lib.vpo_accumulate_rhob.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int32, C.c_int32, C.c_int32]
     lib.vpo_advance_b.argtypes = [C.c_void_p, C.c_float]
@@ -209,6 +216,23 @@ class RefWorld:
 
     def synchronize_jf(self):
         self.kernel(5, None, C.POINTER(abi.FieldArray))(self.fa)
+
+    # divergence cleaning / shared-face synchronisation entries (field_advance.h:186-218)
+    def _k_void(self, idx):
+        self.kernel(idx, None, C.POINTER(abi.FieldArray))(self.fa)
+
+    def _k_double(self, idx):
+        return float(self.kernel(idx, C.c_double, C.POINTER(abi.FieldArray))(self.fa))
+
+    def clear_rhof(self): self._k_void(6)
+    def synchronize_rho(self): self._k_void(7)
+    def synchronize_tang_e_norm_b(self): return self._k_double(10)
+    def compute_div_e_err(self): self._k_void(11)
+    def compute_rms_div_e_err(self): return self._k_double(12)
+    def clean_div_e(self): self._k_void(13)
+    def compute_div_b_err(self): self._k_void(14)
+    def compute_rms_div_b_err(self): return self._k_double(15)
+    def clean_div_b(self): self._k_void(16)
 
     def new_species(self, name, q, m, max_np, max_nm, sort_interval=20):
         sp = self.lib.species(name.encode(), q, m, max_np, max_nm, sort_interval, 0, self.g)

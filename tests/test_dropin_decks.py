@@ -154,3 +154,34 @@ def test_harris_energy_history_matches_reference(mode):
             assert diff / scale < 5e-4, (col, diff, scale)
         elif scale > 0:                                            # noise-driven components: same order of magnitude
             assert diff / scale < 1e-1, (col, diff, scale)
+
+
+def _trace(out):
+    line = [ln for ln in out.splitlines() if ln.startswith("vpic_b200 trace")][-1]
+    return {k: int(v) for k, v in (tok.split("=") for tok in line.split()[2:])}
+
+
+@pytest.mark.parametrize("fields", ["device", "reference"])
+def test_preloaded_deck_uses_the_device_kernels_it_claims(fields):
+    """VPIC_B200_TRACE=1 reports how often each entry point ran on the device.  Under LD_PRELOAD the reference's own
+    field-kernel symbols (advance_b, vacuum_advance_e, clear_jf, synchronize_jf, vacuum_energy_f) are interposed as
+    well, so an unmodified deck advances its fields on the GPU; VPIC_B200_FIELDS=0 hands them back to the reference
+    through dlsym(RTLD_NEXT) — and the deck's answers do not change either way."""
+    path = _need("reconnection_test.scalar")
+    env = {"VPIC_B200_TRACE": "1"}
+    if fields == "reference":
+        env["VPIC_B200_FIELDS"] = "0"
+    d = tempfile.mkdtemp(prefix="trace_")
+    try:
+        rc, out = _run(path, ["--tpp", "1"], True, d, extra_env=env)
+        assert rc == 0 and "normal exit" in out, out[-2000:]
+        t = _trace(out)
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+    assert t["advance_p"] > 0 and t["sort_p"] > 0 and t["load_interpolator_array"] > 0 and t["unload_accumulator_array"] > 0
+    if fields == "device":
+        assert t["advance_b"] >= 2 * t["advance_e"] > 0 and t["clear_jf"] > 0 and t["synchronize_jf"] > 0
+        assert t["field_kernel_fallback_to_reference"] == 0
+    else:
+        assert t["advance_b"] == t["advance_e"] == t["clear_jf"] == 0
+        assert t["field_kernel_fallback_to_reference"] > 0

@@ -160,6 +160,44 @@ def test_field_advance_bit_exact(ref_scalar, oracle, dims, fbc, damp, material):
     assert np.array_equal(bits(f2), bits(W.fields))
 
 
+@pytest.mark.parametrize("dims,fbc,material", [
+    ((6, 5, 4), None, None),
+    ((8, 8, 1), {0: -1, 3: -1}, None),                 # harris-like: pec x walls, degenerate z
+    ((5, 1, 7), {2: -2, 5: -3}, None),                 # symmetric / pmc walls, degenerate y
+    ((6, 5, 4), {0: -4, 3: -4, 2: -4, 5: -1}, None),   # absorbing walls on -x, +x, -z; pec on +z
+    ((7, 4, 5), {0: -1, 3: -4, 1: -2, 4: -3}, DIELECTRIC),
+])
+def test_divergence_cleaning_bit_exact(ref_scalar, oracle, dims, fbc, material):
+    """advance.cc:138-176: clear_rhof / synchronize_rho / compute_div_e_err / clean_div_e, compute_div_b_err /
+    clean_div_b and synchronize_tang_e_norm_b, field array compared bit for bit after every call; the rms values are
+    double sums whose grouping depends on the pipeline count, compared to 1e-13."""
+    rng = np.random.default_rng(17)
+    nx, ny, nz = dims
+    W = R.RefWorld(ref_scalar, nx, ny, nz, fbc=fbc, material=material)
+    f0 = rng.normal(0, 0.05, (W.nv, 20)).astype(np.float32)      # every slot, ghosts included, holds something
+    f0[:, 16:] = 0
+    W.fields[:] = f0
+    f2 = f0.copy()
+    a = W.field_args(f2)
+    pa = C.byref(a)
+
+    def same(what):
+        assert np.array_equal(bits(f2), bits(W.fields)), what
+
+    W.synchronize_rho(); oracle.vpo_synchronize_rho(pa); same("synchronize_rho")
+    for rnd in range(3):
+        W.compute_div_e_err(); oracle.vpo_vacuum_compute_div_e_err(pa); same("compute_div_e_err")
+        np.testing.assert_allclose(oracle.vpo_compute_rms_div_e_err(pa), W.compute_rms_div_e_err(), rtol=1e-13)
+        W.clean_div_e(); oracle.vpo_vacuum_clean_div_e(pa); same("clean_div_e")
+    for rnd in range(3):
+        W.compute_div_b_err(); oracle.vpo_compute_div_b_err(pa); same("compute_div_b_err")
+        np.testing.assert_allclose(oracle.vpo_compute_rms_div_b_err(pa), W.compute_rms_div_b_err(), rtol=1e-13)
+        W.clean_div_b(); oracle.vpo_clean_div_b(pa); same("clean_div_b")
+    e_ref = W.synchronize_tang_e_norm_b(); e_orc = oracle.vpo_synchronize_tang_e_norm_b(pa); same("synchronize_tang_e_norm_b")
+    np.testing.assert_allclose(e_orc, e_ref, rtol=1e-13)
+    W.clear_rhof(); oracle.vpo_clear_rhof(pa); same("clear_rhof")
+
+
 def test_rho_p_and_rhob_bit_exact(ref_scalar, oracle):
     rng = np.random.default_rng(41)
     nx, ny, nz = 5, 4, 6

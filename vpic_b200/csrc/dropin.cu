@@ -37,6 +37,26 @@ int rank_for_log() { return &_world_rank ? _world_rank : 0; }
     fprintf(stderr, __VA_ARGS__); fprintf(stderr, "\n"); } while (0)
 #define DEV(call) do { int _r = (call); if (_r) DROPIN_ERROR("%s failed (%d): %s", #call, _r, vpb_last_error()); } while (0)
 
+// VPIC_B200_TRACE=1: at exit, one line on stderr with how often each entry point ran on the device (and how often a
+// field kernel fell through to the reference's own), so a preloaded run can be checked for what it actually used.
+enum { C_ADVANCE_P, C_SORT_P, C_CENTER_P, C_ENERGY_P, C_RHO_P, C_LOAD_INTERP, C_CLEAR_ACC, C_UNLOAD_ACC, C_ADVANCE_B,
+       C_ADVANCE_E, C_CLEAR_JF, C_SYNC_JF, C_ENERGY_F, C_FIELD_FALLBACK, C_COUNT };
+uint64_t g_calls[C_COUNT];
+void trace_report() {
+  static const char *names[C_COUNT] = {"advance_p", "sort_p", "center_p/uncenter_p", "energy_p", "accumulate_rho_p",
+      "load_interpolator_array", "clear_accumulator_array", "unload_accumulator_array", "advance_b", "advance_e",
+      "clear_jf", "synchronize_jf", "energy_f", "field_kernel_fallback_to_reference"};
+  fprintf(stderr, "vpic_b200 trace[%d]:", rank_for_log());
+  for (int i = 0; i < C_COUNT; i++) fprintf(stderr, " %s=%llu", names[i], (unsigned long long)g_calls[i]);
+  const vpb_lazy::Stats st = vpb_lazy::stats();
+  fprintf(stderr, " lazy_faults=%llu lazy_fault_bytes=%llu\n", (unsigned long long)st.faults, (unsigned long long)st.fault_bytes);
+}
+inline void count_call(int which) {
+  static int trace = -1;
+  if (trace < 0) { const char *e = getenv("VPIC_B200_TRACE"); trace = e && atoi(e) != 0; if (trace) atexit(trace_report); }
+  g_calls[which]++;
+}
+
 struct Mirror {
   void *d = nullptr; size_t cap = 0;
   bool device_valid = false;      // device copy holds the current data
@@ -287,6 +307,7 @@ static int chunk_particles() {
 
 void advance_p(vpb_species_t *sp, vpb_accumulator_array_t *aa, const vpb_interpolator_array_t *ia) {
   if (!sp || !aa || !ia || sp->g != aa->g || sp->g != ia->g) DROPIN_ERROR("Bad args.");
+  count_call(C_ADVANCE_P);
   const vpb_grid_t *g = sp->g;
   const size_t nv = (size_t)g->nv;
   mode();
@@ -381,6 +402,7 @@ void advance_p(vpb_species_t *sp, vpb_accumulator_array_t *aa, const vpb_interpo
 // ---- sort_p: species_advance.h:65-66, sort_p_pipeline.cc:220-371 ------------------------------------------
 void sort_p(vpb_species_t *sp) {
   if (!sp) DROPIN_ERROR("Bad args.");
+  count_call(C_SORT_P);
   const vpb_grid_t *g = sp->g;
   sp->last_sorted = g->step;
   void *p = dev_in(sp->p, (size_t)sp->np * sizeof(vpb_particle_t), (size_t)sp->max_np * sizeof(vpb_particle_t));
@@ -396,6 +418,7 @@ void sort_p(vpb_species_t *sp) {
 // ---- center_p / uncenter_p / energy_p: species_advance.h:90-107 --------------------------------------------
 static void center_common(vpb_species_t *sp, const vpb_interpolator_array_t *ia, bool center) {
   if (!sp || !ia || sp->g != ia->g) DROPIN_ERROR("Bad args.");
+  count_call(C_CENTER_P);
   const vpb_grid_t *g = sp->g;
   const float *di = (const float *)dev_in(ia->i, (size_t)g->nv * sizeof(vpb_interpolator_t));
   void *p = dev_in(sp->p, (size_t)sp->np * sizeof(vpb_particle_t), (size_t)sp->max_np * sizeof(vpb_particle_t));
@@ -409,6 +432,7 @@ void uncenter_p(vpb_species_t *sp, const vpb_interpolator_array_t *ia) { center_
 
 double energy_p(const vpb_species_t *sp, const vpb_interpolator_array_t *ia) {
   if (!sp || !ia || sp->g != ia->g) DROPIN_ERROR("Bad args");
+  count_call(C_ENERGY_P);
   const vpb_grid_t *g = sp->g;
   const float *di = (const float *)dev_in(ia->i, (size_t)g->nv * sizeof(vpb_interpolator_t));
   void *p = dev_in(sp->p, (size_t)sp->np * sizeof(vpb_particle_t), (size_t)sp->max_np * sizeof(vpb_particle_t));
@@ -426,6 +450,7 @@ double energy_p(const vpb_species_t *sp, const vpb_interpolator_array_t *ia) {
 // ---- accumulate_rho_p: species_advance.h:117-119, rho_p.cc:22-113 -----------------------------------------
 void accumulate_rho_p(vpb_field_array_t *fa, const vpb_species_t *sp) {
   if (!fa || !sp || fa->g != sp->g) DROPIN_ERROR("Bad args");
+  count_call(C_RHO_P);
   const vpb_grid_t *g = sp->g;
   const size_t fbytes = (size_t)g->nv * sizeof(vpb_field_t);
   float *df = (float *)dev_in(fa->f, fbytes);
@@ -438,6 +463,7 @@ void accumulate_rho_p(vpb_field_array_t *fa, const vpb_species_t *sp) {
 // ---- interpolator / accumulator glue: sf_interface.h:99-174 ------------------------------------------------
 void load_interpolator_array(vpb_interpolator_array_t *ia, const vpb_field_array_t *fa) {
   if (!ia || !fa || ia->g != fa->g) DROPIN_ERROR("Bad args");
+  count_call(C_LOAD_INTERP);
   const vpb_grid_t *g = ia->g;
   const size_t ibytes = (size_t)g->nv * sizeof(vpb_interpolator_t);
   const float *df = (const float *)dev_in(fa->f, (size_t)g->nv * sizeof(vpb_field_t));
@@ -450,6 +476,7 @@ void load_interpolator_array(vpb_interpolator_array_t *ia, const vpb_field_array
 
 void clear_accumulator_array(vpb_accumulator_array_t *aa) {
   if (!aa) DROPIN_ERROR("Bad args.");
+  count_call(C_CLEAR_ACC);
   const vpb_grid_t *g = aa->g;
   const size_t abytes = (size_t)aa->stride * sizeof(vpb_accumulator_t);
   // host: zero the same voxel window in every block, exactly like clear_array_pipeline.cc:40-67
@@ -479,6 +506,7 @@ void reduce_accumulator_array(vpb_accumulator_array_t *aa) {
 
 void unload_accumulator_array(vpb_field_array_t *fa, const vpb_accumulator_array_t *aa) {
   if (!fa || !aa || fa->g != aa->g) DROPIN_ERROR("Bad args");
+  count_call(C_UNLOAD_ACC);
   const vpb_grid_t *g = fa->g;
   const size_t fbytes = (size_t)g->nv * sizeof(vpb_field_t);
   const float *da = (const float *)dev_in(aa->a, (size_t)aa->stride * sizeof(vpb_accumulator_t));
@@ -528,6 +556,7 @@ static void field_args_of(const vpb_field_array_t *fa, float *df, vpb_field_args
 
 #define FIELD_ENTRY(name, call)                                                            \
   if (!fa) DROPIN_ERROR("Bad args");                                                        \
+  count_call(name);                                                                         \
   const size_t fbytes = (size_t)fa->g->nv * sizeof(vpb_field_t);                            \
   float *df = (float *)dev_in(fa->f, fbytes);                                               \
   vpb_field_args_t a; field_args_of(fa, df, &a);                                            \
@@ -535,12 +564,13 @@ static void field_args_of(const vpb_field_array_t *fa, float *df, vpb_field_args
   dev_written(fa->f, fbytes);                                                               \
   finish_entry();
 
-void vpic_b200_advance_b(vpb_field_array_t *fa, float frac) { FIELD_ENTRY(advance_b, vpb_advance_b(&a, frac, nullptr)) }
-void vpic_b200_advance_e(vpb_field_array_t *fa, float frac) { FIELD_ENTRY(advance_e, vpb_vacuum_advance_e(&a, frac, nullptr)) }
-void vpic_b200_clear_jf(vpb_field_array_t *fa) { FIELD_ENTRY(clear_jf, vpb_clear_jf(&a, nullptr)) }
-void vpic_b200_synchronize_jf(vpb_field_array_t *fa) { FIELD_ENTRY(synchronize_jf, vpb_synchronize_jf(&a, nullptr)) }
+void vpic_b200_advance_b(vpb_field_array_t *fa, float frac) { FIELD_ENTRY(C_ADVANCE_B, vpb_advance_b(&a, frac, nullptr)) }
+void vpic_b200_advance_e(vpb_field_array_t *fa, float frac) { FIELD_ENTRY(C_ADVANCE_E, vpb_vacuum_advance_e(&a, frac, nullptr)) }
+void vpic_b200_clear_jf(vpb_field_array_t *fa) { FIELD_ENTRY(C_CLEAR_JF, vpb_clear_jf(&a, nullptr)) }
+void vpic_b200_synchronize_jf(vpb_field_array_t *fa) { FIELD_ENTRY(C_SYNC_JF, vpb_synchronize_jf(&a, nullptr)) }
 void vpic_b200_energy_f(double *en, const vpb_field_array_t *fa) {
   if (!en || !fa) DROPIN_ERROR("Bad args");
+  count_call(C_ENERGY_F);
   float *df = (float *)dev_in(fa->f, (size_t)fa->g->nv * sizeof(vpb_field_t));
   vpb_field_args_t a; field_args_of(fa, df, &a);
   double *den = (double *)scratch(4, 6 * sizeof(double));
@@ -570,26 +600,31 @@ static void *reference_kernel(const char *name) {
 void advance_b(vpb_field_array_t *fa, float frac) {
   if (fields_on_device(fa)) { vpic_b200_advance_b(fa, frac); return; }
   static auto ref = (void (*)(vpb_field_array_t *, float))reference_kernel("advance_b");
+  count_call(C_FIELD_FALLBACK);
   ref(fa, frac);
 }
 void vacuum_advance_e(vpb_field_array_t *fa, float frac) {
   if (fields_on_device(fa)) { vpic_b200_advance_e(fa, frac); return; }
   static auto ref = (void (*)(vpb_field_array_t *, float))reference_kernel("vacuum_advance_e");
+  count_call(C_FIELD_FALLBACK);
   ref(fa, frac);
 }
 void clear_jf(vpb_field_array_t *fa) {
   if (fields_on_device(fa)) { vpic_b200_clear_jf(fa); return; }
   static auto ref = (void (*)(vpb_field_array_t *))reference_kernel("clear_jf");
+  count_call(C_FIELD_FALLBACK);
   ref(fa);
 }
 void synchronize_jf(vpb_field_array_t *fa) {
   if (fields_on_device(fa)) { vpic_b200_synchronize_jf(fa); return; }
   static auto ref = (void (*)(vpb_field_array_t *))reference_kernel("synchronize_jf");
+  count_call(C_FIELD_FALLBACK);
   ref(fa);
 }
 void vacuum_energy_f(double *en, const vpb_field_array_t *fa) {
   if (fields_on_device(fa)) { vpic_b200_energy_f(en, fa); return; }
   static auto ref = (void (*)(double *, const vpb_field_array_t *))reference_kernel("vacuum_energy_f");
+  count_call(C_FIELD_FALLBACK);
   ref(en, fa);
 }
 
