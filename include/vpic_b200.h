@@ -207,6 +207,24 @@ int vpb_clear_jf(const vpb_field_args_t *a, void *stream);
 int vpb_synchronize_jf(const vpb_field_args_t *a, void *stream);
 int vpb_vacuum_energy_f(const vpb_field_args_t *a, double *en6_dev, void *stream);
 
+/* Divergence cleaning and shared-face synchronisation (src/vpic/advance.cc:138-176) on the same field array:
+ * clear_rhof (sfa.cc:239-256), synchronize_rho (remote.cc:534-620), vacuum_compute_div_e_err / vacuum_clean_div_e
+ * (pipeline/vacuum_{compute_div_e_err,clean_div_e}_pipeline.*), compute_div_b_err / clean_div_b
+ * (pipeline/{compute_div_b_err,clean_div_b}_pipeline.cc), synchronize_tang_e_norm_b (remote.cc:298-416).
+ * The two rms functions and synchronize_tang_e_norm_b leave a partial result in device memory: *sum_dev is the
+ * weighted sum of squared errors over this domain (the caller finishes eps0*sqrt(sum*dV / (nx*ny*nz*dV)) after its
+ * cross-rank sum, compute_rms_div_e_err_pipeline.cc:170-183), *err_dev the local desynchronisation error.
+ * Faces must be local walls or periodic-self (no VPB_FACE_REMOTE yet). */
+int vpb_clear_rhof(const vpb_field_args_t *a, void *stream);
+int vpb_synchronize_rho(const vpb_field_args_t *a, void *stream);
+int vpb_vacuum_compute_div_e_err(const vpb_field_args_t *a, void *stream);
+int vpb_compute_rms_div_e_err(const vpb_field_args_t *a, double *sum_dev, void *stream);
+int vpb_vacuum_clean_div_e(const vpb_field_args_t *a, void *stream);
+int vpb_compute_div_b_err(const vpb_field_args_t *a, void *stream);
+int vpb_compute_rms_div_b_err(const vpb_field_args_t *a, double *sum_dev, void *stream);
+int vpb_clean_div_b(const vpb_field_args_t *a, void *stream);
+int vpb_synchronize_tang_e_norm_b(const vpb_field_args_t *a, double *err_dev, void *stream);
+
 /* Halo planes for VPB_FACE_REMOTE faces (the payload of begin/end_remote_ghost_tang_b, remote.cc:61-134, and of
  * synchronize_jf, remote.cc:417-508).  pack copies the plane a neighbour needs into buf; unpack applies a received
  * plane.  floats per plane: vpb_halo_floats(). */

@@ -60,6 +60,16 @@ void vacuum_advance_e(vpb_field_array_t *fa, float frac);
 void clear_jf(vpb_field_array_t *fa);
 void synchronize_jf(vpb_field_array_t *fa);
 void vacuum_energy_f(double *en6, const vpb_field_array_t *fa);
+/* the divergence-cleaning and shared-face entries of the same table (sfa_private.h; advance.cc:138-176) */
+void   clear_rhof(vpb_field_array_t *fa);
+void   synchronize_rho(vpb_field_array_t *fa);
+void   vacuum_compute_div_e_err(vpb_field_array_t *fa);
+double compute_rms_div_e_err(const vpb_field_array_t *fa);
+void   vacuum_clean_div_e(vpb_field_array_t *fa);
+void   compute_div_b_err(vpb_field_array_t *fa);
+double compute_rms_div_b_err(const vpb_field_array_t *fa);
+void   clean_div_b(vpb_field_array_t *fa);
+double synchronize_tang_e_norm_b(vpb_field_array_t *fa);
 
 /* Device-backed entries for the field_advance_kernels_t table (src/field_advance/field_advance.h:170-218);
  * vpic_b200_install_field_kernels(fa) repoints fa->kernel[0] at them (one material, single rank) — for host builds
@@ -69,6 +79,15 @@ void vpic_b200_advance_e(vpb_field_array_t *fa, float frac);
 void vpic_b200_clear_jf(vpb_field_array_t *fa);
 void vpic_b200_synchronize_jf(vpb_field_array_t *fa);
 void vpic_b200_energy_f(double *en6, const vpb_field_array_t *fa);
+void   vpic_b200_clear_rhof(vpb_field_array_t *fa);
+void   vpic_b200_synchronize_rho(vpb_field_array_t *fa);
+void   vpic_b200_compute_div_e_err(vpb_field_array_t *fa);
+double vpic_b200_compute_rms_div_e_err(const vpb_field_array_t *fa);
+void   vpic_b200_clean_div_e(vpb_field_array_t *fa);
+void   vpic_b200_compute_div_b_err(vpb_field_array_t *fa);
+double vpic_b200_compute_rms_div_b_err(const vpb_field_array_t *fa);
+void   vpic_b200_clean_div_b(vpb_field_array_t *fa);
+double vpic_b200_synchronize_tang_e_norm_b(vpb_field_array_t *fa);
 void vpic_b200_install_field_kernels(vpb_field_array_t *fa);
 
 /* coherence control (new; no reference counterpart) */

@@ -181,7 +181,8 @@ def test_preloaded_deck_uses_the_device_kernels_it_claims(fields):
     assert t["advance_p"] > 0 and t["sort_p"] > 0 and t["load_interpolator_array"] > 0 and t["unload_accumulator_array"] > 0
     if fields == "device":
         assert t["advance_b"] >= 2 * t["advance_e"] > 0 and t["clear_jf"] > 0 and t["synchronize_jf"] > 0
+        assert t["divergence_cleaning_kernels"] > 0                  # the deck cleans div E and div B at intervals
         assert t["field_kernel_fallback_to_reference"] == 0
     else:
-        assert t["advance_b"] == t["advance_e"] == t["clear_jf"] == 0
+        assert t["advance_b"] == t["advance_e"] == t["clear_jf"] == t["divergence_cleaning_kernels"] == 0
         assert t["field_kernel_fallback_to_reference"] > 0

@@ -288,6 +288,57 @@ def test_field_advance(eng, oracle, dims, fbc, damp, material):
     assert np.array_equal(bits(fa.f.cpu().numpy()), bits(f_ref))
 
 
+@pytest.mark.parametrize("dims,fbc,material", [
+    ((6, 5, 4), None, None),
+    ((64, 64, 1), {0: -1, 3: -1}, None),               # harris: pec x walls, one cell in z
+    ((5, 1, 7), {2: -2, 5: -3}, None),                 # symmetric / pmc walls, one cell in y
+    ((40, 24, 16), None, None),
+    ((6, 5, 4), {0: -4, 3: -4, 2: -4, 5: -1}, None),   # absorbing walls
+    ((33, 9, 12), {0: -1, 3: -4, 1: -2, 4: -3}, MATERIAL),
+])
+def test_divergence_cleaning(eng, oracle, dims, fbc, material):
+    """advance.cc:138-176 on the device against the oracle (itself pinned bit-exact against the reference): the field
+    array bit for bit after every call, the three double-precision reductions to 1e-12."""
+    rng = np.random.default_rng(17)
+    nx, ny, nz = dims
+    g = make_grid(nx, ny, nz, fbc=fbc)
+    dg = eng.DeviceGrid(g)
+    f0 = rng.normal(0, 0.05, (g.nv, 20)).astype(np.float32)
+    f0[:, 16:] = 0
+    fa = eng.FieldArray(dg, material=material)
+    fa.f.copy_(torch.from_numpy(f0))
+    f_ref = f0.copy()
+    a = R.OracleFieldArgs()
+    a.f = f_ref.ctypes.data
+    a.nx, a.ny, a.nz = nx, ny, nz
+    a.dt, a.cvac, a.eps0, a.damp = g.dt, g.cvac, g.eps0, 0.0
+    a.dx, a.dy, a.dz, a.dV = g.dx, g.dy, g.dz, g.dV
+    a.rdx, a.rdy, a.rdz = g.rdx, g.rdy, g.rdz
+    for i, (fi, fj, fk) in enumerate(G.FACES):
+        a.bc6[i] = g.bc[G.boundary_index(fi, fj, fk)]
+    if material is not None:
+        a.has_material = 1
+        for i, v in enumerate(material):
+            a.material[i] = v
+    pa = C.byref(a)
+
+    def same(what):
+        assert np.array_equal(bits(fa.f.cpu().numpy()), bits(f_ref)), what
+
+    fa.synchronize_rho(); oracle.vpo_synchronize_rho(pa); same("synchronize_rho")
+    for _ in range(3):
+        fa.compute_div_e_err(); oracle.vpo_vacuum_compute_div_e_err(pa); same("compute_div_e_err")
+        np.testing.assert_allclose(fa.compute_rms_div_e_err(), oracle.vpo_compute_rms_div_e_err(pa), rtol=1e-12)
+        fa.clean_div_e(); oracle.vpo_vacuum_clean_div_e(pa); same("clean_div_e")
+    for _ in range(3):
+        fa.compute_div_b_err(); oracle.vpo_compute_div_b_err(pa); same("compute_div_b_err")
+        np.testing.assert_allclose(fa.compute_rms_div_b_err(), oracle.vpo_compute_rms_div_b_err(pa), rtol=1e-12)
+        fa.clean_div_b(); oracle.vpo_clean_div_b(pa); same("clean_div_b")
+    err = fa.synchronize_tang_e_norm_b(); err_ref = oracle.vpo_synchronize_tang_e_norm_b(pa); same("synchronize_tang_e_norm_b")
+    np.testing.assert_allclose(err, err_ref, rtol=1e-12, atol=1e-300)
+    fa.clear_rhof(); oracle.vpo_clear_rhof(pa); same("clear_rhof")
+
+
 def test_reference_scalar_agrees_when_present(eng, oracle):
     """If the prebuilt unmodified reference travelled with the repo, check the CUDA push against it directly."""
     if not R.have_ref("scalar"):

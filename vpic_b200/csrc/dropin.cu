@@ -7,6 +7,7 @@
 #include "lazy_pages.h"
 #include "../../include/vpic_b200_dropin.h"
 #include <dlfcn.h>
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 #include <unistd.h>
@@ -40,12 +41,12 @@ int rank_for_log() { return &_world_rank ? _world_rank : 0; }
 // VPIC_B200_TRACE=1: at exit, one line on stderr with how often each entry point ran on the device (and how often a
 // field kernel fell through to the reference's own), so a preloaded run can be checked for what it actually used.
 enum { C_ADVANCE_P, C_SORT_P, C_CENTER_P, C_ENERGY_P, C_RHO_P, C_LOAD_INTERP, C_CLEAR_ACC, C_UNLOAD_ACC, C_ADVANCE_B,
-       C_ADVANCE_E, C_CLEAR_JF, C_SYNC_JF, C_ENERGY_F, C_FIELD_FALLBACK, C_COUNT };
+       C_ADVANCE_E, C_CLEAR_JF, C_SYNC_JF, C_ENERGY_F, C_DIV_CLEAN, C_FIELD_FALLBACK, C_COUNT };
 uint64_t g_calls[C_COUNT];
 void trace_report() {
   static const char *names[C_COUNT] = {"advance_p", "sort_p", "center_p/uncenter_p", "energy_p", "accumulate_rho_p",
       "load_interpolator_array", "clear_accumulator_array", "unload_accumulator_array", "advance_b", "advance_e",
-      "clear_jf", "synchronize_jf", "energy_f", "field_kernel_fallback_to_reference"};
+      "clear_jf", "synchronize_jf", "energy_f", "divergence_cleaning_kernels", "field_kernel_fallback_to_reference"};
   fprintf(stderr, "vpic_b200 trace[%d]:", rank_for_log());
   for (int i = 0; i < C_COUNT; i++) fprintf(stderr, " %s=%llu", names[i], (unsigned long long)g_calls[i]);
   const vpb_lazy::Stats st = vpb_lazy::stats();
@@ -628,6 +629,81 @@ void vacuum_energy_f(double *en, const vpb_field_array_t *fa) {
   ref(en, fa);
 }
 
+// ---- divergence cleaning and shared-face synchronisation (field_advance.h:186-218; sfa_private.h) ---------------
+#define DIV_ENTRY(call)                                                                     \
+  if (!fa) DROPIN_ERROR("Bad args");                                                        \
+  count_call(C_DIV_CLEAN);                                                                  \
+  const size_t fbytes = (size_t)fa->g->nv * sizeof(vpb_field_t);                            \
+  float *df = (float *)dev_in(fa->f, fbytes);                                               \
+  vpb_field_args_t a; field_args_of(fa, df, &a);                                            \
+  DEV(call);
+#define DIV_ENTRY_W(call) DIV_ENTRY(call) dev_written(fa->f, fbytes); finish_entry();
+
+void vpic_b200_clear_rhof(vpb_field_array_t *fa) { DIV_ENTRY_W(vpb_clear_rhof(&a, nullptr)) }
+void vpic_b200_synchronize_rho(vpb_field_array_t *fa) { DIV_ENTRY_W(vpb_synchronize_rho(&a, nullptr)) }
+void vpic_b200_compute_div_e_err(vpb_field_array_t *fa) { DIV_ENTRY_W(vpb_vacuum_compute_div_e_err(&a, nullptr)) }
+void vpic_b200_clean_div_e(vpb_field_array_t *fa) { DIV_ENTRY_W(vpb_vacuum_clean_div_e(&a, nullptr)) }
+void vpic_b200_compute_div_b_err(vpb_field_array_t *fa) { DIV_ENTRY_W(vpb_compute_div_b_err(&a, nullptr)) }
+void vpic_b200_clean_div_b(vpb_field_array_t *fa) { DIV_ENTRY_W(vpb_clean_div_b(&a, nullptr)) }
+
+static double rms_finish(const vpb_field_array_t *fa, double *sum_dev) {
+  double s = 0;
+  DEV(vpb_memcpy_d2h(&s, sum_dev, sizeof s, nullptr));
+  DEV(vpb_stream_sync(nullptr));
+  g_d2h += sizeof s;
+  const vpb_grid_t *g = fa->g;
+  double local[2] = {s * g->dV, (g->nx * g->ny * g->nz) * g->dV}, global[2];      // compute_rms_div_e_err_pipeline.cc:175-181
+  if (mp_allsum_d) mp_allsum_d(local, global, 2); else { global[0] = local[0]; global[1] = local[1]; }
+  return g->eps0 * sqrt(global[0] / global[1]);
+}
+double vpic_b200_compute_rms_div_e_err(const vpb_field_array_t *fa) {
+  double *sum = (double *)scratch(5, sizeof(double));
+  DIV_ENTRY(vpb_compute_rms_div_e_err(&a, sum, nullptr))
+  return rms_finish(fa, sum);
+}
+double vpic_b200_compute_rms_div_b_err(const vpb_field_array_t *fa) {
+  double *sum = (double *)scratch(5, sizeof(double));
+  DIV_ENTRY(vpb_compute_rms_div_b_err(&a, sum, nullptr))
+  return rms_finish(fa, sum);
+}
+double vpic_b200_synchronize_tang_e_norm_b(vpb_field_array_t *fa) {
+  double *err = (double *)scratch(5, sizeof(double));
+  DIV_ENTRY(vpb_synchronize_tang_e_norm_b(&a, err, nullptr))
+  dev_written(fa->f, fbytes);
+  double local = 0, global = 0;
+  DEV(vpb_memcpy_d2h(&local, err, sizeof local, nullptr));
+  DEV(vpb_stream_sync(nullptr));
+  g_d2h += sizeof local;
+  finish_entry();
+  if (mp_allsum_d) { mp_allsum_d(&local, &global, 1); return global; }      // remote.cc:413-414
+  return local;
+}
+
+// interposable reference symbols, as for the time-stepping kernels above
+#define FALLBACK_VOID(sym, ours)                                                            \
+  void sym(vpb_field_array_t *fa) {                                                         \
+    if (fields_on_device(fa)) { ours(fa); return; }                                         \
+    static auto ref = (void (*)(vpb_field_array_t *))reference_kernel(#sym);                \
+    count_call(C_FIELD_FALLBACK);                                                           \
+    ref(fa);                                                                                \
+  }
+#define FALLBACK_DOUBLE(sym, ours, qual)                                                    \
+  double sym(qual vpb_field_array_t *fa) {                                                  \
+    if (fields_on_device(fa)) return ours(fa);                                              \
+    static auto ref = (double (*)(qual vpb_field_array_t *))reference_kernel(#sym);         \
+    count_call(C_FIELD_FALLBACK);                                                           \
+    return ref(fa);                                                                         \
+  }
+FALLBACK_VOID(clear_rhof, vpic_b200_clear_rhof)
+FALLBACK_VOID(synchronize_rho, vpic_b200_synchronize_rho)
+FALLBACK_VOID(vacuum_compute_div_e_err, vpic_b200_compute_div_e_err)
+FALLBACK_VOID(vacuum_clean_div_e, vpic_b200_clean_div_e)
+FALLBACK_VOID(compute_div_b_err, vpic_b200_compute_div_b_err)
+FALLBACK_VOID(clean_div_b, vpic_b200_clean_div_b)
+FALLBACK_DOUBLE(compute_rms_div_e_err, vpic_b200_compute_rms_div_e_err, const)
+FALLBACK_DOUBLE(compute_rms_div_b_err, vpic_b200_compute_rms_div_b_err, const)
+FALLBACK_DOUBLE(synchronize_tang_e_norm_b, vpic_b200_synchronize_tang_e_norm_b, )
+
 void vpic_b200_install_field_kernels(vpb_field_array_t *fa) {
   if (!fa) DROPIN_ERROR("Bad args");
   if (const char *why = device_fields_obstacle(fa)) DROPIN_ERROR("the device field advance cannot serve this field array: %s", why);
@@ -636,6 +712,15 @@ void vpic_b200_install_field_kernels(vpb_field_array_t *fa) {
   fa->kernel->energy_f = vpic_b200_energy_f;
   fa->kernel->clear_jf = vpic_b200_clear_jf;
   fa->kernel->synchronize_jf = vpic_b200_synchronize_jf;
+  fa->kernel->clear_rhof = vpic_b200_clear_rhof;
+  fa->kernel->synchronize_rho = vpic_b200_synchronize_rho;
+  fa->kernel->synchronize_tang_e_norm_b = vpic_b200_synchronize_tang_e_norm_b;
+  fa->kernel->compute_div_e_err = vpic_b200_compute_div_e_err;
+  fa->kernel->compute_rms_div_e_err = vpic_b200_compute_rms_div_e_err;
+  fa->kernel->clean_div_e = vpic_b200_clean_div_e;
+  fa->kernel->compute_div_b_err = vpic_b200_compute_div_b_err;
+  fa->kernel->compute_rms_div_b_err = vpic_b200_compute_rms_div_b_err;
+  fa->kernel->clean_div_b = vpic_b200_clean_div_b;
 }
 
 }  // extern "C"

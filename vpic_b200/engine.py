@@ -122,6 +122,32 @@ class FieldArray:
         _lib.check(_lib.load().vpb_vacuum_energy_f(C.byref(self.args()), _ptr(self._en), _stream()), "energy_f")
         return self._en.cpu().numpy().copy()
 
+    # divergence cleaning and shared-face synchronisation (field_advance.h:186-218, advance.cc:138-176)
+    def _call(self, name, *extra):
+        _lib.check(getattr(_lib.load(), name)(C.byref(self.args()), *extra, _stream()), name)
+
+    def clear_rhof(self): self._call("vpb_clear_rhof")
+    def synchronize_rho(self): self._call("vpb_synchronize_rho")
+    def compute_div_e_err(self): self._call("vpb_vacuum_compute_div_e_err")
+    def clean_div_e(self): self._call("vpb_vacuum_clean_div_e")
+    def compute_div_b_err(self): self._call("vpb_compute_div_b_err")
+    def clean_div_b(self): self._call("vpb_clean_div_b")
+
+    def _rms(self, name):
+        """eps0 * sqrt(sum dV / volume) of one domain (compute_rms_div_e_err_pipeline.cc:170-183)."""
+        g = self.g
+        self._call(name, _ptr(self._en))
+        s = float(self._en[0].item())
+        dV = np.float32(g.dV)
+        return float(g.eps0) * float(np.sqrt((s * float(dV)) / float(np.float32(g.nx * g.ny * g.nz) * dV)))
+
+    def compute_rms_div_e_err(self): return self._rms("vpb_compute_rms_div_e_err")
+    def compute_rms_div_b_err(self): return self._rms("vpb_compute_rms_div_b_err")
+
+    def synchronize_tang_e_norm_b(self):
+        self._call("vpb_synchronize_tang_e_norm_b", _ptr(self._en))
+        return float(self._en[0].item())
+
 
 class Species:
     """species_t (species_advance_aos.h:54-94) with device arrays."""
