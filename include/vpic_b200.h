@@ -224,6 +224,9 @@ int vpb_compute_div_b_err(const vpb_field_args_t *a, void *stream);
 int vpb_compute_rms_div_b_err(const vpb_field_args_t *a, double *sum_dev, void *stream);
 int vpb_clean_div_b(const vpb_field_args_t *a, void *stream);
 int vpb_synchronize_tang_e_norm_b(const vpb_field_args_t *a, double *err_dev, void *stream);
+/* initialisation-time entries (src/vpic/initialize.cc): vacuum_compute_rhob, vacuum_compute_curl_b */
+int vpb_vacuum_compute_rhob(const vpb_field_args_t *a, void *stream);
+int vpb_vacuum_compute_curl_b(const vpb_field_args_t *a, void *stream);
 
 /* Halo planes for VPB_FACE_REMOTE faces (the payload of begin/end_remote_ghost_tang_b, remote.cc:61-134, and of
  * synchronize_jf, remote.cc:417-508).  pack copies the plane a neighbour needs into buf; unpack applies a received

@@ -70,6 +70,8 @@ void   compute_div_b_err(vpb_field_array_t *fa);
 double compute_rms_div_b_err(const vpb_field_array_t *fa);
 void   clean_div_b(vpb_field_array_t *fa);
 double synchronize_tang_e_norm_b(vpb_field_array_t *fa);
+void   vacuum_compute_rhob(vpb_field_array_t *fa);
+void   vacuum_compute_curl_b(vpb_field_array_t *fa);
 
 /* Device-backed entries for the field_advance_kernels_t table (src/field_advance/field_advance.h:170-218);
  * vpic_b200_install_field_kernels(fa) repoints fa->kernel[0] at them (one material, single rank) — for host builds
@@ -88,6 +90,8 @@ void   vpic_b200_compute_div_b_err(vpb_field_array_t *fa);
 double vpic_b200_compute_rms_div_b_err(const vpb_field_array_t *fa);
 void   vpic_b200_clean_div_b(vpb_field_array_t *fa);
 double vpic_b200_synchronize_tang_e_norm_b(vpb_field_array_t *fa);
+void   vpic_b200_compute_rhob(vpb_field_array_t *fa);
+void   vpic_b200_compute_curl_b(vpb_field_array_t *fa);
 void vpic_b200_install_field_kernels(vpb_field_array_t *fa);
 
 /* coherence control (new; no reference counterpart) */

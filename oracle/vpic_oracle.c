@@ -924,3 +924,50 @@ double vpo_synchronize_tang_e_norm_b(const vpo_field_args_t *a) {
   }
   return err;
 }
+
+void vpo_vacuum_compute_rhob(const vpo_field_args_t *a) {
+  const int nx = a->nx, ny = a->ny, nz = a->nz;
+  const int hm = a->has_material;
+  const float *m = a->material;
+  const float nc = hm ? m[9] : 1.0f;
+  const float px = (nx > 1) ? a->eps0 * (hm ? m[10] : 1.0f) * a->rdx : 0;
+  const float py = (ny > 1) ? a->eps0 * (hm ? m[11] : 1.0f) * a->rdy : 0;
+  const float pz = (nz > 1) ? a->eps0 * (hm ? m[12] : 1.0f) * a->rdz : 0;
+  float *F = a->f;
+  ghost_norm_e(a);
+# define FF(x, y, z, m) F[(size_t)VOX(x, y, z) * F_STRIDE + (m)]
+  for (int z = 1; z <= nz + 1; z++) for (int y = 1; y <= ny + 1; y++) for (int x = 1; x <= nx + 1; x++)
+    FF(x, y, z, F_RHOB) = nc * (px * (FF(x, y, z, F_EX) - FF(x - 1, y, z, F_EX)) +
+                                py * (FF(x, y, z, F_EY) - FF(x, y - 1, z, F_EY)) +
+                                pz * (FF(x, y, z, F_EZ) - FF(x, y, z - 1, F_EZ)) - FF(x, y, z, F_RHOF));
+# undef FF
+  dims_t d = mkdims(a);                                              /* local_adjust_rhob */
+  for (int fc = 0; fc < 6; fc++) {
+    if (a->bc6[fc] != -1) continue;
+    int X = fc % 3, Y = (X + 1) % 3, Z = (X + 2) % 3, face = fc < 3 ? 1 : d.n[X] + 1;
+    PLANE_LOOP(X, face, Y, 1, d.n[Y] + 1, Z, 1, d.n[Z] + 1, FV(v, F_RHOB) = 0);
+  }
+}
+
+void vpo_vacuum_compute_curl_b(const vpo_field_args_t *a) {
+  const int nx = a->nx, ny = a->ny, nz = a->nz;
+  const int hm = a->has_material;
+  const float *m = a->material;
+  const float rmux = hm ? m[6] : 1, rmuy = hm ? m[7] : 1, rmuz = hm ? m[8] : 1;
+  const float px_muz = ((nx > 1) ? a->cvac * a->dt * a->rdx : 0) * rmuz, px_muy = ((nx > 1) ? a->cvac * a->dt * a->rdx : 0) * rmuy;
+  const float py_mux = ((ny > 1) ? a->cvac * a->dt * a->rdy : 0) * rmux, py_muz = ((ny > 1) ? a->cvac * a->dt * a->rdy : 0) * rmuz;
+  const float pz_muy = ((nz > 1) ? a->cvac * a->dt * a->rdz : 0) * rmuy, pz_mux = ((nz > 1) ? a->cvac * a->dt * a->rdz : 0) * rmux;
+  float *F = a->f;
+  ghost_tang_b(a);
+# define FF(x, y, z, m) F[(size_t)VOX(x, y, z) * F_STRIDE + (m)]
+  for (int z = 1; z <= nz + 1; z++) for (int y = 1; y <= ny + 1; y++) for (int x = 1; x <= nx + 1; x++) {
+    if (x <= nx) FF(x, y, z, F_TCAX) = (py_muz * (FF(x, y, z, F_CBZ) - FF(x, y - 1, z, F_CBZ)) -
+                                        pz_muy * (FF(x, y, z, F_CBY) - FF(x, y, z - 1, F_CBY)));
+    if (y <= ny) FF(x, y, z, F_TCAY) = (pz_mux * (FF(x, y, z, F_CBX) - FF(x, y, z - 1, F_CBX)) -
+                                        px_muz * (FF(x, y, z, F_CBZ) - FF(x - 1, y, z, F_CBZ)));
+    if (z <= nz) FF(x, y, z, F_TCAZ) = (px_muy * (FF(x, y, z, F_CBY) - FF(x - 1, y, z, F_CBY)) -
+                                        py_mux * (FF(x, y, z, F_CBX) - FF(x, y - 1, z, F_CBX)));
+  }
+# undef FF
+  adjust_tang_e(a);
+}

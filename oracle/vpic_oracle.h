@@ -111,6 +111,9 @@ void   vpo_compute_div_b_err(const vpo_field_args_t *a);          /* compute_div
 double vpo_compute_rms_div_b_err(const vpo_field_args_t *a);      /* compute_rms_div_b_err_pipeline.cc */
 void   vpo_clean_div_b(const vpo_field_args_t *a);                /* clean_div_b_pipeline.cc */
 double vpo_synchronize_tang_e_norm_b(const vpo_field_args_t *a);  /* remote.cc:298-416 */
+/* initialisation-time kernels of the same table (initialize.cc): bound charge from div E, TCA from curl B */
+void   vpo_vacuum_compute_rhob(const vpo_field_args_t *a);        /* vacuum_compute_rhob_pipeline.{h,cc} */
+void   vpo_vacuum_compute_curl_b(const vpo_field_args_t *a);      /* vacuum_compute_curl_b_pipeline.{h,cc} */
 
 #ifdef __cplusplus
 }

@@ -50,7 +50,7 @@ def load_oracle():
     lib.vpo_synchronize_jf.argtypes = [C.c_void_p]
     lib.vpo_vacuum_energy_f.argtypes = [C.c_void_p, C.c_void_p]
     for name in ("vpo_clear_rhof", "vpo_synchronize_rho", "vpo_vacuum_compute_div_e_err", "vpo_vacuum_clean_div_e",
-                 "vpo_compute_div_b_err", "vpo_clean_div_b"):
+                 "vpo_compute_div_b_err", "vpo_clean_div_b", "vpo_vacuum_compute_rhob", "vpo_vacuum_compute_curl_b"):
         getattr(lib, name).argtypes = [C.c_void_p]
         getattr(lib, name).restype = None
     for name in ("vpo_compute_rms_div_e_err", "vpo_compute_rms_div_b_err", "vpo_synchronize_tang_e_norm_b"):
@@ -224,6 +224,8 @@ class RefWorld:
     def _k_double(self, idx):
         return float(self.kernel(idx, C.c_double, C.POINTER(abi.FieldArray))(self.fa))
 
+    def compute_rhob(self): self._k_void(8)
+    def compute_curl_b(self): self._k_void(9)
     def clear_rhof(self): self._k_void(6)
     def synchronize_rho(self): self._k_void(7)
     def synchronize_tang_e_norm_b(self): return self._k_double(10)

@@ -337,6 +337,8 @@ def test_divergence_cleaning(eng, oracle, dims, fbc, material):
     err = fa.synchronize_tang_e_norm_b(); err_ref = oracle.vpo_synchronize_tang_e_norm_b(pa); same("synchronize_tang_e_norm_b")
     np.testing.assert_allclose(err, err_ref, rtol=1e-12, atol=1e-300)
     fa.clear_rhof(); oracle.vpo_clear_rhof(pa); same("clear_rhof")
+    fa.compute_rhob(); oracle.vpo_vacuum_compute_rhob(pa); same("compute_rhob")
+    fa.compute_curl_b(); oracle.vpo_vacuum_compute_curl_b(pa); same("compute_curl_b")
 
 
 def test_reference_scalar_agrees_when_present(eng, oracle):

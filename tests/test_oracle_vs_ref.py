@@ -196,6 +196,8 @@ def test_divergence_cleaning_bit_exact(ref_scalar, oracle, dims, fbc, material):
     e_ref = W.synchronize_tang_e_norm_b(); e_orc = oracle.vpo_synchronize_tang_e_norm_b(pa); same("synchronize_tang_e_norm_b")
     np.testing.assert_allclose(e_orc, e_ref, rtol=1e-13)
     W.clear_rhof(); oracle.vpo_clear_rhof(pa); same("clear_rhof")
+    W.compute_rhob(); oracle.vpo_vacuum_compute_rhob(pa); same("compute_rhob")
+    W.compute_curl_b(); oracle.vpo_vacuum_compute_curl_b(pa); same("compute_curl_b")
 
 
 def test_rho_p_and_rhob_bit_exact(ref_scalar, oracle):

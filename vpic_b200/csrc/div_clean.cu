@@ -15,6 +15,7 @@
 //   pipeline/clean_div_b_pipeline.cc                       clean_div_b (+ div-B ghosts remote.cc:208-282,
 //                                                          local.cc:181-217; local_adjust_norm_b)
 //   remote.cc:298-416                                      synchronize_tang_e_norm_b
+//   pipeline/vacuum_compute_rhob_pipeline.{h,cc}           vacuum_compute_rhob (initialisation)
 // As in field_advance.cu the reference's interior-pipeline + host-strip split collapses into one kernel per update
 // over the node box with per-component range predicates.  Faces shared with another rank (VPB_FACE_REMOTE) are not
 // handled here yet; the drop-in layer leaves such field arrays to the reference.
@@ -124,6 +125,23 @@ __global__ void __launch_bounds__(256) div_e_err_kernel(FieldK k, DivECoef c) {
   for (int fc = 0; fc < 6; fc++)
     if ((k.face[fc] == -1 || k.face[fc] == -4) && cc[fc % 3] == (fc < 3 ? 1 : n[fc % 3] + 1)) err = 0.0f;
   *fslot(f, v, S_DIVE) = err;
+}
+
+// vacuum_compute_rhob: the bound charge that makes div E consistent with rhof (initialisation), pec walls zeroed
+__global__ void __launch_bounds__(256) compute_rhob_kernel(FieldK k, DivECoef c) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x + 1, y = blockIdx.y + 1, z = blockIdx.z + 1;
+  const int nx = k.nx, ny = k.ny, nz = k.nz;
+  if (x > nx + 1) return;
+  float4 *f = k.f;
+  const int sy = nx + 2, sz = (nx + 2) * (ny + 2), v = voxel(x, y, z, nx, ny);
+  const float4 e0 = FQ(v, 0);
+  const float exm = FQ(v - 1, 0).x, eym = FQ(v - sy, 0).y, ezm = FQ(v - sz, 0).z;
+  float rhob = c.nc * (((c.px * (e0.x - exm) + c.py * (e0.y - eym)) + c.pz * (e0.z - ezm)) - FQ(v, 3).w);
+  const int n[3] = {nx, ny, nz}; const int cc[3] = {x, y, z};
+#pragma unroll
+  for (int fc = 0; fc < 6; fc++)
+    if (k.face[fc] == -1 && cc[fc % 3] == (fc < 3 ? 1 : n[fc % 3] + 1)) rhob = 0.0f;
+  *fslot(f, v, S_RHOB) = rhob;
 }
 
 __device__ __forceinline__ void block_sum_to(double acc, double *out) {
@@ -353,6 +371,22 @@ extern "C" int vpb_vacuum_compute_div_e_err(const vpb_field_args_t *a, void *str
   c.pz = ((a->nz > 1) ? a->rdz : 0) * (hm ? a->material[12] : 1.0f);
   c.cj = (float)(1. / (double)a->eps0);
   div_e_err_kernel<<<node_grid(a), 256, 0, st>>>(to_k(a), c);
+  VPB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vpb_vacuum_compute_rhob(const vpb_field_args_t *a, void *stream) {
+  DIV_ENTRY("vpb_vacuum_compute_rhob");
+  ghost_norm_e_kernel<<<max_plane_grid(a, 6), 256, 0, st>>>(to_k(a));
+  VPB_LAUNCH_CHECK();
+  const bool hm = a->has_material != 0;
+  DivECoef c;                                                     // vacuum_compute_rhob_pipeline.h:23-26
+  c.nc = hm ? a->material[9] : 1.0f;
+  c.px = (a->nx > 1) ? a->eps0 * (hm ? a->material[10] : 1.0f) * a->rdx : 0;
+  c.py = (a->ny > 1) ? a->eps0 * (hm ? a->material[11] : 1.0f) * a->rdy : 0;
+  c.pz = (a->nz > 1) ? a->eps0 * (hm ? a->material[12] : 1.0f) * a->rdz : 0;
+  c.cj = 0;
+  compute_rhob_kernel<<<node_grid(a), 256, 0, st>>>(to_k(a), c);
   VPB_LAUNCH_CHECK();
   return 0;
 }

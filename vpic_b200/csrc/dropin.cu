@@ -645,6 +645,8 @@ void vpic_b200_compute_div_e_err(vpb_field_array_t *fa) { DIV_ENTRY_W(vpb_vacuum
 void vpic_b200_clean_div_e(vpb_field_array_t *fa) { DIV_ENTRY_W(vpb_vacuum_clean_div_e(&a, nullptr)) }
 void vpic_b200_compute_div_b_err(vpb_field_array_t *fa) { DIV_ENTRY_W(vpb_compute_div_b_err(&a, nullptr)) }
 void vpic_b200_clean_div_b(vpb_field_array_t *fa) { DIV_ENTRY_W(vpb_clean_div_b(&a, nullptr)) }
+void vpic_b200_compute_rhob(vpb_field_array_t *fa) { DIV_ENTRY_W(vpb_vacuum_compute_rhob(&a, nullptr)) }
+void vpic_b200_compute_curl_b(vpb_field_array_t *fa) { DIV_ENTRY_W(vpb_vacuum_compute_curl_b(&a, nullptr)) }
 
 static double rms_finish(const vpb_field_array_t *fa, double *sum_dev) {
   double s = 0;
@@ -700,6 +702,8 @@ FALLBACK_VOID(vacuum_compute_div_e_err, vpic_b200_compute_div_e_err)
 FALLBACK_VOID(vacuum_clean_div_e, vpic_b200_clean_div_e)
 FALLBACK_VOID(compute_div_b_err, vpic_b200_compute_div_b_err)
 FALLBACK_VOID(clean_div_b, vpic_b200_clean_div_b)
+FALLBACK_VOID(vacuum_compute_rhob, vpic_b200_compute_rhob)
+FALLBACK_VOID(vacuum_compute_curl_b, vpic_b200_compute_curl_b)
 FALLBACK_DOUBLE(compute_rms_div_e_err, vpic_b200_compute_rms_div_e_err, const)
 FALLBACK_DOUBLE(compute_rms_div_b_err, vpic_b200_compute_rms_div_b_err, const)
 FALLBACK_DOUBLE(synchronize_tang_e_norm_b, vpic_b200_synchronize_tang_e_norm_b, )
@@ -712,6 +716,8 @@ void vpic_b200_install_field_kernels(vpb_field_array_t *fa) {
   fa->kernel->energy_f = vpic_b200_energy_f;
   fa->kernel->clear_jf = vpic_b200_clear_jf;
   fa->kernel->synchronize_jf = vpic_b200_synchronize_jf;
+  fa->kernel->compute_rhob = vpic_b200_compute_rhob;
+  fa->kernel->compute_curl_b = vpic_b200_compute_curl_b;
   fa->kernel->clear_rhof = vpic_b200_clear_rhof;
   fa->kernel->synchronize_rho = vpic_b200_synchronize_rho;
   fa->kernel->synchronize_tang_e_norm_b = vpic_b200_synchronize_tang_e_norm_b;

@@ -153,6 +153,33 @@ __global__ void __launch_bounds__(256) vacuum_advance_e_kernel(FieldK k, ECoef c
   FQ(v, 0) = e; FQ(v, 2) = t;
 }
 
+// vacuum_compute_curl_b (vacuum_compute_curl_b_pipeline.{h,cc}): TCA = curl B, no damping history — initialisation
+__global__ void __launch_bounds__(256) compute_curl_b_kernel(FieldK k, ECoef c) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x + 1, y = blockIdx.y + 1, z = blockIdx.z + 1;
+  const int nx = k.nx, ny = k.ny, nz = k.nz;
+  if (x > nx + 1) return;
+  float4 *f = k.f;
+  const int sy = nx + 2, sz = (nx + 2) * (ny + 2), v = voxel(x, y, z, nx, ny);
+  float4 e = FQ(v, 0), t = FQ(v, 2);
+  const float4 b0 = FQ(v, 1);
+  const float4 bx = FQ(v - 1, 1), by = FQ(v - sy, 1), bz = FQ(v - sz, 1);
+  if (x <= nx) t.x = (c.py_muz * (b0.z - by.z) - c.pz_muy * (b0.y - bz.y));
+  if (y <= ny) t.y = (c.pz_mux * (b0.x - bz.x) - c.px_muz * (b0.z - bx.z));
+  if (z <= nz) t.z = (c.px_muy * (b0.y - bx.y) - c.py_mux * (b0.x - by.x));
+  const int n[3] = {nx, ny, nz}; const int cc[3] = {x, y, z};
+  bool e_dirty = false;
+#pragma unroll
+  for (int fc = 0; fc < 6; fc++) {                                 // local_adjust_tang_e
+    if (k.face[fc] != -1) continue;
+    const int X = fc % 3, Y = (X + 1) % 3, Z = (X + 2) % 3;
+    if (cc[X] != (fc < 3 ? 1 : n[X] + 1)) continue;
+    if (cc[Y] <= n[Y]) { set_comp(e, Y, 0.0f); set_comp(t, Y, 0.0f); e_dirty = true; }
+    if (cc[Z] <= n[Z]) { set_comp(e, Z, 0.0f); set_comp(t, Z, 0.0f); e_dirty = true; }
+  }
+  if (e_dirty) FQ(v, 0) = e;
+  FQ(v, 2) = t;
+}
+
 // ---- jf ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) clear_jf_kernel(float4 *f, int nv) {
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
@@ -320,6 +347,28 @@ extern "C" int vpb_vacuum_advance_e(const vpb_field_args_t *a, float frac, void 
   c.decayz = hm ? m[4] : 1.0f; c.drivez = hm ? m[5] : 1.0f;
   dim3 grid((a->nx + 1 + 255) / 256, a->ny + 1, a->nz + 1);
   vacuum_advance_e_kernel<<<grid, 256, 0, st>>>(to_k(a), c);
+  VPB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vpb_vacuum_compute_curl_b(const vpb_field_args_t *a, void *stream) {
+  if (int r = check_field_args(a, "vpb_vacuum_compute_curl_b")) return r;
+  cudaStream_t st = as_stream(stream);
+  ghost_tang_b_kernel<<<max_plane_grid(a, 6), 256, 0, st>>>(to_k(a));
+  VPB_LAUNCH_CHECK();
+  const bool hm = a->has_material != 0;
+  const float *m = a->material;
+  const float rmux = hm ? m[6] : 1.0f, rmuy = hm ? m[7] : 1.0f, rmuz = hm ? m[8] : 1.0f;
+  ECoef c;
+  memset(&c, 0, sizeof c);
+  c.px_muz = ((a->nx > 1) ? a->cvac * a->dt * a->rdx : 0) * rmuz;   // vacuum_compute_curl_b_pipeline.h:23-28
+  c.px_muy = ((a->nx > 1) ? a->cvac * a->dt * a->rdx : 0) * rmuy;
+  c.py_mux = ((a->ny > 1) ? a->cvac * a->dt * a->rdy : 0) * rmux;
+  c.py_muz = ((a->ny > 1) ? a->cvac * a->dt * a->rdy : 0) * rmuz;
+  c.pz_muy = ((a->nz > 1) ? a->cvac * a->dt * a->rdz : 0) * rmuy;
+  c.pz_mux = ((a->nz > 1) ? a->cvac * a->dt * a->rdz : 0) * rmux;
+  dim3 grid((a->nx + 1 + 255) / 256, a->ny + 1, a->nz + 1);
+  compute_curl_b_kernel<<<grid, 256, 0, st>>>(to_k(a), c);
   VPB_LAUNCH_CHECK();
   return 0;
 }

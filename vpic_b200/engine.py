@@ -132,6 +132,8 @@ class FieldArray:
     def clean_div_e(self): self._call("vpb_vacuum_clean_div_e")
     def compute_div_b_err(self): self._call("vpb_compute_div_b_err")
     def clean_div_b(self): self._call("vpb_clean_div_b")
+    def compute_rhob(self): self._call("vpb_vacuum_compute_rhob")
+    def compute_curl_b(self): self._call("vpb_vacuum_compute_curl_b")
 
     def _rms(self, name):
         """eps0 * sqrt(sum dV / volume) of one domain (compute_rms_div_e_err_pipeline.cc:170-183)."""

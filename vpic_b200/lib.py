@@ -102,6 +102,8 @@ _PROTOS = {
     "vpb_compute_rms_div_b_err": (C.c_int, [C.POINTER(FieldArgs), c_vp, c_vp]),
     "vpb_clean_div_b": (C.c_int, [C.POINTER(FieldArgs), c_vp]),
     "vpb_synchronize_tang_e_norm_b": (C.c_int, [C.POINTER(FieldArgs), c_vp, c_vp]),
+    "vpb_vacuum_compute_rhob": (C.c_int, [C.POINTER(FieldArgs), c_vp]),
+    "vpb_vacuum_compute_curl_b": (C.c_int, [C.POINTER(FieldArgs), c_vp]),
     "vpb_halo_floats": (C.c_size_t, [c_i32, c_i32, c_i32, C.c_int]),
     "vpb_halo_pack": (C.c_int, [C.POINTER(FieldArgs), C.c_int, C.c_int, c_vp, c_vp]),
     "vpb_halo_unpack": (C.c_int, [C.POINTER(FieldArgs), C.c_int, C.c_int, c_vp, c_vp]),
@@ -113,6 +115,7 @@ DROPIN_SYMBOLS = ["advance_p", "sort_p", "load_interpolator_array", "clear_accum
                   "accumulate_rho_p", "advance_b", "vacuum_advance_e", "clear_jf", "synchronize_jf", "vacuum_energy_f",
                   "clear_rhof", "synchronize_rho", "vacuum_compute_div_e_err", "compute_rms_div_e_err", "vacuum_clean_div_e",
                   "compute_div_b_err", "compute_rms_div_b_err", "clean_div_b", "synchronize_tang_e_norm_b",
+                  "vacuum_compute_rhob", "vacuum_compute_curl_b", "vpic_b200_compute_rhob", "vpic_b200_compute_curl_b",
                   "vpic_b200_clear_rhof", "vpic_b200_synchronize_rho", "vpic_b200_compute_div_e_err",
                   "vpic_b200_compute_rms_div_e_err", "vpic_b200_clean_div_e", "vpic_b200_compute_div_b_err",
                   "vpic_b200_compute_rms_div_b_err", "vpic_b200_clean_div_b", "vpic_b200_synchronize_tang_e_norm_b",
