@@ -255,9 +255,11 @@ extern "C" int vpb_advance_p(const vpb_push_args_t *args, void *stream) {
   if (args->np <= 0) return 0;
   const PushK k = to_push_k(args);
   static bool attr_done = false;
+  static size_t extra_smem = 0;          // profiling: VPB_EXTRA_SMEM_KB pads the CTA's shared memory to lower occupancy
   if (!attr_done) {
+    if (const char *e = getenv("VPB_EXTRA_SMEM_KB")) extra_smem = (size_t)atoi(e) * 1024;
     VPB_CUDA(cudaFuncSetAttribute(advance_p_kernel<VPB_DEPOSIT_RED_V4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    VPB_CUDA(cudaFuncSetAttribute(advance_p_kernel<VPB_DEPOSIT_WARP_SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    VPB_CUDA(cudaFuncSetAttribute(advance_p_kernel<VPB_DEPOSIT_WARP_SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemBytes + extra_smem)));
     VPB_CUDA(cudaFuncSetAttribute(advance_p_kernel<VPB_DEPOSIT_WARP_SEG_MOVERS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     VPB_CUDA(cudaFuncSetAttribute(advance_p_kernel<VPB_DEPOSIT_WARP_SEG_FIRST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     attr_done = true;
@@ -270,7 +272,7 @@ extern "C" int vpb_advance_p(const vpb_push_args_t *args, void *stream) {
     case VPB_DEPOSIT_RED_V4:
       advance_p_kernel<VPB_DEPOSIT_RED_V4><<<grid, kBlock, kSmemBytes, as_stream(stream)>>>(k); break;
     case VPB_DEPOSIT_WARP_SEG:
-      advance_p_kernel<VPB_DEPOSIT_WARP_SEG><<<grid, kBlock, kSmemBytes, as_stream(stream)>>>(k); break;
+      advance_p_kernel<VPB_DEPOSIT_WARP_SEG><<<grid, kBlock, kSmemBytes + extra_smem, as_stream(stream)>>>(k); break;
     case VPB_DEPOSIT_WARP_SEG_MOVERS:
       advance_p_kernel<VPB_DEPOSIT_WARP_SEG_MOVERS><<<grid, kBlock, kSmemBytes, as_stream(stream)>>>(k); break;
     case VPB_DEPOSIT_WARP_SEG_FIRST:

@@ -138,7 +138,23 @@ inline bool strict(const Mirror &m) { return g_mode == VPB_MODE_COHERENT || (g_m
 bool g_copied_back = false;     // an asynchronous device->host copy is in flight: the entry point must not return yet
 void finish_entry() { if (g_copied_back) { DEV(vpb_stream_sync(nullptr)); g_copied_back = false; } }
 
+void drop_mirror(Mirror &m, const void *h) {
+  if (m.lazy) { vpb_lazy::detach(m.lazy, false, nullptr); m.lazy = nullptr; }
+  if (m.pinned) { cudaHostUnregister(const_cast<void *>(h)); cudaGetLastError(); }
+  if (m.d) vpb_free(m.d);
+}
+
 Mirror &mirror(const void *h, size_t bytes, bool may_track = true) {
+  if (g_mirrors.find(h) == g_mirrors.end()) {
+    // A host array seen for the first time.  The host reallocates its arrays (boundary_p.cc:470-552 grows sp->p and
+    // sp->pm) and frees temporaries; a mirror whose host range overlaps the new array describes memory the allocator
+    // has since handed out again, so it is stale: release its device copy instead of leaking it.
+    const char *lo = (const char *)h, *hi = lo + bytes;
+    for (auto it = g_mirrors.begin(); it != g_mirrors.end();) {
+      const char *a = (const char *)it->first, *b = a + it->second.cap;
+      if (a < hi && lo < b) { drop_mirror(it->second, it->first); it = g_mirrors.erase(it); } else ++it;
+    }
+  }
   Mirror &m = g_mirrors[h];
   if (m.cap < bytes) {
     if (m.lazy) { vpb_lazy::detach(m.lazy, true, &g_d2h); m.lazy = nullptr; }
@@ -245,9 +261,7 @@ void vpic_b200_invalidate(const void *h) {
 void vpic_b200_release(const void *h) {
   auto it = g_mirrors.find(h);
   if (it == g_mirrors.end()) return;
-  if (it->second.lazy) vpb_lazy::detach(it->second.lazy, false, nullptr);
-  if (it->second.pinned) cudaHostUnregister(const_cast<void *>(h));
-  if (it->second.d) vpb_free(it->second.d);
+  drop_mirror(it->second, h);
   g_mirrors.erase(it);
 }
 

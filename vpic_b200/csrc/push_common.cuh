@@ -177,7 +177,14 @@ __device__ __forceinline__ int move_p_dev(const PushK &a, float4 &r, float4 &u, 
     float j[12];
     const int dep_vox = vox;
     st = streak_step(a, q, r, u, vox, dispx, dispy, dispz, j);
-    deposit_red_v4(a.accum + (size_t)dep_vox * a.astride, j);
+    if (a.dbg & 32) {                                    // profiling: all the arithmetic, none of the REDs
+      float s = 0.0f;
+#pragma unroll
+      for (int c = 0; c < 12; c++) s += j[c];
+      if (s == 1.2345e30f) a.counters[3] = 1;
+    } else {
+      deposit_red_v4(a.accum + (size_t)dep_vox * a.astride, j);
+    }
   } while (st == 2);
   r.w = __int_as_float(vox);
   return st;
