@@ -228,6 +228,16 @@ int vpb_synchronize_tang_e_norm_b(const vpb_field_args_t *a, double *err_dev, vo
 int vpb_vacuum_compute_rhob(const vpb_field_args_t *a, void *stream);
 int vpb_vacuum_compute_curl_b(const vpb_field_args_t *a, void *stream);
 
+/* Hydro moments (diagnostics behind the reference's hydro dumps): accumulate_hydro_p
+ * (src/species_advance/standard/pipeline/hydro_p_pipeline.cc:19-252) adds the 14 moments of every particle to the 8
+ * nodes of its voxel; synchronize_hydro_array (src/sf_interface/hydro_array.cc:131-309) doubles wall nodes and folds
+ * periodic planes.  hydro = hydro_t[nv], 16 floats each (jx jy jz rho px py pz ke txx tyy tzz tyz tzx txy pad pad). */
+int vpb_accumulate_hydro_p(float *hydro, const void *p, int32_t np, const float *interp, int32_t interp_stride,
+                           float q, float m, float dt, float cvac, float r8V,
+                           int32_t nx, int32_t ny, int32_t nz, void *stream);
+int vpb_clear_hydro(float *hydro, int32_t nx, int32_t ny, int32_t nz, void *stream);
+int vpb_synchronize_hydro(float *hydro, const vpb_field_args_t *geometry, void *stream);   /* f of geometry is ignored */
+
 /* Halo planes for VPB_FACE_REMOTE faces (the payload of begin/end_remote_ghost_tang_b, remote.cc:61-134, and of
  * synchronize_jf, remote.cc:417-508).  pack copies the plane a neighbour needs into buf; unpack applies a received
  * plane.  floats per plane: vpb_halo_floats(). */

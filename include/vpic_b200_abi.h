@@ -170,6 +170,22 @@ typedef struct vpb_field_array {
   vpb_field_advance_kernels_t kernel[1];
 } vpb_field_array_t;
 
+/* hydro moments: src/sf_interface/sf_interface.h:185-200 (hydro_t is 64 B for every SIMD padding) */
+typedef struct vpb_hydro {
+  float jx, jy, jz, rho;
+  float px, py, pz, ke;
+  float txx, tyy, tzz;
+  float tyz, tzx, txy;
+  float pad_[2];
+} vpb_hydro_t;
+
+typedef struct vpb_hydro_array {
+  vpb_hydro_t *h;        /* [(n_pipeline+1) * stride], block 0 = host */
+  int32_t      n_pipeline;
+  int32_t      stride;
+  vpb_grid_t  *g;
+} vpb_hydro_array_t;
+
 /* standard field advance parameters: src/field_advance/standard/sfa_private.h:14-34 */
 typedef struct vpb_material_coefficient {
   float decayx, drivex;

@@ -44,6 +44,11 @@ void uncenter_p(vpb_species_t *sp, const vpb_interpolator_array_t *ia);
 double energy_p(const vpb_species_t *sp, const vpb_interpolator_array_t *ia);
 /* src/species_advance/species_advance.h:117-119 */
 void accumulate_rho_p(vpb_field_array_t *fa, const vpb_species_t *sp);
+/* hydro moments — src/species_advance/species_advance.h:139-148, src/sf_interface/sf_interface.h:216-240 */
+void accumulate_hydro_p(vpb_hydro_array_t *ha, const vpb_species_t *sp, const vpb_interpolator_array_t *ia);
+void clear_hydro_array(vpb_hydro_array_t *ha);
+void reduce_hydro_array(vpb_hydro_array_t *ha);
+void synchronize_hydro_array(vpb_hydro_array_t *ha);
 /* src/sf_interface/sf_interface.h:99-101 */
 void load_interpolator_array(vpb_interpolator_array_t *ia, const vpb_field_array_t *fa);
 /* src/sf_interface/sf_interface.h:147-148,158-159,172-174 */

@@ -971,3 +971,93 @@ void vpo_vacuum_compute_curl_b(const vpo_field_args_t *a) {
 # undef FF
   adjust_tang_e(a);
 }
+
+
+/* ======================================================================== */
+/* Hydro moments.                                                           */
+#define H_STRIDE 16
+
+void vpo_accumulate_hydro_p(float *hydro, const vpo_particle_t *p, int32_t np, const float *interp, int32_t istride,
+                            float qsp, float msp, float qdt_2mc, float cvac, float r8V, int32_t nx, int32_t ny, int32_t nz) {
+  const float qdt_4mc2 = qdt_2mc / (2 * cvac);                       /* hydro_p_pipeline.cc:33-38 */
+  const float mspc = cvac * msp, c = cvac;
+  const float one = 1.0, one_third = 1.0 / 3.0;
+  const int sx = 1, sy = nx + 2, sz = (nx + 2) * (ny + 2);
+  (void)nz;
+  for (int n = 0; n < np; n++) {
+    float dx = p[n].dx, dy = p[n].dy, dz = p[n].dz;
+    int i = p[n].i;
+    float ux = p[n].ux, uy = p[n].uy, uz = p[n].uz, w = p[n].w;
+    const float *f = interp + (size_t)i * istride;
+    ux += qdt_2mc * ((f[0] + dy * f[1]) + dz * (f[2] + dy * f[3]));            /* half E kick, :88-95 */
+    uy += qdt_2mc * ((f[4] + dz * f[5]) + dx * (f[6] + dz * f[7]));
+    uz += qdt_2mc * ((f[8] + dx * f[9]) + dy * (f[10] + dx * f[11]));
+    float w5 = f[12] + dx * f[13], w6 = f[14] + dy * f[15], w7 = f[16] + dz * f[17];
+    float ke_mc = ux * ux + uy * uy + uz * uz;                                   /* :112-115 */
+    float vz = sqrtf(one + ke_mc);
+    ke_mc *= c / (vz + one);
+    vz = c / vz;
+    float w0 = qdt_4mc2 * vz;                                                    /* half Boris rotation, :121-136 */
+    float w1 = w5 * w5 + w6 * w6 + w7 * w7;
+    float w2 = w0 * w0 * w1;
+    float w3 = w0 * (one + (one_third) * w2 * (one + 0.4f * w2));
+    float w4 = w3 / (one + w1 * w3 * w3);
+    w4 += w4;
+    w0 = ux + w3 * (uy * w7 - uz * w6);
+    w1 = uy + w3 * (uz * w5 - ux * w7);
+    w2 = uz + w3 * (ux * w6 - uy * w5);
+    ux += w4 * (w1 * w7 - w2 * w6);
+    uy += w4 * (w2 * w5 - w0 * w7);
+    uz += w4 * (w0 * w6 - w1 * w5);
+    float vx = ux * vz, vy = uy * vz;
+    vz = uz * vz;
+    w0 = r8V * w;                                                                /* trilinear weights, :152-172 */
+    dx *= w0; w1 = w0 + dx; w0 -= dx;
+    w3 = one + dy; w2 = w0 * w3; w3 *= w1;
+    dy = one - dy; w0 *= dy; w1 *= dy;
+    w7 = one + dz; w4 = w0 * w7; w5 = w1 * w7; w6 = w2 * w7; w7 *= w3;
+    dz = one - dz; w0 *= dz; w1 *= dz; w2 *= dz; w3 *= dz;
+    const float wn[8] = {w0, w1, w2, w3, w4, w5, w6, w7};
+    const int node[8] = {i, i + sx, i + sy, i + sy + sx, i + sz, i + sz + sx, i + sz + sy, i + sz + sy + sx};
+    for (int k = 0; k < 8; k++) {                                                /* ACCUM_HYDRO, :178-198 */
+      float *h = hydro + (size_t)node[k] * H_STRIDE;
+      float t = qsp * wn[k];
+      h[0] += t * vx; h[1] += t * vy; h[2] += t * vz; h[3] += t;
+      t = mspc * wn[k];
+      float tx = t * ux, ty = t * uy, tz = t * uz;
+      h[4] += tx; h[5] += ty; h[6] += tz; h[7] += t * ke_mc;
+      h[8] += tx * vx; h[9] += ty * vy; h[10] += tz * vz;
+      h[11] += ty * vz; h[12] += tz * vx; h[13] += tx * vy;
+    }
+  }
+}
+
+void vpo_synchronize_hydro(float *H, const vpo_field_args_t *a) {
+  dims_t d = mkdims(a);
+  for (int fc = 0; fc < 6; fc++) {                                   /* ADJUST_HYDRO: every local wall doubles its nodes */
+    if (a->bc6[fc] >= 0) continue;
+    int X = fc % 3, Y = (X + 1) % 3, Z = (X + 2) % 3, face = fc < 3 ? 1 : d.n[X] + 1;
+    PLANE_LOOP(X, face, Y, 1, d.n[Y] + 1, Z, 1, d.n[Z] + 1, { for (int k = 0; k < 14; k++) H[(size_t)v * H_STRIDE + k] *= 2; });
+  }
+  for (int X = 0; X < 3; X++) {
+    int Y = (X + 1) % 3, Z = (X + 2) % 3;
+    float *msg[2] = {0, 0};
+    for (int side = 0; side < 2; side++) {
+      if (a->bc6[X + 3 * side] < 0) continue;
+      int face = side == 0 ? 1 : d.n[X] + 1;
+      float *p = msg[side] = (float *)malloc(sizeof(float) * (size_t)(1 + 14 * (d.n[Y] + 1) * (d.n[Z] + 1)));
+      *p++ = axis_d(a, X);
+      PLANE_LOOP(X, face, Y, 1, d.n[Y] + 1, Z, 1, d.n[Z] + 1, { for (int k = 0; k < 14; k++) *p++ = H[(size_t)v * H_STRIDE + k]; });
+    }
+    for (int side = 0; side < 2; side++) {
+      if (!msg[side]) continue;
+      float *p = msg[side];
+      float rw = *p++, dX = axis_d(a, X), lw = rw + dX;
+      rw /= lw; lw = dX / lw; lw += lw; rw += rw;
+      int face = side == 0 ? d.n[X] + 1 : 1;
+      PLANE_LOOP(X, face, Y, 1, d.n[Y] + 1, Z, 1, d.n[Z] + 1,
+                 { for (int k = 0; k < 14; k++) { float *h = H + (size_t)v * H_STRIDE + k; *h = lw * (*h) + rw * (*p++); } });
+      free(msg[side]);
+    }
+  }
+}

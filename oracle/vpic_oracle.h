@@ -115,6 +115,13 @@ double vpo_synchronize_tang_e_norm_b(const vpo_field_args_t *a);  /* remote.cc:2
 void   vpo_vacuum_compute_rhob(const vpo_field_args_t *a);        /* vacuum_compute_rhob_pipeline.{h,cc} */
 void   vpo_vacuum_compute_curl_b(const vpo_field_args_t *a);      /* vacuum_compute_curl_b_pipeline.{h,cc} */
 
+/* ---- hydro moments (diagnostics): accumulate_hydro_p (hydro_p_pipeline.cc:19-214) for one pipeline, i.e. particles
+ *      summed in array order; synchronize_hydro_array (hydro_array.cc:131-309) on a single domain.  hydro_t is
+ *      16 floats per voxel: jx jy jz rho px py pz ke txx tyy tzz tyz tzx txy pad pad. ------------------------------ */
+void vpo_accumulate_hydro_p(float *hydro, const vpo_particle_t *p, int32_t np, const float *interp, int32_t interp_stride,
+                            float q, float m, float qdt_2mc, float cvac, float r8V, int32_t nx, int32_t ny, int32_t nz);
+void vpo_synchronize_hydro(float *hydro, const vpo_field_args_t *geometry);   /* uses nx ny nz, bc6, dx dy dz */
+
 #ifdef __cplusplus
 }
 #endif

@@ -49,6 +49,10 @@ def load_oracle():
     lib.vpo_clear_jf.argtypes = [C.c_void_p]
     lib.vpo_synchronize_jf.argtypes = [C.c_void_p]
     lib.vpo_vacuum_energy_f.argtypes = [C.c_void_p, C.c_void_p]
+    lib.vpo_accumulate_hydro_p.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32] + [C.c_float] * 5 + [C.c_int32] * 3
+    lib.vpo_accumulate_hydro_p.restype = None
+    lib.vpo_synchronize_hydro.argtypes = [C.c_void_p, C.c_void_p]
+    lib.vpo_synchronize_hydro.restype = None
     for name in ("vpo_clear_rhof", "vpo_synchronize_rho", "vpo_vacuum_compute_div_e_err", "vpo_vacuum_clean_div_e",
                  "vpo_compute_div_b_err", "vpo_clean_div_b", "vpo_vacuum_compute_rhob", "vpo_vacuum_compute_curl_b"):
         getattr(lib, name).argtypes = [C.c_void_p]
@@ -127,6 +131,11 @@ def load_ref(variant="scalar", tpp=1):
     lib.unload_accumulator_array.argtypes = [C.POINTER(abi.FieldArray), C.POINTER(abi.AccumulatorArray)]
     lib.accumulate_rho_p.argtypes = [C.POINTER(abi.FieldArray), C.POINTER(abi.Species)]
     lib.accumulate_rhob.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(abi.Grid), C.c_float]
+    lib.new_hydro_array.restype = C.POINTER(abi.HydroArray)
+    lib.new_hydro_array.argtypes = [C.POINTER(abi.Grid)]
+    lib.clear_hydro_array.argtypes = [C.POINTER(abi.HydroArray)]
+    lib.synchronize_hydro_array.argtypes = [C.POINTER(abi.HydroArray)]
+    lib.accumulate_hydro_p.argtypes = [C.POINTER(abi.HydroArray), C.POINTER(abi.Species), C.POINTER(abi.InterpolatorArray)]
     lib.move_p.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(abi.Grid), C.c_float]
     lib.move_p.restype = C.c_int
     lib.variant = variant

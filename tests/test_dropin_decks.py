@@ -186,3 +186,60 @@ def test_preloaded_deck_uses_the_device_kernels_it_claims(fields):
     else:
         assert t["advance_b"] == t["advance_e"] == t["clear_jf"] == t["divergence_cleaning_kernels"] == 0
         assert t["field_kernel_fallback_to_reference"] > 0
+
+
+def _tail_floats(path, count):
+    raw = np.fromfile(path, dtype=np.uint8)
+    return raw[len(raw) - 4 * count:].view(np.float32)
+
+
+@pytest.mark.parametrize("mode", ["coherent", "auto"])
+def test_dump_deck_files_match_reference(mode):
+    """test/integrated/to_completion/dump.deck: two steps that dump energies, fields, hydro moments of both species,
+    particles and a checkpoint on every step — every way the reference's host code reads the arrays the device owns
+    (fwrite of whole arrays, accumulate_hydro_p, center_p on a staging buffer, checkpt).  The files written with the
+    hot path on the GPU must match the CPU run's: same names and sizes, payloads within fp32 deposit-order tolerance;
+    then the reference's restart test (--restore checkpt_test.1) has to run to completion on the GPU path too."""
+    path = _need("dump.scalar")
+    nv = 10 * 10 * 3                                             # 8 x 8 x 1 cells plus ghosts
+    runs = {}
+    for tag, preload in (("cpu", False), ("gpu", True)):
+        d = tempfile.mkdtemp(prefix=f"dump_{tag}_")
+        rc, out = _run(path, ["--tpp", "1"], preload, d, extra_env=dict(MODES[mode], VPIC_B200_TRACE="1"))
+        assert rc == 0 and "normal exit" in out, out[-2000:]
+        runs[tag] = (d, out)
+    try:
+        cpu, gpu = runs["cpu"][0], runs["gpu"][0]
+        names = sorted(os.listdir(cpu))
+        assert names == sorted(os.listdir(gpu))
+        for n in names:
+            assert os.path.getsize(os.path.join(cpu, n)) == os.path.getsize(os.path.join(gpu, n)), n
+        t = _trace(runs["gpu"][1])
+        assert t["hydro_kernels"] > 0 and t["advance_p"] > 0
+        for step in (1, 2):
+            for sp in ("e", "i"):
+                a = _tail_floats(os.path.join(cpu, f"{sp}hydro.{step}.0"), nv * 16).reshape(nv, 16)[:, :14]
+                b = _tail_floats(os.path.join(gpu, f"{sp}hydro.{step}.0"), nv * 16).reshape(nv, 16)[:, :14]
+                assert np.abs(a).max() > 0
+                for col in range(14):
+                    scale = np.abs(a[:, col]).max()
+                    assert np.abs(a[:, col] - b[:, col]).max() <= 2e-5 * scale + 1e-30, (sp, step, col)
+            fa_ = _tail_floats(os.path.join(cpu, f"fields.{step}.0"), nv * 20).reshape(nv, 20)
+            fb_ = _tail_floats(os.path.join(gpu, f"fields.{step}.0"), nv * 20).reshape(nv, 20)
+            for lo, hi in ((0, 3), (4, 7), (12, 15)):            # e, cb, jf
+                scale = np.abs(fa_[:, lo:hi]).max()
+                assert np.abs(fa_[:, lo:hi] - fb_[:, lo:hi]).max() <= 5e-5 * scale + 1e-30, (step, lo)
+            for sp in ("e", "i"):
+                pa_ = np.fromfile(os.path.join(cpu, f"{sp}particle.{step}.0"), dtype=np.uint8)
+                pb_ = np.fromfile(os.path.join(gpu, f"{sp}particle.{step}.0"), dtype=np.uint8)
+                npart = 8 * 8 * 8                                # 0.5 * nppc * cells per species
+                qa = pa_[len(pa_) - 32 * npart:].view(np.float32).reshape(npart, 8)
+                qb = pb_[len(pb_) - 32 * npart:].view(np.float32).reshape(npart, 8)
+                assert np.array_equal(qa[:, 3].view(np.int32), qb[:, 3].view(np.int32))       # same voxels, same order
+                np.testing.assert_allclose(qb[:, [0, 1, 2, 4, 5, 6, 7]], qa[:, [0, 1, 2, 4, 5, 6, 7]], rtol=0, atol=2e-5)
+        # the reference's restart test, on the GPU path, from the checkpoint the GPU run wrote
+        rc, out = _run(path, ["--tpp", "1", "--restore", os.path.join(gpu, "checkpt_test.1")], True, gpu, extra_env=MODES[mode])
+        assert rc == 0 and "normal exit" in out, out[-2000:]
+    finally:
+        for d, _ in runs.values():
+            shutil.rmtree(d, ignore_errors=True)

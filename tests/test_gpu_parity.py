@@ -341,6 +341,51 @@ def test_divergence_cleaning(eng, oracle, dims, fbc, material):
     fa.compute_curl_b(); oracle.vpo_vacuum_compute_curl_b(pa); same("compute_curl_b")
 
 
+@pytest.mark.parametrize("dims,fbc,n,sort_first", [((6, 5, 4), None, 20011, True), ((6, 5, 4), None, 20011, False),
+                                                   ((33, 1, 9), {0: -1, 3: -4, 2: -2, 5: -3}, 150001, True)])
+def test_hydro_moments(eng, oracle, dims, fbc, n, sort_first):
+    """accumulate_hydro_p + synchronize_hydro_array against the oracle (pinned bit-exact against the reference): the 14
+    moments per node agree to fp32 summation-order tolerance; sorted input takes the warp-reduced path, unsorted the
+    per-lane REDs."""
+    rng = np.random.default_rng(29)
+    nx, ny, nz = dims
+    g = make_grid(nx, ny, nz, fbc=fbc)
+    dg = eng.DeviceGrid(g)
+    fields = R.random_fields(rng, g.nv)
+    parts = R.random_particles(rng, n, nx, ny, nz, uth=0.4, w=0.3)
+    if sort_first:
+        parts = parts[np.argsort(parts["i"], kind="stable")]
+    fa, ia = eng.FieldArray(dg), eng.InterpolatorArray(dg)
+    fa.f.copy_(torch.from_numpy(fields))
+    eng.load_interpolator_array(ia, fa)
+    sp = eng.Species("e", -1.0, 3.0, n, 16, 20, 0, dg)
+    sp.set_particles(parts)
+    ha = eng.HydroArray(dg)
+    ha.h.fill_(7.0)                                              # clear must really clear
+    ha.clear()
+    eng.accumulate_hydro_p(ha, sp, ia)
+    ha.synchronize(fa)
+    interp = ia.i.cpu().numpy()
+    h_ref = np.zeros((g.nv, 16), np.float32)
+    f32 = np.float32
+    qdt_2mc = f32(f32(f32(-1.0) * f32(g.dt)) / f32(f32(2) * f32(3.0) * f32(g.cvac)))
+    oracle.vpo_accumulate_hydro_p(h_ref.ctypes.data, parts.ctypes.data, n, interp.ctypes.data, interp.shape[1],
+                                  -1.0, 3.0, qdt_2mc, g.cvac, g.r8V, nx, ny, nz)
+    a = R.OracleFieldArgs()
+    a.f = h_ref.ctypes.data
+    a.nx, a.ny, a.nz = nx, ny, nz
+    a.dx, a.dy, a.dz = g.dx, g.dy, g.dz
+    for i, (fi, fj, fk) in enumerate(G.FACES):
+        a.bc6[i] = g.bc[G.boundary_index(fi, fj, fk)]
+    oracle.vpo_synchronize_hydro(h_ref.ctypes.data, C.byref(a))
+    got = ha.h.cpu().numpy()
+    for col in range(14):
+        scale = np.abs(h_ref[:, col]).max()
+        assert scale > 0
+        assert np.abs(got[:, col] - h_ref[:, col]).max() <= 3e-5 * scale, col
+    assert np.array_equal(got[:, 14:], np.zeros_like(got[:, 14:]))
+
+
 def test_reference_scalar_agrees_when_present(eng, oracle):
     """If the prebuilt unmodified reference travelled with the repo, check the CUDA push against it directly."""
     if not R.have_ref("scalar"):

@@ -69,6 +69,12 @@ class AccumulatorArray(C.Structure):
     _fields_ = [("a", C.POINTER(c_f)), ("n_pipeline", c_i32), ("stride", c_i32), ("g", C.POINTER(Grid))]
 
 
+class HydroArray(C.Structure):
+    """hydro_array_t (sf_interface.h:194-200); hydro_t is 16 floats (14 moments + 2 pad) for every SIMD width."""
+    _fields_ = [("h", C.POINTER(c_f)), ("n_pipeline", c_i32), ("stride", c_i32), ("g", C.POINTER(Grid))]
+
+
+HYDRO_FLOATS = 16
 FIELD_FLOATS = 20  # 80-byte field_t
 
 

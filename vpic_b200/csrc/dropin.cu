@@ -41,12 +41,13 @@ int rank_for_log() { return &_world_rank ? _world_rank : 0; }
 // VPIC_B200_TRACE=1: at exit, one line on stderr with how often each entry point ran on the device (and how often a
 // field kernel fell through to the reference's own), so a preloaded run can be checked for what it actually used.
 enum { C_ADVANCE_P, C_SORT_P, C_CENTER_P, C_ENERGY_P, C_RHO_P, C_LOAD_INTERP, C_CLEAR_ACC, C_UNLOAD_ACC, C_ADVANCE_B,
-       C_ADVANCE_E, C_CLEAR_JF, C_SYNC_JF, C_ENERGY_F, C_DIV_CLEAN, C_FIELD_FALLBACK, C_COUNT };
+       C_ADVANCE_E, C_CLEAR_JF, C_SYNC_JF, C_ENERGY_F, C_DIV_CLEAN, C_HYDRO, C_FIELD_FALLBACK, C_COUNT };
 uint64_t g_calls[C_COUNT];
 void trace_report() {
   static const char *names[C_COUNT] = {"advance_p", "sort_p", "center_p/uncenter_p", "energy_p", "accumulate_rho_p",
       "load_interpolator_array", "clear_accumulator_array", "unload_accumulator_array", "advance_b", "advance_e",
-      "clear_jf", "synchronize_jf", "energy_f", "divergence_cleaning_kernels", "field_kernel_fallback_to_reference"};
+      "clear_jf", "synchronize_jf", "energy_f", "divergence_cleaning_kernels", "hydro_kernels",
+      "field_kernel_fallback_to_reference"};
   fprintf(stderr, "vpic_b200 trace[%d]:", rank_for_log());
   for (int i = 0; i < C_COUNT; i++) fprintf(stderr, " %s=%llu", names[i], (unsigned long long)g_calls[i]);
   const vpb_lazy::Stats st = vpb_lazy::stats();
@@ -472,6 +473,81 @@ void accumulate_rho_p(vpb_field_array_t *fa, const vpb_species_t *sp) {
   void *p = dev_in(sp->p, (size_t)sp->np * sizeof(vpb_particle_t), (size_t)sp->max_np * sizeof(vpb_particle_t));
   DEV(vpb_accumulate_rho_p(df, p, sp->np, sp->q, g->r8V, g->nx, g->ny, g->nz, nullptr));
   dev_written(fa->f, fbytes);
+  finish_entry();
+}
+
+// ---- hydro moments: species_advance.h:139-148, sf_interface.h:216-240 --------------------------------------------
+// The device accumulates every particle into block 0 of the hydro array; blocks 1..n_pipeline are never written by
+// this library (they stay as the host left them — zero after new_hydro_array / the reference's own clear).
+static size_t hydro_bytes(const vpb_hydro_array_t *ha) { return (size_t)ha->g->nv * sizeof(vpb_hydro_t); }
+
+void clear_hydro_array(vpb_hydro_array_t *ha) {
+  if (!ha) DROPIN_ERROR("Bad args.");
+  count_call(C_HYDRO);
+  const vpb_grid_t *g = ha->g;
+  mode();
+  Mirror &m = mirror(ha->h, hydro_bytes(ha));
+  if (strict(m)) {
+    // the host array is the truth: clear every block there, exactly like clear_array_pipeline.cc; the next consumer uploads
+    memset(ha->h, 0, (size_t)(ha->n_pipeline + 1) * (size_t)ha->stride * sizeof(vpb_hydro_t));
+    m.device_valid = false; m.host_stale = false;
+    return;
+  }
+  float *dh = (float *)dev_out_only(ha->h, hydro_bytes(ha));
+  DEV(vpb_clear_hydro(dh, g->nx, g->ny, g->nz, nullptr));
+  dev_written(ha->h, hydro_bytes(ha));
+  finish_entry();
+}
+
+void reduce_hydro_array(vpb_hydro_array_t *ha) {
+  if (!ha) DROPIN_ERROR("Bad args.");
+  // nothing to fold in: see above
+}
+
+void accumulate_hydro_p(vpb_hydro_array_t *ha, const vpb_species_t *sp, const vpb_interpolator_array_t *ia) {
+  if (!ha || !sp || !ia || ha->g != sp->g || ha->g != ia->g) DROPIN_ERROR("Bad args.");
+  count_call(C_HYDRO);
+  const vpb_grid_t *g = sp->g;
+  const float *di = (const float *)dev_in(ia->i, (size_t)g->nv * sizeof(vpb_interpolator_t));
+  void *p = dev_in(sp->p, (size_t)sp->np * sizeof(vpb_particle_t), (size_t)sp->max_np * sizeof(vpb_particle_t));
+  float *dh = (float *)dev_in(ha->h, hydro_bytes(ha));
+  DEV(vpb_accumulate_hydro_p(dh, p, sp->np, di, kInterpFloats, sp->q, sp->m, g->dt, g->cvac, g->r8V, g->nx, g->ny, g->nz, nullptr));
+  dev_written(ha->h, hydro_bytes(ha));
+  finish_entry();
+}
+
+static bool hydro_sync_on_device(const vpb_hydro_array_t *ha) {
+  const vpb_grid_t *g = ha->g;
+  static const int off[6][3] = {{-1,0,0},{0,-1,0},{0,0,-1},{1,0,0},{0,1,0},{0,0,1}};
+  for (int f = 0; f < 6; f++) {
+    const int b = g->bc[13 + off[f][0] + 3 * off[f][1] + 9 * off[f][2]];
+    if (b >= 0 && b != g->bc[13]) return false;                  // shared with another rank: the reference's exchange
+  }
+  return true;
+}
+
+void synchronize_hydro_array(vpb_hydro_array_t *ha) {
+  if (!ha) DROPIN_ERROR("NULL hydro array.");
+  if (!hydro_sync_on_device(ha)) {
+    static auto ref = (void (*)(vpb_hydro_array_t *))dlsym(RTLD_NEXT, "synchronize_hydro_array");
+    if (!ref) DROPIN_ERROR("synchronize_hydro_array: faces shared with other ranks need the reference's own exchange, which is not linked in");
+    count_call(C_FIELD_FALLBACK);
+    ref(ha);
+    return;
+  }
+  count_call(C_HYDRO);
+  const vpb_grid_t *g = ha->g;
+  float *dh = (float *)dev_in(ha->h, hydro_bytes(ha));
+  vpb_field_args_t a;
+  memset(&a, 0, sizeof a);
+  a.f = dh; a.nx = g->nx; a.ny = g->ny; a.nz = g->nz; a.dx = g->dx; a.dy = g->dy; a.dz = g->dz;
+  static const int off[6][3] = {{-1,0,0},{0,-1,0},{0,0,-1},{1,0,0},{0,1,0},{0,0,1}};
+  for (int f = 0; f < 6; f++) {
+    const int b = g->bc[13 + off[f][0] + 3 * off[f][1] + 9 * off[f][2]];
+    a.face[f] = b < 0 ? (b < -4 ? -2 : b) : VPB_FACE_PERIODIC_SELF;   // every local wall doubles, whatever its kind
+  }
+  DEV(vpb_synchronize_hydro(dh, &a, nullptr));
+  dev_written(ha->h, hydro_bytes(ha));
   finish_entry();
 }
 

@@ -151,6 +151,31 @@ class FieldArray:
         return float(self._en[0].item())
 
 
+class HydroArray:
+    """hydro_array_t (sf_interface.h:194-200) on the device: one block, hydro_t = 16 floats per voxel."""
+
+    def __init__(self, g: DeviceGrid):
+        self.g = g
+        self.h = torch.zeros((g.nv, abi.HYDRO_FLOATS), dtype=torch.float32, device=g.device)
+
+    def clear(self):
+        g = self.g
+        _lib.check(_lib.load().vpb_clear_hydro(_ptr(self.h), g.nx, g.ny, g.nz, _stream()), "clear_hydro_array")
+
+    def synchronize(self, fa: "FieldArray"):
+        """synchronize_hydro_array; the field array only lends its geometry (faces, cell sizes)."""
+        _lib.check(_lib.load().vpb_synchronize_hydro(_ptr(self.h), C.byref(fa.args()), _stream()), "synchronize_hydro_array")
+
+
+def accumulate_hydro_p(ha: HydroArray, sp: "Species", ia: "InterpolatorArray"):
+    """accumulate_hydro_p(hydro_array_t*, const species_t*, const interpolator_array_t*), species_advance.h:139-148."""
+    _bad_args(ha is None or sp is None or ia is None or ha.g is not sp.g or ha.g is not ia.g, "accumulate_hydro_p")
+    g = sp.g
+    _lib.check(_lib.load().vpb_accumulate_hydro_p(_ptr(ha.h), _ptr(sp.p), sp.np, _ptr(ia.i), ia.stride,
+                                                  sp.q, sp.m, g.dt, g.cvac, g.g.r8V, g.nx, g.ny, g.nz, _stream()),
+               "accumulate_hydro_p")
+
+
 class Species:
     """species_t (species_advance_aos.h:54-94) with device arrays."""
 

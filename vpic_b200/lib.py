@@ -104,6 +104,9 @@ _PROTOS = {
     "vpb_synchronize_tang_e_norm_b": (C.c_int, [C.POINTER(FieldArgs), c_vp, c_vp]),
     "vpb_vacuum_compute_rhob": (C.c_int, [C.POINTER(FieldArgs), c_vp]),
     "vpb_vacuum_compute_curl_b": (C.c_int, [C.POINTER(FieldArgs), c_vp]),
+    "vpb_accumulate_hydro_p": (C.c_int, [c_vp, c_vp, c_i32, c_vp, c_i32] + [c_f] * 5 + [c_i32] * 3 + [c_vp]),
+    "vpb_clear_hydro": (C.c_int, [c_vp, c_i32, c_i32, c_i32, c_vp]),
+    "vpb_synchronize_hydro": (C.c_int, [c_vp, C.POINTER(FieldArgs), c_vp]),
     "vpb_halo_floats": (C.c_size_t, [c_i32, c_i32, c_i32, C.c_int]),
     "vpb_halo_pack": (C.c_int, [C.POINTER(FieldArgs), C.c_int, C.c_int, c_vp, c_vp]),
     "vpb_halo_unpack": (C.c_int, [C.POINTER(FieldArgs), C.c_int, C.c_int, c_vp, c_vp]),
@@ -116,6 +119,7 @@ DROPIN_SYMBOLS = ["advance_p", "sort_p", "load_interpolator_array", "clear_accum
                   "clear_rhof", "synchronize_rho", "vacuum_compute_div_e_err", "compute_rms_div_e_err", "vacuum_clean_div_e",
                   "compute_div_b_err", "compute_rms_div_b_err", "clean_div_b", "synchronize_tang_e_norm_b",
                   "vacuum_compute_rhob", "vacuum_compute_curl_b", "vpic_b200_compute_rhob", "vpic_b200_compute_curl_b",
+                  "accumulate_hydro_p", "clear_hydro_array", "reduce_hydro_array", "synchronize_hydro_array",
                   "vpic_b200_clear_rhof", "vpic_b200_synchronize_rho", "vpic_b200_compute_div_e_err",
                   "vpic_b200_compute_rms_div_e_err", "vpic_b200_clean_div_e", "vpic_b200_compute_div_b_err",
                   "vpic_b200_compute_rms_div_b_err", "vpic_b200_clean_div_b", "vpic_b200_synchronize_tang_e_norm_b",
