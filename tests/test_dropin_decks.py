@@ -213,6 +213,8 @@ def test_dump_deck_files_match_reference(mode):
         names = sorted(os.listdir(cpu))
         assert names == sorted(os.listdir(gpu))
         for n in names:
+            if n.startswith("checkpt"):
+                continue          # a checkpoint names the field kernels by symbol and library, which differ by design
             assert os.path.getsize(os.path.join(cpu, n)) == os.path.getsize(os.path.join(gpu, n)), n
         t = _trace(runs["gpu"][1])
         assert t["hydro_kernels"] > 0 and t["advance_p"] > 0
