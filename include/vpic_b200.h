@@ -243,9 +243,23 @@ int vpb_synchronize_hydro(float *hydro, const vpb_field_args_t *geometry, void *
  * plane.  floats per plane: vpb_halo_floats(). */
 #define VPB_HALO_TANG_B 0
 #define VPB_HALO_JF     1
-size_t vpb_halo_floats(int32_t nx, int32_t ny, int32_t nz, int axis);
+/* the periodic extras of divergence cleaning and shared-face synchronisation:
+ *   RHO             rhof, rhob of the shared node plane (synchronize_rho, remote.cc:547-585): own + remote / mean
+ *   NORM_E          normal E of the first interior node plane into the neighbour's ghost plane (remote.cc:136-206);
+ *                   exchange BEFORE vpb_vacuum_compute_div_e_err / vpb_vacuum_compute_rhob
+ *   DIV_B           div-B error of the first interior cell plane into the neighbour's ghost cells (remote.cc:208-282);
+ *                   exchange BEFORE vpb_clean_div_b
+ *   TANG_E_NORM_B   normal B, tangential E and TCA of the shared plane, averaged with the neighbour's
+ *                   (remote.cc:298-416); vpb_halo_unpack_sync adds the squared differences to *err_dev */
+#define VPB_HALO_RHO           2
+#define VPB_HALO_NORM_E        3
+#define VPB_HALO_DIV_B         4
+#define VPB_HALO_TANG_E_NORM_B 5
+size_t vpb_halo_floats(int32_t nx, int32_t ny, int32_t nz, int axis);                 /* TANG_B and JF planes */
+size_t vpb_halo_floats_kind(int32_t nx, int32_t ny, int32_t nz, int axis, int kind);  /* any kind */
 int vpb_halo_pack(const vpb_field_args_t *a, int kind, int face, float *buf, void *stream);
 int vpb_halo_unpack(const vpb_field_args_t *a, int kind, int face, const float *buf, void *stream);
+int vpb_halo_unpack_sync(const vpb_field_args_t *a, int face, const float *buf, double *err_dev, void *stream);
 
 #ifdef __cplusplus
 }

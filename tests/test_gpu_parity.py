@@ -413,7 +413,7 @@ def test_reference_scalar_agrees_when_present(eng, oracle):
     accum_close(aa.a.cpu().numpy(), W.accum[0])
 
 
-@pytest.mark.parametrize("extra", [[], ["--axis", "0", "--harris"]])
+@pytest.mark.parametrize("extra", [[], ["--axis", "0", "--harris"], ["--clean"], ["--axis", "0", "--harris", "--clean"]])
 def test_multi_gpu_slab(eng, extra):
     """Slab-decomposed run over NCCL vs the undecomposed run (tests/multi_gpu_check.py); needs >= 2 GPUs.
     Second case: x slabs with conducting, particle-reflecting z walls and a sheared B field (C4-like)."""

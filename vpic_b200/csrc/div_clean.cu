@@ -317,9 +317,82 @@ __global__ void __launch_bounds__(256) sync_tang_e_norm_b_self_kernel(FieldK k, 
   block_sum_to(acc, err);
 }
 
+// Halo planes of a face shared with another rank.  The layouts follow the reference's messages without the one-float
+// cell-size header (slabs have equal cells by construction, so lw/rw are the equal-cell constants):
+//   RHO            {rhof, rhob} per node of the shared plane, nodes (Y 1..nY+1, Z 1..nZ+1)
+//   NORM_E         e_X per node of the first interior plane -> neighbour's ghost plane
+//   DIV_B          div_b_err per cell (Y 1..nY, Z 1..nZ) of the first interior plane -> neighbour's ghost cells
+//   TANG_E_NORM_B  cb_X per face cell, then {e_Y, tca_Y} per Y edge, then {e_Z, tca_Z} per Z edge of the shared plane
+__global__ void __launch_bounds__(256) halo_clean_kernel(FieldK k, int kind, int fc, float *buf, bool pack, double *err) {
+  const int n[3] = {k.nx, k.ny, k.nz};
+  const int s[3] = {1, k.nx + 2, (k.nx + 2) * (k.ny + 2)};
+  const int X = fc % 3, Y = (X + 1) % 3, Z = (X + 2) % 3;
+  const int cy = blockIdx.x * blockDim.x + threadIdx.x + 1, cz = blockIdx.y + 1;
+  const bool in_nodes = cy <= n[Y] + 1 && cz <= n[Z] + 1;
+  const bool low = fc < 3;
+  double acc = 0;
+  if (in_nodes) {
+    const int at = cy * s[Y] + cz * s[Z];
+    const int i_node = (cy - 1) + (n[Y] + 1) * (cz - 1), i_cell = (cy - 1) + n[Y] * (cz - 1);
+    const bool in_cell = cy <= n[Y] && cz <= n[Z];
+    if (kind == VPB_HALO_RHO) {
+      const int v = (low ? 1 : n[X] + 1) * s[X] + at;
+      float *rf = fslot(k.f, v, S_RHOF), *rb = fslot(k.f, v, S_RHOB);
+      if (pack) { buf[2 * i_node] = *rf; buf[2 * i_node + 1] = *rb; }
+      else { *rf = 1.0f * *rf + 1.0f * buf[2 * i_node]; *rb = 0.5f * *rb + 0.5f * buf[2 * i_node + 1]; }
+    } else if (kind == VPB_HALO_NORM_E) {
+      if (pack) buf[i_node] = *fslot(k.f, (low ? 1 : n[X]) * s[X] + at, S_EX + X);
+      else {
+        const int v = (low ? 0 : n[X] + 1) * s[X] + at, in1 = v + (low ? s[X] : -s[X]);
+        *fslot(k.f, v, S_EX + X) = 1.0f * buf[i_node] + 0.0f * *fslot(k.f, in1, S_EX + X);
+      }
+    } else if (kind == VPB_HALO_DIV_B) {
+      if (in_cell) {
+        if (pack) buf[i_cell] = *fslot(k.f, (low ? 1 : n[X]) * s[X] + at, S_DIVB);
+        else {
+          const int v = (low ? 0 : n[X] + 1) * s[X] + at, in1 = v + (low ? s[X] : -s[X]);
+          *fslot(k.f, v, S_DIVB) = 1.0f * buf[i_cell] + 0.0f * *fslot(k.f, in1, S_DIVB);
+        }
+      }
+    } else {                                                         // VPB_HALO_TANG_E_NORM_B
+      const int v = (low ? 1 : n[X] + 1) * s[X] + at;
+      float *sec_b = buf, *sec_y = buf + n[Y] * n[Z], *sec_z = sec_y + 2 * n[Y] * (n[Z] + 1);
+      const int i_ey = (cy - 1) + n[Y] * (cz - 1), i_ez = (cy - 1) + (n[Y] + 1) * (cz - 1);
+      auto one = [&](int slot, float *b, bool count) {
+        float *own = fslot(k.f, v, slot);
+        if (pack) { *b = *own; return; }
+        const double w1 = *b, w2 = *own;
+        *own = (float)(0.5 * (w1 + w2));
+        if (count) acc += (w1 - w2) * (w1 - w2);
+      };
+      if (in_cell) one(S_CBX + X, sec_b + i_cell, true);
+      if (cy <= n[Y]) { one(S_EX + Y, sec_y + 2 * i_ey, true); one(S_TCAX + Y, sec_y + 2 * i_ey + 1, false); }
+      if (cz <= n[Z]) { one(S_EX + Z, sec_z + 2 * i_ez, true); one(S_TCAX + Z, sec_z + 2 * i_ez + 1, false); }
+    }
+  }
+  if (err) block_sum_to(acc, err);
+}
+
+size_t halo_clean_floats(int nx, int ny, int nz, int axis, int kind) {
+  const int n[3] = {nx, ny, nz};
+  const size_t nY = n[(axis + 1) % 3], nZ = n[(axis + 2) % 3];
+  switch (kind) {
+    case VPB_HALO_RHO: return 2 * (nY + 1) * (nZ + 1);
+    case VPB_HALO_NORM_E: return (nY + 1) * (nZ + 1);
+    case VPB_HALO_DIV_B: return nY * nZ;
+    case VPB_HALO_TANG_E_NORM_B: return nY * nZ + 2 * nY * (nZ + 1) + 2 * (nY + 1) * nZ;
+  }
+  return 0;
+}
+
+int halo_clean(const vpb_field_args_t *a, int kind, int face, float *buf, bool pack, double *err_dev, void *stream) {
+  halo_clean_kernel<<<plane_grid(a, face % 3, 1), 256, 0, as_stream(stream)>>>(to_k(a), kind, face, buf, pack, err_dev);
+  VPB_LAUNCH_CHECK();
+  return 0;
+}
+
+// faces shared with another rank are exchanged by the caller (vpb_halo_pack / unpack); only a half-periodic axis is an error
 static int no_remote_faces(const vpb_field_args_t *a, const char *who) {
-  for (int i = 0; i < 6; i++)
-    VPB_REQUIRE(a->face[i] != VPB_FACE_REMOTE, "%s: faces shared with another rank are not supported by the device divergence cleaning yet", who);
   for (int X = 0; X < 3; X++)
     VPB_REQUIRE((a->face[X] == VPB_FACE_PERIODIC_SELF) == (a->face[X + 3] == VPB_FACE_PERIODIC_SELF),
                 "%s: axis %d is periodic on one side only", who, X);

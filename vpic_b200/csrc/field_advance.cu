@@ -429,8 +429,24 @@ extern "C" size_t vpb_halo_floats(int32_t nx, int32_t ny, int32_t nz, int axis) 
   return (size_t)(n[Y] + 1) * n[Z] + (size_t)n[Y] * (n[Z] + 1);
 }
 
+extern "C" size_t vpb_halo_floats_kind(int32_t nx, int32_t ny, int32_t nz, int axis, int kind) {
+  if (kind == VPB_HALO_TANG_B || kind == VPB_HALO_JF) return vpb_halo_floats(nx, ny, nz, axis);
+  return halo_clean_floats(nx, ny, nz, axis, kind);
+}
+
+extern "C" int vpb_halo_unpack_sync(const vpb_field_args_t *a, int face, const float *buf, double *err_dev, void *stream) {
+  if (int r = check_field_args(a, "vpb_halo_unpack_sync")) return r;
+  VPB_REQUIRE(buf && err_dev && face >= 0 && face < 6, "vpb_halo_unpack_sync: Bad args");
+  return halo_clean(a, VPB_HALO_TANG_E_NORM_B, face, (float *)buf, false, err_dev, stream);
+}
+
 static int halo_common(const vpb_field_args_t *a, int kind, int face, float *buf, bool pack, void *stream) {
   if (int r = check_field_args(a, "vpb_halo")) return r;
+  if (kind >= VPB_HALO_RHO && kind <= VPB_HALO_TANG_E_NORM_B) {
+    VPB_REQUIRE(buf && face >= 0 && face < 6, "vpb_halo: Bad args");
+    VPB_REQUIRE(pack || kind != VPB_HALO_TANG_E_NORM_B, "vpb_halo_unpack: use vpb_halo_unpack_sync for VPB_HALO_TANG_E_NORM_B");
+    return halo_clean(a, kind, face, buf, pack, nullptr, stream);
+  }
   VPB_REQUIRE(buf && face >= 0 && face < 6 && (kind == VPB_HALO_TANG_B || kind == VPB_HALO_JF), "vpb_halo: Bad args");
   halo_kernel<<<plane_grid(a, face % 3, 1), 256, 0, as_stream(stream)>>>(to_k(a), kind, face, buf, pack);
   VPB_LAUNCH_CHECK();

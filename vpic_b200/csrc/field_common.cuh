@@ -45,4 +45,8 @@ static inline dim3 max_plane_grid(const vpb_field_args_t *a, int nz_blocks) {
 }
 
 
+// div_clean.cu: halo planes of the cleaning / synchronisation kinds (VPB_HALO_RHO .. VPB_HALO_TANG_E_NORM_B)
+int halo_clean(const vpb_field_args_t *a, int kind, int face, float *buf, bool pack, double *err_dev, void *stream);
+size_t halo_clean_floats(int nx, int ny, int nz, int axis, int kind);
+
 }  // namespace vpb

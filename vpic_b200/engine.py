@@ -135,20 +135,26 @@ class FieldArray:
     def compute_rhob(self): self._call("vpb_vacuum_compute_rhob")
     def compute_curl_b(self): self._call("vpb_vacuum_compute_curl_b")
 
-    def _rms(self, name):
-        """eps0 * sqrt(sum dV / volume) of one domain (compute_rms_div_e_err_pipeline.cc:170-183)."""
+    def rms_terms(self, name):
+        """The two local terms of an rms error, [sum * dV, volume] (compute_rms_div_e_err_pipeline.cc:175-178); the
+        caller sums them over ranks and finishes with rms_finish."""
         g = self.g
         self._call(name, _ptr(self._en))
         s = float(self._en[0].item())
         dV = np.float32(g.dV)
-        return float(g.eps0) * float(np.sqrt((s * float(dV)) / float(np.float32(g.nx * g.ny * g.nz) * dV)))
+        return [s * float(dV), float(np.float32(g.nx * g.ny * g.nz) * dV)]
 
-    def compute_rms_div_e_err(self): return self._rms("vpb_compute_rms_div_e_err")
-    def compute_rms_div_b_err(self): return self._rms("vpb_compute_rms_div_b_err")
+    def rms_finish(self, terms):
+        return float(self.g.eps0) * float(np.sqrt(terms[0] / terms[1]))
 
-    def synchronize_tang_e_norm_b(self):
+    def compute_rms_div_e_err(self): return self.rms_finish(self.rms_terms("vpb_compute_rms_div_e_err"))
+    def compute_rms_div_b_err(self): return self.rms_finish(self.rms_terms("vpb_compute_rms_div_b_err"))
+
+    def synchronize_tang_e_norm_b(self, read=True):
+        """Local walls and self-periodic axes; the squared-difference sum stays in self._en[0] (read=False) so that a
+        slab exchange can add its share before the value is read."""
         self._call("vpb_synchronize_tang_e_norm_b", _ptr(self._en))
-        return float(self._en[0].item())
+        return float(self._en[0].item()) if read else None
 
 
 class HydroArray:

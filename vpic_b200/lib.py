@@ -52,7 +52,7 @@ class FieldArgs(C.Structure):
 
 DEPOSIT_DEFAULT, DEPOSIT_RED_V4, DEPOSIT_WARP_SEG, DEPOSIT_WARP_SEG_MOVERS, DEPOSIT_WARP_SEG_FIRST = 0, 1, 2, 3, 4
 FACE_PERIODIC_SELF, FACE_REMOTE = 0, 1
-HALO_TANG_B, HALO_JF = 0, 1
+HALO_TANG_B, HALO_JF, HALO_RHO, HALO_NORM_E, HALO_DIV_B, HALO_TANG_E_NORM_B = 0, 1, 2, 3, 4, 5
 
 # every exported symbol of include/vpic_b200.h: name -> (restype, argtypes)
 _PROTOS = {
@@ -108,6 +108,8 @@ _PROTOS = {
     "vpb_clear_hydro": (C.c_int, [c_vp, c_i32, c_i32, c_i32, c_vp]),
     "vpb_synchronize_hydro": (C.c_int, [c_vp, C.POINTER(FieldArgs), c_vp]),
     "vpb_halo_floats": (C.c_size_t, [c_i32, c_i32, c_i32, C.c_int]),
+    "vpb_halo_floats_kind": (C.c_size_t, [c_i32, c_i32, c_i32, C.c_int, C.c_int]),
+    "vpb_halo_unpack_sync": (C.c_int, [C.POINTER(FieldArgs), C.c_int, c_vp, c_vp, c_vp]),
     "vpb_halo_pack": (C.c_int, [C.POINTER(FieldArgs), C.c_int, C.c_int, c_vp, c_vp]),
     "vpb_halo_unpack": (C.c_int, [C.POINTER(FieldArgs), C.c_int, C.c_int, c_vp, c_vp]),
 }

@@ -63,6 +63,7 @@ class SlabExchange:
         dev = dgrid.device
         self.h_out = [torch.empty(n, dtype=torch.float32, device=dev) for _ in range(2)]
         self.h_in = [torch.empty(n, dtype=torch.float32, device=dev) for _ in range(2)]
+        self._extra = {}
 
     def begin_step(self, sim):
         pass
@@ -112,19 +113,56 @@ class SlabExchange:
         E.finish_advance_p_all(sps)
 
     # ---- fields ---------------------------------------------------------------------------------------------
-    def _halo(self, fa, kind):
+    def _buffers(self, kind):
+        """Send/receive planes for one halo kind (TANG_B and JF share the preallocated pair)."""
+        if kind in (_lib.HALO_TANG_B, _lib.HALO_JF):
+            return self.h_out, self.h_in
+        if kind not in self._extra:
+            g = self.g
+            n = _lib.load().vpb_halo_floats_kind(g.nx, g.ny, g.nz, self.axis, kind)
+            mk = lambda: [torch.empty(n, dtype=torch.float32, device=g.device) for _ in range(2)]
+            self._extra[kind] = (mk(), mk())
+        return self._extra[kind]
+
+    def _halo(self, fa, kind, err=None):
         import ctypes as C
         L = _lib.load()
         a = fa.args()
         st = E._stream()
-        _lib.check(L.vpb_halo_pack(C.byref(a), kind, self.f_lo, E._ptr(self.h_out[0]), st), "halo_pack")
-        _lib.check(L.vpb_halo_pack(C.byref(a), kind, self.f_hi, E._ptr(self.h_out[1]), st), "halo_pack")
-        self.ring.sendrecv(self.h_out[0], self.h_out[1], self.h_in[0], self.h_in[1])
-        _lib.check(L.vpb_halo_unpack(C.byref(a), kind, self.f_lo, E._ptr(self.h_in[0]), st), "halo_unpack")
-        _lib.check(L.vpb_halo_unpack(C.byref(a), kind, self.f_hi, E._ptr(self.h_in[1]), st), "halo_unpack")
+        out, inn = self._buffers(kind)
+        _lib.check(L.vpb_halo_pack(C.byref(a), kind, self.f_lo, E._ptr(out[0]), st), "halo_pack")
+        _lib.check(L.vpb_halo_pack(C.byref(a), kind, self.f_hi, E._ptr(out[1]), st), "halo_pack")
+        self.ring.sendrecv(out[0], out[1], inn[0], inn[1])
+        if kind == _lib.HALO_TANG_E_NORM_B:
+            _lib.check(L.vpb_halo_unpack_sync(C.byref(a), self.f_lo, E._ptr(inn[0]), E._ptr(err), st), "halo_unpack_sync")
+            _lib.check(L.vpb_halo_unpack_sync(C.byref(a), self.f_hi, E._ptr(inn[1]), E._ptr(err), st), "halo_unpack_sync")
+            return
+        _lib.check(L.vpb_halo_unpack(C.byref(a), kind, self.f_lo, E._ptr(inn[0]), st), "halo_unpack")
+        _lib.check(L.vpb_halo_unpack(C.byref(a), kind, self.f_hi, E._ptr(inn[1]), st), "halo_unpack")
 
     def synchronize_jf(self, sim):
         self._halo(sim.field_array, _lib.HALO_JF)
 
     def ghost_tang_b(self, sim):
         self._halo(sim.field_array, _lib.HALO_TANG_B)
+
+    # the periodic extras of divergence cleaning and shared-face synchronisation (remote.cc:136-416,534-620)
+    def synchronize_rho(self, sim):
+        self._halo(sim.field_array, _lib.HALO_RHO)
+
+    def ghost_norm_e(self, sim):
+        self._halo(sim.field_array, _lib.HALO_NORM_E)
+
+    def ghost_div_b(self, sim):
+        self._halo(sim.field_array, _lib.HALO_DIV_B)
+
+    def synchronize_tang_e_norm_b(self, sim, err_dev):
+        """Average the shared planes with the neighbours'; the squared differences are added to err_dev[0]."""
+        self._halo(sim.field_array, _lib.HALO_TANG_E_NORM_B, err=err_dev)
+
+    def allsum(self, values):
+        """mp_allsum_d (src/util/mp/mp.h) for a few host doubles."""
+        t = torch.tensor(values, dtype=torch.float64, device=self.g.device)
+        if self.ring.world > 1:
+            dist.all_reduce(t, group=self.ring.group)
+        return t.cpu().tolist()

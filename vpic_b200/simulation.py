@@ -8,6 +8,7 @@ Order of operations is the reference's:
   boundary_p x num_comm_round                          :73-77   (slab-decomposed runs: NCCL, see parallel.py)
   clear_jf ; unload_accumulator_array ; synchronize_jf :107-110
   advance_b(1/2) ; advance_e(1) ; advance_b(1/2)       :123-137
+  clean_div_e / clean_div_b / synchronize_tang_e_norm_b at their intervals   :138-176
   load_interpolator_array                              :185
 Host hooks of the reference (user_* injections, collisions, emitters, dumps) are outside the hot path and are not
 called here.
@@ -30,6 +31,14 @@ class Simulation:
         self.push_events = None           # list of (start, end) CUDA events around each advance_p when profiling
         self.overlap_exchange = True      # multi-GPU: migrate species k while species k+1 is pushed
         self._side = None
+        # divergence cleaning and shared-face synchronisation (vpic.h: clean_div_e_interval, num_div_e_round, ...);
+        # 0 = off, as in a deck that does not set them
+        self.clean_div_e_interval = 0
+        self.clean_div_b_interval = 0
+        self.sync_shared_interval = 0
+        self.num_div_e_round = 2
+        self.num_div_b_round = 2
+        self.cleaning_log = []            # (step, what, value): the rms errors / desynchronisation the reference prints
 
     def define_species(self, name, q, m, max_np, max_nm, sort_interval=20, sort_out_of_place=0):
         sp = E.Species(name, q, m, max_np, max_nm, sort_interval, sort_out_of_place, self.g)
@@ -109,8 +118,46 @@ class Simulation:
             self.exchange.ghost_tang_b(self)
         fa.advance_e(1.0)
         fa.advance_b(0.5)
+        self._maintain_fields(step)
         E.load_interpolator_array(ia, fa)
         self.g.g.step += 1
+
+    def _allsum(self, values):
+        return self.exchange.allsum(values) if self.exchange is not None else values
+
+    def _maintain_fields(self, step):
+        """advance.cc:138-176: Marder passes on div E and div B and the shared-face synchronisation."""
+        fa, ex = self.field_array, self.exchange
+        if self.clean_div_e_interval > 0 and step % self.clean_div_e_interval == 0:
+            fa.clear_rhof()
+            for sp in self.species_list:
+                E.accumulate_rho_p(fa, sp)
+            fa.synchronize_rho()
+            if ex is not None:
+                ex.synchronize_rho(self)
+            for r in range(self.num_div_e_round):
+                if ex is not None:
+                    ex.ghost_norm_e(self)
+                fa.compute_div_e_err()
+                if r == 0 or r == self.num_div_e_round - 1:
+                    err = fa.rms_finish(self._allsum(fa.rms_terms("vpb_compute_rms_div_e_err")))
+                    self.cleaning_log.append((step, "div_e initial" if r == 0 else "div_e cleaned", err))
+                fa.clean_div_e()
+        if self.clean_div_b_interval > 0 and step % self.clean_div_b_interval == 0:
+            for r in range(self.num_div_b_round):
+                fa.compute_div_b_err()
+                if r == 0 or r == self.num_div_b_round - 1:
+                    err = fa.rms_finish(self._allsum(fa.rms_terms("vpb_compute_rms_div_b_err")))
+                    self.cleaning_log.append((step, "div_b initial" if r == 0 else "div_b cleaned", err))
+                if ex is not None:
+                    ex.ghost_div_b(self)
+                fa.clean_div_b()
+        if self.sync_shared_interval > 0 and step % self.sync_shared_interval == 0:
+            fa.synchronize_tang_e_norm_b(read=False)
+            if ex is not None:
+                ex.synchronize_tang_e_norm_b(self, fa._en)
+            err = self._allsum([float(fa._en[0].item())])[0]
+            self.cleaning_log.append((step, "desynchronization", err))
 
     def energies(self):
         """dump_energies row (src/vpic/dump.cc:38-77): field energies then one kinetic energy per species."""
