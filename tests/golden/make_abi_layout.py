@@ -31,6 +31,8 @@ int main() {
   S(field_t); O(field_t,cbx); O(field_t,tcax); O(field_t,jfx); O(field_t,ematx); O(field_t,cmat);
   S(field_advance_kernels_t); S(field_array_t); O(field_array_t,g); O(field_array_t,params); O(field_array_t,kernel);
   S(material_coefficient_t); S(sfa_params_t); O(sfa_params_t,n_mc); O(sfa_params_t,damp);
+  S(hydro_t); O(hydro_t,rho); O(hydro_t,ke); O(hydro_t,tyz); O(hydro_t,txy);
+  S(hydro_array_t); O(hydro_array_t,n_pipeline); O(hydro_array_t,stride); O(hydro_array_t,g);
   printf("\"end\": 0\n}\n");
   return 0;
 }

@@ -18,7 +18,7 @@ NAMES = {"particle_t": "vpb_particle_t", "particle_mover_t": "vpb_particle_mover
          "accumulator_t": "vpb_accumulator_t", "accumulator_array_t": "vpb_accumulator_array_t",
          "field_t": "vpb_field_t", "field_advance_kernels_t": "vpb_field_advance_kernels_t",
          "field_array_t": "vpb_field_array_t", "material_coefficient_t": "vpb_material_coefficient_t",
-         "sfa_params_t": "vpb_sfa_params_t"}
+         "sfa_params_t": "vpb_sfa_params_t", "hydro_t": "vpb_hydro_t", "hydro_array_t": "vpb_hydro_array_t"}
 
 
 @pytest.mark.parametrize("simd", ["4", "8", "16"])
@@ -50,6 +50,8 @@ def test_ctypes_layout():
     assert C.sizeof(abi.Grid) == g["sizeof(grid_t)"]
     assert C.sizeof(abi.FieldArray) == g["sizeof(field_array_t)"]
     assert C.sizeof(abi.MaterialCoefficient) == g["sizeof(material_coefficient_t)"]
+    assert C.sizeof(abi.HydroArray) == g["sizeof(hydro_array_t)"] and abi.HYDRO_FLOATS * 4 == g["sizeof(hydro_t)"] == 64
+    assert abi.HydroArray.g.offset == g["offsetof(hydro_array_t,g)"] and abi.HydroArray.stride.offset == g["offsetof(hydro_array_t,stride)"]
     for m in ("q", "np", "p", "nm", "pm", "last_sorted", "sort_interval", "partition", "g", "id", "next"):
         assert getattr(abi.Species, m).offset == g[f"offsetof(species_t,{m})"]
     for m in ("step", "t0", "x0", "nx", "dx", "rdx", "sx", "nv", "bc", "range", "neighbor", "rangel", "rangeh", "mp"):

@@ -13,7 +13,7 @@ ap.add_argument("--grid", type=int, default=128); ap.add_argument("--ppc", type=
 ap.add_argument("--reps", type=int, default=5)
 a = ap.parse_args()
 class A: pass
-args = A(); args.grid = a.grid; args.ppc = a.ppc; args.uth = 0.18; args.sort_interval = 20; args.variant = 0
+args = A(); args.grid = a.grid; args.ppc = a.ppc; args.uth = 0.18; args.sort_interval = 20; args.variant = 0; args.scaling = "weak"; args.workload = "uniform"
 torch.cuda.set_device(0)
 dev = torch.device("cuda", 0)
 sim = bench.build_sim(args, 0, 1, dev)
@@ -50,4 +50,20 @@ rec("clear_jf", timeit(lambda: fa.clear_jf()), 2 * 16 * nv)
 rec("synchronize_jf (periodic folds)", timeit(lambda: fa.synchronize_jf()), 0.0 + 6 * 2 * 16 * (a.grid + 1) ** 2)
 rec("energy_p", timeit(lambda: E.energy_p(sp, ia)), 32.0 * np_)
 rec("vacuum_energy_f", timeit(lambda: fa.energy_f()), 32.0 * nv)
+# divergence cleaning, shared-face synchronisation, hydro moments (algorithmic bytes: the field_t slots each one reads / writes)
+rec("accumulate_rho_p", timeit(lambda: E.accumulate_rho_p(fa, sp), reps=3), 32.0 * np_)
+rec("clear_rhof", timeit(lambda: fa.clear_rhof()), 4 * nv)
+rec("synchronize_rho (periodic folds)", timeit(lambda: fa.synchronize_rho()), 6 * 2 * 8 * (a.grid + 1) ** 2)
+rec("vacuum_compute_div_e_err (+ghost planes)", timeit(lambda: fa.compute_div_e_err()), (12 + 4 + 4 + 4) * nv)
+rec("compute_rms_div_e_err", timeit(lambda: fa.compute_rms_div_e_err()), 4 * nv)
+rec("vacuum_clean_div_e", timeit(lambda: fa.clean_div_e()), (4 + 12 + 12) * nv)
+rec("compute_div_b_err", timeit(lambda: fa.compute_div_b_err()), (12 + 4) * nv)
+rec("compute_rms_div_b_err", timeit(lambda: fa.compute_rms_div_b_err()), 4 * nv)
+rec("clean_div_b (+ghost planes)", timeit(lambda: fa.clean_div_b()), (4 + 12 + 12) * nv)
+rec("synchronize_tang_e_norm_b", timeit(lambda: fa.synchronize_tang_e_norm_b()), 6 * 2 * 20 * (a.grid + 1) ** 2)
+ha = E.HydroArray(sim.g)
+rec("accumulate_hydro_p (drifted order)", timeit(lambda: E.accumulate_hydro_p(ha, sp, ia), reps=3), 32.0 * np_ + (72 + 2 * 64) * nv)
+E.sort_p(sp)
+rec("accumulate_hydro_p (just sorted)", timeit(lambda: E.accumulate_hydro_p(ha, sp, ia), reps=3), 32.0 * np_ + (72 + 2 * 64) * nv)
+rec("synchronize_hydro_array (periodic folds)", timeit(lambda: ha.synchronize(fa)), 6 * 2 * 56 * (a.grid + 1) ** 2)
 print(json.dumps(dict(workload=f"{a.grid}^3 cells, {a.ppc} ppc, np={np_}", peak_GBps=peak, kernels=rows), indent=1))

@@ -8,21 +8,17 @@
 //   src/sf_interface/hydro_array.cc:131-309                            synchronize_hydro_array (walls, periodic folds)
 //   src/sf_interface/clear_array.cc / reduce_array.cc                  clear_hydro_array; reduce is the identity here
 // Per-particle arithmetic follows the scalar pipeline exactly (-fmad=false); the sums are atomic, so node values agree
-// with the reference to fp32 summation-order tolerance.  A warp whose lanes all sit in one voxel (the usual case for
-// voxel-sorted particles) reduces each moment across the warp first and issues one set of REDs.
+// with the reference to fp32 summation-order tolerance.  Lanes of a warp that share a voxel (for voxel-sorted
+// particles: all of them, or two or three groups) sum each node's 14 moments with a reduce-scatter butterfly (16
+// shuffles per node instead of 70) and issue one set of REDs per group; lanes in groups of fewer than four go
+// straight to memory.
 #include "field_common.cuh"
 
 namespace vpb {
 
 constexpr int kHydroFloats = 16;
 
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
-__global__ void __launch_bounds__(256) accumulate_hydro_p_kernel(float *__restrict__ hydro, const float4 *__restrict__ p, int np,
+__global__ void __launch_bounds__(256, 2) accumulate_hydro_p_kernel(float *__restrict__ hydro, const float4 *__restrict__ p, int np,
                                                                  const float *__restrict__ interp, int istride,
                                                                  float qsp, float mspc, float c, float qdt_2mc, float qdt_4mc2,
                                                                  float r8V, int sy, int sz) {
@@ -73,36 +69,49 @@ __global__ void __launch_bounds__(256) accumulate_hydro_p_kernel(float *__restri
       dz = one - dz; w0 *= dz; w1 *= dz; w2 *= dz; w3 *= dz;
       wn[0] = w0; wn[1] = w1; wn[2] = w2; wn[3] = w3; wn[4] = w4; wn[5] = w5; wn[6] = w6; wn[7] = w7;
     }
-    const unsigned amask = __ballot_sync(0xffffffffu, valid);
-    const int v_first = __shfl_sync(0xffffffffu, vox, __ffs(amask) - 1);
-    const bool uniform = __all_sync(0xffffffffu, !valid || vox == v_first);
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-      const int node = (uniform ? v_first : vox) + (k & 1) + ((k & 2) ? sy : 0) + ((k & 4) ? sz : 0);
-      float m[14];
-      float t = qsp * wn[k];                                                      // ACCUM_HYDRO, :178-198
+    // moments of node k of this lane's particle (ACCUM_HYDRO, :178-198), padded to the 16 floats of hydro_t
+    auto moments = [&](int k, float (&m)[16]) {
+      float t = qsp * wn[k];
       m[0] = t * vx; m[1] = t * vy; m[2] = t * vz; m[3] = t;
       t = mspc * wn[k];
       const float tx = t * ux, ty = t * uy, tz = t * uz;
       m[4] = tx; m[5] = ty; m[6] = tz; m[7] = t * ke_mc;
       m[8] = tx * vx; m[9] = ty * vy; m[10] = tz * vz;
       m[11] = ty * vz; m[12] = tz * vx; m[13] = tx * vy;
-      if (uniform) {
+      m[14] = 0.0f; m[15] = 0.0f;
+    };
+    const unsigned peers = warp_peers(valid, vox);
+    const bool grouped = valid && __popc(peers) >= 4;
+    if (valid && !grouped) {                                   // stragglers: per-lane REDs
 #pragma unroll
-        for (int q = 0; q < 14; q++) m[q] = warp_sum(m[q]);
-        if (lane < 14) {
-          float mine = m[0];
-#pragma unroll
-          for (int q = 1; q < 14; q++) mine = (lane == q) ? m[q] : mine;
-          red_add(hydro + (size_t)node * kHydroFloats + lane, mine);
-        }
-      } else if (valid) {
-        float *h = hydro + (size_t)node * kHydroFloats;
+      for (int k = 0; k < 8; k++) {
+        float m[16];
+        moments(k, m);
+        float *h = hydro + (size_t)(vox + (k & 1) + ((k & 2) ? sy : 0) + ((k & 4) ? sz : 0)) * kHydroFloats;
         red_add_v4(h, m[0], m[1], m[2], m[3]);
         red_add_v4(h + 4, m[4], m[5], m[6], m[7]);
         red_add_v4(h + 8, m[8], m[9], m[10], m[11]);
         red_add(h + 12, m[12]); red_add(h + 13, m[13]);
       }
+    }
+    unsigned big = __ballot_sync(0xffffffffu, grouped);
+    while (big) {                                              // one pass per voxel shared by >= 4 lanes
+      const int leader = __ffs(big) - 1;
+      const unsigned grp = __shfl_sync(0xffffffffu, peers, leader);
+      const int gv = __shfl_sync(0xffffffffu, vox, leader);
+      const bool mine = grouped && peers == grp;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        float m[16];
+        moments(k, m);
+#pragma unroll
+        for (int q = 0; q < 16; q++) m[q] = mine ? m[q] : 0.0f;
+        warp_reduce_scatter<16>(m);                            // total of moment c in lanes 2c, 2c+1
+        const int c = lane >> 1;
+        if (!(lane & 1) && c < 14)
+          red_add(hydro + (size_t)(gv + (k & 1) + ((k & 2) ? sy : 0) + ((k & 4) ? sz : 0)) * kHydroFloats + c, m[0]);
+      }
+      big &= ~grp;
     }
   }
 }

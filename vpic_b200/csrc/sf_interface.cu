@@ -152,26 +152,56 @@ __global__ void __launch_bounds__(256) center_p_kernel(float4 *__restrict__ p, i
 }
 
 // accumulate_rho_p (rho_p.cc:22-113): trilinear node charges of every particle into field_t.rhof (float 15 of the
-// 20-float field record).  One thread per particle, eight scalar REDs.
+// 20-float field record).  One thread per particle; lanes of a warp that share a voxel (all of them, for voxel-sorted
+// particles) sum their eight node charges with a reduce-scatter and issue eight REDs for the group instead of eight
+// per lane; lanes in groups of fewer than four go straight to memory.
 __global__ void __launch_bounds__(256) accumulate_rho_p_kernel(float *__restrict__ fld, const float4 *__restrict__ p,
                                                                int np, float q_8V, int sy, int sz) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= np) return;
-  const float4 r = p[2 * (size_t)n];
-  const float pw = p[2 * (size_t)n + 1].w;
-  float w0 = r.x, w1 = r.y, w2, w3, w4, w5, w6, w7 = pw * q_8V;
-  const float dz = r.z;
-  const int v = __float_as_int(r.w);
-  w6 = w7 - w0 * w7; w7 = w7 + w0 * w7;
-  w4 = w6 - w1 * w6; w5 = w7 - w1 * w7;
-  w6 = w6 + w1 * w6; w7 = w7 + w1 * w7;
-  w0 = w4 - dz * w4; w1 = w5 - dz * w5; w2 = w6 - dz * w6; w3 = w7 - dz * w7;
-  w4 = w4 + dz * w4; w5 = w5 + dz * w5; w6 = w6 + dz * w6; w7 = w7 + dz * w7;
-  float *f = fld + 15;
-  red_add(f + 20 * (size_t)(v), w0);           red_add(f + 20 * (size_t)(v + 1), w1);
-  red_add(f + 20 * (size_t)(v + sy), w2);      red_add(f + 20 * (size_t)(v + sy + 1), w3);
-  red_add(f + 20 * (size_t)(v + sz), w4);      red_add(f + 20 * (size_t)(v + sz + 1), w5);
-  red_add(f + 20 * (size_t)(v + sz + sy), w6); red_add(f + 20 * (size_t)(v + sz + sy + 1), w7);
+  const int lane = threadIdx.x & 31;
+  const long long rows = ((long long)np + 31) / 32;
+  for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows;
+       row += (long long)gridDim.x * (blockDim.x >> 5)) {
+    const long long n = row * 32 + lane;
+    const bool valid = n < np;
+    float w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int v = 0;
+    if (valid) {
+      const float4 r = p[2 * n];
+      const float pw = p[2 * n + 1].w;
+      float w0 = r.x, w1 = r.y, w2, w3, w4, w5, w6, w7 = pw * q_8V;
+      const float dz = r.z;
+      v = __float_as_int(r.w);
+      w6 = w7 - w0 * w7; w7 = w7 + w0 * w7;
+      w4 = w6 - w1 * w6; w5 = w7 - w1 * w7;
+      w6 = w6 + w1 * w6; w7 = w7 + w1 * w7;
+      w0 = w4 - dz * w4; w1 = w5 - dz * w5; w2 = w6 - dz * w6; w3 = w7 - dz * w7;
+      w4 = w4 + dz * w4; w5 = w5 + dz * w5; w6 = w6 + dz * w6; w7 = w7 + dz * w7;
+      w[0] = w0; w[1] = w1; w[2] = w2; w[3] = w3; w[4] = w4; w[5] = w5; w[6] = w6; w[7] = w7;
+    }
+    const unsigned peers = warp_peers(valid, v);
+    const bool grouped = valid && __popc(peers) >= 4;
+    float *f = fld + 15;
+    if (valid && !grouped) {
+      red_add(f + 20 * (size_t)(v), w[0]);           red_add(f + 20 * (size_t)(v + 1), w[1]);
+      red_add(f + 20 * (size_t)(v + sy), w[2]);      red_add(f + 20 * (size_t)(v + sy + 1), w[3]);
+      red_add(f + 20 * (size_t)(v + sz), w[4]);      red_add(f + 20 * (size_t)(v + sz + 1), w[5]);
+      red_add(f + 20 * (size_t)(v + sz + sy), w[6]); red_add(f + 20 * (size_t)(v + sz + sy + 1), w[7]);
+    }
+    unsigned big = __ballot_sync(0xffffffffu, grouped);
+    while (big) {
+      const int leader = __ffs(big) - 1;
+      const unsigned grp = __shfl_sync(0xffffffffu, peers, leader);
+      const int gv = __shfl_sync(0xffffffffu, v, leader);
+      const bool mine = grouped && peers == grp;
+      float t[8];
+#pragma unroll
+      for (int c = 0; c < 8; c++) t[c] = mine ? w[c] : 0.0f;
+      warp_reduce_scatter<8>(t);
+      const int c = lane >> 2;                                     // node c = (c&1) + sy*(c>>1&1) + sz*(c>>2)
+      if ((lane & 3) == 0) red_add(f + 20 * (size_t)(gv + (c & 1) + ((c & 2) ? sy : 0) + ((c & 4) ? sz : 0)), t[0]);
+      big &= ~grp;
+    }
+  }
 }
 
 }  // namespace vpb
@@ -183,8 +213,9 @@ extern "C" int vpb_accumulate_rho_p(float *fields, const void *p, int32_t np, fl
   VPB_REQUIRE(fields && (p || np == 0) && nx > 0 && ny > 0 && nz > 0, "vpb_accumulate_rho_p: Bad args");
   if (np <= 0) return 0;
   const float q_8V = q * r8V;
-  accumulate_rho_p_kernel<<<(np + 255) / 256, 256, 0, as_stream(stream)>>>(fields, (const float4 *)p, np, q_8V,
-                                                                          nx + 2, (nx + 2) * (ny + 2));
+  long long grid = (((long long)np + 31) / 32 + 7) / 8; if (grid > kSMs * 16) grid = kSMs * 16;
+  accumulate_rho_p_kernel<<<(int)grid, 256, 0, as_stream(stream)>>>(fields, (const float4 *)p, np, q_8V,
+                                                                   nx + 2, (nx + 2) * (ny + 2));
   VPB_LAUNCH_CHECK();
   return 0;
 }

@@ -37,6 +37,42 @@ __device__ __forceinline__ void red_add(float *addr, float a) {
   asm volatile("red.global.add.f32 [%0], %1;" :: "l"(addr), "f"(a) : "memory");
 }
 
+// Warp-wide sum of N values per lane by reduce-scatter (N = 8 or 16): every butterfly step halves the number of values
+// a lane carries, so N values cost N-1 shuffles (plus log2(32/N) for the tail) instead of 5N.  Afterwards the total of
+// value c sits in v[0] of the 32/N lanes with lane / (32/N) == c.
+template <int N>
+__device__ __forceinline__ void warp_reduce_scatter(float (&v)[N]) {
+  static_assert(N == 8 || N == 16, "N");
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int half = N / 2, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
+    const bool hi = (lane & bit) != 0;
+#pragma unroll
+    for (int c = 0; c < half; c++) {
+      const float keep = hi ? v[c + half] : v[c];
+      const float send = hi ? v[c] : v[c + half];
+      v[c] = keep + __shfl_xor_sync(full, send, bit);
+    }
+  }
+#pragma unroll
+  for (int bit = 16 / N; bit >= 1; bit >>= 1) v[0] += __shfl_xor_sync(full, v[0], bit);
+}
+
+// Lanes of a warp that share a key, found cheaply when the whole warp shares one (voxel-sorted particles): returns the
+// peer mask of this lane (0 for inactive lanes).
+__device__ __forceinline__ unsigned warp_peers(bool active, int key) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const unsigned amask = __ballot_sync(full, active);
+  if (amask == 0) return 0u;
+  const int first = __shfl_sync(full, key, __ffs(amask) - 1);
+  const bool uniform = __all_sync(full, !active || key == first);
+  if (uniform) return active ? amask : 0u;
+  const unsigned m = __match_any_sync(full, active ? key : (-1 - lane));
+  return active ? m : 0u;
+}
+
 // 256-bit global accesses (LDG.E.256 / STG.E.256, new on sm_100): one particle_t per instruction, so a warp touches
 // 1 KB of consecutive bytes with every sector fully used.  The address must be 32-byte aligned.
 __device__ __forceinline__ void ld_particle(const float4 *p, float4 &r, float4 &u) {
