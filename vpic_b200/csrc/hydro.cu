@@ -18,7 +18,7 @@ namespace vpb {
 
 constexpr int kHydroFloats = 16;
 
-__global__ void __launch_bounds__(256, 2) accumulate_hydro_p_kernel(float *__restrict__ hydro, const float4 *__restrict__ p, int np,
+__global__ void __launch_bounds__(256, 3) accumulate_hydro_p_kernel(float *__restrict__ hydro, const float4 *__restrict__ p, int np,
                                                                  const float *__restrict__ interp, int istride,
                                                                  float qsp, float mspc, float c, float qdt_2mc, float qdt_4mc2,
                                                                  float r8V, int sy, int sz) {
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256, 2) accumulate_hydro_p_kernel(float *__res
     const unsigned peers = warp_peers(valid, vox);
     const bool grouped = valid && __popc(peers) >= 4;
     if (valid && !grouped) {                                   // stragglers: per-lane REDs
-#pragma unroll
+#pragma unroll 1
       for (int k = 0; k < 8; k++) {
         float m[16];
         moments(k, m);
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(256, 2) accumulate_hydro_p_kernel(float *__res
       const unsigned grp = __shfl_sync(0xffffffffu, peers, leader);
       const int gv = __shfl_sync(0xffffffffu, vox, leader);
       const bool mine = grouped && peers == grp;
-#pragma unroll
+#pragma unroll 1                                               // one node at a time keeps the kernel at 3 CTAs per SM
       for (int k = 0; k < 8; k++) {
         float m[16];
         moments(k, m);
