@@ -6,6 +6,7 @@
 #include "lazy_pages.h"
 
 #include <pthread.h>
+#include <signal.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -166,6 +167,19 @@ static int run() {
   CHECK(vpb_lazy::stats().faults == s0.faults);
   vpb_lazy::detach(r, false, nullptr);
   CHECK(vpb_lazy::active() == 0);
+
+  // --- 8b. somebody installs a SIGSEGV handler after us: the next to_device takes the signal back and chains ------
+  {
+    Arr t = make(12, 128, 0);
+    fill(t.h, t.cap, 3);
+    vpb_lazy::Region *rt = vpb_lazy::attach(t.h, t.cap, t.d);
+    signal(SIGSEGV, SIG_DFL);                                  // e.g. a runtime resetting handlers
+    vpb_lazy::to_device(rt, t.cap, &h2d);
+    device_kernel(t, t.cap);
+    vpb_lazy::device_wrote(rt, t.cap, &d2h);
+    CHECK(same(t.h, t.cap, 3, 1));                             // would crash here without the re-install
+    vpb_lazy::detach(rt, false, nullptr);
+  }
 
   // --- 9. an array with no whole page inside is not tracked -----------------------------------------------------
   {

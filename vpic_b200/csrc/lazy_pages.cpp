@@ -179,6 +179,23 @@ void on_segv(int sig, siginfo_t *si, void *uc) {
   errno = saved_errno;
 }
 
+void install_handler() {
+  struct sigaction sa; memset(&sa, 0, sizeof sa);
+  sa.sa_sigaction = on_segv; sa.sa_flags = SA_SIGINFO | SA_NODEFER;
+  sigemptyset(&sa.sa_mask);
+  struct sigaction prev;
+  if (sigaction(SIGSEGV, &sa, &prev) != 0) fatal("vpic_b200: cannot install the SIGSEGV handler");
+  if (!((prev.sa_flags & SA_SIGINFO) && prev.sa_sigaction == on_segv)) g_old_segv = prev;   // chain to whoever was there
+}
+
+// The host program (an MPI runtime, a crash reporter) may install its own SIGSEGV handler after ours.  Pages are only
+// protected from to_device(), so checking there is enough: take the signal back and chain to the newcomer.
+void ensure_handler() {
+  struct sigaction cur;
+  if (sigaction(SIGSEGV, nullptr, &cur) == 0 && (cur.sa_flags & SA_SIGINFO) && cur.sa_sigaction == on_segv) return;
+  install_handler();
+}
+
 void at_exit() {
   // hand everything back before the process tears down (the host's destructors may walk its arrays)
   Lock lk;
@@ -199,10 +216,7 @@ void init(const Copier &c, size_t chunk_bytes) {
   if (chunk_bytes) g_chunk = chunk_bytes < g_page ? g_page : (chunk_bytes / g_page) * g_page;
   if (pipe2(g_probe, O_NONBLOCK | O_CLOEXEC) != 0) g_probe[0] = g_probe[1] = -1;
   g_mem_fd = open("/proc/self/mem", O_RDWR | O_CLOEXEC);
-  struct sigaction sa; memset(&sa, 0, sizeof sa);
-  sa.sa_sigaction = on_segv; sa.sa_flags = SA_SIGINFO | SA_NODEFER;
-  sigemptyset(&sa.sa_mask);
-  if (sigaction(SIGSEGV, &sa, &g_old_segv) != 0) fatal("vpic_b200: cannot install the SIGSEGV handler");
+  install_handler();
   atexit(at_exit);
   g_installed = true;
 }
@@ -254,6 +268,7 @@ void to_device(Region *r, size_t bytes, uint64_t *h2d_bytes) {
   if (bytes > r->cap) bytes = r->cap;
   if (!bytes) return;
   Lock lk;
+  ensure_handler();
   if (r->ndevice && !still_protected(r)) {
     // remapped under us: every chunk is host-owned again, nothing to copy back
     mprotect(r->lo, (size_t)(r->hi - r->lo), PROT_READ | PROT_WRITE);
