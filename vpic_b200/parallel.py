@@ -82,7 +82,7 @@ class SlabExchange:
             left = torch.tensor([sum(sp.nm for sp in sps)], dtype=torch.int32, device=dev)
             dist.all_reduce(left, group=self.ring.group)
             if int(left.item()) == 0:
-                return
+                return False                      # nobody holds a mover: this round and every later one is a no-op
         packed = [E.boundary_pack(sp, self.face_range, sim.field_array) for sp in sps]
         offs = torch.stack([o for _, o in packed]).cpu()                       # one sync for all species
         n_lo = [int(offs[s, self.f_lo + 1] - offs[s, self.f_lo]) for s in range(len(sps))]
@@ -111,6 +111,7 @@ class SlabExchange:
             E.boundary_inject(sp, sim.accumulator_array, sim.interpolator_array, in_lo, r_lo[s])
             E.boundary_inject(sp, sim.accumulator_array, sim.interpolator_array, in_hi, r_hi[s])
         E.finish_advance_p_all(sps)
+        return True
 
     # ---- fields ---------------------------------------------------------------------------------------------
     def _buffers(self, kind):

@@ -90,12 +90,14 @@ class Simulation:
             main.wait_stream(self._side)
             E.reduce_accumulator_array(aa)
             for _ in range(self.num_comm_round - 1):
-                self.exchange.boundary_p(self)
+                if not self.exchange.boundary_p(self):
+                    break                         # no movers anywhere: the remaining rounds would be empty too
         elif self.exchange is not None:
             E.finish_advance_p_all(self.species_list)
             E.reduce_accumulator_array(aa)
             for _ in range(self.num_comm_round):
-                self.exchange.boundary_p(self)
+                if not self.exchange.boundary_p(self):
+                    break
         else:
             E.finish_advance_p_all(self.species_list)
             E.reduce_accumulator_array(aa)
