@@ -44,6 +44,10 @@ void uncenter_p(vpb_species_t *sp, const vpb_interpolator_array_t *ia);
 double energy_p(const vpb_species_t *sp, const vpb_interpolator_array_t *ia);
 /* src/species_advance/species_advance.h:117-119 */
 void accumulate_rho_p(vpb_field_array_t *fa, const vpb_species_t *sp);
+/* src/boundary/boundary.h:33-38.  Served on the device for a single rank without custom particle-boundary handlers
+ * (movers are then particles that hit an absorbing wall); everything else is forwarded to the reference's own
+ * boundary_p (dlsym RTLD_NEXT).  pbc_list is the reference's particle_bc_t list (opaque here). */
+void boundary_p(void *pbc_list, vpb_species_t *sp_list, vpb_field_array_t *fa, vpb_accumulator_array_t *aa);
 /* hydro moments — src/species_advance/species_advance.h:139-148, src/sf_interface/sf_interface.h:216-240 */
 void accumulate_hydro_p(vpb_hydro_array_t *ha, const vpb_species_t *sp, const vpb_interpolator_array_t *ia);
 void clear_hydro_array(vpb_hydro_array_t *ha);

@@ -662,3 +662,75 @@ def test_boundary_p_absorbing_walls_match_reference(eng, oracle):
         assert rs.c.np == sp.np
         assert np.array_equal(bits(rs.p[:rs.c.np]), bits(sp.particles_host()))
         assert np.abs(got[:, 11] - W.fields[:, 11]).max() <= 2e-5 * np.abs(W.fields[:, 11]).max()
+
+
+_BOUNDARY_SCRIPT = """
+import sys, os, ctypes as C, numpy as np
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, 'tests'))
+import bench, refvpic as R
+from vpic_b200 import lib, grid as G, abi
+mode = sys.argv[1]
+L = lib.load()
+nx, ny, nz, n = 6, 5, 4, 12000
+pbc = {{0: -2, 3: -2, 2: -2}}
+g = G.partition_periodic_box(0,0,0,nx,ny,nz,nx,ny,nz,1,1,1, dt=G.courant_dt(1,1,1,nx,ny,nz,frac=0.98))
+for f, code in pbc.items():
+    g.set_pbc(f, code)
+H = bench.HostWorld(L, g, pinned='register')
+L.vpic_b200_set_lazy_min.argtypes = [C.c_size_t]; L.vpic_b200_set_lazy_min.restype = None
+L.vpic_b200_set_lazy_min(4096)
+L.vpic_b200_set_mode(dict(coherent=0, auto=2)[mode])
+rng = np.random.default_rng(6)
+fields = R.random_fields(rng, g.nv)
+H.fields[:] = fields
+sp = H.new_species('e', -1.0, 1.0, n, n, 20)
+parts = R.random_particles(rng, n, nx, ny, nz, uth=0.5, w=0.7)
+sp.p[:n] = parts.view(np.float32).reshape(-1, 8); sp.c.np = n
+H.load_interpolator()
+L.clear_accumulator_array(C.byref(H.aa))
+L.advance_p(C.byref(sp.c), C.byref(H.aa), C.byref(H.ia))
+L.reduce_accumulator_array(C.byref(H.aa))
+nm = int(sp.c.nm)
+L.boundary_p.argtypes = [C.c_void_p] * 4; L.boundary_p.restype = None
+L.boundary_p(None, C.byref(sp.c), C.byref(H.fa), C.byref(H.aa))
+# the unmodified reference on the same inputs
+ref = R.load_ref('scalar', tpp=1)
+W = R.RefWorld(ref, nx, ny, nz, pbc=pbc)
+W.g.contents.dt = g.dt
+W.fields[:] = fields
+ref.load_interpolator_array(W.ia, W.fa)
+rs = W.new_species('e_bp', -1.0, 1.0, n, n)
+rs.set_particles(parts)
+ref.clear_accumulator_array(W.aa); ref.advance_p(rs.sp, W.aa, W.ia); ref.reduce_accumulator_array(W.aa)
+ref.boundary_p.argtypes = [C.c_void_p] * 4
+ref.boundary_p(None, rs.sp, W.fa, W.aa)
+got = sp.p[:sp.c.np].copy(); want = rs.p[:rs.c.np]
+rhob, rhob_ref = H.fields[:, 11].copy(), W.fields[:, 11].copy()
+others = bool(np.array_equal(np.delete(H.fields, [11, 12, 13, 14], axis=1).view(np.uint32),
+                             np.delete(W.fields, [11, 12, 13, 14], axis=1).view(np.uint32)))
+import json
+print('RESULT ' + json.dumps(dict(nm=nm, np=int(sp.c.np), np_ref=int(rs.c.np), nm_after=int(sp.c.nm),
+      particles=bool(got.nbytes == want.nbytes and np.array_equal(got.view(np.uint8).ravel(), want.view(np.uint8).ravel())),
+      rhob=float(np.abs(rhob - rhob_ref).max() / np.abs(rhob_ref).max()), others=others)))
+L.vpic_b200_set_mode(0)
+"""
+
+
+@pytest.mark.parametrize("mode", ["coherent", "auto"])
+def test_dropin_boundary_p_absorbing_walls(eng, mode):
+    """boundary_p(particle_bc_t*, species_t*, field_array_t*, accumulator_array_t*) on HOST structs, one rank, three
+    absorbing walls: the particle array after the device back-fill must be bit-identical to the one the unmodified
+    reference's boundary_p leaves, and the absorbed charge in rhob must agree to summation-order tolerance."""
+    import subprocess, sys, os, json
+    if not R.have_ref("scalar"):
+        pytest.skip("oracle/_ref not present")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, VPIC_B200_LAZY_CHUNK="8192")
+    r = subprocess.run([sys.executable, "-c", _BOUNDARY_SCRIPT.format(root=root), mode],
+                       capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("RESULT ")][0][7:])
+    assert res["nm"] > 50 and res["nm_after"] == 0 and res["np"] == res["np_ref"] == 12000 - res["nm"], res
+    assert res["particles"], "particle array differs from the reference's after boundary_p"
+    assert res["others"], "boundary_p touched field slots other than rhob"
+    assert res["rhob"] < 2e-5, res["rhob"]

@@ -17,6 +17,7 @@
 // Symbols of the reference host program, present when this library is linked into (or preloaded under) it.
 extern "C" {
 extern int _world_rank __attribute__((weak));                                  // src/util/mp/DMPPolicy.h:32
+extern int _world_size __attribute__((weak));                                  // src/util/mp/DMPPolicy.h:33
 void mp_allsum_d(double *local, double *global, int n) __attribute__((weak));  // src/util/mp/mp.h
 }
 
@@ -41,13 +42,13 @@ int rank_for_log() { return &_world_rank ? _world_rank : 0; }
 // VPIC_B200_TRACE=1: at exit, one line on stderr with how often each entry point ran on the device (and how often a
 // field kernel fell through to the reference's own), so a preloaded run can be checked for what it actually used.
 enum { C_ADVANCE_P, C_SORT_P, C_CENTER_P, C_ENERGY_P, C_RHO_P, C_LOAD_INTERP, C_CLEAR_ACC, C_UNLOAD_ACC, C_ADVANCE_B,
-       C_ADVANCE_E, C_CLEAR_JF, C_SYNC_JF, C_ENERGY_F, C_DIV_CLEAN, C_HYDRO, C_FIELD_FALLBACK, C_COUNT };
+       C_ADVANCE_E, C_CLEAR_JF, C_SYNC_JF, C_ENERGY_F, C_DIV_CLEAN, C_HYDRO, C_BOUNDARY_P, C_FIELD_FALLBACK, C_COUNT };
 uint64_t g_calls[C_COUNT];
 void trace_report() {
   static const char *names[C_COUNT] = {"advance_p", "sort_p", "center_p/uncenter_p", "energy_p", "accumulate_rho_p",
       "load_interpolator_array", "clear_accumulator_array", "unload_accumulator_array", "advance_b", "advance_e",
       "clear_jf", "synchronize_jf", "energy_f", "divergence_cleaning_kernels", "hydro_kernels",
-      "field_kernel_fallback_to_reference"};
+      "boundary_p_species_on_device", "field_kernel_fallback_to_reference"};
   fprintf(stderr, "vpic_b200 trace[%d]:", rank_for_log());
   for (int i = 0; i < C_COUNT; i++) fprintf(stderr, " %s=%llu", names[i], (unsigned long long)g_calls[i]);
   const vpb_lazy::Stats st = vpb_lazy::stats();
@@ -412,6 +413,72 @@ void advance_p(vpb_species_t *sp, vpb_accumulator_array_t *aa, const vpb_interpo
   if (!coherent) dev_written(sp->p, pbytes);
   dev_written(sp->pm, (size_t)nm * sizeof(vpb_particle_mover_t));
   dev_written(aa->a, (size_t)aa->stride * sizeof(vpb_accumulator_t));
+  finish_entry();
+}
+
+// ---- boundary_p: src/boundary/boundary.h:33-38, boundary_p.cc:240-371 ---------------------------------------------
+// On a single rank with no custom particle-boundary handlers the only particles that reach boundary_p are those that
+// hit an absorbing wall: the device removes them (charge into rhob, holes back-filled in the reference's sequential
+// order — bit-identical, tests/test_gpu_parity.py::test_boundary_p_absorbing_walls_match_reference) so the host never
+// walks sp->pm.  Anything else — several ranks (the exchange is the host's MPI), custom handlers (host function
+// pointers) — is the reference's own boundary_p, reached through dlsym(RTLD_NEXT).
+void boundary_p(void *pbc_list, vpb_species_t *sp_list, vpb_field_array_t *fa, vpb_accumulator_array_t *aa) {
+  if (!sp_list) return;                                          // boundary_p.cc:252
+  if (!fa || !aa || sp_list->g != aa->g || fa->g != aa->g) DROPIN_ERROR("Bad args");
+  const vpb_grid_t *g = sp_list->g;
+  bool any = false;
+  for (const vpb_species_t *sp = sp_list; sp; sp = sp->next) any |= sp->nm > 0;
+  const int world = &_world_size ? _world_size : 1;
+  static int enabled = -1;
+  if (enabled < 0) { const char *e = getenv("VPIC_B200_BOUNDARY_P"); enabled = !(e && e[0] == '0'); }
+  bool local_only = world == 1 && !pbc_list && enabled;
+  for (int i = 0; i < 27 && local_only; i++) local_only = g->bc[i] < 0 || g->bc[i] == g->bc[13];
+  if (!local_only) {
+    static auto ref = (void (*)(void *, vpb_species_t *, vpb_field_array_t *, vpb_accumulator_array_t *))dlsym(RTLD_NEXT, "boundary_p");
+    if (!ref) DROPIN_ERROR("boundary_p: several ranks or custom particle boundary handlers need the reference's own boundary_p, which is not linked in");
+    ref(pbc_list, sp_list, fa, aa);
+    return;
+  }
+  if (!any) return;                                              // nothing left the domain: the reference's walk is empty too
+  const size_t nv = (size_t)g->nv;
+  Mirror &mn = mirror(g->neighbor, 6 * nv * sizeof(int64_t), false);
+  if (!mn.device_valid) { DEV(vpb_memcpy_h2d(mn.d, g->neighbor, 6 * nv * sizeof(int64_t), nullptr)); g_h2d += 6 * nv * sizeof(int64_t);
+                          mn.device_valid = true; mn.live_bytes = 6 * nv * sizeof(int64_t); }
+  const size_t fbytes = nv * sizeof(vpb_field_t);
+  for (vpb_species_t *sp = sp_list; sp; sp = sp->next) {
+    if (sp->nm <= 0) continue;
+    count_call(C_BOUNDARY_P);
+    const int nm = sp->nm;
+    vpb_boundary_args_t b;
+    memset(&b, 0, sizeof b);
+    b.p = dev_in(sp->p, (size_t)sp->np * sizeof(vpb_particle_t), (size_t)sp->max_np * sizeof(vpb_particle_t));
+    b.np = sp->np;
+    b.pm = dev_in(sp->pm, (size_t)nm * sizeof(vpb_particle_mover_t), (size_t)sp->max_nm * sizeof(vpb_particle_mover_t));
+    b.nm = nm;
+    b.neighbor = (const int64_t *)mn.d;
+    b.rangel = g->rangel; b.rangeh = g->rangeh; b.rangem = g->range[world];
+    for (int f = 0; f < 6; f++) b.face_range[f] = -1;
+    b.sp_id = sp->id;
+    b.inj = scratch(6, (size_t)nm * sizeof(vpb_particle_injector_t));
+    b.class_offsets = (int32_t *)scratch(7, 9 * sizeof(int32_t));
+    b.scratch_bytes = vpb_boundary_scratch_bytes(nm);
+    b.scratch = scratch(8, b.scratch_bytes);
+    b.fields = (float *)dev_in(fa->f, fbytes);
+    b.q_r8V = sp->q * g->r8V;
+    b.nx = g->nx; b.ny = g->ny; b.nz = g->nz;
+    DEV(vpb_boundary_p_pack(&b, nullptr));
+    int32_t offs[9];
+    DEV(vpb_memcpy_d2h(offs, b.class_offsets, sizeof offs, nullptr));
+    DEV(vpb_stream_sync(nullptr));
+    g_d2h += sizeof offs;
+    if (offs[7] - offs[6] != nm)                                 // every mover must have been absorbed (class 6)
+      DROPIN_ERROR("Species = %s: %d of %d movers left through a face that is neither absorbing nor local; "
+                   "Unknown boundary interaction", sp->name, nm - (offs[7] - offs[6]), nm);
+    sp->np -= nm;
+    sp->nm = 0;
+    dev_written(sp->p, (size_t)sp->np * sizeof(vpb_particle_t));
+    dev_written(fa->f, fbytes);
+  }
   finish_entry();
 }
 

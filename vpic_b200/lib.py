@@ -121,7 +121,7 @@ DROPIN_SYMBOLS = ["advance_p", "sort_p", "load_interpolator_array", "clear_accum
                   "clear_rhof", "synchronize_rho", "vacuum_compute_div_e_err", "compute_rms_div_e_err", "vacuum_clean_div_e",
                   "compute_div_b_err", "compute_rms_div_b_err", "clean_div_b", "synchronize_tang_e_norm_b",
                   "vacuum_compute_rhob", "vacuum_compute_curl_b", "vpic_b200_compute_rhob", "vpic_b200_compute_curl_b",
-                  "accumulate_hydro_p", "clear_hydro_array", "reduce_hydro_array", "synchronize_hydro_array",
+                  "boundary_p", "accumulate_hydro_p", "clear_hydro_array", "reduce_hydro_array", "synchronize_hydro_array",
                   "vpic_b200_clear_rhof", "vpic_b200_synchronize_rho", "vpic_b200_compute_div_e_err",
                   "vpic_b200_compute_rms_div_e_err", "vpic_b200_clean_div_e", "vpic_b200_compute_div_b_err",
                   "vpic_b200_compute_rms_div_b_err", "vpic_b200_clean_div_b", "vpic_b200_synchronize_tang_e_norm_b",
