@@ -191,7 +191,68 @@ static int run() {
   return 0;
 }
 
+// Randomised model check: a long random sequence of entry-point calls with random extents, host reads, host writes
+// and kernel-side accesses, each compared with a byte-exact model of what the program must observe.
+static uint64_t rng_state = 1;
+static uint32_t rnd() { rng_state = rng_state * 6364136223846793005ull + 1442695040888963407ull; return (uint32_t)(rng_state >> 33); }
+
+static int stress(int iterations, uint64_t seed) {
+  rng_state = seed * 2654435761u + 17;
+  vpb_lazy::Copier cp = {fake_h2d, fake_d2h, fake_fatal, nullptr, nullptr};
+  vpb_lazy::init(cp, kChunk);
+  const size_t pages = 64 + rnd() % 64;
+  Arr a = make(pages, 128 * (1 + rnd() % 20), rnd() % 3000);
+  std::vector<char> truth(a.cap);
+  for (size_t i = 0; i < a.cap; i++) { truth[i] = (char)(rnd() & 0x7f); a.h[i] = truth[i]; }
+  vpb_lazy::Region *r = vpb_lazy::attach(a.h, a.cap, a.d);
+  CHECK(r != nullptr);
+  uint64_t h2d = 0, d2h = 0;
+  for (int it = 0; it < iterations; it++) {
+    const uint32_t op = rnd() % 100;
+    size_t off = rnd() % a.cap, len = 1 + rnd() % (op % 7 == 0 ? a.cap : 3 * kPage);
+    if (off + len > a.cap) len = a.cap - off;
+    if (op < 30) {                                            // an entry point: device reads and rewrites [0, ext)
+      const size_t ext = (op % 3 == 0) ? a.cap : 1 + rnd() % a.cap;
+      vpb_lazy::to_device(r, ext, &h2d);
+      CHECK(memcmp(a.d, truth.data(), ext) == 0);            // the device sees exactly what the program last had
+      for (size_t i = 0; i < ext; i++) { a.d[i] = (char)(a.d[i] + 1); truth[i] = (char)(truth[i] + 1); }
+      vpb_lazy::device_wrote(r, ext, &d2h);
+    } else if (op < 40) {                                     // an entry point that only reads (e.g. interpolators in advance_p)
+      const size_t ext = 1 + rnd() % a.cap;
+      vpb_lazy::to_device(r, ext, &h2d);
+      CHECK(memcmp(a.d, truth.data(), ext) == 0);
+    } else if (op < 65) {                                     // host reads a range
+      CHECK(memcmp(a.h + off, truth.data() + off, len) == 0);
+    } else if (op < 85) {                                     // host writes a range
+      for (size_t i = 0; i < len; i++) { const char v = (char)(rnd() & 0x7f); a.h[off + i] = v; truth[off + i] = v; }
+    } else if (op < 92) {                                     // kernel-side read (fwrite): host_access first, then a syscall
+      vpb_lazy::host_access(a.h + off, len);
+      int fd[2]; CHECK(pipe(fd) == 0);
+      const size_t n = len < 4096 ? len : 4096;
+      std::vector<char> got(n);
+      CHECK(write(fd[1], a.h + off, n) == (ssize_t)n && read(fd[0], got.data(), n) == (ssize_t)n);
+      CHECK(memcmp(got.data(), truth.data() + off, n) == 0);
+      close(fd[0]); close(fd[1]);
+    } else if (op < 96) {                                     // explicit sync of a range (vpic_b200_sync_to_host)
+      vpb_lazy::to_host(r, off, len, &d2h);
+      CHECK(memcmp(a.h + off, truth.data() + off, len) == 0);
+    } else {                                                  // two host threads read the whole array at once
+      long expect = 0;
+      for (size_t i = 0; i < a.cap; i++) expect += truth[i];
+      pthread_t th[2]; Reader rd[2];
+      for (int t = 0; t < 2; t++) { rd[t] = {a.h, a.cap, 0}; pthread_create(&th[t], nullptr, reader_main, &rd[t]); }
+      for (int t = 0; t < 2; t++) { pthread_join(th[t], nullptr); CHECK(rd[t].sum == expect); }
+    }
+  }
+  vpb_lazy::detach(r, true, &d2h);
+  CHECK(memcmp(a.h, truth.data(), a.cap) == 0);               // after detach the host holds everything
+  printf("lazy_pages_test: stress ok (%d operations, seed %llu, %llu faults, %.1f MB up, %.1f MB down)\n", iterations,
+         (unsigned long long)seed, (unsigned long long)vpb_lazy::stats().faults, h2d / 1e6, (d2h + vpb_lazy::stats().fault_bytes) / 1e6);
+  return 0;
+}
+
 int main(int argc, char **argv) {
+  if (argc > 3 && !strcmp(argv[1], "--stress")) return stress(atoi(argv[2]), strtoull(argv[3], nullptr, 10)) ? 1 : 0;
   const int rc = run();
   if (rc) return 1;
   if (argc > 1 && !strcmp(argv[1], "--crash")) {             // a genuine wild access must still kill the process

@@ -93,3 +93,7 @@ def test_lazy_pages_state_machine():
     assert r.returncode == 0 and "lazy_pages_test: ok" in r.stdout, r.stdout + r.stderr
     r = subprocess.run([exe, "--crash"], capture_output=True, text=True, timeout=120)
     assert r.returncode == -signal.SIGSEGV, (r.returncode, r.stdout, r.stderr)
+    # randomised model check: entry points with random extents, host reads / writes, syscalls, concurrent readers
+    for seed in (11, 12, 13):
+        r = subprocess.run([exe, "--stress", "4000", str(seed)], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 and "stress ok" in r.stdout, r.stdout + r.stderr
