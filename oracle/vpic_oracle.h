@@ -8,8 +8,11 @@
  * PARITY PINNED: tests/test_oracle_vs_ref.py checks every function here
  * bit-for-bit against the UNMODIFIED reference compiled into
  * oracle/_ref/libvpic_ref_scalar.so (recipe: oracle/Makefile) on seeded
- * inputs, and tests/test_oracle_kat.py re-runs the reference's own
- * known-answer decks (accel, cyclo, interpe, inbndj, outbndj) through it.
+ * inputs (push, move_p, sort, glue, field advance with every wall kind and a
+ * dielectric material, divergence cleaning, hydro moments); the reference
+ * build itself is pinned by its own known-answer decks and golden energy
+ * tests, which pass when built with oracle/Makefile (tests/test_dropin_decks.py
+ * runs them on the CPU path before the GPU path).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may
  * load this library.  The product (vpic_b200/) never does.
