@@ -1,6 +1,7 @@
 """Pins the C restatement (oracle/liboracle.so) bit-for-bit against the UNMODIFIED reference compiled from
 /root/reference (oracle/_ref/libvpic_ref_scalar.so).  CPU only."""
 import ctypes as C
+import os
 import numpy as np
 import pytest
 
@@ -245,3 +246,30 @@ def test_hydro_moments_bit_exact(ref_scalar, oracle, dims, fbc):
     oracle.vpo_synchronize_hydro(h2.ctypes.data, C.byref(a))
     assert np.abs(h2[:, :14]).max() > 0
     assert np.array_equal(bits(h2[:, :14]), bits(h_ref[:W.nv, :14]))
+
+
+@pytest.mark.parametrize("deck", ["accel", "cyclo", "inbndj", "interpe", "outbndj"])
+def test_reference_build_passes_its_own_kat_decks(deck):
+    """The reference as built by oracle/Makefile (MPI shim, plain g++) is only a valid yardstick if it still passes
+    its own known-answer decks (test/integrated/legacy) — on the CPU, nothing of this repo on the path."""
+    import subprocess, tempfile
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", f"{deck}.scalar")
+    if not os.path.exists(path):
+        pytest.skip("deck binaries not built (needs /root/reference at build time)")
+    with tempfile.TemporaryDirectory() as d:
+        r = subprocess.run([path, "1", "1"], cwd=d, capture_output=True, text=True, timeout=600)
+    out = r.stdout + r.stderr
+    assert r.returncode == 0 and "pass" in out and "FAIL" not in out, out[-1500:]
+
+
+def test_reference_build_passes_its_own_golden_energy_test():
+    """test/unit/energy_comparison/3d_test against energies_gold.3d_test, reference alone on the CPU."""
+    import shutil, subprocess, tempfile
+    ref = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref")
+    exe, gold = os.path.join(ref, "3d_test.scalar"), os.path.join(ref, "energies_gold.3d_test")
+    if not (os.path.exists(exe) and os.path.exists(gold)):
+        pytest.skip("golden test binary not built (needs /root/reference at build time)")
+    with tempfile.TemporaryDirectory() as d:
+        shutil.copy(gold, d)
+        r = subprocess.run([exe, "--tpp", "1"], cwd=d, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "All tests passed" in r.stdout + r.stderr, (r.stdout + r.stderr)[-1500:]
