@@ -18,6 +18,13 @@
 //     fwrite/fread, the only I/O calls the reference makes on these arrays, and exports vpic_b200_host_access()
 //     for anything else (MPI on device-owned memory).
 //
+// The handler calls mprotect (async-signal-safe) and the d2h callback (a CUDA copy, which is not).  That is sound here
+// because the signal is synchronous: it is raised by the faulting load or store of host code that, by construction,
+// is never inside the CUDA runtime, malloc or this tracker (none of them touches the protected interior pages, and
+// the tracker's own critical sections are recognised by thread id and passed on to the previous handler), so no lock
+// the callback needs can be held by the interrupted code.  Faults from several host threads are serialised by a spin
+// lock; a fault on an address no tracked array owns goes to the handler that was installed before (or the default).
+//
 // Host-only code with the copies behind function pointers, so the state machine is testable without a GPU
 // (tests/lazy_pages_harness.cpp).
 #pragma once
