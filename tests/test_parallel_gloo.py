@@ -1,6 +1,9 @@
 """N>1 host-side routing (vpic_b200/parallel.py NeighbourRing) over gloo on CPU, world_size 2 and 3.
 What leaves a rank through its low face must arrive through the low neighbour's high face, also when both
-neighbours are the same rank (world_size == 2), and empty messages must be skipped consistently on both sides."""
+neighbours are the same rank (world_size == 2), and empty messages must be skipped consistently on both sides.
+SlabExchange.boundary_p is run the same way with the device kernels replaced by CPU stand-ins: per-species counts
+and payloads, low-face-first injection order, and the rounds stopping after the first one in which nobody holds a
+mover."""
 import os
 import socket
 import sys
@@ -70,3 +73,75 @@ def test_world_size_one_is_a_local_copy():
     in_lo, in_hi = torch.zeros(4), torch.zeros(4)
     ring.sendrecv(a, b, in_lo, in_hi)
     assert torch.equal(in_hi, a) and torch.equal(in_lo, b)
+
+
+def _migration_worker(rank, world, port, q):
+    """SlabExchange.boundary_p with the device kernels replaced by CPU stand-ins: what is routed where, in which
+    order it is injected, and when the rounds stop."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from types import SimpleNamespace as NS
+        from vpic_b200 import engine as E, parallel
+        cpu = torch.device("cpu")
+        nv = 100
+        grid = NS(range=[r * nv for r in range(world + 1)])
+        dg = NS(rank=rank, world_size=world, g=grid, nx=4, ny=4, nz=4, device=cpu)
+        ex = parallel.SlabExchange(dg, axis=1)
+
+        def species(sid, n_lo, n_hi):
+            # a mover record is 12 floats; tag it with (source rank, species, face, running index)
+            rows = [[float(rank), float(sid), float(ex.f_lo), float(k)] + [0.0] * 8 for k in range(n_lo)] + \
+                   [[float(rank), float(sid), float(ex.f_hi), float(k)] + [0.0] * 8 for k in range(n_hi)]
+            return NS(name=f"s{sid}", nm=n_lo + n_hi, np=1000, max_np=10 ** 6, out=(n_lo, n_hi), rows=rows, got=[],
+                      counters=torch.zeros(4, dtype=torch.int32))
+
+        def fake_pack(sp, face_range, fa=None):
+            assert face_range[ex.f_lo] == grid.range[ex.ring.lo] and face_range[ex.f_hi] == grid.range[ex.ring.hi]
+            n_lo, n_hi = sp.out
+            offs = torch.zeros(9, dtype=torch.int32)
+            for c in range(9):                                  # classes ascending: faces 0..5, absorbed, no handler
+                offs[c] = (n_lo if c > ex.f_lo else 0) + (n_hi if c > ex.f_hi else 0)
+            inj = torch.tensor(sp.rows, dtype=torch.float32).reshape(-1, 12) if sp.rows else None
+            sp.np -= sp.nm; sp.nm = 0; sp.out = (0, 0); sp.rows = []
+            return inj, offs
+
+        def fake_inject(sp, aa, ia, inj, n):
+            assert inj.shape[0] == n
+            sp.got += [tuple(int(x) for x in row[:4]) for row in inj.tolist()]
+            sp.np += n
+
+        E.boundary_pack, E.boundary_inject, E.finish_advance_p_all = fake_pack, fake_inject, (lambda sps: None)
+        sps = [species(0, 2 + rank, 1), species(1, 0, 3 if rank % 2 == 0 else 0)]
+        sim = NS(species_list=sps, field_array=None, accumulator_array=None, interpolator_array=None)
+        first = ex.boundary_p(sim)                              # somebody holds movers: a full exchange
+        second = ex.boundary_p(sim)                             # nobody does: one all-reduce, no exchange
+        ok = first is True and second is False
+        lo, hi = ex.ring.lo, ex.ring.hi
+        for sid, sp in enumerate(sps):
+            def sent(src, face):                                # what rank `src` sent out of `face` for this species
+                n_lo, n_hi = (2 + src, 1) if sid == 0 else (0, 3 if src % 2 == 0 else 0)
+                return [(src, sid, face, k) for k in range(n_lo if face == ex.f_lo else n_hi)]
+            # injection order of the reference: low face first.  Through my low face arrive the low neighbour's
+            # high-face movers, through my high face the high neighbour's low-face movers.
+            ok &= sp.got == sent(lo, ex.f_hi) + sent(hi, ex.f_lo)
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_slab_migration_routing_and_round_termination(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_migration_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(r for r, _ in res) == list(range(world))
+    assert all(ok for _, ok in res), res
