@@ -97,3 +97,58 @@ def test_lazy_pages_state_machine():
     for seed in (11, 12, 13):
         r = subprocess.run([exe, "--stress", "4000", str(seed)], capture_output=True, text=True, timeout=300)
         assert r.returncode == 0 and "stress ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_simulation_step_follows_advance_cc_order(monkeypatch):
+    """vpic_b200/simulation.py must call the operators in the order of vpic_simulation::advance
+    (src/vpic/advance.cc:25-185), including the divergence-cleaning block at its intervals.  The operators are replaced
+    by recorders, so this runs without a GPU."""
+    from types import SimpleNamespace as NS
+    import torch
+    from vpic_b200 import engine as E, simulation as S
+    log = []
+    g = G.partition_periodic_box(0, 0, 0, 4, 4, 4, 4, 4, 4, 1, 1, 1, dt=0.1)
+    dg = E.DeviceGrid(g, device="cpu")
+
+    class FakeFields:
+        def __init__(self, *a, **k):
+            self._en = torch.zeros(6, dtype=torch.float64)
+        def __getattr__(self, name):
+            if name.startswith("_"):
+                raise AttributeError(name)
+            def call(*a, **k):
+                log.append(name if not a else f"{name}({a[0]})")
+                return [1.0, 1.0] if name == "rms_terms" else (0.5 if name == "rms_finish" else None)
+            return call
+
+    monkeypatch.setattr(E, "FieldArray", FakeFields)
+    for fn in ("sort_p", "clear_accumulator_array", "advance_p", "reduce_accumulator_array", "unload_accumulator_array",
+               "load_interpolator_array", "accumulate_rho_p", "finish_advance_p_all"):
+        monkeypatch.setattr(E, fn, (lambda name: (lambda *a, **k: log.append(name)))(fn))
+    sim = S.Simulation(dg)
+    for name in ("e", "i"):
+        sim.species_list.append(NS(name=name, sort_interval=2, nm=0, np=10))
+    sim.clean_div_e_interval, sim.clean_div_b_interval, sim.sync_shared_interval = 2, 3, 4
+    sim.num_div_e_round = sim.num_div_b_round = 2
+
+    def step():
+        log.clear()
+        sim.advance()
+        return list(log)
+
+    push = ["clear_accumulator_array", "advance_p", "advance_p", "finish_advance_p_all", "reduce_accumulator_array"]
+    fields = ["clear_jf", "unload_accumulator_array", "synchronize_jf", "advance_b(0.5)", "advance_e(1.0)", "advance_b(0.5)"]
+    div_e = ["clear_rhof", "accumulate_rho_p", "accumulate_rho_p", "synchronize_rho",
+             "compute_div_e_err", "rms_terms(vpb_compute_rms_div_e_err)", "rms_finish([1.0, 1.0])", "clean_div_e",
+             "compute_div_e_err", "rms_terms(vpb_compute_rms_div_e_err)", "rms_finish([1.0, 1.0])", "clean_div_e"]
+    div_b = ["compute_div_b_err", "rms_terms(vpb_compute_rms_div_b_err)", "rms_finish([1.0, 1.0])", "clean_div_b",
+             "compute_div_b_err", "rms_terms(vpb_compute_rms_div_b_err)", "rms_finish([1.0, 1.0])", "clean_div_b"]
+    sync = ["synchronize_tang_e_norm_b"]
+    # step 0: both species sort, every maintenance interval divides 0
+    assert step() == ["sort_p", "sort_p"] + push + fields + div_e + div_b + sync + ["load_interpolator_array"]
+    # step 1: nothing periodic
+    assert step() == push + fields + ["load_interpolator_array"]
+    # step 2: sort and div-E clean; step 3: div-B clean only
+    assert step() == ["sort_p", "sort_p"] + push + fields + div_e + ["load_interpolator_array"]
+    assert step() == push + fields + div_b + ["load_interpolator_array"]
+    assert sim.step == 4 and [w for _, w, _ in sim.cleaning_log][:3] == ["div_e initial", "div_e cleaned", "div_b initial"]
