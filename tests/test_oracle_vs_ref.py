@@ -273,3 +273,24 @@ def test_reference_build_passes_its_own_golden_energy_test():
         shutil.copy(gold, d)
         r = subprocess.run([exe, "--tpp", "1"], cwd=d, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "All tests passed" in r.stdout + r.stderr, (r.stdout + r.stderr)[-1500:]
+
+
+def _grid_heating(preload_env=None, timeout=1800):
+    """Run test/unit/grid_heating (27 000 steps of a hot 2-D electron plasma) and the reference authors' checker."""
+    import subprocess, sys, tempfile
+    ref = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref")
+    exe, chk = os.path.join(ref, "gridHeatingTestElec.scalar"), os.path.join(ref, "grid_heating_check.py")
+    if not (os.path.exists(exe) and os.path.exists(chk)):
+        pytest.skip("grid heating test not built (needs /root/reference at build time)")
+    env = dict(os.environ, **(preload_env or {}))
+    with tempfile.TemporaryDirectory() as d:
+        r = subprocess.run([exe, "--tpp", "1"], cwd=d, env=env, capture_output=True, text=True, timeout=timeout)
+        assert r.returncode == 0 and "1 passed" in r.stdout + r.stderr, (r.stdout + r.stderr)[-1500:]
+        c = subprocess.run([sys.executable, chk, d], capture_output=True, text=True, timeout=300)
+    return r.stdout + r.stderr, c.stdout + c.stderr
+
+
+def test_reference_build_passes_its_own_grid_heating_test():
+    """The heating rate of the reference as built here lies within the 5 standard deviations its authors allow."""
+    _, verdict = _grid_heating()
+    assert "Electron heating rate test PASS" in verdict, verdict[-1500:]
