@@ -11,6 +11,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <sys/mman.h>
+#include <time.h>
 #include <unistd.h>
 #include <vector>
 
@@ -251,7 +252,32 @@ static int stress(int iterations, uint64_t seed) {
   return 0;
 }
 
+// Throughput of the staged fetch path (device -> staging -> /proc/self/mem -> protected pages), the route pageable
+// host arrays take; the copies are memcpy here, so this bounds the host-side overhead of that route.
+static int bandwidth(size_t mb) {
+  vpb_lazy::Copier cp = {fake_h2d, fake_d2h, fake_fatal, nullptr, nullptr};
+  vpb_lazy::init(cp, 2u << 20);
+  const size_t pages = mb * 256;
+  Arr a = make(pages, 128, 0);
+  memset(a.h, 1, a.cap);
+  vpb_lazy::Region *r = vpb_lazy::attach(a.h, a.cap, a.d);
+  uint64_t h2d = 0, d2h = 0;
+  vpb_lazy::to_device(r, a.cap, &h2d);
+  struct timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  long s = 0;
+  for (size_t i = 0; i < a.cap; i += 4096) s += a.h[i];       // one touch per page: faults drive the fetches
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  const double sec = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+  printf("lazy_pages_test: fetched %.0f MB in %llu faults, %.2f GB/s through the staged path (checksum %ld)\n",
+         vpb_lazy::stats().fault_bytes / 1e6, (unsigned long long)vpb_lazy::stats().faults,
+         vpb_lazy::stats().fault_bytes / sec / 1e9, s);
+  vpb_lazy::detach(r, false, &d2h);
+  return 0;
+}
+
 int main(int argc, char **argv) {
+  if (argc > 2 && !strcmp(argv[1], "--bandwidth")) return bandwidth((size_t)atoi(argv[2]));
   if (argc > 3 && !strcmp(argv[1], "--stress")) return stress(atoi(argv[2]), strtoull(argv[3], nullptr, 10)) ? 1 : 0;
   const int rc = run();
   if (rc) return 1;

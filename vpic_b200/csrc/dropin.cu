@@ -72,7 +72,8 @@ struct Mirror {
 std::unordered_map<const void *, Mirror> g_mirrors;
 std::unordered_map<int, Mirror> g_scratch;
 int g_mode = -1;
-bool g_pin = false;
+bool g_pin = false;              // VPIC_B200_PIN=1: page-lock every host array of 1 MB and more
+bool g_pin_tracked = true;       // unless VPIC_B200_PIN=0: page-lock the arrays auto mode tracks (fast fetches, see below)
 uint64_t g_h2d = 0, g_d2h = 0;
 int *g_counters = nullptr;
 // VPB_MODE_AUTO: arrays of at least this many bytes are tracked by page protection, smaller ones are copied on every
@@ -119,6 +120,7 @@ int mode() {
     if (g_mode < 0) DROPIN_ERROR("VPIC_B200_MODE=%s: expected auto, coherent or resident", e);
     const char *p = getenv("VPIC_B200_PIN");
     g_pin = p && atoi(p) != 0;
+    g_pin_tracked = !(p && atoi(p) == 0);
     if (const char *m = getenv("VPIC_B200_LAZY_MIN")) g_lazy_min = (size_t)atoll(m);
   }
   return g_mode;
@@ -168,7 +170,11 @@ Mirror &mirror(const void *h, size_t bytes, bool may_track = true) {
     lazy_setup();
     m.lazy = vpb_lazy::attach(const_cast<void *>(h), m.cap, m.d);
   }
-  if (g_pin && bytes >= (1u << 20) && (!m.pinned || m.pinned_bytes < bytes)) {
+  // Page-locked arrays upload at PCIe rate and, in auto mode, are fetched by DMA straight into their still-protected
+  // pages; pageable ones go through the staged /proc/self/mem route (~1.6 GB/s, tests/lazy_pages_harness.cpp
+  // --bandwidth).  A failed registration (locked-memory limit, already registered by the host) just leaves the array
+  // pageable.
+  if ((g_pin || (g_pin_tracked && m.lazy)) && bytes >= (1u << 20) && (!m.pinned || m.pinned_bytes < bytes)) {
     if (m.pinned) cudaHostUnregister(const_cast<void *>(h));
     m.pinned = cudaHostRegister(const_cast<void *>(h), bytes, cudaHostRegisterDefault) == cudaSuccess;
     m.pinned_bytes = m.pinned ? bytes : 0;
