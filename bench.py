@@ -211,17 +211,7 @@ def run_ours(args):
         out = {"metric": "particle pushes/sec (advance_p+deposit)", "value": value, "unit": "pushes/s",
                "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
                "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-               "config": {"workload": (f"uniform thermal e-/ion plasma, {args.grid}^3 cells " if args.workload == "uniform" else
-                                       f"Harris current sheet (sech^2 sheet + background, B_x = b0 tanh(z/L), drifting e-/ion, "
-                                       f"conducting reflecting z walls), {args.grid}^3 cells ")
-                                      + ("per GPU" if args.scaling == "weak" else "in total")
-                                      + f", {args.ppc} ppc/species" + (" on average" if args.workload == "harris" else "")
-                                      + f", periodic{' in x and y' if args.workload == 'harris' else ''}, "
-                                      f"sort_p every {args.sort_interval} steps"
-                                      + (" (BASELINE.json configs[1])" if (args.grid, args.ppc, args.workload) == (128, 64, "uniform") else ""),
-                          "particles_per_gpu": np_total_local, "decomposition": f"1x{world}x1 slabs",
-                          "l2": f"particle arrays ({np_total_local * 32 / 1e9:.1f} GB per GPU) exceed the 126 MB L2; no flush needed",
-                          "deposit_variant": args.variant},
+               "config": workload_config(args, world, np_total_local), "deposit_variant": args.variant,
                "roofline": roofline, "gpu_launches": int(launches), "clocks": clocks}
     if args.e2e and world == 1:
         e2e = run_e2e(args, device)
@@ -458,25 +448,74 @@ class HostWorld:
 
 
 # ------------------------------------------------------------------------------------------------------------------
-def pick_ref_variant():
-    """Strongest reference build the host CPU can run: V8 AVX2+FMA if the CPU has it, else V4 SSE, else scalar."""
+def ref_variants():
+    """Reference builds this host CPU can run, strongest instruction set first: V16 AVX-512 (CMakeLists.txt:79), V8
+    AVX2+FMA, V4 SSE, scalar.  Which one is FASTEST on this host is measured, not assumed (pick_ref_variant)."""
     flags = ""
     try:
         flags = open("/proc/cpuinfo").read()
     except Exception:
         pass
-    order = (["v8"] if (" avx2" in flags and " fma" in flags) else []) + ["v4", "scalar"]
-    for v in order:
-        if os.path.exists(os.path.join(ROOT, "oracle", "_ref", f"libvpic_ref_{v}.so")):
-            return v
-    return None
+    order = []
+    if all(f" {x}" in flags for x in ("avx512f", "avx512dq", "avx512bw", "avx512vl", "avx2", "fma")):
+        order.append("v16")
+    if " avx2" in flags and " fma" in flags:
+        order.append("v8")
+    order += ["v4", "scalar"]
+    return [v for v in order if os.path.exists(os.path.join(ROOT, "oracle", "_ref", f"libvpic_ref_{v}.so"))]
 
 
-def reference_sample(args, n_steps, grid_n, warm=1):
-    """Time the reference's own CPU hot path (unmodified sources, oracle/_ref) on a bounded sample of the workload."""
+_picked = {}
+
+
+def pick_ref_variant(args=None):
+    """The fastest runnable reference build: every SIMD candidate is timed on a 32^3-cell probe of the workload in its
+    own subprocess (one reference build can be booted per process) and the best one wins."""
+    if "v" in _picked:
+        return _picked["v"]
+    cands = ref_variants()
+    best, rates = (cands[0] if cands else None), {}
+    simd = [v for v in cands if v in ("v16", "v8")]
+    if len(simd) > 1 and args is not None:
+        for v in simd:
+            try:
+                out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--probe-variant", v,
+                                      "--ppc", str(args.ppc), "--uth", str(args.uth), "--sort-interval", str(args.sort_interval)],
+                                     capture_output=True, text=True, timeout=300)
+                rates[v] = float(json.loads(out.stdout.strip().splitlines()[-1])["value"])
+            except Exception:
+                rates[v] = 0.0
+        best = max(simd, key=lambda v: rates[v])
+    _picked["v"], _picked["rates"] = best, rates
+    return best
+
+
+def fill_reference_species(sp, npart, nx, ny, nz, uth, w, rng, chunk=1 << 24):
+    """The synthetic load of build_sim written straight into the reference's particle array, a chunk at a time (the
+    full workload holds 8.6 GB of particles; no second copy is made)."""
+    p = sp.p
+    for a in range(0, npart, chunk):
+        b = min(npart, a + chunk)
+        n = b - a
+        v = p[a:b]
+        for k in ("dx", "dy", "dz"):
+            v[k] = rng.random(n, dtype=np.float32) * np.float32(2) - np.float32(1)
+        ix = rng.integers(1, nx + 1, n, dtype=np.int32)
+        iy = rng.integers(1, ny + 1, n, dtype=np.int32)
+        iz = rng.integers(1, nz + 1, n, dtype=np.int32)
+        v["i"] = ix + (nx + 2) * (iy + (ny + 2) * iz)
+        for k in ("ux", "uy", "uz"):
+            v[k] = rng.standard_normal(n, dtype=np.float32) * np.float32(uth)
+        v["w"] = np.float32(w)
+    sp.c.np = npart
+    sp.c.nm = 0
+
+
+def reference_sample(args, n_steps, grid_n, warm=1, variant=None):
+    """Time the reference's own CPU hot path (unmodified sources, oracle/_ref): the same plasma on a grid_n^3 box."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import refvpic as R
-    variant = pick_ref_variant()
+    variant = variant or pick_ref_variant(args)
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     if variant is None:
         return port_sample(args, grid_n)
@@ -489,9 +528,7 @@ def reference_sample(args, n_steps, grid_n, warm=1):
     species = []
     for name, q, m, uth in (("electron", -1.0, 1.0, args.uth), ("ion", 1.0, 25.0, args.uth / 5.0)):
         sp = W.new_species(name, q, m, npart, max(int(npart * 0.05), 1 << 16), args.sort_interval)
-        parts = R.random_particles(rng, npart, nx, ny, nz, uth=uth, w=1.0 / args.ppc)
-        sp.set_particles(parts)
-        del parts
+        fill_reference_species(sp, npart, nx, ny, nz, uth, 1.0 / args.ppc, rng)
         species.append(sp)
     lib.load_interpolator_array(W.ia, W.fa)
 
@@ -519,10 +556,13 @@ def reference_sample(args, n_steps, grid_n, warm=1):
         times.append(time.perf_counter() - t0)
     total = sum(times)
     pushes = 2 * npart * n_steps
+    probe = _picked.get("rates") or {}
     return {"value": pushes / total, "unit": "pushes/s", "cores": cores, "kind": "reference",
             "sample": f"unmodified reference ({variant} build, pthreads --tpp {cores}), same plasma on a {grid_n}^3-cell box, "
-                      f"{args.ppc} ppc/species, {n_steps} timed steps after {warm} warm-up (first step sorts)",
-            "ms_per_step": 1e3 * total / n_steps, "steps": n_steps}
+                      f"{args.ppc} ppc/species, {n_steps} timed steps after {warm} warm-up (first step sorts)"
+                      + (f"; fastest of the SIMD builds this CPU runs, probed on 32^3 cells: "
+                         + ", ".join(f"{k} {v / 1e6:.0f} M pushes/s" for k, v in probe.items()) if probe else ""),
+            "variant": variant, "grid": grid_n, "ms_per_step": 1e3 * total / n_steps, "steps": n_steps}
 
 
 def port_sample(args, grid_n):
@@ -553,10 +593,10 @@ def port_sample(args, grid_n):
 def cpu_baseline(args, budget_s=15.0):
     # one probing step on a small box, then size the sample to ~budget_s of CPU work
     try:
-        probe = reference_sample(args, 1, 32, warm=1)
-        if probe["kind"] != "reference":
-            return probe
-        rate = probe["value"]
+        if pick_ref_variant(args) is None:
+            return port_sample(args, 32)
+        rates = _picked.get("rates") or {}
+        rate = max(rates.values()) if rates and max(rates.values()) > 0 else 5e8
         grid_n = 64
         per_step = 2 * grid_n ** 3 * args.ppc / rate
         n_steps = int(max(2, min(20, budget_s / max(per_step, 1e-3))))
@@ -565,21 +605,41 @@ def cpu_baseline(args, budget_s=15.0):
         return {"value": None, "unit": "pushes/s", "cores": None, "kind": "reference", "sample": f"failed: {e!r}"}
 
 
+def workload_config(args, world, np_total_local):
+    """`config` of the JSON line; identical on both arms (the reference arm runs the same workload on the host)."""
+    return {"workload": (f"uniform thermal e-/ion plasma, {args.grid}^3 cells " if args.workload == "uniform" else
+                         f"Harris current sheet (sech^2 sheet + background, B_x = b0 tanh(z/L), drifting e-/ion, "
+                         f"conducting reflecting z walls), {args.grid}^3 cells ")
+                        + ("per GPU" if args.scaling == "weak" else "in total")
+                        + f", {args.ppc} ppc/species" + (" on average" if args.workload == "harris" else "")
+                        + f", periodic{' in x and y' if args.workload == 'harris' else ''}, "
+                        f"sort_p every {args.sort_interval} steps"
+                        + (" (BASELINE.json configs[1])" if (args.grid, args.ppc, args.workload) == (128, 64, "uniform") else ""),
+            "particles_per_gpu": np_total_local, "decomposition": f"1x{world}x1 slabs",
+            "l2": f"particle arrays ({np_total_local * 32 / 1e9:.1f} GB per GPU) exceed the 126 MB L2; no flush needed"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    grid_n = args.ref_grid
+    if args.probe_variant:                                  # child of pick_ref_variant: one 32^3 probe of one build
+        res = reference_sample(args, 2, 32, warm=1, variant=args.probe_variant)
+        print(json.dumps({"value": res["value"]}), flush=True)
+        return
+    # The reference arm runs the SAME configuration as our arm at N=1 (the whole 128^3-cell, 64 ppc, two-species box),
+    # every step a whole step of it, on all host threads; --ref-grid shrinks it for a quick look.
+    grid_n = args.ref_grid or args.grid
     res = reference_sample(args, args.steps, grid_n, warm=max(1, args.warmup))
     world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    cfg = workload_config(args, 1, 2 * grid_n ** 3 * args.ppc)
+    if grid_n != args.grid:
+        cfg["workload"] += f"; each step a bounded sample of it: {grid_n}^3 cells on the host cores"
     out = {"impl": "reference", "metric": "particle pushes/sec (advance_p+deposit)", "value": res["value"],
            "unit": "pushes/s", "n_gpus": world, "steps": args.steps, "warmup": max(1, args.warmup),
            "ms_per_step": res.get("ms_per_step"), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "f32", "data": "synthetic",
-           "config": {"workload": f"uniform thermal e-/ion plasma, {args.grid}^3 cells per GPU, {args.ppc} ppc/species, "
-                                  f"periodic, sort_p every {args.sort_interval} steps (BASELINE.json configs[1]); each step "
-                                  f"a bounded sample of it: {grid_n}^3 cells on the host cores"},
-           "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+           "dtype": "f32", "data": "synthetic", "config": cfg,
+           "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample", "variant")},
            "e2e": {"value": res["value"], "unit": "pushes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out), flush=True)
@@ -600,7 +660,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
-    ap.add_argument("--ref-grid", type=int, default=64)
+    ap.add_argument("--ref-grid", type=int, default=0, help="reference arm: cells per side (default: --grid, the full workload)")
+    ap.add_argument("--probe-variant", default="", help=argparse.SUPPRESS)
     ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--workload", default="uniform", choices=["uniform", "harris"],
                     help="uniform thermal plasma (BASELINE.json configs[1], the default) or a Harris current sheet")

@@ -13,8 +13,8 @@
  *     layer 1.  That is the link-time seam described in INTEGRATION.md.
  *
  * Every function returns 0 on success, else a negative vpb error or a positive
- * cudaError_t; vpb_last_error() gives the message.  There is no CPU fallback:
- * without a usable CUDA device every call fails loudly.
+ * cudaError_t; vpb_last_error() gives the message.  This layer has no CPU
+ * fallback: without a usable CUDA device every call fails loudly.
  *
  * Array layouts are the reference's (vpic_b200_abi.h) with runtime strides so
  * one binary serves every SIMD padding of the host build:
@@ -82,7 +82,8 @@ typedef struct vpb_push_args {
   void          *pm;             /* particle_mover_t[max_nm]: movers that left the domain */
   int32_t        max_nm;
   int32_t       *counters;       /* int32[4] device: [0] += movers emitted (may exceed max_nm),
-                                    [1] += movers dropped for lack of room (p.i restored, advance_p_pipeline.cc:223-236) */
+                                    [1] += movers dropped for lack of room (p.i restored, advance_p_pipeline.cc:223-236),
+                                    [2] scratch of the brick kernel (work counter, reset by vpb_advance_p itself) */
   const float   *interp;  int32_t interp_stride;
   float         *accum;   int32_t accum_stride;   /* block 0 of the accumulator array */
   const int64_t *neighbor;       /* grid_t.neighbor, [6*nv]                          */
@@ -94,6 +95,13 @@ typedef struct vpb_push_args {
   const vpb_neighbor_rule_t *neighbor_rule;   /* optional (host pointer): verified closed form of `neighbor` */
   int32_t        debug_skip;     /* must be 0.  Profiling only (results become INVALID): bit0 skip deposits,
                                     bit1 skip the mover phase, bit2 skip particle stores, bit3 skip the interpolator gather */
+  /* Optional (NULL = not available): the partition[nv+1] the species' last vpb_sort_p wrote (device pointer), and the
+   * particle count of that sort (partition[nv]).  With it vpb_advance_p walks the array brick by brick and collects
+   * the deposits of each brick in a shared-memory accumulator tile (advance_p_brick.cu).  The array may have been
+   * changed since the sort (back-fill, appended particles, np != partition_np): partition[] only has to be monotone
+   * with entries in [0, partition_np]; results do not depend on how accurate it still is. */
+  const int32_t *partition;
+  int32_t        partition_np;
 } vpb_push_args_t;
 
 #define VPB_DEPOSIT_DEFAULT      0   /* library's best measured strategy                                  */
@@ -103,6 +111,9 @@ typedef struct vpb_push_args {
 #define VPB_DEPOSIT_WARP_SEG_MOVERS 3 /* as 2, and move_p runs warp-synchronously with the same segmented reduction */
 #define VPB_DEPOSIT_WARP_SEG_FIRST  4 /* as 2, and the FIRST streak of a mover batch (still in the source voxels) is
                                         summed across the warp; later streaks go out as vector REDs          */
+#define VPB_DEPOSIT_BRICK_TILE      5 /* bricks of voxels, warp-private shared-memory accumulator tile flushed by TMA
+                                        bulk reduce, two particles per thread; needs `partition`.  DEFAULT picks this
+                                        when `partition` is given and falls back to 2 otherwise                   */
 
 int vpb_advance_p(const vpb_push_args_t *args, void *stream);
 

@@ -19,7 +19,17 @@
  *                                vpic_b200_sync_to_host(ptr) and host writes need vpic_b200_invalidate(ptr).
  *
  * Errors follow the reference's convention (src/util/util_base.h:267-273): message on stderr as
- * "Error at file(line)[rank]:", then exit(1).  There is no CPU fallback.
+ * "Error at file(line)[rank]:", then exit(1).  A missing or failing CUDA device is such an error: the particle path
+ * (advance_p, sort_p, the interpolator/accumulator glue, energy_p, center_p, ...) has NO CPU fallback.
+ *
+ * Forwards.  A few entry points exist here only because LD_PRELOAD interposes whole symbols: boundary_p,
+ * synchronize_hydro_array and the reference's field kernels (advance_b, vacuum_advance_e, clear_jf, synchronize_jf,
+ * vacuum_energy_f, the divergence-cleaning kernels).  When this library cannot serve one of them on the device —
+ * several MPI ranks without the NCCL seam (vpic_b200_mp.h), more than one material, custom particle-boundary handlers,
+ * VPIC_B200_FIELDS=0 / VPIC_B200_BOUNDARY_P=0 — the call is handed to the HOST PROGRAM's own definition of that symbol
+ * (dlsym(RTLD_NEXT)), i.e. the reference's CPU code runs.  That is never silent: the first forward of each symbol
+ * prints "Warning ...: <symbol> is not served on the device (<why>): forwarding to the host program's own CPU
+ * implementation", VPIC_B200_TRACE=1 counts them, and VPIC_B200_STRICT=1 turns the first forward into an Error.
  */
 #ifndef VPIC_B200_DROPIN_H
 #define VPIC_B200_DROPIN_H

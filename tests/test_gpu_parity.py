@@ -108,6 +108,35 @@ def test_advance_p(eng, oracle, dims, uth, pbc, n, sort_first, variant, use_rule
         assert (got["i"] != parts["i"]).mean() > 0.05
 
 
+@pytest.mark.parametrize("variant", [1, 2])
+def test_advance_p_multi_span_and_grid_cap(eng, oracle, monkeypatch, variant):
+    """The paths the benchmark runs at 134 M particles, forced at 300 k: spans of ONE row and a grid of one CTA per SM
+    (args.debug_skip bits 16-23 and 24-31), so every warp takes several spans, prefetches across span boundaries and
+    carries its mover queue from one span to the next."""
+    monkeypatch.setenv("VPB_DEBUG_SKIP", str((1 << 16) | (1 << 24)))
+    rng = np.random.default_rng(29)
+    nx, ny, nz = 12, 10, 9
+    g = make_grid(nx, ny, nz, pbc={2: -2, 5: -2})               # absorbing z walls: movers are emitted too
+    fields = R.random_fields(rng, g.nv)
+    interp = np.zeros((g.nv, 20), dtype=np.float32)
+    oracle.vpo_load_interpolator(interp.ctypes.data, 20, fields.ctypes.data, nx, ny, nz)
+    n = 300007
+    parts = R.random_particles(rng, n, nx, ny, nz, uth=0.4, w=0.7)
+    parts = parts[np.argsort(parts["i"], kind="stable")]
+    p_ref, pm_ref, acc_ref, _ = oracle_push(oracle, g, parts, interp, -1.0, 1.0, n)
+    dg = eng.DeviceGrid(g)
+    ia, aa = eng.InterpolatorArray(dg), eng.AccumulatorArray(dg)
+    ia.i.copy_(torch.from_numpy(interp))
+    sp = eng.Species("electron", -1.0, 1.0, n, n, 20, 0, dg)
+    sp.set_particles(parts)
+    eng.clear_accumulator_array(aa)
+    eng.advance_p(sp, aa, ia, variant=variant)
+    assert sp.nm == len(pm_ref) > 0
+    assert np.array_equal(bits(sp.particles_host()), bits(p_ref))
+    assert np.array_equal(bits(sp.movers_host()), bits(pm_ref))
+    accum_close(aa.a.cpu().numpy(), acc_ref)
+
+
 def test_neighbor_rule_rejects_irregular_table(eng):
     """A neighbour table that is not the regular structure must fail verification (the kernels then use the table)."""
     g = make_grid(5, 4, 3)
@@ -158,6 +187,29 @@ def test_sort_p(eng, oracle, dims, n):
     # idempotence: sorting sorted data changes nothing
     eng.sort_p(sp)
     assert np.array_equal(bits(sp.particles_host()), bits(p_ref))
+
+
+def test_sort_p_at_scale(eng, oracle):
+    """12 M particles: every CTA of the scatter kernel walks several sub-tiles (re-zeroing its touched-digit bitmap in
+    between) — the path the benchmark's 134 M-particle sorts take.  Order and partition[] bit-exact vs the oracle."""
+    nx, ny, nz = 64, 48, 40
+    n = 12_000_003
+    g = make_grid(nx, ny, nz)
+    gen = np.random.default_rng(8)
+    parts = np.zeros(n, dtype=abi.particle_dtype)
+    parts["i"] = (gen.integers(1, nx + 1, n) + (nx + 2) * (gen.integers(1, ny + 1, n) + (ny + 2) * gen.integers(1, nz + 1, n))).astype(np.int32)
+    parts["w"] = np.arange(n, dtype=np.float32)                # tags (exact in fp32 up to 2^24) expose instability
+    parts["ux"] = gen.random(n, dtype=np.float32)
+    p_ref, aux = parts.copy(), np.zeros_like(parts)
+    part_ref = np.zeros(g.nv + 1, dtype=np.int32)
+    oracle.vpo_sort_p(p_ref.ctypes.data, n, aux.ctypes.data, part_ref.ctypes.data, nx, ny, nz)
+    del aux
+    dg = eng.DeviceGrid(g)
+    sp = eng.Species("e", -1.0, 1.0, n, 16, 20, 0, dg)
+    sp.set_particles(parts)
+    eng.sort_p(sp)
+    assert np.array_equal(bits(sp.particles_host()), bits(p_ref)), "sort order must be bit-exact (stable) at scale"
+    assert np.array_equal(sp.partition.cpu().numpy()[:g.nv], part_ref[:g.nv])
 
 
 def test_sort_movers(eng):

@@ -25,13 +25,12 @@
 namespace vpb {
 
 constexpr int kBlock = 256;
-constexpr int kTile  = kBlock * 4;        // particles per CTA used only to size the grid
 constexpr int kMinBlocks = 3;            // resident CTAs per SM the register budget is tuned for
 
 template <int VARIANT>
-__device__ __forceinline__ void deposit(const PushK &a, int vox, bool active, const float (&j)[12]) {
+__device__ __forceinline__ void deposit(const PushK &a, int vox, bool active, const float (&j)[12], int min_group) {
   if (VARIANT == VPB_DEPOSIT_WARP_SEG || VARIANT == VPB_DEPOSIT_WARP_SEG_MOVERS || VARIANT == VPB_DEPOSIT_WARP_SEG_FIRST) {
-    deposit_warp_segmented(a.accum, a.astride, vox, active, j, ((a.dbg >> 8) & 0xff) ? ((a.dbg >> 8) & 0xff) : kMinGroup);
+    deposit_warp_segmented(a.accum, a.astride, vox, active, j, min_group);
   } else {
     if (active) deposit_red_v4(a.accum + (size_t)vox * a.astride, j);
   }
@@ -43,7 +42,7 @@ constexpr int kQCap  = 64;                 // a warp's queue holds at most 31 ca
 constexpr size_t kSmemBytes = (size_t)kWarps * 3 * kQCap * sizeof(int4);
 
 // One dense batch of queued movers [start, start+count) of this warp's queue, count <= 32.
-template <int VARIANT>
+template <int VARIANT, bool DBG>
 __device__ __forceinline__ void run_movers(const PushK &a, const int4 *q0, const int4 *q1, const int4 *q2,
                                            int start, int count, int lane) {
   const bool act = lane < count;
@@ -60,7 +59,7 @@ __device__ __forceinline__ void run_movers(const PushK &a, const int4 *q0, const
   int left;
   if (VARIANT == VPB_DEPOSIT_WARP_SEG_MOVERS) left = move_p_warp<false, true>(a, act, rr, uu, dispx, dispy, dispz);
   else if (VARIANT == VPB_DEPOSIT_WARP_SEG_FIRST) left = move_p_warp<true, false>(a, act, rr, uu, dispx, dispy, dispz);
-  else left = act ? move_p_dev(a, rr, uu, dispx, dispy, dispz) : 0;
+  else left = act ? move_p_dev<DBG>(a, rr, uu, dispx, dispy, dispz) : 0;
   if (act) {
     if (left) {
       const int slot = atomicAdd(a.counters, 1);
@@ -75,7 +74,8 @@ __device__ __forceinline__ void run_movers(const PushK &a, const int4 *q0, const
   }
 }
 
-template <int VARIANT>
+// DBG = false (every production launch) compiles the profiling switches of args.debug_skip out of the loop.
+template <int VARIANT, bool DBG>
 __global__ void __launch_bounds__(kBlock, kMinBlocks) advance_p_kernel(const PushK a) {
   // Every warp is autonomous: it walks rows of 32 consecutive particles (rows of one CTA are adjacent, so its
   // warps share interpolator lines in L1), keeps its own mover queue in shared memory and never meets a block-wide
@@ -83,6 +83,8 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) advance_p_kernel(const Pus
   // its whole state {r, u, disp, index} (three 16-byte planes, conflict-free), so finishing it needs no reload;
   // movers are finished 32 at a time, leftovers ride along to the warp's next row.
   extern __shared__ int4 s_q[];
+  const int dbg = DBG ? a.dbg : 0;
+  const int min_group = ((dbg >> 8) & 0xff) ? ((dbg >> 8) & 0xff) : kMinGroup;
   const float one = 1.0f;
   const float one_third = (float)(1.0 / 3.0);
   const float two_fifteenths = (float)(2.0 / 15.0);
@@ -95,7 +97,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) advance_p_kernel(const Pus
 
   // Rows are dealt to warps in spans of kSpan consecutive rows: consecutive rows of voxel-sorted particles share
   // their interpolator (64 ppc = 2 rows per voxel), so a warp's next gather usually hits the lines it just used.
-  const int span_rows = ((a.dbg >> 16) & 0xff) ? ((a.dbg >> 16) & 0xff) : kSpan;    // profiling override
+  const int span_rows = a.span;                                         // kSpan, fewer for small species (host)
   const int n_spans = (n_rows + span_rows - 1) / span_rows;
   int span = blockIdx.x * kWarps + w;
   int row = span * span_rows;
@@ -121,7 +123,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) advance_p_kernel(const Pus
       const float4 *f = reinterpret_cast<const float4 *>(a.interp + (size_t)ii * a.istride);
       float4 fex = make_float4(.01f, .02f, .03f, .04f), fey = fex, fez = fex, fb0 = fex;
       float2 fb1 = make_float2(.01f, .02f);
-      if (!(a.dbg & 8)) {
+      if (!(dbg & 8)) {
         fex = __ldg(f); fey = __ldg(f + 1); fez = __ldg(f + 2); fb0 = __ldg(f + 3);
         fb1 = __ldg(reinterpret_cast<const float2 *>(f + 4));
       }
@@ -154,10 +156,10 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) advance_p_kernel(const Pus
       v0 = dx + ux; v1 = dy + uy; v2 = dz + uz;                     // streak midpoint
       v3 = v0 + ux; v4 = v1 + uy; const float v5n = v2 + uz;        // new position
       inb = (v3 <= one) && (v4 <= one) && (v5n <= one) && (-v3 <= one) && (-v4 <= one) && (-v5n <= one);
-      if (a.dbg & 2) inb = true;
+      if (dbg & 2) inb = true;
       if (inb) {
         const float qw = un.w * a.qsp;
-        if (!(a.dbg & 4)) st_particle(a.p + 2 * (size_t)i, make_float4(v3, v4, v5n, r.w), un);
+        if (!(dbg & 4)) st_particle(a.p + 2 * (size_t)i, make_float4(v3, v4, v5n, r.w), un);
         const float v5 = (((qw * ux) * uy) * uz) * one_third;
         streak_currents(qw, ux, uy, uz, v0, v1, v2, v5, j);
       } else {
@@ -176,17 +178,17 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) advance_p_kernel(const Pus
       }
       nq += __popc(lm);
     }
-    deposit<VARIANT>(a, ii, inb && !(a.dbg & 1), j);
+    deposit<VARIANT>(a, ii, inb && !(dbg & 1), j, min_group);
     if (nq >= 32) {                                                     // a full batch; the rest carries over
       __syncwarp();
       nq -= 32;
-      run_movers<VARIANT>(a, q0, q1, q2, nq, 32, lane);
+      run_movers<VARIANT, DBG>(a, q0, q1, q2, nq, 32, lane);
       __syncwarp();
     }
     row = next_row; span = next_span;
   }
   __syncwarp();
-  if (nq > 0) run_movers<VARIANT>(a, q0, q1, q2, 0, nq, lane);
+  if (nq > 0) run_movers<VARIANT, DBG>(a, q0, q1, q2, 0, nq, lane);
 }
 
 // Check the closed-form neighbour rule against the table for every interior voxel and face.
@@ -199,6 +201,8 @@ __global__ void __launch_bounds__(256) verify_neighbor_rule_kernel(PushK a, int 
   for (int f = 0; f < 6; f++) bad += (neighbor_of(a, vox, f) != __ldg(a.neighbor + 6ll * vox + f));
   if (bad) atomicAdd(mismatch, bad);
 }
+
+int advance_p_brick(const vpb_push_args_t *args, const PushK &k, cudaStream_t st);   // advance_p_brick.cu
 
 }  // namespace vpb
 
@@ -253,33 +257,52 @@ extern "C" int vpb_advance_p(const vpb_push_args_t *args, void *stream) {
               ((uintptr_t)args->p & 31) == 0 && args->p_first >= 0,
               "vpb_advance_p: particles must be 32-byte aligned, the other arrays 16-byte aligned");
   if (args->np <= 0) return 0;
-  const PushK k = to_push_k(args);
-  static bool attr_done = false;
-  static size_t extra_smem = 0;          // profiling: VPB_EXTRA_SMEM_KB pads the CTA's shared memory to lower occupancy
-  if (!attr_done) {
-    if (const char *e = getenv("VPB_EXTRA_SMEM_KB")) extra_smem = (size_t)atoi(e) * 1024;
-    VPB_CUDA(cudaFuncSetAttribute(advance_p_kernel<VPB_DEPOSIT_RED_V4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    VPB_CUDA(cudaFuncSetAttribute(advance_p_kernel<VPB_DEPOSIT_WARP_SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemBytes + extra_smem)));
-    VPB_CUDA(cudaFuncSetAttribute(advance_p_kernel<VPB_DEPOSIT_WARP_SEG_MOVERS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    VPB_CUDA(cudaFuncSetAttribute(advance_p_kernel<VPB_DEPOSIT_WARP_SEG_FIRST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    attr_done = true;
+  PushK k = to_push_k(args);
+  // Default strategy: the linear kernel below (warp-segmented reduction + vector REDs).  The brick/tile kernel is
+  // bit-identical in particle state but measured slower on B200 in round 2, so it runs only when
+  // asked for (variant VPB_DEPOSIT_BRICK_TILE, or VPB_BRICK_DEFAULT=1 in the environment).
+  static int brick_default = -1;
+  if (brick_default < 0) { const char *e = getenv("VPB_BRICK_DEFAULT"); brick_default = e && atoi(e) != 0; }
+  if (args->variant == VPB_DEPOSIT_BRICK_TILE || (args->variant == VPB_DEPOSIT_DEFAULT && brick_default)) {
+    VPB_REQUIRE(args->nx > 0 && args->ny > 0 && args->nz > 0, "vpb_advance_p: Bad grid");
+    const int served = (args->debug_skip == 0) ? advance_p_brick(args, k, as_stream(stream)) : 0;
+    if (served < 0) return -1;
+    if (served > 0) return 0;
   }
-  const int ntiles = (args->np + kTile - 1) / kTile;
+  static size_t extra_smem = 0;          // profiling: VPB_EXTRA_SMEM_KB pads the CTA's shared memory to lower occupancy
+  static bool env_done = false;
+  if (!env_done) { if (const char *e = getenv("VPB_EXTRA_SMEM_KB")) extra_smem = (size_t)atoi(e) * 1024; env_done = true; }
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = kSMs; }
+  const bool dbg = args->debug_skip != 0;
+  const int n_rows = (args->np + 31) / 32;
+  // spans of kSpan rows per warp; small species get shorter spans so that every SM still has warps to run
+  int span_rows = ((args->debug_skip >> 16) & 0xff) ? ((args->debug_skip >> 16) & 0xff) : kSpan;
+  if (!((args->debug_skip >> 16) & 0xff)) {
+    const int fill = n_rows / (sms * 32);
+    if (fill < span_rows) span_rows = fill < 4 ? 4 : fill;
+  }
+  k.span = span_rows;
+  const int n_spans = (n_rows + span_rows - 1) / span_rows;
+  // one warp per span of rows, capped at a grid of many short CTAs (side-stream kernels slot in between them)
   const int gmul = ((args->debug_skip >> 24) & 0xff) ? ((args->debug_skip >> 24) & 0xff) : 32;     // profiling override
-  const int grid = ntiles < kSMs * gmul ? ntiles : kSMs * gmul;   // many short CTAs: side-stream kernels slot in between them
-  int variant = args->variant == VPB_DEPOSIT_DEFAULT ? VPB_DEPOSIT_WARP_SEG : args->variant;
+  const int need = (n_spans + kWarps - 1) / kWarps;
+  const int grid = need < sms * gmul ? need : sms * gmul;
+  int variant = (args->variant == VPB_DEPOSIT_DEFAULT || args->variant == VPB_DEPOSIT_BRICK_TILE) ? VPB_DEPOSIT_WARP_SEG : args->variant;
+  const size_t smem = kSmemBytes + (variant == VPB_DEPOSIT_WARP_SEG ? extra_smem : 0);
+#define VPB_LAUNCH_AP(V, D) do {                                                                                      \
+    static bool attr_done = false;                                                                                    \
+    if (!attr_done) { VPB_CUDA(cudaFuncSetAttribute(advance_p_kernel<V, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_done = true; } \
+    advance_p_kernel<V, D><<<grid, kBlock, smem, as_stream(stream)>>>(k); } while (0)
   switch (variant) {
-    case VPB_DEPOSIT_RED_V4:
-      advance_p_kernel<VPB_DEPOSIT_RED_V4><<<grid, kBlock, kSmemBytes, as_stream(stream)>>>(k); break;
-    case VPB_DEPOSIT_WARP_SEG:
-      advance_p_kernel<VPB_DEPOSIT_WARP_SEG><<<grid, kBlock, kSmemBytes + extra_smem, as_stream(stream)>>>(k); break;
-    case VPB_DEPOSIT_WARP_SEG_MOVERS:
-      advance_p_kernel<VPB_DEPOSIT_WARP_SEG_MOVERS><<<grid, kBlock, kSmemBytes, as_stream(stream)>>>(k); break;
-    case VPB_DEPOSIT_WARP_SEG_FIRST:
-      advance_p_kernel<VPB_DEPOSIT_WARP_SEG_FIRST><<<grid, kBlock, kSmemBytes, as_stream(stream)>>>(k); break;
+    case VPB_DEPOSIT_RED_V4:          if (dbg) VPB_LAUNCH_AP(VPB_DEPOSIT_RED_V4, true); else VPB_LAUNCH_AP(VPB_DEPOSIT_RED_V4, false); break;
+    case VPB_DEPOSIT_WARP_SEG:        if (dbg) VPB_LAUNCH_AP(VPB_DEPOSIT_WARP_SEG, true); else VPB_LAUNCH_AP(VPB_DEPOSIT_WARP_SEG, false); break;
+    case VPB_DEPOSIT_WARP_SEG_MOVERS: if (dbg) VPB_LAUNCH_AP(VPB_DEPOSIT_WARP_SEG_MOVERS, true); else VPB_LAUNCH_AP(VPB_DEPOSIT_WARP_SEG_MOVERS, false); break;
+    case VPB_DEPOSIT_WARP_SEG_FIRST:  if (dbg) VPB_LAUNCH_AP(VPB_DEPOSIT_WARP_SEG_FIRST, true); else VPB_LAUNCH_AP(VPB_DEPOSIT_WARP_SEG_FIRST, false); break;
     default:
       VPB_REQUIRE(false, "vpb_advance_p: unknown deposit variant %d", variant);
   }
+#undef VPB_LAUNCH_AP
   VPB_LAUNCH_CHECK();
   return 0;
 }

@@ -39,6 +39,20 @@ int rank_for_log() { return &_world_rank ? _world_rank : 0; }
     fprintf(stderr, __VA_ARGS__); fprintf(stderr, "\n"); } while (0)
 #define DEV(call) do { int _r = (call); if (_r) DROPIN_ERROR("%s failed (%d): %s", #call, _r, vpb_last_error()); } while (0)
 
+// An entry point that this library cannot serve on the device hands the call to the host program's own (CPU)
+// definition of the same symbol.  That is never silent: the first forward of every symbol prints a WARNING, and
+// VPIC_B200_STRICT=1 turns it into an ERROR (exit 1), for runs that must not touch a CPU kernel.
+#define FORWARD_NOTICE(sym, why) do {                                                                       \
+    static bool _told = false;                                                                              \
+    if (!_told) {                                                                                           \
+      _told = true;                                                                                         \
+      static int strict = -1;                                                                               \
+      if (strict < 0) { const char *e_ = getenv("VPIC_B200_STRICT"); strict = e_ && atoi(e_) != 0; }        \
+      if (strict) DROPIN_ERROR("%s is not served on the device (%s) and VPIC_B200_STRICT=1 forbids the host program's CPU implementation", sym, why); \
+      DROPIN_WARNING("%s is not served on the device (%s): forwarding to the host program's own CPU implementation "     \
+                     "(said once per symbol; VPIC_B200_STRICT=1 makes it an error)", sym, why);            \
+    } } while (0)
+
 // VPIC_B200_TRACE=1: at exit, one line on stderr with how often each entry point ran on the device (and how often a
 // field kernel fell through to the reference's own), so a preloaded run can be checked for what it actually used.
 enum { C_ADVANCE_P, C_SORT_P, C_CENTER_P, C_ENERGY_P, C_RHO_P, C_LOAD_INTERP, C_CLEAR_ACC, C_UNLOAD_ACC, C_ADVANCE_B,
@@ -328,6 +342,9 @@ static int chunk_particles() {
   return c;
 }
 
+struct SortInfo { int32_t *part = nullptr; size_t cap = 0; int32_t np = 0; int64_t nv = 0; };
+static std::unordered_map<const void *, SortInfo> g_sort_info;     // by species_t address
+
 void advance_p(vpb_species_t *sp, vpb_accumulator_array_t *aa, const vpb_interpolator_array_t *ia) {
   if (!sp || !aa || !ia || sp->g != aa->g || sp->g != ia->g) DROPIN_ERROR("Bad args.");
   count_call(C_ADVANCE_P);
@@ -366,6 +383,11 @@ void advance_p(vpb_species_t *sp, vpb_accumulator_array_t *aa, const vpb_interpo
 
   const size_t pbytes = (size_t)sp->np * sizeof(vpb_particle_t);
   if (!coherent) {
+    // the partition of this species' last sort_p (device-private copy) lets advance_p work brick by brick
+    auto it = g_sort_info.find(sp);
+    if (it != g_sort_info.end() && it->second.nv == (int64_t)g->nv && it->second.part) {
+      a.partition = it->second.part; a.partition_np = it->second.np;
+    }
     a.p = dev_in(sp->p, pbytes, (size_t)sp->max_np * sizeof(vpb_particle_t));
     a.np = sp->np;
     DEV(vpb_advance_p(&a, nullptr));
@@ -442,6 +464,9 @@ void boundary_p(void *pbc_list, vpb_species_t *sp_list, vpb_field_array_t *fa, v
   if (!local_only) {
     static auto ref = (void (*)(void *, vpb_species_t *, vpb_field_array_t *, vpb_accumulator_array_t *))dlsym(RTLD_NEXT, "boundary_p");
     if (!ref) DROPIN_ERROR("boundary_p: several ranks or custom particle boundary handlers need the reference's own boundary_p, which is not linked in");
+    FORWARD_NOTICE("boundary_p", world > 1 ? "several ranks: the particle exchange is the host program's MPI" :
+                                 pbc_list ? "custom particle boundary handlers are host function pointers" :
+                                 enabled ? "a face leads to another domain" : "VPIC_B200_BOUNDARY_P=0");
     ref(pbc_list, sp_list, fa, aa);
     return;
   }
@@ -499,6 +524,14 @@ void sort_p(vpb_species_t *sp) {
   void *aux = scratch(1, (size_t)(sp->np > 0 ? sp->np : 1) * sizeof(vpb_particle_t));
   const size_t need = vpb_sort_scratch_bytes(sp->np > 0 ? sp->np : 1, g->nv);
   DEV(vpb_sort_p(p, sp->np, aux, part, g->nx, g->ny, g->nz, scratch(2, need), need, nullptr));
+  {
+    // keep a device-private copy for advance_p's brick walk: the host owns sp->partition and may do anything to it
+    SortInfo &si = g_sort_info[sp];
+    const size_t bytes = ((size_t)g->nv + 1) * sizeof(int32_t);
+    if (si.cap < bytes) { if (si.part) vpb_free(si.part); si.part = nullptr; DEV(vpb_malloc((void **)&si.part, bytes)); si.cap = bytes; }
+    DEV(vpb_memcpy_d2d(si.part, part, bytes, nullptr));
+    si.np = sp->np; si.nv = g->nv;
+  }
   dev_written(sp->p, (size_t)sp->np * sizeof(vpb_particle_t));
   dev_written(sp->partition, ((size_t)g->nv + 1) * sizeof(int32_t));
   finish_entry();
@@ -605,6 +638,7 @@ void synchronize_hydro_array(vpb_hydro_array_t *ha) {
     static auto ref = (void (*)(vpb_hydro_array_t *))dlsym(RTLD_NEXT, "synchronize_hydro_array");
     if (!ref) DROPIN_ERROR("synchronize_hydro_array: faces shared with other ranks need the reference's own exchange, which is not linked in");
     count_call(C_FIELD_FALLBACK);
+    FORWARD_NOTICE("synchronize_hydro_array", "a face is shared with another rank");
     ref(ha);
     return;
   }
@@ -756,6 +790,11 @@ static bool fields_on_device(const vpb_field_array_t *fa) {
   if (enabled < 0) { const char *e = getenv("VPIC_B200_FIELDS"); enabled = !(e && atoi(e) == 0 && e[0] == '0'); }
   return enabled && fa && fa->g && !device_fields_obstacle(fa);
 }
+static const char *why_not_on_device(const vpb_field_array_t *fa) {
+  if (!fa || !fa->g) return "no field array";
+  if (const char *why = device_fields_obstacle(fa)) return why;
+  return "VPIC_B200_FIELDS=0";
+}
 static void *reference_kernel(const char *name) {
   void *f = dlsym(RTLD_NEXT, name);
   if (!f) DROPIN_ERROR("%s: this field array needs the reference's own kernel, which is not linked in", name);
@@ -765,30 +804,35 @@ void advance_b(vpb_field_array_t *fa, float frac) {
   if (fields_on_device(fa)) { vpic_b200_advance_b(fa, frac); return; }
   static auto ref = (void (*)(vpb_field_array_t *, float))reference_kernel("advance_b");
   count_call(C_FIELD_FALLBACK);
+  FORWARD_NOTICE("advance_b", why_not_on_device(fa));
   ref(fa, frac);
 }
 void vacuum_advance_e(vpb_field_array_t *fa, float frac) {
   if (fields_on_device(fa)) { vpic_b200_advance_e(fa, frac); return; }
   static auto ref = (void (*)(vpb_field_array_t *, float))reference_kernel("vacuum_advance_e");
   count_call(C_FIELD_FALLBACK);
+  FORWARD_NOTICE("vacuum_advance_e", why_not_on_device(fa));
   ref(fa, frac);
 }
 void clear_jf(vpb_field_array_t *fa) {
   if (fields_on_device(fa)) { vpic_b200_clear_jf(fa); return; }
   static auto ref = (void (*)(vpb_field_array_t *))reference_kernel("clear_jf");
   count_call(C_FIELD_FALLBACK);
+  FORWARD_NOTICE("clear_jf", why_not_on_device(fa));
   ref(fa);
 }
 void synchronize_jf(vpb_field_array_t *fa) {
   if (fields_on_device(fa)) { vpic_b200_synchronize_jf(fa); return; }
   static auto ref = (void (*)(vpb_field_array_t *))reference_kernel("synchronize_jf");
   count_call(C_FIELD_FALLBACK);
+  FORWARD_NOTICE("synchronize_jf", why_not_on_device(fa));
   ref(fa);
 }
 void vacuum_energy_f(double *en, const vpb_field_array_t *fa) {
   if (fields_on_device(fa)) { vpic_b200_energy_f(en, fa); return; }
   static auto ref = (void (*)(double *, const vpb_field_array_t *))reference_kernel("vacuum_energy_f");
   count_call(C_FIELD_FALLBACK);
+  FORWARD_NOTICE("vacuum_energy_f", why_not_on_device(fa));
   ref(en, fa);
 }
 
@@ -850,6 +894,7 @@ double vpic_b200_synchronize_tang_e_norm_b(vpb_field_array_t *fa) {
     if (fields_on_device(fa)) { ours(fa); return; }                                         \
     static auto ref = (void (*)(vpb_field_array_t *))reference_kernel(#sym);                \
     count_call(C_FIELD_FALLBACK);                                                           \
+    FORWARD_NOTICE(#sym, why_not_on_device(fa));                                            \
     ref(fa);                                                                                \
   }
 #define FALLBACK_DOUBLE(sym, ours, qual)                                                    \
@@ -857,6 +902,7 @@ double vpic_b200_synchronize_tang_e_norm_b(vpb_field_array_t *fa) {
     if (fields_on_device(fa)) return ours(fa);                                              \
     static auto ref = (double (*)(qual vpb_field_array_t *))reference_kernel(#sym);         \
     count_call(C_FIELD_FALLBACK);                                                           \
+    FORWARD_NOTICE(#sym, why_not_on_device(fa));                                            \
     return ref(fa);                                                                         \
   }
 FALLBACK_VOID(clear_rhof, vpic_b200_clear_rhof)

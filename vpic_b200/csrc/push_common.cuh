@@ -32,6 +32,7 @@ struct PushK {
   const long long *neighbor; long long rangel, rangeh;
   float qdt_2mc, cdt_dx, cdt_dy, cdt_dz, qsp;
   int dbg;
+  int span;                       // rows of 32 particles a warp of the linear kernel takes at a time
   NbRule nb;
 };
 
@@ -85,22 +86,18 @@ __device__ __forceinline__ void deposit_warp_segmented(float *accum, int astride
                                                        const float (&j)[12], int min_group = kMinGroup) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
-  const int key = active ? vox : (-1 - lane);
-  // right after a sort most warps sit in a single voxel: one shuffle + vote finds that out, match.any is the
-  // (slow) general case
-  const unsigned amask = __ballot_sync(full, active);
-  if (amask == 0) return;
-  const int v_first = __shfl_sync(full, vox, __ffs(amask) - 1);
-  const bool uniform = __all_sync(full, !active || vox == v_first);
-  const unsigned peers = uniform ? (active ? amask : 0u) : __match_any_sync(full, key);
-  const bool grouped = active && (__popc(peers) >= min_group);
-  if (active && !grouped) deposit_red_v4(accum + (size_t)vox * astride, j);
-  unsigned big = __ballot_sync(full, grouped);
-  while (big) {
-    const int leader = __ffs(big) - 1;
-    const unsigned grp = __shfl_sync(full, peers, leader);
-    const int gv = __shfl_sync(full, vox, leader);
-    const bool mine = grouped && (peers == grp);
+  // Voxel-sorted rows hold one or two voxels (three at low ppc): peel off up to three voxels in lane order with a
+  // shuffle and a vote each.  (match.any would find every group at once, but it costs ~7 cycles per distinct key —
+  // 211 cycles for a fully drifted row, tools/ubench_r2.cu — and drifted rows have nothing worth grouping.)
+  unsigned rest = __ballot_sync(full, active);
+  bool todo = active;
+#pragma unroll 1
+  for (int g = 0; g < 3 && rest; g++) {
+    const int gv = __shfl_sync(full, vox, __ffs(rest) - 1);
+    const bool mine = todo && vox == gv;
+    const unsigned grp = __ballot_sync(full, mine);
+    rest &= ~grp;
+    if (__popc(grp) < min_group) continue;
     float v[16];
 #pragma unroll
     for (int c = 0; c < 12; c++) v[c] = mine ? j[c] : 0.0f;
@@ -117,11 +114,12 @@ __device__ __forceinline__ void deposit_warp_segmented(float *accum, int astride
         v[c] = keep + __shfl_xor_sync(full, send, bit);
       }
     }
-    float tot = v[0] + __shfl_xor_sync(full, v[0], 1);
+    const float tot = v[0] + __shfl_xor_sync(full, v[0], 1);
     const int comp = lane >> 1;
     if (!(lane & 1) && comp < 12) red_add(accum + (size_t)gv * astride + comp, tot);
-    big &= ~grp;
+    if (mine) todo = false;
   }
+  if (todo) deposit_red_v4(accum + (size_t)vox * astride, j);          // stragglers: three vector REDs
 }
 
 // One streak of move_p, scalar variant of the reference (move_p.cc:233-375), on registers: advance the particle to
@@ -169,6 +167,7 @@ __device__ __forceinline__ int streak_step(const PushK &a, float q, float4 &r, f
 }
 
 // move_p for one particle per thread: every streak goes to memory as three vector REDs.
+template <bool DBG = false>
 __device__ __forceinline__ int move_p_dev(const PushK &a, float4 &r, float4 &u, float &dispx, float &dispy, float &dispz) {
   const float q = a.qsp * u.w;
   int vox = __float_as_int(r.w);
@@ -177,7 +176,7 @@ __device__ __forceinline__ int move_p_dev(const PushK &a, float4 &r, float4 &u, 
     float j[12];
     const int dep_vox = vox;
     st = streak_step(a, q, r, u, vox, dispx, dispy, dispz, j);
-    if (a.dbg & 32) {                                    // profiling: all the arithmetic, none of the REDs
+    if (DBG && (a.dbg & 32)) {                           // profiling: all the arithmetic, none of the REDs
       float s = 0.0f;
 #pragma unroll
       for (int c = 0; c < 12; c++) s += j[c];
@@ -232,13 +231,16 @@ static inline PushK to_push_k(const vpb_push_args_t *args) {
   k.neighbor = (const long long *)args->neighbor; k.rangel = args->rangel; k.rangeh = args->rangeh;
   k.qdt_2mc = args->qdt_2mc; k.cdt_dx = args->cdt_dx; k.cdt_dy = args->cdt_dy; k.cdt_dz = args->cdt_dz; k.qsp = args->qsp;
   k.dbg = args->debug_skip;
+  k.span = 64;
   k.nb.use = 0;
+  // grid geometry (always): strides of the voxel index and their float reciprocals for fast_div
+  k.nb.nx = args->nx; k.nb.ny = args->ny; k.nb.nz = args->nz;
+  k.nb.sy = args->nx + 2; k.nb.sz = (args->nx + 2) * (args->ny + 2);
+  k.nb.inv_sy = 1.0f / (float)k.nb.sy; k.nb.inv_sz = 1.0f / (float)k.nb.sz;
+  for (int f = 0; f < 6; f++) { k.nb.act[f] = 0; k.nb.delta[f] = 0; }
   const vpb_neighbor_rule_t *nr = args->neighbor_rule;
   if (nr && nr->valid && nr->nx == args->nx && nr->ny == args->ny && nr->nz == args->nz) {
     k.nb.use = 1;
-    k.nb.nx = nr->nx; k.nb.ny = nr->ny; k.nb.nz = nr->nz;
-    k.nb.sy = nr->nx + 2; k.nb.sz = (nr->nx + 2) * (nr->ny + 2);
-    k.nb.inv_sy = 1.0f / (float)k.nb.sy; k.nb.inv_sz = 1.0f / (float)k.nb.sz;
     for (int f = 0; f < 6; f++) { k.nb.act[f] = nr->act[f]; k.nb.delta[f] = nr->delta[f]; }
   }
   return k;

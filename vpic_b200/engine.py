@@ -199,6 +199,7 @@ class Species:
         self.partition = torch.zeros(g.nv + 1, dtype=torch.int32, device=dev)
         self.counters = torch.zeros(4, dtype=torch.int32, device=dev)
         self.n_ignored = 0
+        self.partition_np = -1            # particle count of the last sort_p (partition[] valid), -1 = never sorted
         self._aux = None
         self._scratch = None
         self._mv_scratch = None
@@ -214,6 +215,7 @@ class Species:
         _bad_args(n > self.max_np, "set_particles")
         self.p[:n].copy_(t)
         self.np, self.nm = n, 0
+        self.partition_np = -1
 
     def particles_host(self):
         return self.p[:self.np].cpu().numpy().reshape(-1).view(abi.particle_dtype)
@@ -250,6 +252,8 @@ def advance_p(sp: Species, aa: AccumulatorArray, ia: InterpolatorArray, variant=
     if rule is not None:
         a.neighbor_rule = rule
     a.debug_skip = int(os.environ.get("VPB_DEBUG_SKIP", "0"))
+    if sp.partition_np >= 0:              # partition[] of the last sort_p: advance_p walks the array brick by brick
+        a.partition, a.partition_np = sp.partition.data_ptr(), sp.partition_np
     L = _lib.load()
     _lib.check(L.vpb_advance_p(C.byref(a), _stream()), "advance_p")
     if sync:
@@ -294,6 +298,7 @@ def sort_p(sp: Species):
         sp._scratch = torch.empty(need, dtype=torch.uint8, device=g.device)
     _lib.check(L.vpb_sort_p(_ptr(sp.p), sp.np, _ptr(sp._aux), _ptr(sp.partition), g.nx, g.ny, g.nz,
                             _ptr(sp._scratch), sp._scratch.numel(), _stream()), "sort_p")
+    sp.partition_np = sp.np
 
 
 def load_interpolator_array(ia: InterpolatorArray, fa: FieldArray):

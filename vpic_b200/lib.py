@@ -30,7 +30,8 @@ class PushArgs(C.Structure):
                 ("neighbor", c_vp), ("rangel", c_i64), ("rangeh", c_i64),
                 ("qdt_2mc", c_f), ("cdt_dx", c_f), ("cdt_dy", c_f), ("cdt_dz", c_f), ("qsp", c_f),
                 ("nx", c_i32), ("ny", c_i32), ("nz", c_i32),
-                ("variant", c_i32), ("p_first", c_i32), ("neighbor_rule", C.POINTER(NeighborRule)), ("debug_skip", c_i32)]
+                ("variant", c_i32), ("p_first", c_i32), ("neighbor_rule", C.POINTER(NeighborRule)), ("debug_skip", c_i32),
+                ("partition", c_vp), ("partition_np", c_i32)]
 
 
 class BoundaryArgs(C.Structure):
@@ -51,6 +52,7 @@ class FieldArgs(C.Structure):
 
 
 DEPOSIT_DEFAULT, DEPOSIT_RED_V4, DEPOSIT_WARP_SEG, DEPOSIT_WARP_SEG_MOVERS, DEPOSIT_WARP_SEG_FIRST = 0, 1, 2, 3, 4
+DEPOSIT_BRICK_TILE = 5
 FACE_PERIODIC_SELF, FACE_REMOTE = 0, 1
 HALO_TANG_B, HALO_JF, HALO_RHO, HALO_NORM_E, HALO_DIV_B, HALO_TANG_E_NORM_B = 0, 1, 2, 3, 4, 5
 
