@@ -146,10 +146,28 @@ typedef struct vpb_boundary_args {
                                             (accumulate_rhob, rho_p.cc:126-213) */
   float          q_r8V;                  /* species charge * grid r8V, for rhob */
   int32_t        nx, ny, nz;
+  int32_t        absorb_all;             /* 1: every mover is treated as absorbed — what vpic_simulation::advance does with
+                                            movers that are still unresolved after the last communication round
+                                            (src/vpic/advance.cc:78-101: charge into rhob, particle removed) */
 } vpb_boundary_args_t;
 size_t vpb_boundary_scratch_bytes(int32_t nm);
 int    vpb_boundary_p_pack(const vpb_boundary_args_t *args, void *stream);
 int    vpb_boundary_p_inject(const vpb_push_args_t *push, const void *inj, int32_t n, void *stream);
+
+/* Fixed-capacity migration messages (no count handshake, no host synchronisation inside a round).  A message is a
+ * 16-byte header {int32 count, sp_id, capacity, 0} — the header the reference reserves in front of its own injector
+ * buffers, src/boundary/boundary_p.cc:205-211 — followed by `cap` particle_injector_t slots; vpb_boundary_msg_bytes(cap)
+ * bytes in all.  Both neighbours use the same cap, so the send and the receive can be posted without knowing the count.
+ *   vpb_boundary_p_stage       copies class `face` of a vpb_boundary_p_pack result into msg and writes the header.
+ *   vpb_boundary_p_inject_msg  appends the records of a received message at p[push->np + *added ...) in the reference's
+ *                              order, finishes their moves, then adds the count to *added (device int).
+ * status (device int32[2]): [0] |= 1 when a count exceeded cap (records beyond cap were NOT sent), |= 2 when the particle
+ * array was full; [1] = largest count staged since it was last cleared.  The caller reads it once per step. */
+size_t vpb_boundary_msg_bytes(int32_t cap);
+int    vpb_boundary_p_stage(const void *inj, const int32_t *class_offsets, int32_t face, int32_t cap, int32_t sp_id,
+                            void *msg, int32_t *status, void *stream);
+int    vpb_boundary_p_inject_msg(const vpb_push_args_t *push, const void *msg, int32_t cap, int32_t max_np,
+                                 int32_t *added, int32_t *status, void *stream);
 
 /* ---- sort_p ---------------------------------------------------------------
  * Replaces sort_p_pipeline (src/species_advance/standard/pipeline/sort_p_pipeline.cc:220-371):

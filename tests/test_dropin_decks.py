@@ -278,16 +278,18 @@ def test_lpi_2d_deck_matches_reference_and_reports_its_forwards():
     base = {"VPIC_LPI_STEPS": str(steps), "VPIC_LPI_NPPC": nppc}
     runs = {}
     try:
-        for tag, preload in (("cpu", False), ("gpu", True)):
+        # "cpu4": the same CPU binary with another thread count — another summation order of the same deposits, the
+        # yardstick for how far two legitimate runs of this deck drift apart in 245 steps
+        for tag, preload, tpp in (("cpu", False, "8"), ("cpu4", False, "4"), ("gpu", True, "8")):
             d = tempfile.mkdtemp(prefix=f"lpi_{tag}_")
             env = dict(os.environ, **base)
             if preload:
                 env.update({"LD_PRELOAD": LIB, "VPIC_B200_TRACE": "1"})
-            r = subprocess.run([path, "--tpp", "8"], cwd=d, env=env, capture_output=True, text=True, timeout=3000)
+            r = subprocess.run([path, "--tpp", tpp], cwd=d, env=env, capture_output=True, text=True, timeout=3000)
             out = r.stdout + r.stderr
             assert r.returncode == 0 and "normal exit" in out, out[-3000:]
             runs[tag] = (d, out)
-        cpu, gpu = runs["cpu"][0], runs["gpu"][0]
+        cpu, gpu, cpu4 = runs["cpu"][0], runs["gpu"][0], runs["cpu4"][0]
         out = runs["gpu"][1]
         # the forward is loud, once, and names its reason
         warn = [ln for ln in out.splitlines() if "is not served on the device" in ln]
@@ -308,25 +310,22 @@ def test_lpi_2d_deck_matches_reference_and_reports_its_forwards():
             a = np.fromfile(os.path.join(cpu, rel), dtype=np.uint8)
             b = np.fromfile(os.path.join(gpu, rel), dtype=np.uint8)
             assert a.size == b.size == size
+            c = np.fromfile(os.path.join(cpu4, rel), dtype=np.uint8)
             nfl = (size // 4) * 3 // 4                            # the last three quarters of the file are all payload
-            fa_ = a[size - 4 * nfl:].view(np.float32)
-            fb_ = b[size - 4 * nfl:].view(np.float32)
+            fa_, fb_, fc_ = (x[size - 4 * nfl:].view(np.float32).astype(np.float64) for x in (a, b, c))
             assert np.isfinite(fa_).all() and np.isfinite(fb_).all()
-            worst = worst_rms = 0.0
-            # variable-major bands: compare each band of the tail against its own scale
-            for k, (xa, xb) in enumerate(zip(np.array_split(fa_, nband * 3), np.array_split(fb_, nband * 3))):
-                scale = np.abs(xa).max()
-                if scale == 0:
-                    assert np.abs(xb).max() == 0
-                    continue
-                # 245 steps of reordered fp32 deposits; one particle that crosses a wall a step earlier or later also
-                # shifts the host RNG stream of the reflux walls, so later re-injections differ particle by particle:
-                # the bound is statistical (rms) with a loose cap on single cells
-                err = np.abs(xa - xb).max() / scale
-                rms = np.sqrt(np.mean((xa.astype(np.float64) - xb) ** 2)) / max(np.sqrt(np.mean(xa.astype(np.float64) ** 2)), 1e-30)
-                worst = max(worst, err); worst_rms = max(worst_rms, rms)
-                assert err < 0.1 and rms < 1e-2, (rel, k, err, rms)
-            print(f"{rel}: max band error {worst:.2e} of the band's peak, rms {worst_rms:.2e}")
+            # 245 steps of reordered fp32 deposits; one particle that reaches a wall a step earlier or later also shifts
+            # the host RNG stream of the reflux walls, so later re-injections differ particle by particle.  The bound is
+            # therefore statistical, band by band (the dumps are variable-major), and relative to the distance between
+            # two CPU runs of the same binary that differ only in their thread count.
+            worst = 0.0
+            for k, (xa, xb, xc) in enumerate(zip(*(np.array_split(x, nband * 3) for x in (fa_, fb_, fc_)))):
+                norm = max(np.sqrt(np.mean(xa ** 2)), 1e-30)
+                d_gpu = np.sqrt(np.mean((xa - xb) ** 2)) / norm
+                d_cpu = np.sqrt(np.mean((xa - xc) ** 2)) / norm
+                worst = max(worst, d_gpu)
+                assert d_gpu <= 3 * d_cpu + 1e-4 and d_gpu < 0.05, (rel, k, d_gpu, d_cpu)
+            print(f"{rel}: largest rms distance GPU path vs CPU {worst:.2e} (relative to the band's rms)")
         # strict mode: the same run must refuse to use the CPU implementation
         d = tempfile.mkdtemp(prefix="lpi_strict_")
         runs["strict"] = (d, "")

@@ -28,6 +28,7 @@ struct BoundK {
   long long face_range[6];
   int sp_id;
   float *fields; float q_r8V; int nx, ny, nz;
+  int absorb_all;
 };
 
 // class of a mover: 0..5 = send through that face, 6 = absorbed, 7 = no device handler (dropped with a count)
@@ -44,7 +45,7 @@ __global__ void __launch_bounds__(256) bp_build_injectors_kernel(BoundK k, int4 
   const long long nn = __ldg(k.neighbor + 6ll * voxel + face);
   int cls = 7;
   int dst_voxel = voxel;
-  if (nn == -2 /* absorb_particles, grid.h:30 */) {
+  if (nn == -2 /* absorb_particles, grid.h:30 */ || k.absorb_all) {
     cls = 6;
     if (k.fields) {                       // accumulate_rhob (rho_p.cc:126-213): the absorbed charge stays on the wall
       const int sy = k.nx + 2, sz = (k.nx + 2) * (k.ny + 2);
@@ -137,9 +138,78 @@ __global__ void __launch_bounds__(128) bp_inject_kernel(PushK a, const int4 *inj
   a.p[2 * (size_t)i + 1] = u;
 }
 
+// ---- fixed-capacity messages with the count in a 16-byte header (the reference reserves the same header in front of
+// its injector buffers, boundary_p.cc:205-211) -------------------------------------------------------------------
+// A message is int4 header {count, sp_id, capacity, 0} followed by `cap` particle_injector_t slots.  Sender and
+// receiver agree on `cap` ahead of time, so the exchange needs no count handshake and no host synchronisation: the
+// count travels inside the message and is read by the injection kernel on the device.
+__global__ void __launch_bounds__(256) bp_stage_kernel(const int4 *inj, const int *class_offsets, int face, int cap, int sp_id,
+                                                       int4 *msg, int *status) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int first = class_offsets[face], n = class_offsets[face + 1] - first;
+  if (j == 0) {
+    msg[0] = make_int4(n, sp_id, cap, 0);
+    if (n > cap) atomicOr(status, 1);                              // capacity exceeded: reported, never silent
+    atomicMax(status + 1, n);                                      // largest message of the step (sizes the next ones)
+  }
+  if (j >= n || j >= cap) return;
+  const int4 *src = inj + 3 * (size_t)(first + j);
+  int4 *dst = msg + 1 + 3 * (size_t)j;
+  dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+}
+
+// Injection of a received message: record count-1-j lands at p[base + *added + j] (the reference's reverse walk).
+__global__ void __launch_bounds__(128) bp_inject_msg_kernel(PushK a, const int4 *msg, int cap, int base, int max_np,
+                                                            const int *added, int *status) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = min(msg[0].x, cap);
+  if (j >= n) return;
+  const int i = base + *added + j;
+  if (i >= max_np) { atomicOr(status, 2); return; }                // no room left in the particle array
+  const int4 *rec = msg + 1 + 3 * (size_t)(n - 1 - j);
+  const int4 w0 = rec[0], w1 = rec[1], w2 = rec[2];
+  float4 r = make_float4(__int_as_float(w0.x), __int_as_float(w0.y), __int_as_float(w0.z), __int_as_float(w0.w));
+  float4 u = make_float4(__int_as_float(w1.x), __int_as_float(w1.y), __int_as_float(w1.z), __int_as_float(w1.w));
+  float dispx = __int_as_float(w2.x), dispy = __int_as_float(w2.y), dispz = __int_as_float(w2.z);
+  const int left = move_p_dev(a, r, u, dispx, dispy, dispz);
+  if (left) {
+    const int slot = atomicAdd(a.counters, 1);
+    if (slot < a.max_nm) a.pm[slot] = make_int4(__float_as_int(dispx), __float_as_int(dispy), __float_as_int(dispz), i);
+    else { atomicAdd(a.counters + 1, 1); r.w = __int_as_float(__float_as_int(r.w) >> 3); }
+  }
+  a.p[2 * (size_t)i] = r;
+  a.p[2 * (size_t)i + 1] = u;
+}
+__global__ void bp_bump_kernel(int *added, const int4 *msg, int cap) { *added += min(msg[0].x, cap); }
+
 }  // namespace vpb
 
 using namespace vpb;
+
+extern "C" size_t vpb_boundary_msg_bytes(int32_t cap) { return 16 + (size_t)(cap < 0 ? 0 : cap) * 48; }
+
+extern "C" int vpb_boundary_p_stage(const void *inj, const int32_t *class_offsets, int32_t face, int32_t cap, int32_t sp_id,
+                                    void *msg, int32_t *status, void *stream) {
+  VPB_REQUIRE(class_offsets && msg && status && face >= 0 && face < 6 && cap >= 0, "vpb_boundary_p_stage: Bad args.");
+  bp_stage_kernel<<<(cap + 256) / 256, 256, 0, as_stream(stream)>>>((const int4 *)inj, class_offsets, face, cap, sp_id,
+                                                                    (int4 *)msg, status);
+  VPB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vpb_boundary_p_inject_msg(const vpb_push_args_t *push, const void *msg, int32_t cap, int32_t max_np,
+                                         int32_t *added, int32_t *status, void *stream) {
+  VPB_REQUIRE(push && push->p && push->accum && push->neighbor && push->counters && msg && added && status && cap >= 0,
+              "vpb_boundary_p_inject_msg: Bad args.");
+  if (cap == 0) return 0;
+  const PushK k = to_push_k(push);
+  cudaStream_t st = as_stream(stream);
+  bp_inject_msg_kernel<<<(cap + 127) / 128, 128, 0, st>>>(k, (const int4 *)msg, cap, push->np, max_np, added, status);
+  VPB_LAUNCH_CHECK();
+  bp_bump_kernel<<<1, 1, 0, st>>>(added, (const int4 *)msg, cap);
+  VPB_LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" size_t vpb_boundary_scratch_bytes(int32_t nm) {
   if (nm < 1) nm = 1;
@@ -159,6 +229,7 @@ extern "C" int vpb_boundary_p_pack(const vpb_boundary_args_t *b, void *stream) {
   for (int f = 0; f < 6; f++) k.face_range[f] = b->face_range[f];
   k.sp_id = b->sp_id;
   k.fields = b->fields; k.q_r8V = b->q_r8V; k.nx = b->nx; k.ny = b->ny; k.nz = b->nz;
+  k.absorb_all = b->absorb_all;
   VPB_REQUIRE(!b->fields || (b->nx > 0 && b->ny > 0 && b->nz > 0), "vpb_boundary_p_pack: grid size missing for rhob");
   int4 *tmp = (int4 *)b->scratch;
   void *sort_scratch = (char *)b->scratch + (((size_t)b->nm * 48 + 255) / 256) * 256;

@@ -357,7 +357,7 @@ def uncenter_p(sp: Species, ia: InterpolatorArray):
 
 # ---- boundary_p, particle side (src/boundary/boundary_p.cc:257-371,595-711) ----------------------------------
 
-def boundary_pack(sp: Species, face_range, fa: FieldArray = None):
+def boundary_pack(sp: Species, face_range, fa: FieldArray = None, absorb_all=False):
     """Turn this species' movers into per-face injector buffers and back-fill the holes they leave.
 
     Returns (inj, offsets_dev): inj is a [nm, 12] float32 view of particle_injector_t records grouped by class,
@@ -381,6 +381,7 @@ def boundary_pack(sp: Species, face_range, fa: FieldArray = None):
     b.sp_id = getattr(sp, "id", 0)
     b.inj, b.class_offsets = inj.data_ptr(), offs.data_ptr()
     b.scratch, b.scratch_bytes = scratch.data_ptr(), need
+    b.absorb_all = 1 if absorb_all else 0
     if fa is not None:                                   # absorbed particles leave their charge in rhob
         b.fields, b.q_r8V = fa.f.data_ptr(), float(np.float32(np.float32(sp.q) * np.float32(g.g.r8V)))
         b.nx, b.ny, b.nz = g.nx, g.ny, g.nz
@@ -413,3 +414,47 @@ def boundary_inject(sp: Species, aa: AccumulatorArray, ia: InterpolatorArray, in
         a.neighbor_rule = rule
     _lib.check(_lib.load().vpb_boundary_p_inject(C.byref(a), _ptr(inj), n, _stream()), "boundary_p_inject")
     sp.np += n
+
+
+# ---- fixed-capacity migration messages (count in the header; no host synchronisation inside a round) ----------
+
+def boundary_msg_floats(cap):
+    """float32 elements of a migration message of capacity `cap` (16-byte header + cap particle_injector_t)."""
+    return 4 + 12 * int(cap)
+
+
+def boundary_stage(inj, offs, face, cap, sp_id, msg, status):
+    """Copy class `face` of a boundary_pack result into the fixed-capacity message `msg` and write its header."""
+    _lib.check(_lib.load().vpb_boundary_p_stage(_ptr(inj), _ptr(offs), face, cap, sp_id, _ptr(msg), _ptr(status), _stream()),
+               "boundary_p_stage")
+
+
+def boundary_inject_msg(sp: Species, aa: AccumulatorArray, ia: InterpolatorArray, msg, cap, added, status):
+    """Append the records of a received message behind p[sp.np + added) (device-side count) and finish their moves."""
+    g = sp.g
+    a = _lib.PushArgs()
+    a.p, a.np = sp.p.data_ptr(), sp.np
+    a.pm, a.max_nm = sp.pm.data_ptr(), sp.max_nm
+    a.counters = sp.counters.data_ptr()
+    a.interp, a.interp_stride = ia.i.data_ptr(), ia.stride
+    a.accum, a.accum_stride = aa.a.data_ptr(), aa.stride_floats
+    a.neighbor, a.rangel, a.rangeh = g.neighbor.data_ptr(), g.rangel, g.rangeh
+    a.qdt_2mc, a.cdt_dx, a.cdt_dy, a.cdt_dz, a.qsp = sp.push_constants()
+    a.nx, a.ny, a.nz = g.nx, g.ny, g.nz
+    rule = g.neighbor_rule()
+    if rule is not None:
+        a.neighbor_rule = rule
+    _lib.check(_lib.load().vpb_boundary_p_inject_msg(C.byref(a), _ptr(msg), cap, sp.max_np, _ptr(added), _ptr(status), _stream()),
+               "boundary_p_inject_msg")
+
+
+def drop_unresolved_movers(sp: Species, fa: FieldArray):
+    """Movers still unresolved after the last communication round (src/vpic/advance.cc:78-101): the reference warns,
+    puts their charge into rhob and removes them from the particle array; so does this."""
+    if sp.nm == 0:
+        return 0
+    import warnings
+    n = sp.nm
+    warnings.warn(f"Ignoring {n} unprocessed {sp.name} movers (increase num_comm_round)")
+    boundary_pack(sp, [-1] * 6, fa, absorb_all=True)
+    return n

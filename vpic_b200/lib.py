@@ -39,7 +39,7 @@ class BoundaryArgs(C.Structure):
     _fields_ = [("p", c_vp), ("np", c_i32), ("pm", c_vp), ("nm", c_i32), ("neighbor", c_vp),
                 ("rangel", c_i64), ("rangeh", c_i64), ("rangem", c_i64), ("face_range", c_i64 * 6),
                 ("sp_id", c_i32), ("inj", c_vp), ("class_offsets", c_vp), ("scratch", c_vp), ("scratch_bytes", C.c_size_t),
-                ("fields", c_vp), ("q_r8V", c_f), ("nx", c_i32), ("ny", c_i32), ("nz", c_i32)]
+                ("fields", c_vp), ("q_r8V", c_f), ("nx", c_i32), ("ny", c_i32), ("nz", c_i32), ("absorb_all", c_i32)]
 
 
 class FieldArgs(C.Structure):
@@ -79,6 +79,9 @@ _PROTOS = {
     "vpb_boundary_scratch_bytes": (C.c_size_t, [c_i32]),
     "vpb_boundary_p_pack": (C.c_int, [C.POINTER(BoundaryArgs), c_vp]),
     "vpb_boundary_p_inject": (C.c_int, [C.POINTER(PushArgs), c_vp, c_i32, c_vp]),
+    "vpb_boundary_msg_bytes": (C.c_size_t, [c_i32]),
+    "vpb_boundary_p_stage": (C.c_int, [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
+    "vpb_boundary_p_inject_msg": (C.c_int, [C.POINTER(PushArgs), c_vp, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "vpb_sort_scratch_bytes": (C.c_size_t, [c_i32, c_i32]),
     "vpb_sort_movers_scratch_bytes": (C.c_size_t, [c_i32]),
     "vpb_sort_movers": (C.c_int, [c_vp, c_i32, c_vp, C.c_size_t, c_vp]),

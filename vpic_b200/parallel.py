@@ -11,6 +11,8 @@ when world_size == 2).  All collectives here are neighbour send/recv — the pat
 unpacking, back-fill and injection are CUDA kernels (boundary_p.cu, field_advance.cu); this module only routes
 buffers.  The same routing runs over gloo with CPU tensors in the CPU test-suite.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -64,9 +66,117 @@ class SlabExchange:
         self.h_out = [torch.empty(n, dtype=torch.float32, device=dev) for _ in range(2)]
         self.h_in = [torch.empty(n, dtype=torch.float32, device=dev) for _ in range(2)]
         self._extra = {}
+        # fixed-capacity migration (boundary_p_fixed): per-species message buffers and deferred results
+        self.fixed = os.environ.get("VPB_EXCHANGE_FIXED", "1") != "0"
+        self.calibration_steps = 2          # steps that use the counted exchange and measure the message sizes
+        self._steps_seen = 0
+        self._mig = {}
+        self._pending = None
+        # After an injection a particle can become a mover again only at a wall that absorbs (or a custom handler):
+        # every other face of a slab is periodic-self, reflecting or one of the two shared ones it just came through.
+        nb = getattr(dgrid.g, "neighbor", None)                  # particle boundary codes live in grid_t.neighbor (< 0)
+        self.inject_may_emit = bool((nb <= -2).any()) if nb is not None else False
 
+    # ---- deferred bookkeeping of the fixed-capacity exchange ------------------------------------------------------
     def begin_step(self, sim):
-        pass
+        self.resolve(sim)
+
+    def resolve(self, sim):
+        """Read what the last fixed-capacity round left on the device: particles appended per species, capacity and
+        array overflows, and the largest message anywhere in the ring (which sizes the next step's messages)."""
+        if self._pending is None:
+            return
+        ev, host, sps = self._pending
+        self._pending = None
+        ev.synchronize()
+        vals = host.tolist()
+        gmax = vals[-1]
+        for k, sp in enumerate(sps):
+            added, status, emitted = vals[3 * k], vals[3 * k + 1], vals[3 * k + 2]
+            sp.np += added
+            if status & 1:
+                raise RuntimeError(f"species {sp.name}: a migration message exceeded its capacity of {self._mig[sp.id]['cap']} "
+                                   "particles (set VPB_EXCHANGE_FIXED=0 for the counted exchange)")
+            if status & 2:
+                raise RuntimeError(f"species {sp.name}: injected particles exceed max_np={sp.max_np}")
+            if status & 4:
+                raise RuntimeError(f"species {sp.name}: particles hit a boundary with no device handler (custom particle "
+                                   "boundary conditions stay on the host)")
+            if emitted and not self.inject_may_emit:
+                raise RuntimeError(f"species {sp.name}: {emitted} injected particles became movers again although no wall "
+                                   "of this slab can emit them")
+        # every rank sees the same ring-wide maximum, so every rank picks the same capacity for the next step
+        for sp in sps:
+            m = self._mig[sp.id]
+            if gmax > m["cap"] // 2:
+                self._alloc(sp, 4 * gmax)
+
+    def _alloc(self, sp, cap):
+        cap = max(4096, (int(cap) + 1023) // 1024 * 1024)
+        dev = self.g.device
+        n = E.boundary_msg_floats(cap)
+        old = self._mig.get(sp.id)
+        self._mig[sp.id] = {
+            "cap": cap,
+            "out": [torch.zeros(n, dtype=torch.float32, device=dev) for _ in range(2)],
+            "in": [torch.zeros(n, dtype=torch.float32, device=dev) for _ in range(2)],
+            "added": old["added"] if old else torch.zeros(1, dtype=torch.int32, device=dev),
+            "status": old["status"] if old else torch.zeros(2, dtype=torch.int32, device=dev),
+        }
+
+    def boundary_p_fixed(self, sim, species):
+        """First communication round of boundary_p for `species` with fixed-capacity messages: pack, stage, one batch
+        of neighbour sends and receives whose sizes both sides know in advance, inject.  No device-to-host read and no
+        collective: the counts ride in the message headers (boundary_p.cc:205-211 reserves the same header) and are
+        consumed by the injection kernel; sp.np catches up at the next resolve()."""
+        for sp in species:
+            m = self._mig[sp.id]
+            cap = m["cap"]
+            inj, offs = E.boundary_pack(sp, self.face_range, sim.field_array)
+            m["status"][0:1].bitwise_or_(((offs[8] - offs[7]) > 0).to(torch.int32).reshape(1) * 4)   # class 7: no device handler
+            E.boundary_stage(inj, offs, self.f_lo, cap, sp.id, m["out"][0], m["status"])
+            E.boundary_stage(inj, offs, self.f_hi, cap, sp.id, m["out"][1], m["status"])
+            self.ring.sendrecv(m["out"][0], m["out"][1], m["in"][0], m["in"][1])
+            sp.counters.zero_()
+            m["added"].zero_()
+            # injection order of the reference: faces 0..5, so the low face first
+            E.boundary_inject_msg(sp, sim.accumulator_array, sim.interpolator_array, m["in"][0], cap, m["added"], m["status"])
+            E.boundary_inject_msg(sp, sim.accumulator_array, sim.interpolator_array, m["in"][1], cap, m["added"], m["status"])
+
+    def end_fixed(self, sim, species):
+        """Queue the read-back of the step's device-side results (one small copy, resolved at the next step)."""
+        dev = self.g.device
+        parts = []
+        for sp in species:
+            m = self._mig[sp.id]
+            parts += [m["added"], m["status"][0:1], sp.counters[0:1]]
+        sizes = torch.stack([self._mig[sp.id]["status"][1] for sp in species]).max().reshape(1)
+        if self.ring.world > 1:
+            dist.all_reduce(sizes, op=dist.ReduceOp.MAX, group=self.ring.group)
+        flat = torch.cat(parts + [sizes])
+        host = torch.empty(flat.shape, dtype=torch.int32, pin_memory=(dev.type == "cuda"))
+        host.copy_(flat, non_blocking=True)
+        for sp in species:
+            self._mig[sp.id]["status"].zero_()
+        ev = torch.cuda.Event() if dev.type == "cuda" else _NoEvent()
+        ev.record()
+        self._pending = (ev, host, list(species))
+
+    def use_fixed(self, sim):
+        """Counted exchange for the first steps (they measure the message sizes), fixed-capacity messages afterwards."""
+        if not self.fixed:
+            return False
+        if self._steps_seen < self.calibration_steps:
+            return False
+        if not self._mig:
+            cmax = torch.tensor([self._calib_max], dtype=torch.int32, device=self.g.device)
+            if self.ring.world > 1:
+                dist.all_reduce(cmax, op=dist.ReduceOp.MAX, group=self.ring.group)
+            for sp in sim.species_list:
+                self._alloc(sp, 4 * int(cmax.item()))
+        return True
+
+    _calib_max = 0
 
     # ---- particles ------------------------------------------------------------------------------------------
     def boundary_p(self, sim, species=None, check_empty=True):
@@ -87,6 +197,7 @@ class SlabExchange:
         offs = torch.stack([o for _, o in packed]).cpu()                       # one sync for all species
         n_lo = [int(offs[s, self.f_lo + 1] - offs[s, self.f_lo]) for s in range(len(sps))]
         n_hi = [int(offs[s, self.f_hi + 1] - offs[s, self.f_hi]) for s in range(len(sps))]
+        self._calib_max = max([self._calib_max] + n_lo + n_hi)
         for s, sp in enumerate(sps):
             if int(offs[s, 8] - offs[s, 7]):
                 raise RuntimeError(f"species {sp.name}: {int(offs[s, 8] - offs[s, 7])} particles hit a boundary with "
@@ -167,3 +278,9 @@ class SlabExchange:
         if self.ring.world > 1:
             dist.all_reduce(t, group=self.ring.group)
         return t.cpu().tolist()
+
+
+class _NoEvent:
+    """CPU stand-in for torch.cuda.Event (the gloo tests run the same bookkeeping without a device)."""
+    def record(self): pass
+    def synchronize(self): pass

@@ -56,9 +56,16 @@ class Simulation:
             self.exchange.begin_step(self)
         E.load_interpolator_array(self.interpolator_array, self.field_array)
 
+    def sync_counts(self):
+        """Bring sp.np up to date with what the last migration round appended on the device (multi-GPU runs defer that
+        read to the next step)."""
+        if self.exchange is not None:
+            self.exchange.resolve(self)
+
     def advance(self):
         fa, ia, aa = self.field_array, self.interpolator_array, self.accumulator_array
         step = self.step
+        self.sync_counts()
         for sp in self.species_list:
             if sp.sort_interval > 0 and step % sp.sort_interval == 0:
                 E.sort_p(sp)
@@ -82,22 +89,39 @@ class Simulation:
             main = torch.cuda.current_stream()
             if self._side is None:
                 self._side = torch.cuda.Stream(priority=-1)
+            fixed = self.exchange.use_fixed(self)
             with torch.cuda.stream(self._side):
                 for sp, ev in zip(self.species_list, done):
                     self._side.wait_event(ev)
                     E.finish_advance_p_all([sp])
-                    self.exchange.boundary_p(self, species=[sp], check_empty=False)
+                    if fixed:
+                        self.exchange.boundary_p_fixed(self, [sp])
+                    else:
+                        self.exchange.boundary_p(self, species=[sp], check_empty=False)
+                if fixed:
+                    self.exchange.end_fixed(self, self.species_list)
             main.wait_stream(self._side)
             E.reduce_accumulator_array(aa)
-            for _ in range(self.num_comm_round - 1):
-                if not self.exchange.boundary_p(self):
-                    break                         # no movers anywhere: the remaining rounds would be empty too
+            if fixed and not self.exchange.inject_may_emit:
+                pass      # the later rounds are provably empty (no wall of this slab turns an injected particle into a mover)
+            else:
+                if fixed:
+                    self.exchange.resolve(self)
+                    E.finish_advance_p_all(self.species_list)
+                for _ in range(self.num_comm_round - 1):
+                    if not self.exchange.boundary_p(self):
+                        break                     # no movers anywhere: the remaining rounds would be empty too
+                for sp in self.species_list:
+                    E.drop_unresolved_movers(sp, fa)          # advance.cc:78-101
+            self.exchange._steps_seen += 1
         elif self.exchange is not None:
             E.finish_advance_p_all(self.species_list)
             E.reduce_accumulator_array(aa)
             for _ in range(self.num_comm_round):
                 if not self.exchange.boundary_p(self):
                     break
+            for sp in self.species_list:
+                E.drop_unresolved_movers(sp, fa)              # advance.cc:78-101
         else:
             E.finish_advance_p_all(self.species_list)
             E.reduce_accumulator_array(aa)
@@ -106,16 +130,28 @@ class Simulation:
                 if sp.nm:
                     _, offs = E.boundary_pack(sp, [-1] * 6, fa)
                     o = offs.cpu()
-                    if int(o[8] - o[6]) != int(o[8]):
+                    if int(o[8] - o[7]) != 0:                     # class 7: neither absorbed nor sent anywhere
                         raise RuntimeError(f"species {sp.name}: particles left through a face that is neither local, "
                                            "absorbing nor shared with another rank (custom boundary handlers stay on "
                                            "the host)")
         fa.clear_jf()
         E.unload_accumulator_array(fa, aa)
         fa.synchronize_jf()
-        if self.exchange is not None:
-            self.exchange.synchronize_jf(self)
-        fa.advance_b(0.5)
+        if self.exchange is not None and self.overlap_exchange:
+            # the shared-plane current sums travel on the side stream while the first half B advance (which does not
+            # read jf) runs on the main one
+            main = torch.cuda.current_stream()
+            if self._side is None:
+                self._side = torch.cuda.Stream(priority=-1)
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                self.exchange.synchronize_jf(self)
+            fa.advance_b(0.5)
+            main.wait_stream(self._side)
+        else:
+            if self.exchange is not None:
+                self.exchange.synchronize_jf(self)
+            fa.advance_b(0.5)
         if self.exchange is not None:
             self.exchange.ghost_tang_b(self)
         fa.advance_e(1.0)
@@ -163,6 +199,7 @@ class Simulation:
 
     def energies(self):
         """dump_energies row (src/vpic/dump.cc:38-77): field energies then one kinetic energy per species."""
+        self.sync_counts()
         en_f = self.field_array.energy_f()
         en_p = [E.energy_p(sp, self.interpolator_array) for sp in self.species_list]
         return list(en_f) + en_p
