@@ -177,6 +177,7 @@ def run_ours(args):
     e0.record()
     pushes = 0
     for _ in range(args.steps):
+        sim.sync_counts()                      # multi-GPU: particles the last migration appended (deferred read)
         pushes += sum(sp.np for sp in sim.species_list)
         sim.advance()
     e1.record()

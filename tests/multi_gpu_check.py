@@ -148,6 +148,7 @@ def main():
     for step in range(args.steps):
         ref.advance()
         sim.advance()
+        sim.sync_counts()                      # the fixed-capacity exchange defers sp.np to the next step
         # particles: total conserved, and my slab's particles match the single-domain run's particles in my region
         for sref, sloc in zip(ref.species_list, sim.species_list):
             tot = torch.tensor([sloc.np], dtype=torch.int64, device=dev)

@@ -450,6 +450,222 @@ void advance_p(vpb_species_t *sp, vpb_accumulator_array_t *aa, const vpb_interpo
 // order — bit-identical, tests/test_gpu_parity.py::test_boundary_p_absorbing_walls_match_reference) so the host never
 // walks sp->pm.  Anything else — several ranks (the exchange is the host's MPI), custom handlers (host function
 // pointers) — is the reference's own boundary_p, reached through dlsym(RTLD_NEXT).
+
+// ---- several ranks: the exchange rides the HOST PROGRAM's own message passing ---------------------------------------
+// Under an MPI host (one rank per GPU) the device kernels of this library do all the particle and field work; what has
+// to travel between ranks — injector records, halo planes — is staged through host memory and sent with the reference's
+// own mp_* port API (src/util/mp/mp.h, DMPPolicy.h:228-343: mp_size_*_buffer, mp_begin/end_send/recv on g->mp), found
+// at run time in the host program.  Ports and tags are the reference's: port = BOUNDARY index of the face, a message
+// carries the sender's port as its tag (boundary_p.cc:392-446, remote.cc:40-58).  The NCCL route (no host staging) is
+// the Python host's (vpic_b200/parallel.py); this one needs nothing but the MPI the host already has.
+struct HostMP {
+  bool ok = false;
+  void *(*send_buffer)(void *, int) = nullptr; void *(*recv_buffer)(void *, int) = nullptr;
+  void (*size_send)(void *, int, int) = nullptr; void (*size_recv)(void *, int, int) = nullptr;
+  void (*begin_send)(void *, int, int, int, int) = nullptr; void (*begin_recv)(void *, int, int, int, int) = nullptr;
+  void (*end_send)(void *, int) = nullptr; void (*end_recv)(void *, int) = nullptr;
+};
+static HostMP &host_mp() {
+  static HostMP h;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    static int enabled = -1;
+    if (enabled < 0) { const char *e = getenv("VPIC_B200_MULTIRANK"); enabled = !(e && e[0] == '0'); }
+    *(void **)&h.send_buffer = dlsym(RTLD_DEFAULT, "mp_send_buffer");   *(void **)&h.recv_buffer = dlsym(RTLD_DEFAULT, "mp_recv_buffer");
+    *(void **)&h.size_send = dlsym(RTLD_DEFAULT, "mp_size_send_buffer"); *(void **)&h.size_recv = dlsym(RTLD_DEFAULT, "mp_size_recv_buffer");
+    *(void **)&h.begin_send = dlsym(RTLD_DEFAULT, "mp_begin_send");     *(void **)&h.begin_recv = dlsym(RTLD_DEFAULT, "mp_begin_recv");
+    *(void **)&h.end_send = dlsym(RTLD_DEFAULT, "mp_end_send");         *(void **)&h.end_recv = dlsym(RTLD_DEFAULT, "mp_end_recv");
+    h.ok = enabled && h.send_buffer && h.recv_buffer && h.size_send && h.size_recv && h.begin_send && h.begin_recv && h.end_send && h.end_recv;
+  }
+  return h;
+}
+static const int kFaceOff[6][3] = {{-1,0,0},{0,-1,0},{0,0,-1},{1,0,0},{0,1,0},{0,0,1}};
+static inline int face_port(int f) { return 13 + kFaceOff[f][0] + 3 * kFaceOff[f][1] + 9 * kFaceOff[f][2]; }          // BOUNDARY(i,j,k)
+static inline int face_port_rev(int f) { return 13 - kFaceOff[f][0] - 3 * kFaceOff[f][1] - 9 * kFaceOff[f][2]; }
+// the rank behind face f when that face is shared with ANOTHER rank, else -1
+static inline int face_peer(const vpb_grid_t *g, int f) { const int b = g->bc[face_port(f)]; return (b >= 0 && b != g->bc[13]) ? b : -1; }
+static bool any_shared_face(const vpb_grid_t *g) { for (int f = 0; f < 6; f++) if (face_peer(g, f) >= 0) return true; return false; }
+
+// One message of out_bytes[f] bytes from out_dev[f] to the rank behind every shared face, and the matching message from
+// it into in_dev[f] (in_bytes[f] bytes; both sides know the sizes).  Zero-sized messages are skipped on both sides.
+static void exchange_faces(const vpb_grid_t *g, void *const out_dev[6], const size_t out_bytes[6],
+                           void *const in_dev[6], const size_t in_bytes[6]) {
+  HostMP &mp = host_mp();
+  for (int f = 0; f < 6; f++) {
+    const int peer = face_peer(g, f);
+    if (peer < 0 || !in_bytes[f]) continue;
+    mp.size_recv(g->mp, face_port(f), (int)in_bytes[f]);
+    mp.begin_recv(g->mp, face_port(f), (int)in_bytes[f], peer, face_port_rev(f));
+  }
+  for (int f = 0; f < 6; f++) {
+    const int peer = face_peer(g, f);
+    if (peer < 0 || !out_bytes[f]) continue;
+    mp.size_send(g->mp, face_port(f), (int)out_bytes[f]);
+    DEV(vpb_memcpy_d2h(mp.send_buffer(g->mp, face_port(f)), out_dev[f], out_bytes[f], nullptr));
+    g_d2h += out_bytes[f];
+  }
+  DEV(vpb_stream_sync(nullptr));
+  for (int f = 0; f < 6; f++) {
+    const int peer = face_peer(g, f);
+    if (peer < 0 || !out_bytes[f]) continue;
+    mp.begin_send(g->mp, face_port(f), (int)out_bytes[f], peer, face_port(f));
+  }
+  for (int f = 0; f < 6; f++) {
+    const int peer = face_peer(g, f);
+    if (peer < 0 || !in_bytes[f]) continue;
+    mp.end_recv(g->mp, face_port(f));
+    DEV(vpb_memcpy_h2d(in_dev[f], mp.recv_buffer(g->mp, face_port(f)), in_bytes[f], nullptr));
+    g_h2d += in_bytes[f];
+  }
+  DEV(vpb_stream_sync(nullptr));                                 // the receive buffers may be reused after this
+  for (int f = 0; f < 6; f++) if (face_peer(g, f) >= 0 && out_bytes[f]) mp.end_send(g->mp, face_port(f));
+}
+
+static std::unordered_map<const void *, bool> g_movers_unsorted;  // species whose sp->pm was filled by an injection
+
+// One communication round of boundary_p on several ranks (boundary_p.cc:41-750 without custom handlers): pack on the
+// device, exchange counts and then injector records through the host's ports, inject on the device in the reference's
+// order (faces 0..5, every buffer last record first).
+static void boundary_p_multirank(vpb_species_t *sp_list, vpb_field_array_t *fa, vpb_accumulator_array_t *aa,
+                                 const vpb_interpolator_array_t *ia_unused) {
+  (void)ia_unused;
+  const vpb_grid_t *g = sp_list->g;
+  const int world = _world_size;
+  const size_t nv = (size_t)g->nv;
+  Mirror &mn = mirror(g->neighbor, 6 * nv * sizeof(int64_t), false);
+  if (!mn.device_valid) { DEV(vpb_memcpy_h2d(mn.d, g->neighbor, 6 * nv * sizeof(int64_t), nullptr)); g_h2d += 6 * nv * sizeof(int64_t);
+                          mn.device_valid = true; mn.live_bytes = 6 * nv * sizeof(int64_t); }
+  const size_t fbytes = nv * sizeof(vpb_field_t);
+  std::vector<vpb_species_t *> sps;
+  for (vpb_species_t *sp = sp_list; sp; sp = sp->next) sps.push_back(sp);
+  const int S = (int)sps.size();
+  // ---- pack every species; injector records stay on the device, grouped by destination face
+  std::vector<void *> inj(S, nullptr);
+  std::vector<int32_t> offs((size_t)S * 9, 0);
+  float *df = nullptr;
+  for (int s = 0; s < S; s++) {
+    vpb_species_t *sp = sps[s];
+    if (sp->nm <= 0) continue;
+    count_call(C_BOUNDARY_P);
+    const int nm = sp->nm;
+    void *dpm = dev_in(sp->pm, (size_t)nm * sizeof(vpb_particle_mover_t), (size_t)sp->max_nm * sizeof(vpb_particle_mover_t));
+    if (g_movers_unsorted[sp] && nm > 1) {
+      const size_t need = vpb_sort_movers_scratch_bytes(nm);
+      DEV(vpb_sort_movers(dpm, nm, scratch(0, need), need, nullptr));
+    }
+    g_movers_unsorted[sp] = false;
+    vpb_boundary_args_t b;
+    memset(&b, 0, sizeof b);
+    b.p = dev_in(sp->p, (size_t)sp->np * sizeof(vpb_particle_t), (size_t)sp->max_np * sizeof(vpb_particle_t));
+    b.np = sp->np; b.pm = dpm; b.nm = nm;
+    b.neighbor = (const int64_t *)mn.d;
+    b.rangel = g->rangel; b.rangeh = g->rangeh; b.rangem = g->range[world];
+    for (int f = 0; f < 6; f++) { const int peer = face_peer(g, f); b.face_range[f] = peer >= 0 ? g->range[peer] : -1; }
+    b.sp_id = sp->id;
+    inj[s] = scratch(100 + s, (size_t)nm * sizeof(vpb_particle_injector_t));
+    b.inj = inj[s];
+    b.class_offsets = (int32_t *)scratch(7, 9 * sizeof(int32_t));
+    b.scratch_bytes = vpb_boundary_scratch_bytes(nm);
+    b.scratch = scratch(8, b.scratch_bytes);
+    if (!df) df = (float *)dev_in(fa->f, fbytes);
+    b.fields = df; b.q_r8V = sp->q * g->r8V; b.nx = g->nx; b.ny = g->ny; b.nz = g->nz;
+    DEV(vpb_boundary_p_pack(&b, nullptr));
+    DEV(vpb_memcpy_d2h(&offs[(size_t)s * 9], b.class_offsets, 9 * sizeof(int32_t), nullptr));
+    DEV(vpb_stream_sync(nullptr));
+    g_d2h += 9 * sizeof(int32_t);
+    const int32_t *o = &offs[(size_t)s * 9];
+    if (o[8] - o[7] != 0)
+      DROPIN_ERROR("Species = %s: %d movers left through a face that is neither absorbing, local nor shared with another rank; "
+                   "Unknown boundary interaction", sp->name, o[8] - o[7]);
+    sp->np -= nm;
+    sp->nm = 0;
+    dev_written(sp->p, (size_t)sp->np * sizeof(vpb_particle_t));
+  }
+  if (df) dev_written(fa->f, fbytes);
+  // ---- counts: int32[S] per shared face, both ways
+  void *cnt_out[6], *cnt_in[6]; size_t cnt_bytes[6];
+  std::vector<int32_t> n_send((size_t)6 * S, 0), n_recv((size_t)6 * S, 0);
+  int32_t *cnt_dev = (int32_t *)scratch(9, (size_t)12 * S * sizeof(int32_t));
+  for (int f = 0; f < 6; f++) {
+    cnt_bytes[f] = face_peer(g, f) >= 0 ? (size_t)S * sizeof(int32_t) : 0;
+    for (int s = 0; s < S; s++) n_send[(size_t)f * S + s] = offs[(size_t)s * 9 + f + 1] - offs[(size_t)s * 9 + f];
+    cnt_out[f] = cnt_dev + (size_t)f * S; cnt_in[f] = cnt_dev + (size_t)(6 + f) * S;
+  }
+  DEV(vpb_memcpy_h2d(cnt_dev, n_send.data(), (size_t)6 * S * sizeof(int32_t), nullptr));
+  exchange_faces(g, cnt_out, cnt_bytes, cnt_in, cnt_bytes);
+  DEV(vpb_memcpy_d2h(n_recv.data(), cnt_dev + (size_t)6 * S, (size_t)6 * S * sizeof(int32_t), nullptr));
+  DEV(vpb_stream_sync(nullptr));
+  // ---- payload: for every shared face the records of all species, species by species
+  void *pay_out[6], *pay_in[6]; size_t out_bytes[6], in_bytes[6];
+  for (int f = 0; f < 6; f++) {
+    size_t so = 0, si = 0;
+    if (face_peer(g, f) >= 0) for (int s = 0; s < S; s++) { so += (size_t)n_send[(size_t)f * S + s]; si += (size_t)n_recv[(size_t)f * S + s]; }
+    out_bytes[f] = so * sizeof(vpb_particle_injector_t); in_bytes[f] = si * sizeof(vpb_particle_injector_t);
+    pay_out[f] = out_bytes[f] ? scratch(20 + f, out_bytes[f]) : nullptr;
+    pay_in[f] = in_bytes[f] ? scratch(30 + f, in_bytes[f]) : nullptr;
+    size_t at = 0;
+    for (int s = 0; s < S && out_bytes[f]; s++) {
+      const size_t n = (size_t)n_send[(size_t)f * S + s];
+      if (!n) continue;
+      DEV(vpb_memcpy_d2d((char *)pay_out[f] + at, (char *)inj[s] + (size_t)offs[(size_t)s * 9 + f] * sizeof(vpb_particle_injector_t),
+                         n * sizeof(vpb_particle_injector_t), nullptr));
+      at += n * sizeof(vpb_particle_injector_t);
+    }
+  }
+  exchange_faces(g, pay_out, out_bytes, pay_in, in_bytes);
+  // ---- inject: faces in ascending order, per species (the arrays of different species are independent)
+  bool any_in = false;
+  for (int f = 0; f < 6; f++) any_in |= in_bytes[f] != 0;
+  if (any_in) {
+    const float *di = nullptr;
+    float *da = (float *)dev_in(aa->a, (size_t)aa->stride * sizeof(vpb_accumulator_t));
+    for (int s = 0; s < S; s++) {
+      vpb_species_t *sp = sps[s];
+      int total = 0;
+      for (int f = 0; f < 6; f++) total += n_recv[(size_t)f * S + s];
+      if (!total) continue;
+      if (sp->np + total > sp->max_np)
+        DROPIN_ERROR("Species = %s: %d incoming particles do not fit (np = %d, max_np = %d); give the species more headroom",
+                     sp->name, total, sp->np, sp->max_np);
+      vpb_push_args_t a;
+      memset(&a, 0, sizeof a);
+      a.p = dev_in(sp->p, (size_t)sp->np * sizeof(vpb_particle_t), (size_t)sp->max_np * sizeof(vpb_particle_t));
+      a.pm = dev_out_only(sp->pm, (size_t)sp->max_nm * sizeof(vpb_particle_mover_t));
+      a.max_nm = sp->max_nm;
+      a.counters = counters();
+      DEV(vpb_memset(a.counters, 0, 4 * sizeof(int), nullptr));
+      a.interp = (const float *)di; a.interp_stride = kInterpFloats;      // move_p needs no interpolator
+      a.accum = da; a.accum_stride = kAccumFloats;
+      a.neighbor = (const int64_t *)mn.d; a.rangel = g->rangel; a.rangeh = g->rangeh;
+      a.qdt_2mc = qdt_2mc_of(sp);
+      a.cdt_dx = g->cvac * g->dt * g->rdx; a.cdt_dy = g->cvac * g->dt * g->rdy; a.cdt_dz = g->cvac * g->dt * g->rdz;
+      a.qsp = sp->q;
+      a.nx = g->nx; a.ny = g->ny; a.nz = g->nz;
+      for (int f = 0; f < 6; f++) {
+        const int n = n_recv[(size_t)f * S + s];
+        if (!n) continue;
+        size_t at = 0;
+        for (int s2 = 0; s2 < s; s2++) at += (size_t)n_recv[(size_t)f * S + s2] * sizeof(vpb_particle_injector_t);
+        a.np = sp->np;
+        DEV(vpb_boundary_p_inject(&a, (char *)pay_in[f] + at, n, nullptr));
+        sp->np += n;
+      }
+      int c[4];
+      DEV(vpb_memcpy_d2h(c, a.counters, sizeof c, nullptr));
+      DEV(vpb_stream_sync(nullptr));
+      g_d2h += sizeof c;
+      sp->nm = c[0] < sp->max_nm ? c[0] : sp->max_nm;
+      if (c[1]) DROPIN_WARNING("Species = %s ran out of storage for %i movers.", sp->name, c[1]);
+      g_movers_unsorted[sp] = sp->nm > 1;
+      dev_written(sp->p, (size_t)sp->np * sizeof(vpb_particle_t));
+      dev_written(sp->pm, (size_t)sp->nm * sizeof(vpb_particle_mover_t));
+    }
+    dev_written(aa->a, (size_t)aa->stride * sizeof(vpb_accumulator_t));
+  }
+  finish_entry();
+}
+
 void boundary_p(void *pbc_list, vpb_species_t *sp_list, vpb_field_array_t *fa, vpb_accumulator_array_t *aa) {
   if (!sp_list) return;                                          // boundary_p.cc:252
   if (!fa || !aa || sp_list->g != aa->g || fa->g != aa->g) DROPIN_ERROR("Bad args");
@@ -461,6 +677,14 @@ void boundary_p(void *pbc_list, vpb_species_t *sp_list, vpb_field_array_t *fa, v
   if (enabled < 0) { const char *e = getenv("VPIC_B200_BOUNDARY_P"); enabled = !(e && e[0] == '0'); }
   bool local_only = world == 1 && !pbc_list && enabled;
   for (int i = 0; i < 27 && local_only; i++) local_only = g->bc[i] < 0 || g->bc[i] == g->bc[13];
+  if (!local_only && world > 1 && !pbc_list && enabled && g->mp && host_mp().ok) {
+    // several ranks, standard walls only: device pack / inject around an exchange through the host's own ports
+    int rounds_any = 0;
+    for (const vpb_species_t *sp = sp_list; sp; sp = sp->next) rounds_any |= sp->nm > 0;
+    (void)rounds_any;                      // every rank must take part in the exchange, movers or not
+    boundary_p_multirank(sp_list, fa, aa, nullptr);
+    return;
+  }
   if (!local_only) {
     static auto ref = (void (*)(void *, vpb_species_t *, vpb_field_array_t *, vpb_accumulator_array_t *))dlsym(RTLD_NEXT, "boundary_p");
     if (!ref) DROPIN_ERROR("boundary_p: several ranks or custom particle boundary handlers need the reference's own boundary_p, which is not linked in");
@@ -729,7 +953,8 @@ static const char *device_fields_obstacle(const vpb_field_array_t *fa) {
   const int self = g->bc[13];
   for (int f = 0; f < 6; f++) {
     const int b = g->bc[13 + off[f][0] + 3 * off[f][1] + 9 * off[f][2]];          // BOUNDARY(i,j,k), grid.h:16
-    if (b >= 0 && b != self) return "a face is shared with another rank (multi-rank halo exchange runs through the NCCL path)";
+    if (b >= 0 && b != self && !(g->mp && host_mp().ok))
+      return "a face is shared with another rank and the host program's mp_* ports were not found";
     if (b < -4) return "a field boundary condition the device kernels do not know";
   }
   return nullptr;
@@ -746,10 +971,31 @@ static void field_args_of(const vpb_field_array_t *fa, float *df, vpb_field_args
   static const int off[6][3] = {{-1,0,0},{0,-1,0},{0,0,-1},{1,0,0},{0,1,0},{0,0,1}};
   for (int f = 0; f < 6; f++) {
     const int b = g->bc[13 + off[f][0] + 3 * off[f][1] + 9 * off[f][2]];
-    a->face[f] = b < 0 ? b : VPB_FACE_PERIODIC_SELF;
+    a->face[f] = b < 0 ? b : (b == g->bc[13] ? VPB_FACE_PERIODIC_SELF : VPB_FACE_REMOTE);
   }
   a->has_material = 1;                                       // material_coefficient_t, sfa_private.h:14-25
   memcpy(a->material, prm->mc, 13 * sizeof(float));
+}
+
+// Halo planes of the faces shared with other ranks (begin/end_remote_ghost_*, synchronize_* of remote.cc): packed and
+// unpacked by the device kernels, carried by exchange_faces.  No-op on a single rank.
+static void remote_halo(const vpb_field_array_t *fa, const vpb_field_args_t &a, int kind, double *err_dev = nullptr) {
+  const vpb_grid_t *g = fa->g;
+  if (!any_shared_face(g)) return;
+  void *out[6], *in[6]; size_t bytes[6];
+  for (int f = 0; f < 6; f++) {
+    bytes[f] = 0; out[f] = in[f] = nullptr;
+    if (face_peer(g, f) < 0) continue;
+    bytes[f] = vpb_halo_floats_kind(g->nx, g->ny, g->nz, f % 3, kind) * sizeof(float);
+    out[f] = scratch(40 + f, bytes[f]); in[f] = scratch(50 + f, bytes[f]);
+    DEV(vpb_halo_pack(&a, kind, f, (float *)out[f], nullptr));
+  }
+  exchange_faces(g, out, bytes, in, bytes);
+  for (int f = 0; f < 6; f++) {
+    if (!bytes[f]) continue;
+    if (kind == VPB_HALO_TANG_E_NORM_B) DEV(vpb_halo_unpack_sync(&a, f, (const float *)in[f], err_dev, nullptr));
+    else DEV(vpb_halo_unpack(&a, kind, f, (const float *)in[f], nullptr));
+  }
 }
 
 #define FIELD_ENTRY(name, call)                                                            \
@@ -763,9 +1009,17 @@ static void field_args_of(const vpb_field_array_t *fa, float *df, vpb_field_args
   finish_entry();
 
 void vpic_b200_advance_b(vpb_field_array_t *fa, float frac) { FIELD_ENTRY(C_ADVANCE_B, vpb_advance_b(&a, frac, nullptr)) }
-void vpic_b200_advance_e(vpb_field_array_t *fa, float frac) { FIELD_ENTRY(C_ADVANCE_E, vpb_vacuum_advance_e(&a, frac, nullptr)) }
+void vpic_b200_advance_e(vpb_field_array_t *fa, float frac) {
+  // tangential-B ghost planes of shared faces first (begin/end_remote_ghost_tang_b, remote.cc:61-134)
+  FIELD_ENTRY(C_ADVANCE_E, (remote_halo(fa, a, VPB_HALO_TANG_B), vpb_vacuum_advance_e(&a, frac, nullptr)))
+}
 void vpic_b200_clear_jf(vpb_field_array_t *fa) { FIELD_ENTRY(C_CLEAR_JF, vpb_clear_jf(&a, nullptr)) }
-void vpic_b200_synchronize_jf(vpb_field_array_t *fa) { FIELD_ENTRY(C_SYNC_JF, vpb_synchronize_jf(&a, nullptr)) }
+static int sync_jf_all(const vpb_field_array_t *fa, const vpb_field_args_t &a) {
+  const int r = vpb_synchronize_jf(&a, nullptr);               // walls and self-periodic axes
+  if (!r) remote_halo(fa, a, VPB_HALO_JF);                     // shared planes: own + remote (remote.cc:417-508)
+  return r;
+}
+void vpic_b200_synchronize_jf(vpb_field_array_t *fa) { FIELD_ENTRY(C_SYNC_JF, sync_jf_all(fa, a)) }
 void vpic_b200_energy_f(double *en, const vpb_field_array_t *fa) {
   if (!en || !fa) DROPIN_ERROR("Bad args");
   count_call(C_ENERGY_F);
@@ -847,12 +1101,13 @@ void vacuum_energy_f(double *en, const vpb_field_array_t *fa) {
 #define DIV_ENTRY_W(call) DIV_ENTRY(call) dev_written(fa->f, fbytes); finish_entry();
 
 void vpic_b200_clear_rhof(vpb_field_array_t *fa) { DIV_ENTRY_W(vpb_clear_rhof(&a, nullptr)) }
-void vpic_b200_synchronize_rho(vpb_field_array_t *fa) { DIV_ENTRY_W(vpb_synchronize_rho(&a, nullptr)) }
-void vpic_b200_compute_div_e_err(vpb_field_array_t *fa) { DIV_ENTRY_W(vpb_vacuum_compute_div_e_err(&a, nullptr)) }
+static int step_then_halo(const vpb_field_array_t *fa, const vpb_field_args_t &a, int r, int kind) { if (!r) remote_halo(fa, a, kind); return r; }
+void vpic_b200_synchronize_rho(vpb_field_array_t *fa) { DIV_ENTRY_W(step_then_halo(fa, a, vpb_synchronize_rho(&a, nullptr), VPB_HALO_RHO)) }
+void vpic_b200_compute_div_e_err(vpb_field_array_t *fa) { DIV_ENTRY_W((remote_halo(fa, a, VPB_HALO_NORM_E), vpb_vacuum_compute_div_e_err(&a, nullptr))) }
 void vpic_b200_clean_div_e(vpb_field_array_t *fa) { DIV_ENTRY_W(vpb_vacuum_clean_div_e(&a, nullptr)) }
 void vpic_b200_compute_div_b_err(vpb_field_array_t *fa) { DIV_ENTRY_W(vpb_compute_div_b_err(&a, nullptr)) }
-void vpic_b200_clean_div_b(vpb_field_array_t *fa) { DIV_ENTRY_W(vpb_clean_div_b(&a, nullptr)) }
-void vpic_b200_compute_rhob(vpb_field_array_t *fa) { DIV_ENTRY_W(vpb_vacuum_compute_rhob(&a, nullptr)) }
+void vpic_b200_clean_div_b(vpb_field_array_t *fa) { DIV_ENTRY_W((remote_halo(fa, a, VPB_HALO_DIV_B), vpb_clean_div_b(&a, nullptr))) }
+void vpic_b200_compute_rhob(vpb_field_array_t *fa) { DIV_ENTRY_W((remote_halo(fa, a, VPB_HALO_NORM_E), vpb_vacuum_compute_rhob(&a, nullptr))) }
 void vpic_b200_compute_curl_b(vpb_field_array_t *fa) { DIV_ENTRY_W(vpb_vacuum_compute_curl_b(&a, nullptr)) }
 
 static double rms_finish(const vpb_field_array_t *fa, double *sum_dev) {
@@ -878,6 +1133,7 @@ double vpic_b200_compute_rms_div_b_err(const vpb_field_array_t *fa) {
 double vpic_b200_synchronize_tang_e_norm_b(vpb_field_array_t *fa) {
   double *err = (double *)scratch(5, sizeof(double));
   DIV_ENTRY(vpb_synchronize_tang_e_norm_b(&a, err, nullptr))
+  remote_halo(fa, a, VPB_HALO_TANG_E_NORM_B, err);             // shared planes averaged with the neighbour's (remote.cc:298-416)
   dev_written(fa->f, fbytes);
   double local = 0, global = 0;
   DEV(vpb_memcpy_d2h(&local, err, sizeof local, nullptr));

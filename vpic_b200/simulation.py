@@ -167,6 +167,7 @@ class Simulation:
         """advance.cc:138-176: Marder passes on div E and div B and the shared-face synchronisation."""
         fa, ex = self.field_array, self.exchange
         if self.clean_div_e_interval > 0 and step % self.clean_div_e_interval == 0:
+            self.sync_counts()                 # accumulate_rho_p needs the particles this step's migration appended
             fa.clear_rhof()
             for sp in self.species_list:
                 E.accumulate_rho_p(fa, sp)
