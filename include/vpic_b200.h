@@ -163,6 +163,11 @@ int    vpb_boundary_p_inject(const vpb_push_args_t *push, const void *inj, int32
  *                              order, finishes their moves, then adds the count to *added (device int).
  * status (device int32[2]): [0] |= 1 when a count exceeded cap (records beyond cap were NOT sent), |= 2 when the particle
  * array was full; [1] = largest count staged since it was last cleared.  The caller reads it once per step. */
+/* move_p for one particle (src/species_advance/species_advance.h:152-157, move_p.cc:216-378): *mover_dev is a
+ * particle_mover_t on the device (in: displacement and particle index, out: what is left of it), *result_dev receives
+ * the reference's return value.  push supplies p, accum, neighbor, rangel/rangeh, qsp and the grid size. */
+int    vpb_move_p(const vpb_push_args_t *push, void *mover_dev, int32_t *result_dev, void *stream);
+
 size_t vpb_boundary_msg_bytes(int32_t cap);
 int    vpb_boundary_p_stage(const void *inj, const int32_t *class_offsets, int32_t face, int32_t cap, int32_t sp_id,
                             void *msg, int32_t *status, void *stream);
@@ -266,6 +271,11 @@ int vpb_accumulate_hydro_p(float *hydro, const void *p, int32_t np, const float 
                            int32_t nx, int32_t ny, int32_t nz, void *stream);
 int vpb_clear_hydro(float *hydro, int32_t nx, int32_t ny, int32_t nz, void *stream);
 int vpb_synchronize_hydro(float *hydro, const vpb_field_args_t *geometry, void *stream);   /* f of geometry is ignored */
+/* node planes of faces shared with another rank (hydro_array.cc:203-262): pack the plane the neighbour behind `face`
+ * shares with us, unpack adds the plane received through `face` (own + remote); vpb_hydro_halo_floats per plane */
+size_t vpb_hydro_halo_floats(int32_t nx, int32_t ny, int32_t nz, int axis);
+int vpb_hydro_halo_pack(float *hydro, const vpb_field_args_t *geometry, int face, float *buf, void *stream);
+int vpb_hydro_halo_unpack(float *hydro, const vpb_field_args_t *geometry, int face, const float *buf, void *stream);
 
 /* Halo planes for VPB_FACE_REMOTE faces (the payload of begin/end_remote_ghost_tang_b, remote.cc:61-134, and of
  * synchronize_jf, remote.cc:417-508).  pack copies the plane a neighbour needs into buf; unpack applies a received

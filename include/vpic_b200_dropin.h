@@ -48,6 +48,9 @@ extern "C" {
 void advance_p(vpb_species_t *sp, vpb_accumulator_array_t *aa, const vpb_interpolator_array_t *ia);
 /* src/species_advance/species_advance.h:65-66 */
 void sort_p(vpb_species_t *sp);
+/* src/species_advance/species_advance.h:152-157 — single particles from host code (inject_particle, emitters): runs
+ * on the device while the particle's memory is device-owned, otherwise it is the host program's own move_p (forward) */
+int move_p(vpb_particle_t *p0, vpb_particle_mover_t *pm, vpb_accumulator_t *a0, const vpb_grid_t *g, const float qsp);
 /* src/species_advance/species_advance.h:90-107 */
 void center_p(vpb_species_t *sp, const vpb_interpolator_array_t *ia);
 void uncenter_p(vpb_species_t *sp, const vpb_interpolator_array_t *ia);

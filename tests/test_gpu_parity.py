@@ -786,3 +786,66 @@ def test_dropin_boundary_p_absorbing_walls(eng, mode):
     assert res["particles"], "particle array differs from the reference's after boundary_p"
     assert res["others"], "boundary_p touched field slots other than rhob"
     assert res["rhob"] < 2e-5, res["rhob"]
+
+
+def test_dropin_move_p_runs_on_the_device_when_the_arrays_live_there(eng, oracle):
+    """move_p(particle_t*, particle_mover_t*, accumulator_t*, const grid_t*, qsp) — species_advance.h:152-157 — is what
+    inject_particle and the emitters call on single particles.  In resident mode, after an advance_p has left the
+    arrays on the device, the exported symbol must move the particle THERE (no page of the particle array comes back)
+    and produce the reference's result: same particle bytes, same mover, same return value, same deposits."""
+    import subprocess, sys, os, json, textwrap
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = textwrap.dedent(f"""
+        import sys, ctypes as C, numpy as np
+        sys.path.insert(0, {root!r}); sys.path.insert(0, {os.path.join(root, 'tests')!r})
+        import bench, refvpic as R
+        from vpic_b200 import lib, grid as G, abi
+        L = lib.load(); orc = R.load_oracle()
+        nx, ny, nz, n = 7, 6, 5, 5003
+        g = G.partition_periodic_box(0,0,0,nx,ny,nz,nx,ny,nz,1,1,1, dt=G.courant_dt(1,1,1,nx,ny,nz,frac=0.98))
+        g.set_pbc(2, -2); g.set_pbc(5, -1)                      # one absorbing and one reflecting z wall
+        H = bench.HostWorld(L, g, pinned=True)
+        L.vpic_b200_set_mode(1)                                  # resident
+        rng = np.random.default_rng(12)
+        sp = H.new_species('e', -1.0, 1.0, n, n, 20)
+        parts = R.random_particles(rng, n, nx, ny, nz, uth=0.0, w=0.5)
+        sp.p[:n] = parts.view(np.float32).reshape(-1, 8); sp.c.np = n
+        H.load_interpolator()
+        L.clear_accumulator_array(C.byref(H.aa))
+        L.advance_p(C.byref(sp.c), C.byref(H.aa), C.byref(H.ia))        # zero momenta, zero fields: nothing moves
+        L.vpic_b200_sync_to_host.argtypes = [C.c_void_p]; L.vpic_b200_sync_to_host.restype = None
+        L.vpic_b200_transfer_bytes.argtypes = [C.c_void_p]
+        L.vpic_b200_sync_to_host(None)
+        p_ref = sp.p[:n].reshape(-1).view(abi.particle_dtype).copy()
+        acc_ref = H.accum.copy()
+        # the arrays are on the device again after the next hot-path call
+        L.clear_accumulator_array(C.byref(H.aa)); acc_ref[:] = 0
+        L.advance_p(C.byref(sp.c), C.byref(H.aa), C.byref(H.ia))
+        L.move_p.restype = C.c_int
+        L.move_p.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float]
+        before = (C.c_uint64 * 2)(); L.vpic_b200_transfer_bytes(before)
+        moves = []
+        for k in range(40):
+            mv = np.zeros(1, dtype=abi.mover_dtype)
+            mv['i'] = int(rng.integers(0, n))
+            mv['dispx'], mv['dispy'], mv['dispz'] = (rng.uniform(-0.9, 0.9, 3)).astype(np.float32)
+            mv2 = mv.copy()
+            ret = L.move_p(sp.p.ctypes.data, mv.ctypes.data, H.accum.ctypes.data, C.byref(H.G), C.c_float(-1.0))
+            ret2 = orc.vpo_move_p(p_ref.ctypes.data, mv2.ctypes.data, acc_ref.ctypes.data, 12, g.neighbor.ctypes.data,
+                                  g.rangel, g.rangeh, C.c_float(-1.0))
+            moves.append(bool(ret == ret2 and np.array_equal(mv.view(np.uint8), mv2.view(np.uint8))))
+        after = (C.c_uint64 * 2)(); L.vpic_b200_transfer_bytes(after)
+        L.vpic_b200_sync_to_host(None)
+        got = sp.p[:n].reshape(-1).view(abi.particle_dtype)
+        ok = dict(moves=all(moves), particles=bool(np.array_equal(got.view(np.uint8), p_ref.view(np.uint8))),
+                  accum=float(np.abs(H.accum - acc_ref).max() / max(np.abs(acc_ref).max(), 1e-30)),
+                  d2h_during_moves=int(after[1] - before[1]), changed=int((got['i'] != parts['i']).sum()))
+        L.vpic_b200_set_mode(0)
+        print('RESULT ' + json.dumps(ok))
+    """)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("RESULT ")][0][7:])
+    assert res["moves"] and res["particles"] and res["accum"] < 1e-5, res
+    assert res["changed"] > 5                                    # particles really crossed cells
+    assert res["d2h_during_moves"] < 40 * 64, res                # only movers and return values crossed PCIe

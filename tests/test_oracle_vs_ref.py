@@ -262,6 +262,25 @@ def test_reference_build_passes_its_own_kat_decks(deck):
     assert r.returncode == 0 and "pass" in out and "FAIL" not in out, out[-1500:]
 
 
+def test_reference_pcomm_deck_passes_on_eight_shim_ranks():
+    """test/integrated/legacy/pcomm.deck is the reference's own known-answer test of particle migration: eight MPI
+    ranks (2 x 2 x 2), particles aimed across faces, edges and corners, exact voxels and offsets within 11 ulp on
+    arrival.  It needs MPI; here the eight ranks are processes on oracle/mpi_shim's shared-memory transport
+    (oracle/mpi_shim/shimrun).  Passing it pins that transport — the multi-rank oracle of the multi-GPU path."""
+    import subprocess, tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = os.path.join(root, "oracle", "_ref", "pcomm.scalar")
+    if not os.path.exists(path):
+        pytest.skip("deck binaries not built (needs /root/reference at build time)")
+    with tempfile.TemporaryDirectory() as d:
+        r = subprocess.run([os.path.join(root, "oracle", "mpi_shim", "shimrun"), "-n", "8", path, "1", "1"],
+                           cwd=d, capture_output=True, text=True, timeout=600)
+        logs = "".join(open(os.path.join(d, f)).read() for f in sorted(os.listdir(d)) if f.startswith("shimrun."))
+    out = r.stdout + r.stderr
+    assert r.returncode == 0 and "pass" in out and "FAIL" not in out + logs, (out + logs)[-1500:]
+    assert "8 (MPI) ranks" in out
+
+
 def test_reference_build_passes_its_own_golden_energy_test():
     """test/unit/energy_comparison/3d_test against energies_gold.3d_test, reference alone on the CPU."""
     import shutil, subprocess, tempfile

@@ -182,6 +182,20 @@ __global__ void __launch_bounds__(128) bp_inject_msg_kernel(PushK a, const int4 
 }
 __global__ void bp_bump_kernel(int *added, const int4 *msg, int cap) { *added += min(msg[0].x, cap); }
 
+// move_p for ONE particle (src/species_advance/standard/move_p.cc:216-378): mover = {dispx, dispy, dispz, i} in and out,
+// result[0] = the reference's return value (1: the particle is still in use, p.i = 8*voxel+face).
+__global__ void move_p_single_kernel(PushK a, int4 *mover, int *result) {
+  const int4 mv = mover[0];
+  const int i = mv.w;
+  float4 r = a.p[2 * (size_t)i], u = a.p[2 * (size_t)i + 1];
+  float dispx = __int_as_float(mv.x), dispy = __int_as_float(mv.y), dispz = __int_as_float(mv.z);
+  const int left = move_p_dev(a, r, u, dispx, dispy, dispz);
+  a.p[2 * (size_t)i] = r;
+  a.p[2 * (size_t)i + 1] = u;
+  mover[0] = make_int4(__float_as_int(dispx), __float_as_int(dispy), __float_as_int(dispz), i);
+  result[0] = left;
+}
+
 }  // namespace vpb
 
 using namespace vpb;
@@ -207,6 +221,14 @@ extern "C" int vpb_boundary_p_inject_msg(const vpb_push_args_t *push, const void
   bp_inject_msg_kernel<<<(cap + 127) / 128, 128, 0, st>>>(k, (const int4 *)msg, cap, push->np, max_np, added, status);
   VPB_LAUNCH_CHECK();
   bp_bump_kernel<<<1, 1, 0, st>>>(added, (const int4 *)msg, cap);
+  VPB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vpb_move_p(const vpb_push_args_t *push, void *mover_dev, int32_t *result_dev, void *stream) {
+  VPB_REQUIRE(push && push->p && push->accum && push->neighbor && mover_dev && result_dev, "vpb_move_p: Bad args.");
+  const PushK k = to_push_k(push);
+  move_p_single_kernel<<<1, 1, 0, as_stream(stream)>>>(k, (int4 *)mover_dev, result_dev);
   VPB_LAUNCH_CHECK();
   return 0;
 }

@@ -737,6 +737,63 @@ void boundary_p(void *pbc_list, vpb_species_t *sp_list, vpb_field_array_t *fa, v
   finish_entry();
 }
 
+// ---- move_p: species_advance.h:152-157, move_p.cc:216-378 ---------------------------------------------------
+// Host code moves single particles through this symbol: inject_particle (src/vpic/misc.cc:95), the emitters
+// (src/emitter/child_langmuir.cc:114), the reference's own boundary_p.  While the particle's part of the array and
+// the accumulators live on the device (auto / resident mode, between hot-path calls) the move runs there — one thread,
+// nothing faults back.  While they are host-owned (deck initialisation: millions of inject_particle calls before the
+// first advance_p) a device round trip per particle would be absurd, so the call goes to the host program's own
+// move_p — loudly, like every other forward.
+int move_p(vpb_particle_t *p0, vpb_particle_mover_t *pm, vpb_accumulator_t *a0, const vpb_grid_t *g, const float qsp) {
+  if (!p0 || !pm || !a0 || !g) DROPIN_ERROR("Bad args");
+  mode();
+  bool on_device = false;
+  auto it = g_mirrors.find(p0);
+  if (it != g_mirrors.end() && it->second.d && it->second.device_valid) {
+    Mirror &m = it->second;
+    const size_t off = (size_t)pm->i * sizeof(vpb_particle_t);
+    on_device = m.lazy ? vpb_lazy::device_owns(m.lazy, off) : (g_mode == VPB_MODE_RESIDENT && m.host_stale && off < m.live_bytes);
+  }
+  static auto ref = (int (*)(vpb_particle_t *, vpb_particle_mover_t *, vpb_accumulator_t *, const vpb_grid_t *, float))dlsym(RTLD_NEXT, "move_p");
+  if (!on_device && ref) {
+    // said once; not an error under VPIC_B200_STRICT: this is host code moving one particle in host memory, not a kernel
+    static bool told = false;
+    if (!told) { told = true; DROPIN_WARNING("move_p on a particle in host-owned memory (single-particle calls from host code, e.g. inject_particle "
+                                             "during initialisation) is served by the host program's own move_p (said once)"); }
+    return ref(p0, pm, a0, g, qsp);
+  }
+  const size_t nv = (size_t)g->nv;
+  Mirror &mn = mirror(g->neighbor, 6 * nv * sizeof(int64_t), false);
+  if (!mn.device_valid) { DEV(vpb_memcpy_h2d(mn.d, g->neighbor, 6 * nv * sizeof(int64_t), nullptr)); g_h2d += 6 * nv * sizeof(int64_t);
+                          mn.device_valid = true; mn.live_bytes = 6 * nv * sizeof(int64_t); }
+  vpb_push_args_t a;
+  memset(&a, 0, sizeof a);
+  Mirror &mp_ = it != g_mirrors.end() ? it->second : mirror(p0, ((size_t)pm->i + 1) * sizeof(vpb_particle_t));
+  const size_t pbytes = mp_.cap;
+  a.p = dev_in(p0, mp_.live_bytes > ((size_t)pm->i + 1) * sizeof(vpb_particle_t) ? mp_.live_bytes : ((size_t)pm->i + 1) * sizeof(vpb_particle_t), pbytes);
+  a.np = pm->i + 1;
+  // the accumulator array: the caller passes block 0 (aa->a); its mirror is keyed by the same pointer
+  auto ia_ = g_mirrors.find(a0);
+  const size_t abytes = ia_ != g_mirrors.end() ? ia_->second.cap : (size_t)((nv + 1) / 2 * 2) * sizeof(vpb_accumulator_t);
+  a.accum = (float *)dev_in(a0, abytes);
+  a.accum_stride = kAccumFloats;
+  a.counters = counters();
+  a.neighbor = (const int64_t *)mn.d; a.rangel = g->rangel; a.rangeh = g->rangeh;
+  a.qsp = qsp;
+  a.nx = g->nx; a.ny = g->ny; a.nz = g->nz;
+  char *tmp = (char *)scratch(60, 64);
+  DEV(vpb_memcpy_h2d(tmp, pm, sizeof *pm, nullptr));
+  DEV(vpb_move_p(&a, tmp, (int32_t *)(tmp + 32), nullptr));
+  int32_t left = 0;
+  DEV(vpb_memcpy_d2h(pm, tmp, sizeof *pm, nullptr));
+  DEV(vpb_memcpy_d2h(&left, tmp + 32, sizeof left, nullptr));
+  DEV(vpb_stream_sync(nullptr));
+  dev_written(p0, ((size_t)pm->i + 1) * sizeof(vpb_particle_t) > mp_.live_bytes ? ((size_t)pm->i + 1) * sizeof(vpb_particle_t) : mp_.live_bytes);
+  dev_written(a0, abytes);
+  finish_entry();
+  return left;
+}
+
 // ---- sort_p: species_advance.h:65-66, sort_p_pipeline.cc:220-371 ------------------------------------------
 void sort_p(vpb_species_t *sp) {
   if (!sp) DROPIN_ERROR("Bad args.");
@@ -858,11 +915,11 @@ static bool hydro_sync_on_device(const vpb_hydro_array_t *ha) {
 
 void synchronize_hydro_array(vpb_hydro_array_t *ha) {
   if (!ha) DROPIN_ERROR("NULL hydro array.");
-  if (!hydro_sync_on_device(ha)) {
+  if (!hydro_sync_on_device(ha) && !(ha->g->mp && host_mp().ok)) {
     static auto ref = (void (*)(vpb_hydro_array_t *))dlsym(RTLD_NEXT, "synchronize_hydro_array");
     if (!ref) DROPIN_ERROR("synchronize_hydro_array: faces shared with other ranks need the reference's own exchange, which is not linked in");
     count_call(C_FIELD_FALLBACK);
-    FORWARD_NOTICE("synchronize_hydro_array", "a face is shared with another rank");
+    FORWARD_NOTICE("synchronize_hydro_array", "a face is shared with another rank and the host program's mp_* ports were not found");
     ref(ha);
     return;
   }
@@ -875,9 +932,21 @@ void synchronize_hydro_array(vpb_hydro_array_t *ha) {
   static const int off[6][3] = {{-1,0,0},{0,-1,0},{0,0,-1},{1,0,0},{0,1,0},{0,0,1}};
   for (int f = 0; f < 6; f++) {
     const int b = g->bc[13 + off[f][0] + 3 * off[f][1] + 9 * off[f][2]];
-    a.face[f] = b < 0 ? (b < -4 ? -2 : b) : VPB_FACE_PERIODIC_SELF;   // every local wall doubles, whatever its kind
+    a.face[f] = b < 0 ? (b < -4 ? -2 : b) : (b == g->bc[13] ? VPB_FACE_PERIODIC_SELF : VPB_FACE_REMOTE);   // every local wall doubles, whatever its kind
   }
   DEV(vpb_synchronize_hydro(dh, &a, nullptr));
+  if (any_shared_face(g)) {                                      // shared node planes: own + remote (hydro_array.cc:203-262)
+    void *out[6], *in[6]; size_t bytes[6];
+    for (int f = 0; f < 6; f++) {
+      bytes[f] = 0; out[f] = in[f] = nullptr;
+      if (face_peer(g, f) < 0) continue;
+      bytes[f] = vpb_hydro_halo_floats(g->nx, g->ny, g->nz, f % 3) * sizeof(float);
+      out[f] = scratch(40 + f, bytes[f]); in[f] = scratch(50 + f, bytes[f]);
+      DEV(vpb_hydro_halo_pack(dh, &a, f, (float *)out[f], nullptr));
+    }
+    exchange_faces(g, out, bytes, in, bytes);
+    for (int f = 0; f < 6; f++) if (bytes[f]) DEV(vpb_hydro_halo_unpack(dh, &a, f, (const float *)in[f], nullptr));
+  }
   dev_written(ha->h, hydro_bytes(ha));
   finish_entry();
 }

@@ -151,9 +151,45 @@ __global__ void __launch_bounds__(256) sync_hydro_self_kernel(float *hydro, Fiel
   }
 }
 
+// shared node plane of one face, 14 moments per node (the payload of hydro_array.cc:203-226): pack copies it out,
+// unpack forms own + remote (equal cell sizes on both sides: lw = rw = 1, hydro_array.cc:236-262)
+__global__ void __launch_bounds__(256) hydro_halo_kernel(float *hydro, FieldK k, int face, float *buf, bool unpack) {
+  const int X = face % 3, Y = (X + 1) % 3, Z = (X + 2) % 3;
+  const int n[3] = {k.nx, k.ny, k.nz};
+  const int s[3] = {1, k.nx + 2, (k.nx + 2) * (k.ny + 2)};
+  const int cy = blockIdx.x * blockDim.x + threadIdx.x + 1, cz = blockIdx.y + 1;
+  if (cy > n[Y] + 1 || cz > n[Z] + 1) return;
+  const int plane = face < 3 ? 1 : n[X] + 1;
+  float *h = hydro + (size_t)(plane * s[X] + cy * s[Y] + cz * s[Z]) * kHydroFloats;
+  float *b = buf + 14 * ((size_t)(cz - 1) * (n[Y] + 1) + (cy - 1));
+#pragma unroll
+  for (int q = 0; q < 14; q++) { if (unpack) h[q] = h[q] + b[q]; else b[q] = h[q]; }
+}
+
 }  // namespace vpb
 
 using namespace vpb;
+
+extern "C" size_t vpb_hydro_halo_floats(int32_t nx, int32_t ny, int32_t nz, int axis) {
+  const int n[3] = {nx, ny, nz};
+  return 14 * (size_t)(n[(axis + 1) % 3] + 1) * (size_t)(n[(axis + 2) % 3] + 1);
+}
+extern "C" int vpb_hydro_halo_pack(float *hydro, const vpb_field_args_t *geometry, int face, float *buf, void *stream) {
+  vpb_field_args_t g = *geometry; g.f = hydro;
+  if (int r = check_field_args(&g, "vpb_hydro_halo_pack")) return r;
+  VPB_REQUIRE(buf && face >= 0 && face < 6, "vpb_hydro_halo_pack: Bad args");
+  hydro_halo_kernel<<<plane_grid(&g, face % 3, 1), 256, 0, as_stream(stream)>>>(hydro, to_k(&g), face, buf, false);
+  VPB_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int vpb_hydro_halo_unpack(float *hydro, const vpb_field_args_t *geometry, int face, const float *buf, void *stream) {
+  vpb_field_args_t g = *geometry; g.f = hydro;
+  if (int r = check_field_args(&g, "vpb_hydro_halo_unpack")) return r;
+  VPB_REQUIRE(buf && face >= 0 && face < 6, "vpb_hydro_halo_unpack: Bad args");
+  hydro_halo_kernel<<<plane_grid(&g, face % 3, 1), 256, 0, as_stream(stream)>>>(hydro, to_k(&g), face, const_cast<float *>(buf), true);
+  VPB_LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" int vpb_accumulate_hydro_p(float *hydro, const void *p, int32_t np, const float *interp, int32_t interp_stride,
                                       float q, float m, float dt, float cvac, float r8V,
@@ -186,8 +222,7 @@ extern "C" int vpb_synchronize_hydro(float *hydro, const vpb_field_args_t *geome
   g.f = hydro;                                                     // only the geometry of the argument block is used
   const vpb_field_args_t *a = &g;
   if (int r = check_field_args(a, "vpb_synchronize_hydro")) return r;
-  for (int i = 0; i < 6; i++)
-    VPB_REQUIRE(a->face[i] != VPB_FACE_REMOTE, "vpb_synchronize_hydro: faces shared with another rank are not supported yet");
+  // faces shared with another rank: the caller exchanges their node planes (vpb_hydro_halo_pack / _unpack)
   cudaStream_t st = as_stream(stream);
   bool any_local = false;
   for (int i = 0; i < 6; i++) any_local |= a->face[i] < 0;
@@ -198,7 +233,7 @@ extern "C" int vpb_synchronize_hydro(float *hydro, const vpb_field_args_t *geome
   for (int X = 0; X < 3; X++) {
     if (a->face[X] == VPB_FACE_PERIODIC_SELF && a->face[X + 3] == VPB_FACE_PERIODIC_SELF) {
       sync_hydro_self_kernel<<<plane_grid(a, X, 1), 256, 0, st>>>(hydro, to_k(a), X); VPB_LAUNCH_CHECK();
-    } else {
+    } else if (a->face[X] != VPB_FACE_REMOTE && a->face[X + 3] != VPB_FACE_REMOTE) {
       VPB_REQUIRE(a->face[X] != VPB_FACE_PERIODIC_SELF && a->face[X + 3] != VPB_FACE_PERIODIC_SELF,
                   "vpb_synchronize_hydro: axis %d is periodic on one side only", X);
     }

@@ -356,6 +356,14 @@ int host_access(const void *p, size_t n) {
   return touched;
 }
 
+bool device_owns(Region *r, size_t off) {
+  if (!r || off >= r->cap) return false;
+  char *a = r->h + off;
+  if (a < r->lo || a >= r->hi) return false;            // the edges are always host-owned
+  Lock lk;
+  return r->ndevice && r->state[chunk_of(r, a)] != HOST;
+}
+
 int active() { return (int)g_stats.regions; }
 
 Stats stats() { return g_stats; }

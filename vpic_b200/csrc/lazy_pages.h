@@ -57,6 +57,7 @@ void device_wrote(Region *r, size_t bytes, uint64_t *d2h_bytes);  // edge bytes 
 void to_host(Region *r, size_t off, size_t bytes, uint64_t *d2h_bytes);
 void forget_device(Region *r);                         // the host copy is declared current everywhere
 int host_access(const void *p, size_t n);              // [p,p+n) made host-owned in every attached region
+bool device_owns(Region *r, size_t off);               // is the byte at offset `off` currently owned by the device?
 int active();                                          // number of attached regions
 Stats stats();
 

@@ -79,6 +79,7 @@ _PROTOS = {
     "vpb_boundary_scratch_bytes": (C.c_size_t, [c_i32]),
     "vpb_boundary_p_pack": (C.c_int, [C.POINTER(BoundaryArgs), c_vp]),
     "vpb_boundary_p_inject": (C.c_int, [C.POINTER(PushArgs), c_vp, c_i32, c_vp]),
+    "vpb_move_p": (C.c_int, [C.POINTER(PushArgs), c_vp, c_vp, c_vp]),
     "vpb_boundary_msg_bytes": (C.c_size_t, [c_i32]),
     "vpb_boundary_p_stage": (C.c_int, [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "vpb_boundary_p_inject_msg": (C.c_int, [C.POINTER(PushArgs), c_vp, c_i32, c_i32, c_vp, c_vp, c_vp]),
@@ -112,6 +113,9 @@ _PROTOS = {
     "vpb_accumulate_hydro_p": (C.c_int, [c_vp, c_vp, c_i32, c_vp, c_i32] + [c_f] * 5 + [c_i32] * 3 + [c_vp]),
     "vpb_clear_hydro": (C.c_int, [c_vp, c_i32, c_i32, c_i32, c_vp]),
     "vpb_synchronize_hydro": (C.c_int, [c_vp, C.POINTER(FieldArgs), c_vp]),
+    "vpb_hydro_halo_floats": (C.c_size_t, [c_i32, c_i32, c_i32, C.c_int]),
+    "vpb_hydro_halo_pack": (C.c_int, [c_vp, C.POINTER(FieldArgs), C.c_int, c_vp, c_vp]),
+    "vpb_hydro_halo_unpack": (C.c_int, [c_vp, C.POINTER(FieldArgs), C.c_int, c_vp, c_vp]),
     "vpb_halo_floats": (C.c_size_t, [c_i32, c_i32, c_i32, C.c_int]),
     "vpb_halo_floats_kind": (C.c_size_t, [c_i32, c_i32, c_i32, C.c_int, C.c_int]),
     "vpb_halo_unpack_sync": (C.c_int, [C.POINTER(FieldArgs), C.c_int, c_vp, c_vp, c_vp]),
@@ -120,7 +124,7 @@ _PROTOS = {
 }
 
 # the reference's own extern "C" symbols that the drop-in layer exports (include/vpic_b200_dropin.h)
-DROPIN_SYMBOLS = ["advance_p", "sort_p", "load_interpolator_array", "clear_accumulator_array",
+DROPIN_SYMBOLS = ["advance_p", "sort_p", "move_p", "load_interpolator_array", "clear_accumulator_array",
                   "reduce_accumulator_array", "unload_accumulator_array", "energy_p", "center_p", "uncenter_p",
                   "accumulate_rho_p", "advance_b", "vacuum_advance_e", "clear_jf", "synchronize_jf", "vacuum_energy_f",
                   "clear_rhof", "synchronize_rho", "vacuum_compute_div_e_err", "compute_rms_div_e_err", "vacuum_clean_div_e",
