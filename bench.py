@@ -278,10 +278,13 @@ def run_e2e(args, device):
         t0 = time.perf_counter()
         pushes = 0
         energies = None
-        for _ in range(steps):
+        movers = 0
+        for k in range(steps):
             pushes += sum(sp.c.np for sp in species)
             H.advance(species)
-            if diagnostics:
+            movers += sum(sp.c.nm for sp in species)          # the per-step result the host reads back: sp->nm
+            if diagnostics and (k + 1) % args.e2e_energy_interval == 0:
+                # dump_energies at the deck's energies_interval: six field energies and one kinetic energy per species
                 L.vpic_b200_energy_f(en_f, C.byref(H.fa))
                 energies = [float(x) for x in en_f] + [L.energy_p(C.byref(sp.c), C.byref(H.ia)) for sp in species]
         torch.cuda.synchronize()
@@ -317,7 +320,8 @@ def run_e2e(args, device):
         "api": "drop-in extern C symbols (advance_p(species_t*,accumulator_array_t*,interpolator_array_t*), sort_p, "
                "clear/reduce/unload_accumulator_array, field kernels, load_interpolator_array, energy_p, energy_f) on "
                "page-locked HOST arrays, VPB_MODE_AUTO: host memory stays the program's truth (any host access faults "
-               "the data back); per step the host reads sp->nm, both kinetic energies and the six field energies"})
+               f"the data back); every step the host reads sp->nm of both species, every {args.e2e_energy_interval} steps "
+               "(a deck's energies_interval) both kinetic energies and the six field energies"})
     return auto
 
 
@@ -659,6 +663,8 @@ def main():
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--e2e", type=int, default=1)
     ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--e2e-energy-interval", type=int, default=10,
+                    help="e2e leg: steps between dump_energies-style diagnostics (energy_f + energy_p per species)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--ref-grid", type=int, default=0, help="reference arm: cells per side (default: --grid, the full workload)")

@@ -394,4 +394,5 @@ def test_harris_two_ranks_on_the_gpu_match_the_two_rank_reference(mode):
     for col in range(1, a.shape[1]):
         scale = np.abs(a[:, col]).max()
         if scale > 1e-3 * np.abs(tot_a).max():                      # the components that carry the energy
-            assert np.abs(a[:, col] - b[:, col]).max() <= 5e-4 * scale, col
+            # two ranks: the shared planes add one more reordering of fp32 sums per step than the one-rank run has
+            assert np.abs(a[:, col] - b[:, col]).max() <= 2e-3 * scale, col

@@ -796,7 +796,7 @@ def test_dropin_move_p_runs_on_the_device_when_the_arrays_live_there(eng, oracle
     import subprocess, sys, os, json, textwrap
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     code = textwrap.dedent(f"""
-        import sys, ctypes as C, numpy as np
+        import sys, json, ctypes as C, numpy as np
         sys.path.insert(0, {root!r}); sys.path.insert(0, {os.path.join(root, 'tests')!r})
         import bench, refvpic as R
         from vpic_b200 import lib, grid as G, abi
