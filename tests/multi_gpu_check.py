@@ -145,6 +145,14 @@ def main():
 
     worst = dict(count=0, part=0.0, field=0.0, energy=0.0)
     ok = True
+    # Outlier bookkeeping.  A particle may deviate by more than rounding only through the one documented mechanism: it
+    # landed within rounding of a cell face in one of the two runs (the interpolation of the normal E component is
+    # discontinuous there, so the two filings are kicked differently from then on).  Every outlier must be IDENTIFIED
+    # as such: its tag must have been seen within 4 ulp of a face, in either run, during the last few steps before it
+    # first deviated.  An outlier without that history fails the check.
+    near_face_age = [dict() for _ in species]                 # per species: tag -> steps since it was last seen on a face
+    known_outliers = [set() for _ in species]
+    unexplained = 0
     for step in range(args.steps):
         ref.advance()
         sim.advance()
@@ -177,6 +185,29 @@ def main():
             delta = np.zeros(len(mine))
             for k in ("dx", "dy", "dz", "ux", "uy", "uz"):
                 delta = np.maximum(delta, np.abs(mine[k] - mine_ref[k]) * sel)
+            # identify every outlier (deviation beyond fp32 reordering noise, or filed under another voxel)
+            si = [sref.name for sref in ref.species_list].index(sref.name)
+            ages = near_face_age[si]
+            for k_ in list(ages):
+                ages[k_] += 1
+                if ages[k_] > 6:
+                    del ages[k_]
+            for arr in (mine, mine_ref):
+                edge = np.maximum(np.maximum(np.abs(arr["dx"]), np.abs(arr["dy"])), np.abs(arr["dz"])) > 1.0 - 5e-7
+                for t_ in arr["w"][edge]:
+                    ages[float(t_)] = 0
+            out_mask = (delta > 2e-4) | ~sel
+            for t_ in mine["w"][out_mask]:
+                t_ = float(t_)
+                if t_ in known_outliers[si]:
+                    continue
+                if t_ in ages:
+                    known_outliers[si].add(t_)
+                else:
+                    unexplained += 1
+                    if unexplained <= 5:
+                        j = int(np.where(mine["w"] == np.float32(t_))[0][0])
+                        print(f"[{rank}] step {step} {sloc.name}: UNEXPLAINED outlier: slab {mine[j]} single {mine_ref[j]}")
             if len(delta) > 8:
                 srt = np.sort(delta)
                 worst["part"] = max(worst["part"], float(srt[-9]))          # all but the 8 largest
@@ -229,6 +260,9 @@ def main():
     worst.pop("reported", None)
     ok &= worst["count"] <= 4 and worst["part"] < 5e-4 and worst["field"] < 2e-3 and worst["energy"] < 1e-4
     ok &= worst.get("part_outliers", 0) <= 8 and worst.get("field_max", 0.0) < 2e-2
+    worst["identified_face_bifurcations"] = sum(len(k_) for k_ in known_outliers)
+    worst["unexplained_outliers"] = unexplained
+    ok &= unexplained == 0
     if not ok:
         print(f"[{rank}] FAILED with worst {worst}")
     flag = torch.tensor([0 if ok else 1], device=dev)
