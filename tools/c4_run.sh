@@ -11,7 +11,7 @@ export VPIC_REC_NX=$NX VPIC_REC_NY=$NY VPIC_REC_NZ=$NZ VPIC_REC_NPPC=$NPPC VPIC_
 export VPIC_SHIM_HEAP_MB=${VPIC_SHIM_HEAP_MB:-256}
 if [ "$MODE" = gpu ]; then
   export LD_PRELOAD=$ROOT/vpic_b200/libvpic_b200.so VPIC_B200_TRACE=1 VPIC_B200_STRICT=1
-  GFLAG=-g; TPP=1
+  GFLAG=-g; [ -n "$C4_SHARE_GPU" ] && GFLAG=; TPP=1
 else
   GFLAG=; TPP=$(( $(nproc) / N )); [ $TPP -lt 1 ] && TPP=1
 fi
@@ -44,6 +44,9 @@ if loop > 0:
 tr = [ln for ln in out.splitlines() if ln.startswith("vpic_b200 trace[0]")]
 if tr:
     res["trace_rank0"] = tr[-1][:600]
+    hs = [ln for ln in out.splitlines() if ln.startswith("vpic_b200 host seconds[0]")]
+    if hs:
+        res["host_seconds_rank0"] = hs[-1]
 try:
     en = [ln.split() for ln in open("rundata/energies") if not ln.startswith("%")]
     res["energies_first_last"] = [en[0], en[-1]]

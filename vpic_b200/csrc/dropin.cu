@@ -58,6 +58,16 @@ int rank_for_log() { return &_world_rank ? _world_rank : 0; }
 enum { C_ADVANCE_P, C_SORT_P, C_CENTER_P, C_ENERGY_P, C_RHO_P, C_LOAD_INTERP, C_CLEAR_ACC, C_UNLOAD_ACC, C_ADVANCE_B,
        C_ADVANCE_E, C_CLEAR_JF, C_SYNC_JF, C_ENERGY_F, C_DIV_CLEAN, C_HYDRO, C_BOUNDARY_P, C_FIELD_FALLBACK, C_COUNT };
 uint64_t g_calls[C_COUNT];
+// VPIC_B200_TRACE=1 also accumulates host wall time per phase of the entry points that synchronise with the device
+enum { T_ADV_PREP, T_ADV_KERNEL_WAIT, T_ADV_MOVER_SORT, T_ADV_FINISH, T_BP_PACK, T_BP_EXCHANGE, T_BP_INJECT, T_HALO, T_COUNT };
+double g_phase_s[T_COUNT];
+bool g_trace_on = false;
+static inline double now_s() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+struct Phase {                          // adds the time since construction / the last mark() to a phase
+  double t0; bool on;
+  Phase() : t0(0), on(g_trace_on) { if (on) t0 = now_s(); }
+  void mark(int which) { if (on) { const double t = now_s(); g_phase_s[which] += t - t0; t0 = t; } }
+};
 void trace_report() {
   static const char *names[C_COUNT] = {"advance_p", "sort_p", "center_p/uncenter_p", "energy_p", "accumulate_rho_p",
       "load_interpolator_array", "clear_accumulator_array", "unload_accumulator_array", "advance_b", "advance_e",
@@ -67,10 +77,15 @@ void trace_report() {
   for (int i = 0; i < C_COUNT; i++) fprintf(stderr, " %s=%llu", names[i], (unsigned long long)g_calls[i]);
   const vpb_lazy::Stats st = vpb_lazy::stats();
   fprintf(stderr, " lazy_faults=%llu lazy_fault_bytes=%llu\n", (unsigned long long)st.faults, (unsigned long long)st.fault_bytes);
+  static const char *pn[T_COUNT] = {"advance_p.prepare", "advance_p.kernel+count_read", "advance_p.mover_sort", "advance_p.finish",
+                                    "boundary_p.pack", "boundary_p.exchange", "boundary_p.inject", "field_halo_exchange"};
+  fprintf(stderr, "vpic_b200 host seconds[%d]:", rank_for_log());
+  for (int i = 0; i < T_COUNT; i++) fprintf(stderr, " %s=%.4f", pn[i], g_phase_s[i]);
+  fprintf(stderr, "\n");
 }
 inline void count_call(int which) {
   static int trace = -1;
-  if (trace < 0) { const char *e = getenv("VPIC_B200_TRACE"); trace = e && atoi(e) != 0; if (trace) atexit(trace_report); }
+  if (trace < 0) { const char *e = getenv("VPIC_B200_TRACE"); trace = e && atoi(e) != 0; g_trace_on = trace; if (trace) atexit(trace_report); }
   g_calls[which]++;
 }
 
@@ -342,12 +357,14 @@ static int chunk_particles() {
   return c;
 }
 
+static std::unordered_map<const void *, bool> g_movers_unsorted;  // species whose sp->pm was filled by an injection
 struct SortInfo { int32_t *part = nullptr; size_t cap = 0; int32_t np = 0; int64_t nv = 0; };
 static std::unordered_map<const void *, SortInfo> g_sort_info;     // by species_t address
 
 void advance_p(vpb_species_t *sp, vpb_accumulator_array_t *aa, const vpb_interpolator_array_t *ia) {
   if (!sp || !aa || !ia || sp->g != aa->g || sp->g != ia->g) DROPIN_ERROR("Bad args.");
   count_call(C_ADVANCE_P);
+  Phase ph;
   const vpb_grid_t *g = sp->g;
   const size_t nv = (size_t)g->nv;
   mode();
@@ -390,6 +407,7 @@ void advance_p(vpb_species_t *sp, vpb_accumulator_array_t *aa, const vpb_interpo
     }
     a.p = dev_in(sp->p, pbytes, (size_t)sp->max_np * sizeof(vpb_particle_t));
     a.np = sp->np;
+    ph.mark(T_ADV_PREP);
     DEV(vpb_advance_p(&a, nullptr));
   } else {
     DEV(vpb_stream_sync(nullptr));                          // interp/accum/counters are in place
@@ -426,6 +444,7 @@ void advance_p(vpb_species_t *sp, vpb_accumulator_array_t *aa, const vpb_interpo
   DEV(vpb_stream_sync(nullptr));
   g_d2h += sizeof c;
   const int nm = c[0] < sp->max_nm ? c[0] : sp->max_nm;
+  ph.mark(T_ADV_KERNEL_WAIT);
   if (c[1]) {
 #ifdef EXIT_ON_LOST_MOVER
     DROPIN_ERROR("Species = %s ran out of storage for %i movers.  This is an extremely serious problem that affects the physics of your run.", sp->name, c[1]);
@@ -437,11 +456,14 @@ void advance_p(vpb_species_t *sp, vpb_accumulator_array_t *aa, const vpb_interpo
     const size_t need = vpb_sort_movers_scratch_bytes(nm);
     DEV(vpb_sort_movers(a.pm, nm, scratch(0, need), need, nullptr));
   }
+  g_movers_unsorted[sp] = false;
+  ph.mark(T_ADV_MOVER_SORT);
   sp->nm = nm;
   if (!coherent) dev_written(sp->p, pbytes);
   dev_written(sp->pm, (size_t)nm * sizeof(vpb_particle_mover_t));
   dev_written(aa->a, (size_t)aa->stride * sizeof(vpb_accumulator_t));
   finish_entry();
+  ph.mark(T_ADV_FINISH);
 }
 
 // ---- boundary_p: src/boundary/boundary.h:33-38, boundary_p.cc:240-371 ---------------------------------------------
@@ -487,42 +509,70 @@ static inline int face_port_rev(int f) { return 13 - kFaceOff[f][0] - 3 * kFaceO
 static inline int face_peer(const vpb_grid_t *g, int f) { const int b = g->bc[face_port(f)]; return (b >= 0 && b != g->bc[13]) ? b : -1; }
 static bool any_shared_face(const vpb_grid_t *g) { for (int f = 0; f < 6; f++) if (face_peer(g, f) >= 0) return true; return false; }
 
-// One message of out_bytes[f] bytes from out_dev[f] to the rank behind every shared face, and the matching message from
-// it into in_dev[f] (in_bytes[f] bytes; both sides know the sizes).  Zero-sized messages are skipped on both sides.
-static void exchange_faces(const vpb_grid_t *g, void *const out_dev[6], const size_t out_bytes[6],
-                           void *const in_dev[6], const size_t in_bytes[6]) {
+// The host's port buffers are plain heap memory; copies to and from pageable memory crawl, so the buffers this layer
+// uses are sized with head room and page-locked once.  Only this layer sizes these ports while it serves the entry
+// points that use them, so a buffer is unregistered before the call that may reallocate it.
+struct PortBuf { void *ptr = nullptr; size_t cap = 0; bool pinned = false; };
+static PortBuf g_port_buf[2][27];
+static void *port_buffer(const vpb_grid_t *g, int port, bool send, size_t bytes) {
   HostMP &mp = host_mp();
+  PortBuf &b = g_port_buf[send ? 1 : 0][port];
+  if (bytes > b.cap) {
+    if (b.pinned) { cudaHostUnregister(b.ptr); cudaGetLastError(); b.pinned = false; }
+    const size_t want = bytes * 2 > (64u << 10) ? bytes * 2 : (64u << 10);
+    if (send) mp.size_send(g->mp, port, (int)want); else mp.size_recv(g->mp, port, (int)want);
+    b.ptr = send ? mp.send_buffer(g->mp, port) : mp.recv_buffer(g->mp, port);
+    b.cap = want;
+    b.pinned = cudaHostRegister(b.ptr, want, cudaHostRegisterDefault) == cudaSuccess;
+    if (!b.pinned) cudaGetLastError();
+  }
+  return b.ptr;
+}
+
+static void release_port_buffers() {       // before code outside this layer (a forwarded call) may resize the ports
+  for (auto &dir : g_port_buf) for (PortBuf &b : dir) {
+    if (b.pinned) { cudaHostUnregister(b.ptr); cudaGetLastError(); }
+    b = PortBuf();
+  }
+}
+
+// One message per shared face, both ways.  `on_device`: the buffers are device memory (staged through the ports'
+// page-locked host buffers); otherwise host memory.  Sizes are known to both sides; zero-sized messages are skipped.
+static void exchange_faces(const vpb_grid_t *g, void *const out[6], const size_t out_bytes[6],
+                           void *const in[6], const size_t in_bytes[6], bool on_device = true) {
+  HostMP &mp = host_mp();
+  void *rbuf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   for (int f = 0; f < 6; f++) {
     const int peer = face_peer(g, f);
     if (peer < 0 || !in_bytes[f]) continue;
-    mp.size_recv(g->mp, face_port(f), (int)in_bytes[f]);
+    rbuf[f] = port_buffer(g, face_port(f), false, in_bytes[f]);
     mp.begin_recv(g->mp, face_port(f), (int)in_bytes[f], peer, face_port_rev(f));
   }
+  bool copied = false;
   for (int f = 0; f < 6; f++) {
     const int peer = face_peer(g, f);
     if (peer < 0 || !out_bytes[f]) continue;
-    mp.size_send(g->mp, face_port(f), (int)out_bytes[f]);
-    DEV(vpb_memcpy_d2h(mp.send_buffer(g->mp, face_port(f)), out_dev[f], out_bytes[f], nullptr));
-    g_d2h += out_bytes[f];
+    void *sb = port_buffer(g, face_port(f), true, out_bytes[f]);
+    if (on_device) { DEV(vpb_memcpy_d2h(sb, out[f], out_bytes[f], nullptr)); g_d2h += out_bytes[f]; copied = true; }
+    else memcpy(sb, out[f], out_bytes[f]);
   }
-  DEV(vpb_stream_sync(nullptr));
+  if (copied) DEV(vpb_stream_sync(nullptr));
   for (int f = 0; f < 6; f++) {
     const int peer = face_peer(g, f);
     if (peer < 0 || !out_bytes[f]) continue;
     mp.begin_send(g->mp, face_port(f), (int)out_bytes[f], peer, face_port(f));
   }
+  copied = false;
   for (int f = 0; f < 6; f++) {
     const int peer = face_peer(g, f);
     if (peer < 0 || !in_bytes[f]) continue;
     mp.end_recv(g->mp, face_port(f));
-    DEV(vpb_memcpy_h2d(in_dev[f], mp.recv_buffer(g->mp, face_port(f)), in_bytes[f], nullptr));
-    g_h2d += in_bytes[f];
+    if (on_device) { DEV(vpb_memcpy_h2d(in[f], rbuf[f], in_bytes[f], nullptr)); g_h2d += in_bytes[f]; copied = true; }
+    else memcpy(in[f], rbuf[f], in_bytes[f]);
   }
-  DEV(vpb_stream_sync(nullptr));                                 // the receive buffers may be reused after this
+  if (copied) DEV(vpb_stream_sync(nullptr));                     // the receive buffers may be reused after this
   for (int f = 0; f < 6; f++) if (face_peer(g, f) >= 0 && out_bytes[f]) mp.end_send(g->mp, face_port(f));
 }
-
-static std::unordered_map<const void *, bool> g_movers_unsorted;  // species whose sp->pm was filled by an injection
 
 // One communication round of boundary_p on several ranks (boundary_p.cc:41-750 without custom handlers): pack on the
 // device, exchange counts and then injector records through the host's ports, inject on the device in the reference's
@@ -541,8 +591,11 @@ static void boundary_p_multirank(vpb_species_t *sp_list, vpb_field_array_t *fa, 
   for (vpb_species_t *sp = sp_list; sp; sp = sp->next) sps.push_back(sp);
   const int S = (int)sps.size();
   // ---- pack every species; injector records stay on the device, grouped by destination face
+  Phase ph;
   std::vector<void *> inj(S, nullptr);
   std::vector<int32_t> offs((size_t)S * 9, 0);
+  std::vector<int> packed_nm(S, 0);
+  int32_t *offs_dev = (int32_t *)scratch(7, (size_t)9 * S * sizeof(int32_t));
   float *df = nullptr;
   for (int s = 0; s < S; s++) {
     vpb_species_t *sp = sps[s];
@@ -565,37 +618,40 @@ static void boundary_p_multirank(vpb_species_t *sp_list, vpb_field_array_t *fa, 
     b.sp_id = sp->id;
     inj[s] = scratch(100 + s, (size_t)nm * sizeof(vpb_particle_injector_t));
     b.inj = inj[s];
-    b.class_offsets = (int32_t *)scratch(7, 9 * sizeof(int32_t));
+    b.class_offsets = offs_dev + (size_t)s * 9;
     b.scratch_bytes = vpb_boundary_scratch_bytes(nm);
     b.scratch = scratch(8, b.scratch_bytes);
     if (!df) df = (float *)dev_in(fa->f, fbytes);
     b.fields = df; b.q_r8V = sp->q * g->r8V; b.nx = g->nx; b.ny = g->ny; b.nz = g->nz;
     DEV(vpb_boundary_p_pack(&b, nullptr));
-    DEV(vpb_memcpy_d2h(&offs[(size_t)s * 9], b.class_offsets, 9 * sizeof(int32_t), nullptr));
-    DEV(vpb_stream_sync(nullptr));
-    g_d2h += 9 * sizeof(int32_t);
-    const int32_t *o = &offs[(size_t)s * 9];
-    if (o[8] - o[7] != 0)
-      DROPIN_ERROR("Species = %s: %d movers left through a face that is neither absorbing, local nor shared with another rank; "
-                   "Unknown boundary interaction", sp->name, o[8] - o[7]);
+    packed_nm[s] = nm;
     sp->np -= nm;
     sp->nm = 0;
     dev_written(sp->p, (size_t)sp->np * sizeof(vpb_particle_t));
   }
-  if (df) dev_written(fa->f, fbytes);
+  if (df) {                                                      // somebody packed: one read of every species' class offsets
+    DEV(vpb_memcpy_d2h(offs.data(), offs_dev, (size_t)9 * S * sizeof(int32_t), nullptr));
+    DEV(vpb_stream_sync(nullptr));
+    g_d2h += (size_t)9 * S * sizeof(int32_t);
+    for (int s = 0; s < S; s++) {
+      if (!packed_nm[s]) { for (int c = 0; c < 9; c++) offs[(size_t)s * 9 + c] = 0; continue; }
+      const int32_t *o = &offs[(size_t)s * 9];
+      if (o[8] - o[7] != 0)
+        DROPIN_ERROR("Species = %s: %d movers left through a face that is neither absorbing, local nor shared with another rank; "
+                     "Unknown boundary interaction", sps[s]->name, o[8] - o[7]);
+    }
+    dev_written(fa->f, fbytes);
+  }
+  ph.mark(T_BP_PACK);
   // ---- counts: int32[S] per shared face, both ways
   void *cnt_out[6], *cnt_in[6]; size_t cnt_bytes[6];
   std::vector<int32_t> n_send((size_t)6 * S, 0), n_recv((size_t)6 * S, 0);
-  int32_t *cnt_dev = (int32_t *)scratch(9, (size_t)12 * S * sizeof(int32_t));
   for (int f = 0; f < 6; f++) {
     cnt_bytes[f] = face_peer(g, f) >= 0 ? (size_t)S * sizeof(int32_t) : 0;
     for (int s = 0; s < S; s++) n_send[(size_t)f * S + s] = offs[(size_t)s * 9 + f + 1] - offs[(size_t)s * 9 + f];
-    cnt_out[f] = cnt_dev + (size_t)f * S; cnt_in[f] = cnt_dev + (size_t)(6 + f) * S;
+    cnt_out[f] = &n_send[(size_t)f * S]; cnt_in[f] = &n_recv[(size_t)f * S];
   }
-  DEV(vpb_memcpy_h2d(cnt_dev, n_send.data(), (size_t)6 * S * sizeof(int32_t), nullptr));
-  exchange_faces(g, cnt_out, cnt_bytes, cnt_in, cnt_bytes);
-  DEV(vpb_memcpy_d2h(n_recv.data(), cnt_dev + (size_t)6 * S, (size_t)6 * S * sizeof(int32_t), nullptr));
-  DEV(vpb_stream_sync(nullptr));
+  exchange_faces(g, cnt_out, cnt_bytes, cnt_in, cnt_bytes, false);
   // ---- payload: for every shared face the records of all species, species by species
   void *pay_out[6], *pay_in[6]; size_t out_bytes[6], in_bytes[6];
   for (int f = 0; f < 6; f++) {
@@ -614,6 +670,7 @@ static void boundary_p_multirank(vpb_species_t *sp_list, vpb_field_array_t *fa, 
     }
   }
   exchange_faces(g, pay_out, out_bytes, pay_in, in_bytes);
+  ph.mark(T_BP_EXCHANGE);
   // ---- inject: faces in ascending order, per species (the arrays of different species are independent)
   bool any_in = false;
   for (int f = 0; f < 6; f++) any_in |= in_bytes[f] != 0;
@@ -664,6 +721,7 @@ static void boundary_p_multirank(vpb_species_t *sp_list, vpb_field_array_t *fa, 
     dev_written(aa->a, (size_t)aa->stride * sizeof(vpb_accumulator_t));
   }
   finish_entry();
+  ph.mark(T_BP_INJECT);
 }
 
 void boundary_p(void *pbc_list, vpb_species_t *sp_list, vpb_field_array_t *fa, vpb_accumulator_array_t *aa) {
@@ -691,6 +749,7 @@ void boundary_p(void *pbc_list, vpb_species_t *sp_list, vpb_field_array_t *fa, v
     FORWARD_NOTICE("boundary_p", world > 1 ? "several ranks: the particle exchange is the host program's MPI" :
                                  pbc_list ? "custom particle boundary handlers are host function pointers" :
                                  enabled ? "a face leads to another domain" : "VPIC_B200_BOUNDARY_P=0");
+    release_port_buffers();
     ref(pbc_list, sp_list, fa, aa);
     return;
   }
@@ -1059,7 +1118,9 @@ static void remote_halo(const vpb_field_array_t *fa, const vpb_field_args_t &a, 
     out[f] = scratch(40 + f, bytes[f]); in[f] = scratch(50 + f, bytes[f]);
     DEV(vpb_halo_pack(&a, kind, f, (float *)out[f], nullptr));
   }
+  Phase ph;
   exchange_faces(g, out, bytes, in, bytes);
+  ph.mark(T_HALO);
   for (int f = 0; f < 6; f++) {
     if (!bytes[f]) continue;
     if (kind == VPB_HALO_TANG_E_NORM_B) DEV(vpb_halo_unpack_sync(&a, f, (const float *)in[f], err_dev, nullptr));

@@ -94,9 +94,13 @@ static int exclusive_scan_inplace(int *data, int n, int *tmp /* >= ceil(n/kScanT
 // Items are VEC int4 words; the key is word KEYW's .w (particle_t.i and particle_mover_t.i sit in word 0,
 // the destination class of a particle_injector_t rides in word 2).
 
+// key_count (optional, first pass of sort_p only): key_count[k] += number of items with full key k, 0 <= k < n_keys.
+// Its exclusive scan is partition[] (sort_p_pipeline.cc:183-193,335-340), so the sorted array never has to be read
+// again to build it.  Equal keys imply equal digits, so one match on the full key serves both histograms.
 template <int VEC, int KEYW, int BITS>
 __global__ void __launch_bounds__(kSortBlock) radix_hist_kernel(const int4 *items, int n, int per_block, int shift,
-                                                                int *hist /* [1<<BITS][gridDim.x] */) {
+                                                                int *hist /* [1<<BITS][gridDim.x] */,
+                                                                int *key_count = nullptr, int n_keys = 0) {
   constexpr int R = 1 << BITS;
   __shared__ int s_hist[R];
   for (int d = threadIdx.x; d < R; d += kSortBlock) s_hist[d] = 0;
@@ -107,9 +111,18 @@ __global__ void __launch_bounds__(kSortBlock) radix_hist_kernel(const int4 *item
   for (int i0 = lo; i0 < hi; i0 += kSortBlock) {
     const int i = i0 + threadIdx.x;
     const bool valid = i < hi;
-    const int d = valid ? ((items[(size_t)i * VEC + KEYW].w >> shift) & (R - 1)) : (R + lane);
-    const unsigned peers = __match_any_sync(0xffffffffu, d);
-    if (valid && lane == __ffs(peers) - 1) atomicAdd(&s_hist[d], __popc(peers));
+    const int key = valid ? items[(size_t)i * VEC + KEYW].w : 0;
+    const int d = valid ? ((key >> shift) & (R - 1)) : (R + lane);
+    if (key_count) {
+      const unsigned peers = __match_any_sync(0xffffffffu, valid ? key : (-1 - lane));
+      if (valid && lane == __ffs(peers) - 1) {
+        atomicAdd(&s_hist[d], __popc(peers));
+        if ((unsigned)key < (unsigned)n_keys) atomicAdd(&key_count[key], __popc(peers));
+      }
+    } else {
+      const unsigned peers = __match_any_sync(0xffffffffu, d);
+      if (valid && lane == __ffs(peers) - 1) atomicAdd(&s_hist[d], __popc(peers));
+    }
   }
   __syncthreads();
   for (int d = threadIdx.x; d < R; d += kSortBlock) hist[d * gridDim.x + blockIdx.x] = s_hist[d];
@@ -119,9 +132,13 @@ __global__ void __launch_bounds__(kSortBlock) radix_hist_kernel(const int4 *item
 // current sub-tile (s_wcount) and a bitmap of the digits the sub-tile touched.  Only touched digits are prefixed and
 // re-zeroed, so an 11-bit digit (2048 bins x 8 warps) costs no more per sub-tile than an 8-bit one when the input is
 // nearly sorted (a sub-tile of voxel-ordered particles touches a few dozen digits).
+// next_hist (optional): the [digit][CTA] histogram of the NEXT pass, filled from the output positions this pass
+// assigns (an item written to position o belongs to CTA o / per_block of the next pass), so the next pass needs no
+// read of its own to count.  Must be zero on entry.
 template <int VEC, int KEYW, int BITS>
 __global__ void __launch_bounds__(kSortBlock) radix_scatter_kernel(const int4 *src, int4 *dst, int n, int per_block,
-                                                                   int shift, const int *offs /* scanned hist */) {
+                                                                   int shift, const int *offs /* scanned hist */,
+                                                                   int *next_hist = nullptr) {
   constexpr int R = 1 << BITS;
   constexpr int kWords = R / 32;
   extern __shared__ int s_dyn[];
@@ -185,8 +202,15 @@ __global__ void __launch_bounds__(kSortBlock) radix_scatter_kernel(const int4 *s
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < kIPT; j++) {
+      const int o = digit[j] >= 0 ? s_wcount[w * R + digit[j]] + rank[j] : 0;
+      if (next_hist) {
+        // (next digit, next CTA) pairs repeat along a run of voxel-ordered items: one atomic per distinct pair per warp
+        const int nd = (it[j][KEYW].w >> (shift + BITS)) & (R - 1);
+        const int cell = digit[j] >= 0 ? nd * (int)gridDim.x + o / per_block : -1 - lane;
+        const unsigned pp = __match_any_sync(0xffffffffu, cell);
+        if (digit[j] >= 0 && lane == __ffs(pp) - 1) atomicAdd(&next_hist[cell], __popc(pp));
+      }
       if (digit[j] >= 0) {
-        const int o = s_wcount[w * R + digit[j]] + rank[j];
         if (VEC == 2) {
           const int4 a0 = it[j][0], a1 = it[j][VEC - 1];
           st_particle(reinterpret_cast<float4 *>(dst) + 2 * (size_t)o,
@@ -229,7 +253,7 @@ static int ceil_log2(int64_t x) { int b = 0; while (((int64_t)1 << b) < x) b++; 
 
 struct SortPlan { int nblocks, per_block, scan_tmp; size_t hist_bytes, total_bytes; };
 
-static SortPlan plan_sort(int n, int bits = 11) {
+static SortPlan plan_sort(int n, int bits = 11, int n_keys = 0) {
   const int R = 1 << bits;
   SortPlan s;
   int nb = (n + kSubTile - 1) / kSubTile;
@@ -241,40 +265,47 @@ static SortPlan plan_sort(int n, int bits = 11) {
   nb = (n + per - 1) / per; if (nb < 1) nb = 1;
   s.nblocks = nb; s.per_block = per;
   s.scan_tmp = (R * nb + kScanTile - 1) / kScanTile;
+  const int key_tmp = (n_keys + 1 + kScanTile - 1) / kScanTile;           // the partition scan shares the temporary
+  if (key_tmp > s.scan_tmp) s.scan_tmp = key_tmp;
   s.hist_bytes = (size_t)R * nb * sizeof(int);
-  s.total_bytes = ((s.hist_bytes + 255) / 256) * 256 + (size_t)s.scan_tmp * sizeof(int) + 256;
+  // two histograms: the pass that runs and the next one, which the running scatter fills
+  s.total_bytes = 2 * (((s.hist_bytes + 255) / 256) * 256) + (size_t)s.scan_tmp * sizeof(int) + 256;
   return s;
 }
 
-template <int VEC, int KEYW, int BITS>
-static int radix_pass(const int4 *src, int4 *dst, int n, int shift, const SortPlan &pl, int *hist, int *tmp, cudaStream_t st) {
+// LSD radix sort of n items on the low key_bits of the key.  WIDE: 11-bit digits (two passes cover the 22 bits of a
+// 128^3 grid), else 8-bit digits (small arrays: movers, injectors).  The result ends in a or b (*result_in_b).
+// Only the first pass reads its input to count; every scatter fills the histogram of the pass after it.
+// key_count / n_keys: see radix_hist_kernel (zeroed by the caller).
+template <int VEC, int KEYW, bool WIDE>
+static int radix_sort(int4 *a, int4 *b, int n, int key_bits, void *scratch, size_t scratch_bytes, cudaStream_t st,
+                      bool *result_in_b, int *key_count = nullptr, int n_keys = 0) {
+  constexpr int BITS = WIDE ? 11 : 8;
   constexpr int R = 1 << BITS;
   constexpr size_t smem = ((size_t)R * (1 + kSortWarps) + R / 32) * sizeof(int);
+  const SortPlan pl = plan_sort(n, BITS, n_keys);
+  VPB_REQUIRE(scratch && scratch_bytes >= pl.total_bytes, "sort: scratch too small (%zu < %zu)", scratch_bytes, pl.total_bytes);
   static bool attr_done = false;
   if (!attr_done) {
     VPB_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<VEC, KEYW, BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  radix_hist_kernel<VEC, KEYW, BITS><<<pl.nblocks, kSortBlock, 0, st>>>(src, n, pl.per_block, shift, hist);  VPB_LAUNCH_CHECK();
-  int r = exclusive_scan_inplace(hist, R * pl.nblocks, tmp, st); if (r) return r;
-  radix_scatter_kernel<VEC, KEYW, BITS><<<pl.nblocks, kSortBlock, smem, st>>>(src, dst, n, pl.per_block, shift, hist);  VPB_LAUNCH_CHECK();
-  return 0;
-}
-
-// LSD radix sort of n items on the low key_bits of the key.  WIDE: 11-bit digits (two passes cover the 22 bits of a
-// 128^3 grid), else 8-bit digits (small arrays: movers, injectors).  The result ends in a or b (*result_in_b).
-template <int VEC, int KEYW, bool WIDE>
-static int radix_sort(int4 *a, int4 *b, int n, int key_bits, void *scratch, size_t scratch_bytes, cudaStream_t st,
-                      bool *result_in_b) {
-  constexpr int BITS = WIDE ? 11 : 8;
-  const SortPlan pl = plan_sort(n, BITS);
-  VPB_REQUIRE(scratch && scratch_bytes >= pl.total_bytes, "sort: scratch too small (%zu < %zu)", scratch_bytes, pl.total_bytes);
-  int *hist = (int *)scratch;
-  int *tmp = (int *)((char *)scratch + ((pl.hist_bytes + 255) / 256) * 256);
+  const size_t hb = ((pl.hist_bytes + 255) / 256) * 256;
+  int *hist[2] = {(int *)scratch, (int *)((char *)scratch + hb)};
+  int *tmp = (int *)((char *)scratch + 2 * hb);
   int4 *src = a, *dst = b;
+  int cur = 0;
+  radix_hist_kernel<VEC, KEYW, BITS><<<pl.nblocks, kSortBlock, 0, st>>>(src, n, pl.per_block, 0, hist[cur], key_count, n_keys);
+  VPB_LAUNCH_CHECK();
   for (int shift = 0; shift < key_bits; shift += BITS) {
-    int r = radix_pass<VEC, KEYW, BITS>(src, dst, n, shift, pl, hist, tmp, st); if (r) return r;
+    const bool more = shift + BITS < key_bits;
+    if (more) VPB_CUDA(cudaMemsetAsync(hist[cur ^ 1], 0, pl.hist_bytes, st));
+    int r = exclusive_scan_inplace(hist[cur], R * pl.nblocks, tmp, st); if (r) return r;
+    radix_scatter_kernel<VEC, KEYW, BITS><<<pl.nblocks, kSortBlock, smem, st>>>(src, dst, n, pl.per_block, shift, hist[cur],
+                                                                               more ? hist[cur ^ 1] : nullptr);
+    VPB_LAUNCH_CHECK();
     int4 *t = src; src = dst; dst = t;
+    cur ^= 1;
   }
   *result_in_b = (src == b);
   return 0;
@@ -305,8 +336,9 @@ int radix_split_injectors(int4 *a, int4 *b, int n, void *scratch, size_t scratch
 
 using namespace vpb;
 
-extern "C" size_t vpb_sort_scratch_bytes(int32_t n_items, int32_t /*n_keys_hint*/) {
-  return plan_sort(n_items > 0 ? n_items : 1, 11).total_bytes;     // the wider plan covers both digit widths
+extern "C" size_t vpb_sort_scratch_bytes(int32_t n_items, int32_t n_keys_hint) {
+  // the wider plan covers both digit widths; n_keys_hint = nv sizes the partition scan's temporary
+  return plan_sort(n_items > 0 ? n_items : 1, 11, n_keys_hint > 0 ? n_keys_hint : 0).total_bytes;
 }
 
 extern "C" int vpb_sort_p(void *p, int32_t np, void *aux, int32_t *partition, int32_t nx, int32_t ny, int32_t nz,
@@ -322,10 +354,16 @@ extern "C" int vpb_sort_p(void *p, int32_t np, void *aux, int32_t *partition, in
     // 11-bit digits when they save a pass (e.g. 22 key bits: 2 passes instead of 3), else 8-bit digits
     const int kb = ceil_log2(nv);
     const bool wide = (kb + 10) / 11 < (kb + 7) / 8;
-    int r = wide ? radix_sort<2, 0, true>((int4 *)p, (int4 *)aux, np, kb, scratch, scratch_bytes, st, &in_aux)
-                 : radix_sort<2, 0, false>((int4 *)p, (int4 *)aux, np, kb, scratch, scratch_bytes, st, &in_aux);
+    // partition[] = exclusive scan of the per-voxel counts, which the first histogram pass gathers on its way
+    VPB_CUDA(cudaMemsetAsync(partition, 0, ((size_t)nv + 1) * sizeof(int), st));
+    int r = wide ? radix_sort<2, 0, true>((int4 *)p, (int4 *)aux, np, kb, scratch, scratch_bytes, st, &in_aux, partition, nv)
+                 : radix_sort<2, 0, false>((int4 *)p, (int4 *)aux, np, kb, scratch, scratch_bytes, st, &in_aux, partition, nv);
     if (r) return r;
     if (in_aux) VPB_CUDA(cudaMemcpyAsync(p, aux, (size_t)np * 32, cudaMemcpyDeviceToDevice, st));
+    const SortPlan pl = plan_sort(np, wide ? 11 : 8, nv);
+    int *tmp = (int *)((char *)scratch + 2 * (((pl.hist_bytes + 255) / 256) * 256));
+    r = exclusive_scan_inplace(partition, nv + 1, tmp, st); if (r) return r;
+    return 0;
   }
   const int threads = 256;
   partition_kernel<<<(np + 1 + threads - 1) / threads, threads, 0, st>>>((const int4 *)p, np, nv, partition);
