@@ -114,9 +114,9 @@ def build_sim(args, rank, world, device):
         z = torch.arange(nz + 2, device=device, dtype=torch.float64) - 0.5 - 0.5 * nz     # cell-centred distance from zc
         f3 = sim.field_array.f.view(nz + 2, ny + 2, nx + 2, -1)
         f3[..., 4] = (b0 * torch.tanh(z / L_sheet)).to(torch.float32)[:, None, None]       # cbx(z)
-    for name, q, m, uth in (("electron", -1.0, 1.0, args.uth), ("ion", 1.0, 25.0, args.uth / 5.0)):
+    for k, (name, q, m, uth) in enumerate((("electron", -1.0, 1.0, args.uth), ("ion", 1.0, 25.0, args.uth / 5.0))):
         max_np = int(npart * (1.25 if world > 1 else 1.0)) + 1024
-        sp = sim.define_species(name, q, m, max_np, max(int(npart * 0.05), 1 << 16), args.sort_interval)
+        sp = sim.define_species(name, q, m, max_np, max(int(npart * 0.05), 1 << 16), sort_intervals(args)[k])
         # synthetic load, in random order like the reference's inject_particle loop; sort_p at step 0 orders it
         p = sp.p[:npart]
         p[:, 0:3] = torch.rand((npart, 3), generator=gen, device=device) * 2 - 1
@@ -260,8 +260,8 @@ def run_e2e(args, device):
     npart = nx * ny * nz * args.ppc
     rng = np.random.default_rng(7)
     species = []
-    for name, q, m, uth in (("electron", -1.0, 1.0, args.uth), ("ion", 1.0, 25.0, args.uth / 5.0)):
-        sp = H.new_species(name, q, m, npart, max(int(npart * 0.05), 1 << 16), args.sort_interval)
+    for k, (name, q, m, uth) in enumerate((("electron", -1.0, 1.0, args.uth), ("ion", 1.0, 25.0, args.uth / 5.0))):
+        sp = H.new_species(name, q, m, npart, max(int(npart * 0.05), 1 << 16), sort_intervals(args)[k])
         H.fill_uniform(sp, npart, rng, uth, 1.0 / args.ppc)
         species.append(sp)
     en_f = (C.c_double * 6)()
@@ -531,15 +531,15 @@ def reference_sample(args, n_steps, grid_n, warm=1, variant=None):
     npart = nx * ny * nz * args.ppc
     rng = np.random.default_rng(5)
     species = []
-    for name, q, m, uth in (("electron", -1.0, 1.0, args.uth), ("ion", 1.0, 25.0, args.uth / 5.0)):
-        sp = W.new_species(name, q, m, npart, max(int(npart * 0.05), 1 << 16), args.sort_interval)
+    for k, (name, q, m, uth) in enumerate((("electron", -1.0, 1.0, args.uth), ("ion", 1.0, 25.0, args.uth / 5.0))):
+        sp = W.new_species(name, q, m, npart, max(int(npart * 0.05), 1 << 16), sort_intervals(args)[k])
         fill_reference_species(sp, npart, nx, ny, nz, uth, 1.0 / args.ppc, rng)
         species.append(sp)
     lib.load_interpolator_array(W.ia, W.fa)
 
     def step(k):
-        for sp in species:
-            if k % args.sort_interval == 0:
+        for sp, every in zip(species, sort_intervals(args)):
+            if k % every == 0:
                 lib.sort_p(sp.sp)
         lib.clear_accumulator_array(W.aa)
         for sp in species:
@@ -610,6 +610,13 @@ def cpu_baseline(args, budget_s=15.0):
         return {"value": None, "unit": "pushes/s", "cores": None, "kind": "reference", "sample": f"failed: {e!r}"}
 
 
+def sort_intervals(args):
+    """--sort-interval N or E,I: species_t.sort_interval of the electrons and of the ions (a deck sets it per species,
+    sample/harris:181-182 uses 40 for the ions and 20 for the electrons)."""
+    v = [int(x) for x in str(args.sort_interval).split(",")]
+    return (v[0], v[0]) if len(v) == 1 else (v[0], v[1])
+
+
 def workload_config(args, world, np_total_local):
     """`config` of the JSON line; identical on both arms (the reference arm runs the same workload on the host)."""
     return {"workload": (f"uniform thermal e-/ion plasma, {args.grid}^3 cells " if args.workload == "uniform" else
@@ -618,7 +625,7 @@ def workload_config(args, world, np_total_local):
                         + ("per GPU" if args.scaling == "weak" else "in total")
                         + f", {args.ppc} ppc/species" + (" on average" if args.workload == "harris" else "")
                         + f", periodic{' in x and y' if args.workload == 'harris' else ''}, "
-                        f"sort_p every {args.sort_interval} steps"
+                        f"sort_p every {sort_intervals(args)[0]} (electrons) / {sort_intervals(args)[1]} (ions) steps"
                         + (" (BASELINE.json configs[1])" if (args.grid, args.ppc, args.workload) == (128, 64, "uniform") else ""),
             "particles_per_gpu": np_total_local, "decomposition": f"1x{world}x1 slabs",
             "l2": f"particle arrays ({np_total_local * 32 / 1e9:.1f} GB per GPU) exceed the 126 MB L2; no flush needed"}
@@ -659,7 +666,7 @@ def main():
     ap.add_argument("--grid", type=int, default=128)
     ap.add_argument("--ppc", type=int, default=64)
     ap.add_argument("--uth", type=float, default=0.18)
-    ap.add_argument("--sort-interval", type=int, default=20)
+    ap.add_argument("--sort-interval", default="20", help="steps between sort_p calls: N, or E,I for electrons and ions")
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--e2e", type=int, default=1)
     ap.add_argument("--e2e-steps", type=int, default=20)

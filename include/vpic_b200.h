@@ -102,6 +102,11 @@ typedef struct vpb_push_args {
    * with entries in [0, partition_np]; results do not depend on how accurate it still is. */
   const int32_t *partition;
   int32_t        partition_np;
+  /* Optional (NULL = off): apply the order of a vpb_sort_p_index on the fly.  The particle advanced into position k is
+   * p[perm[k]] and it is written to p_out[k] (p_out != p, 32 B aligned, np particles; p_first must be 0).  The result in
+   * p_out, the movers and the accumulators are exactly those of vpb_sort_p followed by vpb_advance_p on p. */
+  const int32_t *perm;
+  void          *p_out;
 } vpb_push_args_t;
 
 #define VPB_DEPOSIT_DEFAULT      0   /* library's best measured strategy                                  */
@@ -181,6 +186,19 @@ int    vpb_boundary_p_inject_msg(const vpb_push_args_t *push, const void *msg, i
 int vpb_sort_p(void *p, int32_t np, void *aux, int32_t *partition,
                int32_t nx, int32_t ny, int32_t nz,
                void *scratch, size_t scratch_bytes, void *stream);
+/* The same order and partition[] without moving the particles: perm[k] = index in p of the particle that sort_p would
+ * put at position k (a stable LSD sort of 8-byte (voxel, index) pairs instead of 32-byte particles).  The particles
+ * move once, inside the next vpb_advance_p (push args perm / p_out), or in vpb_permute_p when no push follows.
+ * keys (optional): int32[np], the voxel of every particle, when the caller already holds it; else p is read.
+ * work: >= vpb_sort_index_work_bytes(np) bytes (the species' aux particle array is large enough);
+ * scratch: >= vpb_sort_index_scratch_bytes(np, nv). */
+size_t vpb_sort_index_work_bytes(int32_t np);
+size_t vpb_sort_index_scratch_bytes(int32_t n_items, int32_t n_keys_hint);
+int vpb_sort_p_index(const void *p, const int32_t *keys, int32_t np, int32_t *perm, int32_t *partition,
+                     int32_t nx, int32_t ny, int32_t nz, void *work, size_t work_bytes,
+                     void *scratch, size_t scratch_bytes, void *stream);
+/* dst[k] = p[perm[k]] for k < np (dst != p) */
+int vpb_permute_p(const void *p, int32_t np, const int32_t *perm, void *dst, void *stream);
 
 /* ---- interpolator / accumulator glue ---------------------------------------
  * load_interpolator_pipeline_scalar  (src/sf_interface/pipeline/interpolator_array_pipeline.cc:21-135)

@@ -212,6 +212,72 @@ def test_sort_p_at_scale(eng, oracle):
     assert np.array_equal(sp.partition.cpu().numpy()[:g.nv], part_ref[:g.nv])
 
 
+@pytest.mark.parametrize("dims,n", [((7, 6, 5), 17777), ((32, 32, 32), 300000), ((64, 64, 1), 262144), ((3, 3, 3), 1),
+                                    ((3, 3, 3), 0), ((130, 70, 40), 50000), ((300, 300, 64), 200000), ((40, 30, 20), 3_000_001)])
+def test_sort_p_deferred_settles_to_the_reference_order(eng, oracle, dims, n):
+    """sort_p(defer=True) sorts (voxel, index) pairs and leaves the particles in place; reading the array (or any other
+    operator) applies the order.  Order and partition[] bit-exact vs the oracle, for one-, two- and three-pass digit plans
+    (300x300x64 cells need 23 key bits) and for CTAs that walk several sub-tiles (3 M particles)."""
+    rng = np.random.default_rng(29)
+    nx, ny, nz = dims
+    g = make_grid(nx, ny, nz)
+    parts = R.random_particles(rng, n, nx, ny, nz)
+    parts["w"] = np.arange(n, dtype=np.float32)           # tag to expose any instability
+    p_ref, aux = parts.copy(), np.zeros_like(parts)
+    part_ref = np.zeros(g.nv + 1, dtype=np.int32)
+    oracle.vpo_sort_p(p_ref.ctypes.data, n, aux.ctypes.data, part_ref.ctypes.data, nx, ny, nz)
+    dg = eng.DeviceGrid(g)
+    sp = eng.Species("e", -1.0, 1.0, max(n, 1), 16, 20, 0, dg)
+    sp.set_particles(parts)
+    eng.sort_p(sp, defer=True)
+    assert sp._perm_pending == (n > 1)
+    assert np.array_equal(sp.partition.cpu().numpy()[:g.nv], part_ref[:g.nv])
+    if n > 1:
+        assert np.array_equal(bits(sp._p[:n].cpu().numpy().reshape(-1).view(abi.particle_dtype)), bits(parts)), "not moved yet"
+    assert np.array_equal(bits(sp.particles_host()), bits(p_ref)), "settled order must be bit-exact (stable)"
+    assert not sp._perm_pending
+    eng.sort_p(sp, defer=True)                            # sorted input: the identity order
+    assert np.array_equal(bits(sp.particles_host()), bits(p_ref))
+
+
+@pytest.mark.parametrize("case", [0, 1, 2, 3])
+def test_sort_p_deferred_fused_into_advance_p(eng, oracle, case):
+    """The advance_p that follows a deferred sort_p loads p[perm[k]] and stores position k of the other buffer: particle
+    bytes, movers and partition[] identical to sort_p followed by advance_p, accumulators to summation-order tolerance.
+    Cases: periodic box; absorbing walls (movers leave the domain); few particles per row of a big grid; the span and
+    grid overrides do not apply here (debug switches are off in this variant), so a 1.2 M-particle case covers warps
+    that take several spans."""
+    rng = np.random.default_rng(31 + case)
+    dims, n, pbc, uth = [((12, 10, 8), 40011, None, 0.3), ((9, 7, 6), 20000, {i: -2 for i in range(6)}, 0.6),
+                         ((48, 40, 36), 30001, None, 0.25), ((24, 20, 16), 1_200_007, None, 0.2)][case]
+    nx, ny, nz = dims
+    g = make_grid(nx, ny, nz, pbc=pbc) if pbc else make_grid(nx, ny, nz)
+    fields = R.random_fields(rng, g.nv)
+    parts = R.random_particles(rng, n, nx, ny, nz, uth=uth)
+    dg = eng.DeviceGrid(g)
+    fa, ia = eng.FieldArray(dg), eng.InterpolatorArray(dg)
+    fa.f.copy_(torch.from_numpy(fields))
+    eng.load_interpolator_array(ia, fa)
+    out = []
+    for defer in (False, True):
+        aa = eng.AccumulatorArray(dg)
+        sp = eng.Species("e", -1.0, 1.0, n, n, 20, 0, dg)
+        sp.set_particles(parts)
+        eng.clear_accumulator_array(aa)
+        eng.sort_p(sp, defer=defer)
+        eng.advance_p(sp, aa, ia)
+        assert not sp._perm_pending
+        out.append((sp.particles_host().copy(), sp.movers_host().copy(), sp.nm, sp.partition.cpu().numpy().copy(),
+                    aa.a.cpu().numpy().copy()))
+    (p0, m0, nm0, part0, a0), (p1, m1, nm1, part1, a1) = out
+    assert nm0 == nm1 and (pbc is None or nm0 > 0)
+    assert np.array_equal(bits(p0), bits(p1)), "particles after the fused sort+push must be bit-identical"
+    assert np.array_equal(bits(m0), bits(m1))
+    assert np.array_equal(part0, part1)
+    scale = max(np.abs(a0).max(), 1e-30)
+    assert np.abs(a0 - a1).max() <= 2e-5 * scale
+
+
 def test_sort_movers(eng):
     from vpic_b200 import lib
     L = lib.load()

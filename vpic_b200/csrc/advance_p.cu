@@ -70,13 +70,15 @@ __device__ __forceinline__ void run_movers(const PushK &a, const int4 *q0, const
         rr.w = __int_as_float(__float_as_int(rr.w) >> 3);
       }
     }
-    st_particle(a.p + 2 * (size_t)i, rr, uu);
+    st_particle(a.pout + 2 * (size_t)i, rr, uu);
   }
 }
 
 // DBG = false (every production launch) compiles the profiling switches of args.debug_skip out of the loop.
-template <int VARIANT, bool DBG>
-__global__ void __launch_bounds__(kBlock, kMinBlocks) advance_p_kernel(const PushK a) {
+// GATHER applies the order of an index sort on the fly: position k is loaded from p[perm[k]] (perm one row further
+// ahead than the particles) and stored to pout[k].
+template <int VARIANT, bool DBG, bool GATHER = false>
+__global__ void __launch_bounds__(kBlock, GATHER ? 4 : kMinBlocks) advance_p_kernel(const PushK a) {
   // Every warp is autonomous: it walks rows of 32 consecutive particles (rows of one CTA are adjacent, so its
   // warps share interpolator lines in L1), keeps its own mover queue in shared memory and never meets a block-wide
   // barrier.  The next row's particles are requested before the current row is processed.  A queued mover carries
@@ -102,7 +104,16 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) advance_p_kernel(const Pus
   int span = blockIdx.x * kWarps + w;
   int row = span * span_rows;
   float4 rn = make_float4(0.f, 0.f, 0.f, 0.f), un_next = rn;
-  if (span < n_spans && row * 32 + lane < a.np) ld_particle(a.p + 2 * (size_t)(a.first + row * 32 + lane), rn, un_next);
+  // the row after `r` of this warp: same span, or the first row of its next span
+  auto step_row = [&](int &r, int &s) { r++; if (r == (s + 1) * span_rows || r >= n_rows) { s += warps_total; r = s * span_rows; } };
+  int src_next = 0;                                                     // GATHER: perm entry of the row after `row`
+  if (span < n_spans && row * 32 + lane < a.np)
+    ld_particle(a.p + 2 * (size_t)(GATHER ? __ldg(a.perm + row * 32 + lane) : a.first + row * 32 + lane), rn, un_next);
+  if (GATHER) {
+    int r1 = row, s1 = span;
+    step_row(r1, s1);
+    if (s1 < n_spans && r1 * 32 + lane < a.np) src_next = __ldg(a.perm + r1 * 32 + lane);
+  }
 
 #pragma unroll 1
   while (span < n_spans) {
@@ -110,10 +121,15 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) advance_p_kernel(const Pus
     const int i = a.first + row * 32 + lane;
     const bool valid = row * 32 + lane < a.np;
     // advance to the next row of this warp (same span, or the first row of its next span) and request it now
-    int next_row = row + 1, next_span = span;
-    if (next_row == (span + 1) * span_rows || next_row >= n_rows) { next_span = span + warps_total; next_row = next_span * span_rows; }
+    int next_row = row, next_span = span;
+    step_row(next_row, next_span);
     if (next_span < n_spans && next_row * 32 + lane < a.np)
-      ld_particle(a.p + 2 * (size_t)(a.first + next_row * 32 + lane), rn, un_next);
+      ld_particle(a.p + 2 * (size_t)(GATHER ? src_next : a.first + next_row * 32 + lane), rn, un_next);
+    if (GATHER) {
+      int r2 = next_row, s2 = next_span;
+      step_row(r2, s2);
+      if (s2 < n_spans && r2 * 32 + lane < a.np) src_next = __ldg(a.perm + r2 * 32 + lane);
+    }
     const int ii = __float_as_int(r.w);
     bool inb = false;
     float j[12];
@@ -159,7 +175,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) advance_p_kernel(const Pus
       if (dbg & 2) inb = true;
       if (inb) {
         const float qw = un.w * a.qsp;
-        if (!(dbg & 4)) st_particle(a.p + 2 * (size_t)i, make_float4(v3, v4, v5n, r.w), un);
+        if (!(dbg & 4)) st_particle(a.pout + 2 * (size_t)i, make_float4(v3, v4, v5n, r.w), un);
         const float v5 = (((qw * ux) * uy) * uz) * one_third;
         streak_currents(qw, ux, uy, uz, v0, v1, v2, v5, j);
       } else {
@@ -256,6 +272,9 @@ extern "C" int vpb_advance_p(const vpb_push_args_t *args, void *stream) {
   VPB_REQUIRE((((uintptr_t)args->interp | (uintptr_t)args->accum | (uintptr_t)args->pm) & 15) == 0 &&
               ((uintptr_t)args->p & 31) == 0 && args->p_first >= 0,
               "vpb_advance_p: particles must be 32-byte aligned, the other arrays 16-byte aligned");
+  VPB_REQUIRE(!args->perm || (args->p_out && args->p_out != args->p && ((uintptr_t)args->p_out & 31) == 0 && args->p_first == 0 &&
+                              args->debug_skip == 0),
+              "vpb_advance_p: perm needs a separate 32-byte aligned p_out and p_first == 0");
   if (args->np <= 0) return 0;
   PushK k = to_push_k(args);
   // Default strategy: the linear kernel below (warp-segmented reduction + vector REDs).  The brick/tile kernel is
@@ -263,7 +282,7 @@ extern "C" int vpb_advance_p(const vpb_push_args_t *args, void *stream) {
   // asked for (variant VPB_DEPOSIT_BRICK_TILE, or VPB_BRICK_DEFAULT=1 in the environment).
   static int brick_default = -1;
   if (brick_default < 0) { const char *e = getenv("VPB_BRICK_DEFAULT"); brick_default = e && atoi(e) != 0; }
-  if (args->variant == VPB_DEPOSIT_BRICK_TILE || (args->variant == VPB_DEPOSIT_DEFAULT && brick_default)) {
+  if (!args->perm && (args->variant == VPB_DEPOSIT_BRICK_TILE || (args->variant == VPB_DEPOSIT_DEFAULT && brick_default))) {
     VPB_REQUIRE(args->nx > 0 && args->ny > 0 && args->nz > 0, "vpb_advance_p: Bad grid");
     const int served = (args->debug_skip == 0) ? advance_p_brick(args, k, as_stream(stream)) : 0;
     if (served < 0) return -1;
@@ -288,7 +307,7 @@ extern "C" int vpb_advance_p(const vpb_push_args_t *args, void *stream) {
   const int gmul = ((args->debug_skip >> 24) & 0xff) ? ((args->debug_skip >> 24) & 0xff) : 32;     // profiling override
   const int need = (n_spans + kWarps - 1) / kWarps;
   const int grid = need < sms * gmul ? need : sms * gmul;
-  int variant = (args->variant == VPB_DEPOSIT_DEFAULT || args->variant == VPB_DEPOSIT_BRICK_TILE) ? VPB_DEPOSIT_WARP_SEG : args->variant;
+  int variant = (args->variant == VPB_DEPOSIT_DEFAULT || args->variant == VPB_DEPOSIT_BRICK_TILE || args->perm) ? VPB_DEPOSIT_WARP_SEG : args->variant;
   const size_t smem = kSmemBytes + (variant == VPB_DEPOSIT_WARP_SEG ? extra_smem : 0);
 #define VPB_LAUNCH_AP(V, D) do {                                                                                      \
     static bool attr_done = false;                                                                                    \
@@ -296,7 +315,13 @@ extern "C" int vpb_advance_p(const vpb_push_args_t *args, void *stream) {
     advance_p_kernel<V, D><<<grid, kBlock, smem, as_stream(stream)>>>(k); } while (0)
   switch (variant) {
     case VPB_DEPOSIT_RED_V4:          if (dbg) VPB_LAUNCH_AP(VPB_DEPOSIT_RED_V4, true); else VPB_LAUNCH_AP(VPB_DEPOSIT_RED_V4, false); break;
-    case VPB_DEPOSIT_WARP_SEG:        if (dbg) VPB_LAUNCH_AP(VPB_DEPOSIT_WARP_SEG, true); else VPB_LAUNCH_AP(VPB_DEPOSIT_WARP_SEG, false); break;
+    case VPB_DEPOSIT_WARP_SEG:
+      if (args->perm) {
+        static bool gattr = false;
+        if (!gattr) { VPB_CUDA(cudaFuncSetAttribute(advance_p_kernel<VPB_DEPOSIT_WARP_SEG, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); gattr = true; }
+        advance_p_kernel<VPB_DEPOSIT_WARP_SEG, false, true><<<grid, kBlock, smem, as_stream(stream)>>>(k);
+      } else if (dbg) VPB_LAUNCH_AP(VPB_DEPOSIT_WARP_SEG, true); else VPB_LAUNCH_AP(VPB_DEPOSIT_WARP_SEG, false);
+      break;
     case VPB_DEPOSIT_WARP_SEG_MOVERS: if (dbg) VPB_LAUNCH_AP(VPB_DEPOSIT_WARP_SEG_MOVERS, true); else VPB_LAUNCH_AP(VPB_DEPOSIT_WARP_SEG_MOVERS, false); break;
     case VPB_DEPOSIT_WARP_SEG_FIRST:  if (dbg) VPB_LAUNCH_AP(VPB_DEPOSIT_WARP_SEG_FIRST, true); else VPB_LAUNCH_AP(VPB_DEPOSIT_WARP_SEG_FIRST, false); break;
     default:

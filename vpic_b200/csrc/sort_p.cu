@@ -129,9 +129,9 @@ __global__ void __launch_bounds__(kSortBlock) radix_hist_kernel(const int4 *item
 }
 
 // Stable scatter of one digit.  Shared memory: next output slot per digit (s_base), per-warp digit counters of the
-// current sub-tile (s_wcount) and a bitmap of the digits the sub-tile touched.  Only touched digits are prefixed and
-// re-zeroed, so an 11-bit digit (2048 bins x 8 warps) costs no more per sub-tile than an 8-bit one when the input is
-// nearly sorted (a sub-tile of voxel-ordered particles touches a few dozen digits).
+// current sub-tile (s_wcount) and the range of digits the sub-tile touched.  Only that range is prefixed and re-zeroed,
+// so an 11-bit digit (2048 bins x 8 warps) costs no more per sub-tile than an 8-bit one when the input is nearly
+// sorted (a sub-tile of voxel-ordered particles touches a few dozen consecutive digits).
 // next_hist (optional): the [digit][CTA] histogram of the NEXT pass, filled from the output positions this pass
 // assigns (an item written to position o belongs to CTA o / per_block of the next pass), so the next pass needs no
 // read of its own to count.  Must be zero on entry.
@@ -140,16 +140,15 @@ __global__ void __launch_bounds__(kSortBlock) radix_scatter_kernel(const int4 *s
                                                                    int shift, const int *offs /* scanned hist */,
                                                                    int *next_hist = nullptr) {
   constexpr int R = 1 << BITS;
-  constexpr int kWords = R / 32;
   extern __shared__ int s_dyn[];
   int *s_base = s_dyn;                                  // [R]
   int *s_wcount = s_dyn + R;                            // [kSortWarps][R]
-  unsigned *s_touched = reinterpret_cast<unsigned *>(s_dyn + R + kSortWarps * R);   // [kWords]
+  int *s_range = s_dyn + R + kSortWarps * R;            // [2]: lowest and highest digit the current sub-tile touched
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
   for (int d = tid; d < R; d += kSortBlock) s_base[d] = offs[d * gridDim.x + blockIdx.x];
   for (int d = tid; d < R * kSortWarps; d += kSortBlock) s_wcount[d] = 0;
-  for (int d = tid; d < kWords; d += kSortBlock) s_touched[d] = 0u;
+  if (tid == 0) { s_range[0] = R; s_range[1] = -1; }
   const int lo = blockIdx.x * per_block;
   const int hi = min(n, lo + per_block);
   __syncthreads();
@@ -181,23 +180,20 @@ __global__ void __launch_bounds__(kSortBlock) radix_scatter_kernel(const int4 *s
       __syncwarp();
       if (valid && lane == __ffs(peers) - 1) {
         s_wcount[w * R + d] = before + __popc(peers);
-        if (before == 0) atomicOr(&s_touched[d >> 5], 1u << (d & 31));
+        if (before == 0) { atomicMin(&s_range[0], d); atomicMax(&s_range[1], d); }
       }
       __syncwarp();
       rank[j] = before + __popc(peers & lt_mask);
     }
     __syncthreads();
-    // exclusive prefix over warps for every touched digit; thread t walks bitmap words t, t+256, ...
-    for (int word = tid; word < kWords; word += kSortBlock) {
-      unsigned bitsw = s_touched[word];
-      while (bitsw) {
-        const int d = word * 32 + __ffs(bitsw) - 1;
-        bitsw &= bitsw - 1;
-        int run = s_base[d];
+    // exclusive prefix over warps for every digit in the touched range, one thread per digit: a sub-tile of nearly
+    // sorted items touches a few dozen CONSECUTIVE digits (a bitmap walk left them all to one or two threads)
+    const int dlo = s_range[0], dhi = s_range[1];
+    for (int d = dlo + tid; d <= dhi; d += kSortBlock) {
+      int run = s_base[d];
 #pragma unroll
-        for (int ww = 0; ww < kSortWarps; ww++) { const int c = s_wcount[ww * R + d]; s_wcount[ww * R + d] = run; run += c; }
-        s_base[d] = run;
-      }
+      for (int ww = 0; ww < kSortWarps; ww++) { const int c = s_wcount[ww * R + d]; s_wcount[ww * R + d] = run; run += c; }
+      s_base[d] = run;
     }
     __syncthreads();
 #pragma unroll
@@ -224,16 +220,11 @@ __global__ void __launch_bounds__(kSortBlock) radix_scatter_kernel(const int4 *s
     }
     __syncthreads();
     // re-zero the counters this sub-tile used
-    for (int word = tid; word < kWords; word += kSortBlock) {
-      unsigned bitsw = s_touched[word];
-      if (bitsw) s_touched[word] = 0u;
-      while (bitsw) {
-        const int d = word * 32 + __ffs(bitsw) - 1;
-        bitsw &= bitsw - 1;
+    for (int d = dlo + tid; d <= dhi; d += kSortBlock) {
 #pragma unroll
-        for (int ww = 0; ww < kSortWarps; ww++) s_wcount[ww * R + d] = 0;
-      }
+      for (int ww = 0; ww < kSortWarps; ww++) s_wcount[ww * R + d] = 0;
     }
+    if (tid == 0) { s_range[0] = R; s_range[1] = -1; }
     __syncthreads();
   }
 }
@@ -253,15 +244,15 @@ static int ceil_log2(int64_t x) { int b = 0; while (((int64_t)1 << b) < x) b++; 
 
 struct SortPlan { int nblocks, per_block, scan_tmp; size_t hist_bytes, total_bytes; };
 
-static SortPlan plan_sort(int n, int bits = 11, int n_keys = 0) {
+static SortPlan plan_sort(int n, int bits = 11, int n_keys = 0, int sub_tile = kSubTile) {
   const int R = 1 << bits;
   SortPlan s;
-  int nb = (n + kSubTile - 1) / kSubTile;
+  int nb = (n + sub_tile - 1) / sub_tile;
   if (nb < 1) nb = 1;
   if (nb > kMaxSortBlocks) nb = kMaxSortBlocks;
   int per = (n + nb - 1) / nb;
-  per = ((per + kSubTile - 1) / kSubTile) * kSubTile;          // whole sub-tiles per CTA
-  if (per < kSubTile) per = kSubTile;
+  per = ((per + sub_tile - 1) / sub_tile) * sub_tile;          // whole sub-tiles per CTA
+  if (per < sub_tile) per = sub_tile;
   nb = (n + per - 1) / per; if (nb < 1) nb = 1;
   s.nblocks = nb; s.per_block = per;
   s.scan_tmp = (R * nb + kScanTile - 1) / kScanTile;
@@ -309,6 +300,183 @@ static int radix_sort(int4 *a, int4 *b, int n, int key_bits, void *scratch, size
   }
   *result_in_b = (src == b);
   return 0;
+}
+
+// ---- index sort: the order of sort_p without moving the particles -----------------------------------------------
+// vpb_sort_p_index sorts (voxel, index) pairs — 8 bytes per particle and pass instead of 64 — and leaves perm[k] = the
+// index of the particle that belongs at position k.  The particles themselves move once, inside the advance_p that
+// follows (it reads p[perm[k]] and writes position k of the other buffer), or in vpb_permute_p when none follows.
+//   key_hist_kernel      voxel of every particle (read from the particles, or from a key array a previous advance_p
+//                        left) -> compact key array, digit-0 histogram per CTA, per-voxel counts for partition[]
+//   pair_scatter_kernel  one stable LSD pass; SRC 0: keys (index implicit) / 1: pairs, DST 0: pairs / 1: index only
+constexpr int kPairIPT = 8;                             // 2048 pairs per sub-tile; 24 registers of items keep 3 CTAs per SM
+constexpr int kPairSubTile = kSortBlock * kPairIPT;
+
+template <int BITS>
+__global__ void __launch_bounds__(kSortBlock) key_hist_kernel(const int4 *p, const int *keys_in, int *keys_out, int n,
+                                                              int per_block, int *hist, int *key_count, int n_keys) {
+  constexpr int R = 1 << BITS;
+  __shared__ int s_hist[R];
+  for (int d = threadIdx.x; d < R; d += kSortBlock) s_hist[d] = 0;
+  __syncthreads();
+  const int lo = blockIdx.x * per_block;
+  const int hi = min(n, lo + per_block);
+  const int lane = threadIdx.x & 31;
+  for (int i0 = lo; i0 < hi; i0 += kSortBlock) {
+    const int i = i0 + threadIdx.x;
+    const bool valid = i < hi;
+    int key = 0;
+    if (valid) {
+      if (keys_in) key = keys_in[i];
+      else { key = p[2 * (size_t)i].w; keys_out[i] = key; }
+    }
+    const int d = key & (R - 1);
+    const unsigned peers = __match_any_sync(0xffffffffu, valid ? key : (-1 - lane));
+    if (valid && lane == __ffs(peers) - 1) {
+      atomicAdd(&s_hist[d], __popc(peers));
+      if ((unsigned)key < (unsigned)n_keys) atomicAdd(&key_count[key], __popc(peers));
+    }
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < R; d += kSortBlock) hist[d * gridDim.x + blockIdx.x] = s_hist[d];
+}
+
+template <int BITS, int SRC, int DST>
+__global__ void __launch_bounds__(kSortBlock, 3) pair_scatter_kernel(const void *src_, void *dst_, int n, int per_block,
+                                                                  int shift, const int *offs, int *next_hist) {
+  constexpr int R = 1 << BITS;
+  extern __shared__ int s_dyn[];
+  int *s_base = s_dyn;                                  // [R]
+  int *s_wcount = s_dyn + R;                            // [kSortWarps][R]
+  int *s_range = s_dyn + R + kSortWarps * R;            // [2]: lowest and highest digit the current sub-tile touched
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  for (int d = tid; d < R; d += kSortBlock) s_base[d] = offs[d * gridDim.x + blockIdx.x];
+  for (int d = tid; d < R * kSortWarps; d += kSortBlock) s_wcount[d] = 0;
+  if (tid == 0) { s_range[0] = R; s_range[1] = -1; }
+  const int lo = blockIdx.x * per_block;
+  const int hi = min(n, lo + per_block);
+  __syncthreads();
+
+  for (int t0 = lo; t0 < hi; t0 += kPairSubTile) {
+    int key[kPairIPT], idx[kPairIPT], rank[kPairIPT];
+    // warp-striped as in radix_scatter_kernel: warp w owns [t0 + w*32*IPT, +32*IPT), step j covers 32 consecutive items
+#pragma unroll
+    for (int j = 0; j < kPairIPT; j++) {
+      const int i = t0 + w * 32 * kPairIPT + j * 32 + lane;
+      if (i < hi) {
+        if (SRC == 0) { key[j] = static_cast<const int *>(src_)[i]; idx[j] = i; }
+        else { const int2 v = static_cast<const int2 *>(src_)[i]; key[j] = v.x; idx[j] = v.y; }
+      } else { key[j] = 0; idx[j] = -1; }
+    }
+#pragma unroll
+    for (int j = 0; j < kPairIPT; j++) {
+      const bool valid = idx[j] >= 0;
+      const int d = valid ? ((key[j] >> shift) & (R - 1)) : (R + lane);
+      const unsigned peers = __match_any_sync(0xffffffffu, d);
+      int before = 0;
+      if (valid) before = s_wcount[w * R + d];
+      __syncwarp();
+      if (valid && lane == __ffs(peers) - 1) {
+        s_wcount[w * R + d] = before + __popc(peers);
+        if (before == 0) { atomicMin(&s_range[0], d); atomicMax(&s_range[1], d); }
+      }
+      __syncwarp();
+      rank[j] = before + __popc(peers & lt_mask);
+    }
+    __syncthreads();
+    // exclusive prefix over warps for every digit in the touched range, one thread per digit: a sub-tile of nearly
+    // sorted items touches a few dozen CONSECUTIVE digits (a bitmap walk left them all to one or two threads)
+    const int dlo = s_range[0], dhi = s_range[1];
+    for (int d = dlo + tid; d <= dhi; d += kSortBlock) {
+      int run = s_base[d];
+#pragma unroll
+      for (int ww = 0; ww < kSortWarps; ww++) { const int c = s_wcount[ww * R + d]; s_wcount[ww * R + d] = run; run += c; }
+      s_base[d] = run;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kPairIPT; j++) {
+      const bool valid = idx[j] >= 0;
+      const int o = valid ? s_wcount[w * R + ((key[j] >> shift) & (R - 1))] + rank[j] : 0;
+      if (next_hist) {
+        const int nd = (key[j] >> (shift + BITS)) & (R - 1);
+        const int cell = valid ? nd * (int)gridDim.x + o / per_block : -1 - lane;
+        const unsigned pp = __match_any_sync(0xffffffffu, cell);
+        if (valid && lane == __ffs(pp) - 1) atomicAdd(&next_hist[cell], __popc(pp));
+      }
+      if (valid) {
+        if (DST == 0) static_cast<int2 *>(dst_)[o] = make_int2(key[j], idx[j]);
+        else static_cast<int *>(dst_)[o] = idx[j];
+      }
+    }
+    __syncthreads();
+    // re-zero the counters this sub-tile used
+    for (int d = dlo + tid; d <= dhi; d += kSortBlock) {
+#pragma unroll
+      for (int ww = 0; ww < kSortWarps; ww++) s_wcount[ww * R + d] = 0;
+    }
+    if (tid == 0) { s_range[0] = R; s_range[1] = -1; }
+    __syncthreads();
+  }
+}
+
+template <int BITS, int SRC, int DST>
+static int launch_pair_scatter(const SortPlan &pl, const void *src, void *dst, int n, int shift, const int *offs,
+                               int *next_hist, cudaStream_t st) {
+  constexpr int R = 1 << BITS;
+  constexpr size_t smem = ((size_t)R * (1 + kSortWarps) + R / 32) * sizeof(int);
+  static bool attr_done = false;
+  if (!attr_done) {
+    VPB_CUDA(cudaFuncSetAttribute(pair_scatter_kernel<BITS, SRC, DST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  pair_scatter_kernel<BITS, SRC, DST><<<pl.nblocks, kSortBlock, smem, st>>>(src, dst, n, pl.per_block, shift, offs, next_hist);
+  VPB_LAUNCH_CHECK();
+  return 0;
+}
+
+static size_t index_sort_work_bytes(int n) { return (((size_t)n * 4 + 255) / 256) * 256 + 2 * ((((size_t)n * 8 + 255) / 256) * 256); }
+
+template <int BITS>
+static int index_sort(const int4 *p, const int *keys_in, int n, int key_bits, int *perm, char *work, void *scratch,
+                      size_t scratch_bytes, cudaStream_t st, int *key_count, int n_keys) {
+  constexpr int R = 1 << BITS;
+  const SortPlan pl = plan_sort(n, BITS, n_keys, kPairSubTile);
+  VPB_REQUIRE(scratch && scratch_bytes >= pl.total_bytes, "sort: scratch too small (%zu < %zu)", scratch_bytes, pl.total_bytes);
+  const size_t hb = ((pl.hist_bytes + 255) / 256) * 256;
+  int *hist[2] = {(int *)scratch, (int *)((char *)scratch + hb)};
+  int *tmp = (int *)((char *)scratch + 2 * hb);
+  int *keys = (int *)work;
+  const size_t kb_bytes = (((size_t)n * 4 + 255) / 256) * 256, pb_bytes = (((size_t)n * 8 + 255) / 256) * 256;
+  void *pairs[2] = {work + kb_bytes, work + kb_bytes + pb_bytes};
+  key_hist_kernel<BITS><<<pl.nblocks, kSortBlock, 0, st>>>(p, keys_in, keys, n, pl.per_block, hist[0], key_count, n_keys);
+  VPB_LAUNCH_CHECK();
+  const void *src = keys_in ? (const void *)keys_in : (const void *)keys;
+  int cur = 0, pc = 0;
+  for (int shift = 0; shift < key_bits; shift += BITS) {
+    const bool first = shift == 0, last = shift + BITS >= key_bits;
+    if (!last) VPB_CUDA(cudaMemsetAsync(hist[cur ^ 1], 0, pl.hist_bytes, st));
+    int r = exclusive_scan_inplace(hist[cur], R * pl.nblocks, tmp, st); if (r) return r;
+    void *dst = last ? (void *)perm : pairs[pc];
+    int *nh = last ? nullptr : hist[cur ^ 1];
+    if (first && last)       r = launch_pair_scatter<BITS, 0, 1>(pl, src, dst, n, shift, hist[cur], nh, st);
+    else if (first)          r = launch_pair_scatter<BITS, 0, 0>(pl, src, dst, n, shift, hist[cur], nh, st);
+    else if (last)           r = launch_pair_scatter<BITS, 1, 1>(pl, src, dst, n, shift, hist[cur], nh, st);
+    else                     r = launch_pair_scatter<BITS, 1, 0>(pl, src, dst, n, shift, hist[cur], nh, st);
+    if (r) return r;
+    src = dst; pc ^= 1; cur ^= 1;
+  }
+  return 0;
+}
+
+// dst[k] = p[perm[k]]: one 32-byte sector gathered per particle, consecutive stores
+__global__ void __launch_bounds__(256) permute_p_kernel(const float4 *p, const int *perm, float4 *dst, int n) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  float4 r, u;
+  ld_particle(p + 2 * (size_t)__ldg(perm + k), r, u);
+  st_particle(dst + 2 * (size_t)k, r, u);
 }
 
 // class start offsets of a one-pass split: scanned hist[c * nblocks] is where class c begins
@@ -367,6 +535,42 @@ extern "C" int vpb_sort_p(void *p, int32_t np, void *aux, int32_t *partition, in
   }
   const int threads = 256;
   partition_kernel<<<(np + 1 + threads - 1) / threads, threads, 0, st>>>((const int4 *)p, np, nv, partition);
+  VPB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" size_t vpb_sort_index_work_bytes(int32_t np) { return index_sort_work_bytes(np > 0 ? np : 1); }
+
+extern "C" size_t vpb_sort_index_scratch_bytes(int32_t n_items, int32_t n_keys_hint) {
+  return plan_sort(n_items > 0 ? n_items : 1, 11, n_keys_hint > 0 ? n_keys_hint : 0, kPairSubTile).total_bytes;
+}
+
+extern "C" int vpb_sort_p_index(const void *p, const int32_t *keys, int32_t np, int32_t *perm, int32_t *partition,
+                                int32_t nx, int32_t ny, int32_t nz, void *work, size_t work_bytes,
+                                void *scratch, size_t scratch_bytes, void *stream) {
+  VPB_REQUIRE((p || keys) && perm && partition && np >= 0 && nx > 0 && ny > 0 && nz > 0, "vpb_sort_p_index: Bad args");
+  cudaStream_t st = as_stream(stream);
+  const int64_t nv64 = (int64_t)(nx + 2) * (ny + 2) * (nz + 2);
+  VPB_REQUIRE(nv64 < (1ll << 31), "vpb_sort_p_index: too many voxels");
+  const int nv = (int)nv64;
+  if (np == 0) { VPB_CUDA(cudaMemsetAsync(partition, 0, ((size_t)nv + 1) * sizeof(int), st)); return 0; }
+  VPB_REQUIRE(work && work_bytes >= index_sort_work_bytes(np), "vpb_sort_p_index: work area too small (%zu < %zu)",
+              work_bytes, index_sort_work_bytes(np));
+  const int kb = ceil_log2(nv) > 0 ? ceil_log2(nv) : 1;
+  const bool wide = (kb + 10) / 11 < (kb + 7) / 8;
+  VPB_CUDA(cudaMemsetAsync(partition, 0, ((size_t)nv + 1) * sizeof(int), st));
+  int r = wide ? index_sort<11>((const int4 *)p, keys, np, kb, perm, (char *)work, scratch, scratch_bytes, st, partition, nv)
+               : index_sort<8>((const int4 *)p, keys, np, kb, perm, (char *)work, scratch, scratch_bytes, st, partition, nv);
+  if (r) return r;
+  const SortPlan pl = plan_sort(np, wide ? 11 : 8, nv, kPairSubTile);
+  int *tmp = (int *)((char *)scratch + 2 * (((pl.hist_bytes + 255) / 256) * 256));
+  return exclusive_scan_inplace(partition, nv + 1, tmp, st);
+}
+
+extern "C" int vpb_permute_p(const void *p, int32_t np, const int32_t *perm, void *dst, void *stream) {
+  VPB_REQUIRE(np >= 0 && (np == 0 || (p && perm && dst && p != dst)), "vpb_permute_p: Bad args");
+  if (np == 0) return 0;
+  permute_p_kernel<<<(np + 255) / 256, 256, 0, as_stream(stream)>>>((const float4 *)p, perm, (float4 *)dst, np);
   VPB_LAUNCH_CHECK();
   return 0;
 }

@@ -194,7 +194,9 @@ class Species:
         self.sort_interval, self.sort_out_of_place = sort_interval, sort_out_of_place
         self.last_sorted = -(2 ** 63)
         dev = g.device
-        self.p = torch.zeros((self.max_np, 8), dtype=torch.float32, device=dev)
+        self._p = torch.zeros((self.max_np, 8), dtype=torch.float32, device=dev)
+        self._perm = None                 # order of a deferred sort_p the next advance_p applies (sort_p(sp, defer=True))
+        self._perm_pending = False
         self.pm = torch.zeros((self.max_nm, 4), dtype=torch.float32, device=dev)
         self.partition = torch.zeros(g.nv + 1, dtype=torch.int32, device=dev)
         self.counters = torch.zeros(4, dtype=torch.int32, device=dev)
@@ -205,6 +207,22 @@ class Species:
         self._mv_scratch = None
         self._en = torch.zeros(1, dtype=torch.float64, device=dev)
 
+    @property
+    def p(self):
+        """particle_t array [max_np, 8 floats].  Reading it settles a deferred sort first, so every user except the
+        advance_p that consumes the order sees the array sort_p promised."""
+        if self._perm_pending:
+            self.settle()
+        return self._p
+
+    def settle(self):
+        """Apply a pending sort_p order now (vpb_permute_p into the aux array, then swap)."""
+        if not self._perm_pending:
+            return
+        self._perm_pending = False
+        _lib.check(_lib.load().vpb_permute_p(_ptr(self._p), self.np, _ptr(self._perm), _ptr(self._aux), _stream()), "permute_p")
+        self._p, self._aux = self._aux, self._p
+
     def set_particles(self, arr):
         """arr: numpy structured array (abi.particle_dtype) or float32 [n,8] tensor."""
         if isinstance(arr, np.ndarray):
@@ -213,7 +231,8 @@ class Species:
             t = arr
         n = t.shape[0]
         _bad_args(n > self.max_np, "set_particles")
-        self.p[:n].copy_(t)
+        self._perm_pending = False
+        self._p[:n].copy_(t)
         self.np, self.nm = n, 0
         self.partition_np = -1
 
@@ -239,7 +258,12 @@ def advance_p(sp: Species, aa: AccumulatorArray, ia: InterpolatorArray, variant=
     g = sp.g
     sp.counters.zero_()
     a = _lib.PushArgs()
-    a.p, a.np = sp.p.data_ptr(), sp.np
+    gather = sp._perm_pending and variant in (_lib.DEPOSIT_DEFAULT, 2) and not int(os.environ.get("VPB_DEBUG_SKIP", "0"))
+    if gather:                            # the push applies the order of the deferred sort_p: p[perm[k]] -> aux[k]
+        a.p, a.np = sp._p.data_ptr(), sp.np
+        a.perm, a.p_out = sp._perm.data_ptr(), sp._aux.data_ptr()
+    else:
+        a.p, a.np = sp.p.data_ptr(), sp.np
     a.pm, a.max_nm = sp.pm.data_ptr(), sp.max_nm
     a.counters = sp.counters.data_ptr()
     a.interp, a.interp_stride = ia.i.data_ptr(), ia.stride
@@ -256,6 +280,9 @@ def advance_p(sp: Species, aa: AccumulatorArray, ia: InterpolatorArray, variant=
         a.partition, a.partition_np = sp.partition.data_ptr(), sp.partition_np
     L = _lib.load()
     _lib.check(L.vpb_advance_p(C.byref(a), _stream()), "advance_p")
+    if gather:
+        sp._perm_pending = False
+        sp._p, sp._aux = sp._aux, sp._p
     if sync:
         finish_advance_p(sp)
 
@@ -285,19 +312,35 @@ def finish_advance_p_all(species):
                        "sort_movers")
 
 
-def sort_p(sp: Species):
-    """sort_p(species_t*), species_advance.h:65-66."""
+def sort_p(sp: Species, defer=False):
+    """sort_p(species_t*), species_advance.h:65-66.  defer=True computes the same order and partition[] from 8-byte
+    (voxel, index) pairs and leaves the particles where they are; the next advance_p(sp, ...) moves them while it pushes
+    them (one pass over the particle array instead of five), anything else that looks at sp.p settles the order first."""
     _bad_args(sp is None, "sort_p")
     L = _lib.load()
     g = sp.g
+    sp.settle()
     sp.last_sorted = g.step
     if sp._aux is None or sp._aux.shape[0] < sp.np:
         sp._aux = torch.empty((sp.max_np, 8), dtype=torch.float32, device=g.device)
-    need = L.vpb_sort_scratch_bytes(max(sp.np, 1), g.nv)
-    if sp._scratch is None or sp._scratch.numel() < need:
-        sp._scratch = torch.empty(need, dtype=torch.uint8, device=g.device)
-    _lib.check(L.vpb_sort_p(_ptr(sp.p), sp.np, _ptr(sp._aux), _ptr(sp.partition), g.nx, g.ny, g.nz,
-                            _ptr(sp._scratch), sp._scratch.numel(), _stream()), "sort_p")
+    if defer and sp.np > 1:
+        need = L.vpb_sort_index_scratch_bytes(max(sp.np, 1), g.nv)
+        if sp._scratch is None or sp._scratch.numel() < need:
+            sp._scratch = torch.empty(need, dtype=torch.uint8, device=g.device)
+        if sp._perm is None:
+            sp._perm = torch.empty(sp.max_np, dtype=torch.int32, device=g.device)
+        work_bytes = sp._aux.numel() * 4
+        _bad_args(work_bytes < L.vpb_sort_index_work_bytes(sp.np), "sort_p")
+        _lib.check(L.vpb_sort_p_index(_ptr(sp._p), None, sp.np, _ptr(sp._perm), _ptr(sp.partition), g.nx, g.ny, g.nz,
+                                      _ptr(sp._aux), work_bytes, _ptr(sp._scratch), sp._scratch.numel(), _stream()),
+                   "sort_p")
+        sp._perm_pending = True
+    else:
+        need = L.vpb_sort_scratch_bytes(max(sp.np, 1), g.nv)
+        if sp._scratch is None or sp._scratch.numel() < need:
+            sp._scratch = torch.empty(need, dtype=torch.uint8, device=g.device)
+        _lib.check(L.vpb_sort_p(_ptr(sp._p), sp.np, _ptr(sp._aux), _ptr(sp.partition), g.nx, g.ny, g.nz,
+                                _ptr(sp._scratch), sp._scratch.numel(), _stream()), "sort_p")
     sp.partition_np = sp.np
 
 

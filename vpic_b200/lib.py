@@ -31,7 +31,8 @@ class PushArgs(C.Structure):
                 ("qdt_2mc", c_f), ("cdt_dx", c_f), ("cdt_dy", c_f), ("cdt_dz", c_f), ("qsp", c_f),
                 ("nx", c_i32), ("ny", c_i32), ("nz", c_i32),
                 ("variant", c_i32), ("p_first", c_i32), ("neighbor_rule", C.POINTER(NeighborRule)), ("debug_skip", c_i32),
-                ("partition", c_vp), ("partition_np", c_i32)]
+                ("partition", c_vp), ("partition_np", c_i32),
+                ("perm", c_vp), ("p_out", c_vp)]
 
 
 class BoundaryArgs(C.Structure):
@@ -87,6 +88,10 @@ _PROTOS = {
     "vpb_sort_movers_scratch_bytes": (C.c_size_t, [c_i32]),
     "vpb_sort_movers": (C.c_int, [c_vp, c_i32, c_vp, C.c_size_t, c_vp]),
     "vpb_sort_p": (C.c_int, [c_vp, c_i32, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, C.c_size_t, c_vp]),
+    "vpb_sort_index_work_bytes": (C.c_size_t, [c_i32]),
+    "vpb_sort_index_scratch_bytes": (C.c_size_t, [c_i32, c_i32]),
+    "vpb_sort_p_index": (C.c_int, [c_vp, c_vp, c_i32, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, C.c_size_t, c_vp, C.c_size_t, c_vp]),
+    "vpb_permute_p": (C.c_int, [c_vp, c_i32, c_vp, c_vp, c_vp]),
     "vpb_load_interpolator": (C.c_int, [c_vp, c_i32, c_vp, c_i32, c_i32, c_i32, c_vp]),
     "vpb_clear_accumulator": (C.c_int, [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "vpb_unload_accumulator": (C.c_int, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_f, c_f, c_f, c_f, c_vp]),

@@ -13,6 +13,8 @@ Order of operations is the reference's:
 Host hooks of the reference (user_* injections, collisions, emitters, dumps) are outside the hot path and are not
 called here.
 """
+import os
+
 import torch
 
 from . import engine as E
@@ -28,6 +30,9 @@ class Simulation:
         self.num_comm_round = num_comm_round
         self.exchange = exchange          # parallel.SlabExchange for multi-GPU runs, None on one GPU
         self.deposit_variant = 0
+        # sort_p computes the order only and the advance_p that follows moves the particles while it pushes them
+        # (engine.sort_p(defer=True)); VPB_DEFER_SORT=0 restores the stand-alone sort
+        self.defer_sort = os.environ.get("VPB_DEFER_SORT", "1") != "0"
         self.push_events = None           # list of (start, end) CUDA events around each advance_p when profiling
         self.overlap_exchange = True      # multi-GPU: migrate species k while species k+1 is pushed
         self._side = None
@@ -68,7 +73,7 @@ class Simulation:
         self.sync_counts()
         for sp in self.species_list:
             if sp.sort_interval > 0 and step % sp.sort_interval == 0:
-                E.sort_p(sp)
+                E.sort_p(sp, defer=self.defer_sort)
         E.clear_accumulator_array(aa)
         done = []
         for sp in self.species_list:
