@@ -199,6 +199,8 @@ int vpb_sort_p_index(const void *p, const int32_t *keys, int32_t np, int32_t *pe
                      void *scratch, size_t scratch_bytes, void *stream);
 /* dst[k] = p[perm[k]] for k < np (dst != p) */
 int vpb_permute_p(const void *p, int32_t np, const int32_t *perm, void *dst, void *stream);
+/* the inverse for a few particles: p[perm[k]] = src[k] for k < n (perm may point into the middle of an order) */
+int vpb_unpermute_p(void *p, int32_t n, const int32_t *perm, const void *src, void *stream);
 
 /* ---- interpolator / accumulator glue ---------------------------------------
  * load_interpolator_pipeline_scalar  (src/sf_interface/pipeline/interpolator_array_pipeline.cc:21-135)

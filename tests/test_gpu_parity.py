@@ -622,6 +622,96 @@ def test_dropin_symbols_on_host_structs(eng, oracle, mode):
         assert faults > 0 and fault_bytes > 0 and regions >= 4 and remaps == 0, res
 
 
+_DEFER_SCRIPT = """
+import sys, os, ctypes as C, numpy as np
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, 'tests'))
+import bench, refvpic as R
+from vpic_b200 import lib, grid as G, abi
+mode, scenario = sys.argv[1], sys.argv[2]
+L = lib.load(); orc = R.load_oracle()
+nx, ny, nz, n = 9, 8, 7, 70001
+g = G.partition_periodic_box(0,0,0,nx,ny,nz,nx,ny,nz,1,1,1, dt=G.courant_dt(1,1,1,nx,ny,nz,frac=0.98))
+H = bench.HostWorld(L, g, pinned='register')
+L.vpic_b200_set_lazy_min.argtypes = [C.c_size_t]; L.vpic_b200_set_lazy_min.restype = None
+L.vpic_b200_set_lazy_min(4096)
+L.vpic_b200_sync_to_host.argtypes = [C.c_void_p]; L.vpic_b200_sync_to_host.restype = None
+L.vpic_b200_set_mode(dict(resident=1, auto=2)[mode])
+rng = np.random.default_rng(33)
+fld = R.random_fields(rng, g.nv) * 0.05
+H.fields[:] = fld
+sp = H.new_species('e', -1.0, 1.0, n + 64, n, 3)
+parts = R.random_particles(rng, n, nx, ny, nz, uth=0.3, w=0.5)
+sp.p[:n] = parts.view(np.float32).reshape(-1, 8); sp.c.np = n
+H.load_interpolator()
+# oracle: sort, the same host edit, push
+interp = np.zeros((g.nv, 20), np.float32)
+orc.vpo_load_interpolator(interp.ctypes.data, 20, fld.ctypes.data, nx, ny, nz)
+p2, aux = parts.copy(), np.zeros_like(parts); part = np.zeros(g.nv + 1, np.int32)
+orc.vpo_sort_p(p2.ctypes.data, n, aux.ctypes.data, part.ctypes.data, nx, ny, nz)
+sorted_ref = p2.copy()
+L.sort_p(C.byref(sp.c))
+seen = {{}}
+edit = None
+if scenario == 'edge_write':          # the first particles live in the unprotected head of the array (never faults)
+    edit = [0, 3]
+elif scenario == 'interior_read':     # a host read in the middle faults a chunk back: the order is applied first
+    if mode == 'resident': L.vpic_b200_sync_to_host(sp.p.ctypes.data)
+    k = n // 2
+    seen['mid'] = bool(np.array_equal(sp.p[k].view(np.uint32), sorted_ref[k:k+1].view(np.uint32).reshape(-1)))
+    edit = [k]
+elif scenario == 'edge_read':
+    if mode == 'resident': L.vpic_b200_sync_to_host(sp.p.ctypes.data)
+    seen['first'] = bool(np.array_equal(sp.p[0].view(np.uint32), sorted_ref[0:1].view(np.uint32).reshape(-1)))
+    seen['fourth'] = bool(np.array_equal(sp.p[3].view(np.uint32), sorted_ref[3:4].view(np.uint32).reshape(-1)))
+if edit and not (mode == 'resident' and scenario == 'edge_write'):
+    for k in edit:
+        sp.p[k, 4] += np.float32(0.03125); p2['ux'][k] += np.float32(0.03125)
+    if mode == 'resident':
+        L.vpic_b200_invalidate.argtypes = [C.c_void_p]; L.vpic_b200_invalidate.restype = None
+        L.vpic_b200_invalidate(sp.p.ctypes.data)
+L.clear_accumulator_array(C.byref(H.aa))
+L.advance_p(C.byref(sp.c), C.byref(H.aa), C.byref(H.ia))
+if mode == 'resident': L.vpic_b200_sync_to_host(None)
+pm2 = np.zeros(n, dtype=abi.mover_dtype); acc2 = np.zeros(((g.nv + 1)//2*2, 12), np.float32)
+f32 = np.float32; dt = f32(g.dt)
+a = R.OraclePushArgs(p2.ctypes.data, n, pm2.ctypes.data, n, interp.ctypes.data, 20, acc2.ctypes.data, 12,
+                     g.neighbor.ctypes.data, g.rangel, g.rangeh, f32(f32(f32(-1)*dt)/f32(2)), dt, dt, dt, f32(-1))
+orc.vpo_advance_p(C.byref(a), None)
+got = sp.p[:n].reshape(-1).view(abi.particle_dtype)
+bad = np.nonzero(np.any(got.view(np.uint32).reshape(n, 8) != p2.view(np.uint32).reshape(n, 8), axis=1))[0]
+res = dict(seen=seen, particles=int(bad.size), first_bad=[int(x) for x in bad[:5]],
+           partition=bool(np.array_equal(sp.partition[:g.nv], part[:g.nv])),
+           accum=float(np.abs(H.accum - acc2).max() / np.abs(acc2).max()))
+L.vpic_b200_set_mode(0)
+import json; print('RESULT ' + json.dumps(res))
+"""
+
+
+@pytest.mark.parametrize("mode", ["auto", "resident"])
+@pytest.mark.parametrize("scenario", ["plain", "edge_read", "edge_write", "interior_read"])
+def test_dropin_deferred_sort_is_invisible_to_the_host(eng, oracle, mode, scenario):
+    """sort_p of the drop-in layer only computes the order; the next advance_p moves the particles.  A host that reads
+    or edits particles in between (collision operators do, advance.cc:44-47) must still see and get the sorted array:
+    reads at the unprotected ends of the array, reads that fault a chunk back, edits at the ends that the fused push
+    has to pick up in sorted positions.  Result after the push bit-identical to the oracle's sort -> edit -> push."""
+    import subprocess, sys, os, json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, VPIC_B200_LAZY_CHUNK="16384", VPIC_B200_TRACE="1")
+    r = subprocess.run([sys.executable, "-c", _DEFER_SCRIPT.format(root=root), mode, scenario],
+                       capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("RESULT ")][0][7:])
+    assert res["particles"] == 0 and res["partition"] and res["accum"] < 2e-5, res
+    assert all(res["seen"].values()), res
+    trace = [ln for ln in r.stderr.splitlines() if "sort_p_fused_into_advance_p" in ln][0]
+    fused = int(trace.split("sort_p_fused_into_advance_p=")[1].split()[0])
+    settled = int(trace.split("sort_p_applied_separately=")[1].split()[0])
+    if scenario == "interior_read" or (mode == "resident" and scenario == "edge_read"):
+        assert (fused, settled) == (0, 1), trace           # the host looked: the order was applied on its own
+    else:
+        assert (fused, settled) == (1, 0), trace
+
+
 _AUTO_SCRIPT = """
 import sys, os, ctypes as C, numpy as np
 sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, 'tests'))

@@ -58,6 +58,7 @@ int rank_for_log() { return &_world_rank ? _world_rank : 0; }
 enum { C_ADVANCE_P, C_SORT_P, C_CENTER_P, C_ENERGY_P, C_RHO_P, C_LOAD_INTERP, C_CLEAR_ACC, C_UNLOAD_ACC, C_ADVANCE_B,
        C_ADVANCE_E, C_CLEAR_JF, C_SYNC_JF, C_ENERGY_F, C_DIV_CLEAN, C_HYDRO, C_BOUNDARY_P, C_FIELD_FALLBACK, C_COUNT };
 uint64_t g_calls[C_COUNT];
+uint64_t g_sorts_fused = 0, g_sorts_settled = 0;   // deferred sort_p orders applied inside advance_p / applied on their own
 // VPIC_B200_TRACE=1 also accumulates host wall time per phase of the entry points that synchronise with the device
 enum { T_ADV_PREP, T_ADV_KERNEL_WAIT, T_ADV_MOVER_SORT, T_ADV_FINISH, T_BP_PACK, T_BP_EXCHANGE, T_BP_INJECT, T_HALO, T_COUNT };
 double g_phase_s[T_COUNT];
@@ -76,6 +77,8 @@ void trace_report() {
   fprintf(stderr, "vpic_b200 trace[%d]:", rank_for_log());
   for (int i = 0; i < C_COUNT; i++) fprintf(stderr, " %s=%llu", names[i], (unsigned long long)g_calls[i]);
   const vpb_lazy::Stats st = vpb_lazy::stats();
+  fprintf(stderr, " sort_p_fused_into_advance_p=%llu sort_p_applied_separately=%llu", (unsigned long long)g_sorts_fused,
+          (unsigned long long)g_sorts_settled);
   fprintf(stderr, " lazy_faults=%llu lazy_fault_bytes=%llu\n", (unsigned long long)st.faults, (unsigned long long)st.fault_bytes);
   static const char *pn[T_COUNT] = {"advance_p.prepare", "advance_p.kernel+count_read", "advance_p.mover_sort", "advance_p.finish",
                                     "boundary_p.pack", "boundary_p.exchange", "boundary_p.inject", "field_halo_exchange"};
@@ -112,11 +115,54 @@ int *g_counters = nullptr;
 size_t g_lazy_min = (32u << 20) + 4096;
 int g_device = 0;
 
+// ---- deferred sort_p -------------------------------------------------------------------------------------------------
+// sort_p sorts (voxel, index) pairs and keeps the order in `perm`; the advance_p that follows moves the particles while
+// it pushes them (vpb_sort_p_index / vpb_push_args_t.perm).  Until then the device copy of the particle array is still
+// in the old order, so everything else that could look at it applies the order first: any entry point that asks for
+// the array (mirror()), a host access that faults a chunk back (the copy callbacks below), vpic_b200_sync_to_host.
+// The unprotected ends of a tracked array are written to the host in the new order right away (sort_p below).
+struct PendingSort { int32_t *perm = nullptr; size_t perm_cap = 0; void *aux = nullptr; size_t aux_cap = 0; bool pending = false; int32_t np = 0; };
+std::unordered_map<const void *, PendingSort> g_pending;       // by host particle array
+int g_npending = 0;
+void lazy_fatal(const char *msg);
+
+void settle_inplace(Mirror &m, PendingSort &ps) {
+  ps.pending = false; g_npending--; g_sorts_settled++;
+  cudaSetDevice(g_device);
+  if (vpb_permute_p(m.d, ps.np, ps.perm, ps.aux, nullptr) != 0 ||
+      cudaMemcpy(m.d, ps.aux, (size_t)ps.np * sizeof(vpb_particle_t), cudaMemcpyDeviceToDevice) != cudaSuccess)
+    lazy_fatal("vpic_b200: could not apply a deferred sort_p");
+}
+void settle_host(const void *h) {
+  if (!g_npending) return;
+  auto it = g_pending.find(h);
+  if (it == g_pending.end() || !it->second.pending) return;
+  auto mi = g_mirrors.find(h);
+  if (mi != g_mirrors.end()) settle_inplace(mi->second, it->second);
+}
+void settle_dev(const void *d) {
+  if (!g_npending) return;
+  for (auto &kv : g_pending) {
+    if (!kv.second.pending) continue;
+    auto mi = g_mirrors.find(kv.first);
+    if (mi == g_mirrors.end()) continue;
+    const char *a = (const char *)mi->second.d;
+    if ((const char *)d >= a && (const char *)d < a + mi->second.cap) { settle_inplace(mi->second, kv.second); return; }
+  }
+}
+void cancel_pending(const void *h, bool release) {
+  auto it = g_pending.find(h);
+  if (it == g_pending.end()) return;
+  if (it->second.pending) { it->second.pending = false; g_npending--; }
+  if (release) { if (it->second.perm) vpb_free(it->second.perm); if (it->second.aux) vpb_free(it->second.aux); g_pending.erase(it); }
+}
+
 int lazy_h2d(void *d, const void *h, size_t n) { return vpb_memcpy_h2d(d, h, n, nullptr); }
 int lazy_d2h(void *h, const void *d, size_t n) {
   // may run inside the SIGSEGV handler on any host thread: bind the device, copy on the legacy default stream (which
   // orders it after every kernel the entry points launched) and return only when the bytes are in host memory
   cudaSetDevice(g_device);
+  settle_dev(d);
   return cudaMemcpy(h, d, n, cudaMemcpyDeviceToHost) != cudaSuccess;
 }
 // Page-locked (cudaHostRegister'ed) destination: the copy engine writes it without going through the CPU's page
@@ -126,6 +172,7 @@ bool g_dma_into_protected = true;
 int lazy_d2h_protected(void *h, const void *d, size_t n) {
   if (!g_dma_into_protected) return 1;
   cudaSetDevice(g_device);
+  settle_dev(d);
   cudaPointerAttributes a0, a1;
   if (cudaPointerGetAttributes(&a0, h) != cudaSuccess || cudaPointerGetAttributes(&a1, (char *)h + n - 1) != cudaSuccess ||
       a0.type != cudaMemoryTypeHost || a1.type != cudaMemoryTypeHost) { cudaGetLastError(); return 1; }
@@ -172,12 +219,14 @@ bool g_copied_back = false;     // an asynchronous device->host copy is in fligh
 void finish_entry() { if (g_copied_back) { DEV(vpb_stream_sync(nullptr)); g_copied_back = false; } }
 
 void drop_mirror(Mirror &m, const void *h) {
+  cancel_pending(h, true);
   if (m.lazy) { vpb_lazy::detach(m.lazy, false, nullptr); m.lazy = nullptr; }
   if (m.pinned) { cudaHostUnregister(const_cast<void *>(h)); cudaGetLastError(); }
   if (m.d) vpb_free(m.d);
 }
 
 Mirror &mirror(const void *h, size_t bytes, bool may_track = true) {
+  settle_host(h);
   if (g_mirrors.find(h) == g_mirrors.end()) {
     // A host array seen for the first time.  The host reallocates its arrays (boundary_p.cc:470-552 grows sp->p and
     // sp->pm) and frees temporaries; a mirror whose host range overlaps the new array describes memory the allocator
@@ -256,6 +305,7 @@ void *scratch(int id, size_t bytes) {
 int *counters() { if (!g_counters) DEV(vpb_malloc((void **)&g_counters, 4 * sizeof(int))); return g_counters; }
 
 void sync_one(const void *h, Mirror &m) {
+  settle_host(h);
   if (m.lazy) { vpb_lazy::to_host(m.lazy, 0, m.cap, &g_d2h); return; }
   if (m.host_stale && m.live_bytes) {
     DEV(vpb_memcpy_d2h(const_cast<void *>(h), m.d, m.live_bytes, nullptr)); g_d2h += m.live_bytes;
@@ -291,7 +341,9 @@ void vpic_b200_sync_to_host(const void *h) {
 
 void vpic_b200_invalidate(const void *h) {
   auto drop = [](Mirror &m) { if (m.lazy) vpb_lazy::forget_device(m.lazy); m.device_valid = false; m.host_stale = false; };
-  if (h) { auto it = g_mirrors.find(h); if (it != g_mirrors.end()) drop(it->second); return; }
+  // the host declares its copy current: an order that was still waiting for the device copy has nothing left to apply to
+  if (h) { cancel_pending(h, false); auto it = g_mirrors.find(h); if (it != g_mirrors.end()) drop(it->second); return; }
+  for (auto &kv : g_pending) if (kv.second.pending) { kv.second.pending = false; g_npending--; }
   for (auto &kv : g_mirrors) drop(kv.second);
 }
 
@@ -405,10 +457,43 @@ void advance_p(vpb_species_t *sp, vpb_accumulator_array_t *aa, const vpb_interpo
     if (it != g_sort_info.end() && it->second.nv == (int64_t)g->nv && it->second.part) {
       a.partition = it->second.part; a.partition_np = it->second.np;
     }
-    a.p = dev_in(sp->p, pbytes, (size_t)sp->max_np * sizeof(vpb_particle_t));
-    a.np = sp->np;
-    ph.mark(T_ADV_PREP);
-    DEV(vpb_advance_p(&a, nullptr));
+    PendingSort *ps = nullptr;
+    if (g_npending) {
+      auto pit = g_pending.find(sp->p);
+      if (pit != g_pending.end() && pit->second.pending && pit->second.np == sp->np && g_mirrors.find(sp->p) != g_mirrors.end())
+        ps = &pit->second;
+    }
+    if (ps) {
+      // The sort_p before this call left its order in ps->perm: load p[perm[k]], store position k of the other buffer.
+      // Every interior chunk is device-owned (sort_p made it so; a host access since then would have applied the order
+      // and cleared `pending`); what the host holds at the unprotected ends goes to the device in sorted positions.
+      Mirror &m = g_mirrors[sp->p];
+      if (m.lazy) {
+        size_t head_end, tail_begin;
+        vpb_lazy::edges(m.lazy, &head_end, &tail_begin);
+        const size_t rng[2][2] = {{0, head_end < pbytes ? head_end : pbytes}, {tail_begin < pbytes ? tail_begin : pbytes, pbytes}};
+        for (int e = 0; e < 2; e++) {
+          const size_t b0 = rng[e][0], b1 = rng[e][1];
+          if (b1 <= b0) continue;
+          DEV(vpb_memcpy_h2d((char *)ps->aux + b0, (const char *)sp->p + b0, b1 - b0, nullptr)); g_h2d += b1 - b0;
+          DEV(vpb_unpermute_p(m.d, (int32_t)((b1 - b0) / sizeof(vpb_particle_t)), ps->perm + b0 / sizeof(vpb_particle_t),
+                              (char *)ps->aux + b0, nullptr));
+        }
+      }
+      ps->pending = false; g_npending--; g_sorts_fused++;
+      a.p = m.d; a.perm = ps->perm; a.p_out = ps->aux; a.np = sp->np;
+      a.partition = nullptr;
+      ph.mark(T_ADV_PREP);
+      DEV(vpb_advance_p(&a, nullptr));
+      void *t = m.d; m.d = ps->aux; ps->aux = t;                      // same capacity (sort_p allocated aux with m.cap)
+      if (m.lazy) vpb_lazy::set_device(m.lazy, m.d);
+      m.device_valid = true; if (pbytes > m.live_bytes) m.live_bytes = pbytes;
+    } else {
+      a.p = dev_in(sp->p, pbytes, (size_t)sp->max_np * sizeof(vpb_particle_t));
+      a.np = sp->np;
+      ph.mark(T_ADV_PREP);
+      DEV(vpb_advance_p(&a, nullptr));
+    }
   } else {
     DEV(vpb_stream_sync(nullptr));                          // interp/accum/counters are in place
     Mirror &mp = mirror(sp->p, (size_t)sp->max_np * sizeof(vpb_particle_t));
@@ -854,16 +939,59 @@ int move_p(vpb_particle_t *p0, vpb_particle_mover_t *pm, vpb_accumulator_t *a0, 
 }
 
 // ---- sort_p: species_advance.h:65-66, sort_p_pipeline.cc:220-371 ------------------------------------------
+static bool defer_sort_enabled() {
+  static int v = -1;
+  if (v < 0) { const char *e = getenv("VPIC_B200_DEFER_SORT"); v = !(e && atoi(e) == 0); }
+  return v != 0;
+}
+
 void sort_p(vpb_species_t *sp) {
   if (!sp) DROPIN_ERROR("Bad args.");
   count_call(C_SORT_P);
   const vpb_grid_t *g = sp->g;
   sp->last_sorted = g->step;
-  void *p = dev_in(sp->p, (size_t)sp->np * sizeof(vpb_particle_t), (size_t)sp->max_np * sizeof(vpb_particle_t));
+  const size_t pbytes = (size_t)sp->np * sizeof(vpb_particle_t), cap = (size_t)sp->max_np * sizeof(vpb_particle_t);
+  void *p = dev_in(sp->p, pbytes, cap);
   int32_t *part = (int32_t *)dev_out_only(sp->partition, ((size_t)g->nv + 1) * sizeof(int32_t));
-  void *aux = scratch(1, (size_t)(sp->np > 0 ? sp->np : 1) * sizeof(vpb_particle_t));
-  const size_t need = vpb_sort_scratch_bytes(sp->np > 0 ? sp->np : 1, g->nv);
-  DEV(vpb_sort_p(p, sp->np, aux, part, g->nx, g->ny, g->nz, scratch(2, need), need, nullptr));
+  Mirror &m = g_mirrors[sp->p];
+  // Deferred: only the order is computed here, the advance_p that follows moves the particles (see PendingSort).  Not
+  // for arrays that are copied on every call (the host must get the sorted array back now).
+  bool defer = defer_sort_enabled() && sp->np > 1 && !strict(m) && (m.lazy || g_mode == VPB_MODE_RESIDENT);
+  size_t head_end = 0, tail_begin = pbytes;
+  if (defer && m.lazy) {
+    vpb_lazy::edges(m.lazy, &head_end, &tail_begin);
+    if ((head_end | tail_begin) % sizeof(vpb_particle_t)) defer = false;     // a page boundary inside a particle
+  }
+  if (defer) {
+    PendingSort &ps = g_pending[sp->p];
+    const size_t perm_bytes = (size_t)sp->max_np * sizeof(int32_t);
+    if (ps.perm_cap < perm_bytes) { if (ps.perm) vpb_free(ps.perm); ps.perm = nullptr; DEV(vpb_malloc((void **)&ps.perm, perm_bytes)); ps.perm_cap = perm_bytes; }
+    if (ps.aux_cap != m.cap) { if (ps.aux) vpb_free(ps.aux); ps.aux = nullptr; DEV(vpb_malloc(&ps.aux, m.cap)); ps.aux_cap = m.cap; }
+    if (ps.aux_cap < vpb_sort_index_work_bytes(sp->np)) defer = false;       // cannot happen for max_np >= np; be safe
+    if (defer) {
+      const size_t need = vpb_sort_index_scratch_bytes(sp->np, g->nv);
+      DEV(vpb_sort_p_index(p, nullptr, sp->np, ps.perm, part, g->nx, g->ny, g->nz, ps.aux, ps.aux_cap, scratch(2, need), need, nullptr));
+      ps.pending = true; ps.np = sp->np; g_npending++;
+      if (m.lazy) {
+        // the unprotected ends of the host array: sorted contents now (a host read there cannot fault)
+        const size_t rng[2][2] = {{0, head_end < pbytes ? head_end : pbytes}, {tail_begin < pbytes ? tail_begin : pbytes, pbytes}};
+        for (int e = 0; e < 2; e++) {
+          const size_t b0 = rng[e][0], b1 = rng[e][1];
+          if (b1 <= b0) continue;
+          DEV(vpb_permute_p(p, (int32_t)((b1 - b0) / sizeof(vpb_particle_t)), ps.perm + b0 / sizeof(vpb_particle_t), (char *)ps.aux + b0, nullptr));
+          DEV(vpb_memcpy_d2h((char *)sp->p + b0, (char *)ps.aux + b0, b1 - b0, nullptr)); g_d2h += b1 - b0;
+          g_copied_back = true;
+        }
+      } else {
+        m.host_stale = true;
+      }
+    }
+  }
+  if (!defer) {
+    void *aux = scratch(1, (size_t)(sp->np > 0 ? sp->np : 1) * sizeof(vpb_particle_t));
+    const size_t need = vpb_sort_scratch_bytes(sp->np > 0 ? sp->np : 1, g->nv);
+    DEV(vpb_sort_p(p, sp->np, aux, part, g->nx, g->ny, g->nz, scratch(2, need), need, nullptr));
+  }
   {
     // keep a device-private copy for advance_p's brick walk: the host owns sp->partition and may do anything to it
     SortInfo &si = g_sort_info[sp];
@@ -872,7 +1000,7 @@ void sort_p(vpb_species_t *sp) {
     DEV(vpb_memcpy_d2d(si.part, part, bytes, nullptr));
     si.np = sp->np; si.nv = g->nv;
   }
-  dev_written(sp->p, (size_t)sp->np * sizeof(vpb_particle_t));
+  if (!defer) dev_written(sp->p, pbytes);
   dev_written(sp->partition, ((size_t)g->nv + 1) * sizeof(int32_t));
   finish_entry();
 }

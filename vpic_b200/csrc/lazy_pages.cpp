@@ -364,6 +364,17 @@ bool device_owns(Region *r, size_t off) {
   return r->ndevice && r->state[chunk_of(r, a)] != HOST;
 }
 
+void set_device(Region *r, void *dev) {
+  if (!r) return;
+  Lock lk;
+  r->d = (char *)dev;
+}
+
+void edges(Region *r, size_t *head_end, size_t *tail_begin) {
+  *head_end = (size_t)(r->lo - r->h);
+  *tail_begin = (size_t)(r->hi - r->h);
+}
+
 int active() { return (int)g_stats.regions; }
 
 Stats stats() { return g_stats; }

@@ -58,6 +58,9 @@ void to_host(Region *r, size_t off, size_t bytes, uint64_t *d2h_bytes);
 void forget_device(Region *r);                         // the host copy is declared current everywhere
 int host_access(const void *p, size_t n);              // [p,p+n) made host-owned in every attached region
 bool device_owns(Region *r, size_t off);               // is the byte at offset `off` currently owned by the device?
+void set_device(Region *r, void *dev);                 // the device copy now lives at `dev` (same contents, same capacity)
+// the unprotected ends of the array: bytes [0, *head_end) and [*tail_begin, cap) are never device-owned
+void edges(Region *r, size_t *head_end, size_t *tail_begin);
 int active();                                          // number of attached regions
 Stats stats();
 

@@ -470,6 +470,15 @@ static int index_sort(const int4 *p, const int *keys_in, int n, int key_bits, in
   return 0;
 }
 
+// p[perm[k]] = src[k]: puts particles given in sorted positions back where the unsorted array holds them
+__global__ void __launch_bounds__(256) unpermute_p_kernel(float4 *p, const int *perm, const float4 *src, int n) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  float4 r, u;
+  ld_particle(src + 2 * (size_t)k, r, u);
+  st_particle(p + 2 * (size_t)__ldg(perm + k), r, u);
+}
+
 // dst[k] = p[perm[k]]: one 32-byte sector gathered per particle, consecutive stores
 __global__ void __launch_bounds__(256) permute_p_kernel(const float4 *p, const int *perm, float4 *dst, int n) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -571,6 +580,14 @@ extern "C" int vpb_permute_p(const void *p, int32_t np, const int32_t *perm, voi
   VPB_REQUIRE(np >= 0 && (np == 0 || (p && perm && dst && p != dst)), "vpb_permute_p: Bad args");
   if (np == 0) return 0;
   permute_p_kernel<<<(np + 255) / 256, 256, 0, as_stream(stream)>>>((const float4 *)p, perm, (float4 *)dst, np);
+  VPB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vpb_unpermute_p(void *p, int32_t n, const int32_t *perm, const void *src, void *stream) {
+  VPB_REQUIRE(n >= 0 && (n == 0 || (p && perm && src)), "vpb_unpermute_p: Bad args");
+  if (n == 0) return 0;
+  unpermute_p_kernel<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>((float4 *)p, perm, (const float4 *)src, n);
   VPB_LAUNCH_CHECK();
   return 0;
 }
