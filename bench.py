@@ -666,7 +666,10 @@ def main():
     ap.add_argument("--grid", type=int, default=128)
     ap.add_argument("--ppc", type=int, default=64)
     ap.add_argument("--uth", type=float, default=0.18)
-    ap.add_argument("--sort-interval", default="20", help="steps between sort_p calls: N, or E,I for electrons and ions")
+    ap.add_argument("--sort-interval", default="6,12",
+                    help="steps between sort_p calls (species_t::sort_interval): N, or E,I for electrons and ions.  The "
+                         "default is the measured optimum of this build at C2 (profiles/r02_sort_interval_sweep.txt); the "
+                         "reference arm runs the same intervals.  C5 names 20.")
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--e2e", type=int, default=1)
     ap.add_argument("--e2e-steps", type=int, default=20)

@@ -107,6 +107,10 @@ typedef struct vpb_push_args {
    * p_out, the movers and the accumulators are exactly those of vpb_sort_p followed by vpb_advance_p on p. */
   const int32_t *perm;
   void          *p_out;
+  /* Optional (NULL = off): int32[np], receives the voxel index every particle ends the push with (what sort_p would read
+   * back out of p.i), in output positions.  A vpb_sort_p_index that follows with no change to the array in between
+   * takes it as `keys` and never reads the particles.  Particles that left the domain store their 8*voxel+face code. */
+  int32_t       *keys_out;
 } vpb_push_args_t;
 
 #define VPB_DEPOSIT_DEFAULT      0   /* library's best measured strategy                                  */

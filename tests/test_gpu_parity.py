@@ -278,6 +278,39 @@ def test_sort_p_deferred_fused_into_advance_p(eng, oracle, case):
     assert np.abs(a0 - a1).max() <= 2e-5 * scale
 
 
+@pytest.mark.parametrize("case", [0, 1])
+def test_sort_p_deferred_takes_its_keys_from_the_previous_push(eng, oracle, case):
+    """advance_p(emit_keys=True) leaves every particle's voxel in a compact array; the deferred sort_p that follows sorts
+    those and never reads the particles.  Two steps (push, sort, push) with and without the short cut: identical bytes.
+    Case 1 has absorbing walls: movers leave the domain, so the keys must be ignored (sp.nm != 0)."""
+    rng = np.random.default_rng(41 + case)
+    dims, n, pbc, uth = [((14, 12, 10), 150011, None, 0.35), ((9, 7, 6), 20000, {i: -2 for i in range(6)}, 0.6)][case]
+    nx, ny, nz = dims
+    g = make_grid(nx, ny, nz, pbc=pbc) if pbc else make_grid(nx, ny, nz)
+    fields = R.random_fields(rng, g.nv)
+    parts = R.random_particles(rng, n, nx, ny, nz, uth=uth)
+    dg = eng.DeviceGrid(g)
+    fa, ia = eng.FieldArray(dg), eng.InterpolatorArray(dg)
+    fa.f.copy_(torch.from_numpy(fields))
+    eng.load_interpolator_array(ia, fa)
+    out = []
+    for fast in (False, True):
+        aa = eng.AccumulatorArray(dg)
+        sp = eng.Species("e", -1.0, 1.0, n, n, 20, 0, dg)
+        sp.set_particles(parts)
+        eng.clear_accumulator_array(aa)
+        eng.advance_p(sp, aa, ia, emit_keys=fast)
+        used_keys = fast and sp._keys_valid and sp.nm == 0
+        if sp.nm:                                            # what boundary_p does on one rank: absorbed particles go
+            eng.boundary_pack(sp, [-1] * 6, fa)
+        eng.sort_p(sp, defer=fast)
+        eng.advance_p(sp, aa, ia)
+        out.append((sp.particles_host().copy(), sp.np, sp.partition.cpu().numpy().copy(), used_keys))
+    (p0, np0, part0, _), (p1, np1, part1, used) = out
+    assert used == (case == 0)
+    assert np0 == np1 and np.array_equal(bits(p0), bits(p1)) and np.array_equal(part0, part1)
+
+
 def test_sort_movers(eng):
     from vpic_b200 import lib
     L = lib.load()

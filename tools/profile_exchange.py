@@ -3,7 +3,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 from vpic_b200 import engine as E
 class A: pass
-args=A(); args.grid=128; args.ppc=64; args.uth=0.18; args.sort_interval=20; args.variant=0
+args=A(); args.grid=128; args.ppc=64; args.uth=0.18; args.sort_interval="20"; args.variant=0
 rank=int(os.environ['RANK']); world=int(os.environ['WORLD_SIZE']); local=int(os.environ['LOCAL_RANK'])
 torch.cuda.set_device(local); dev=torch.device('cuda',local)
 dist.init_process_group('nccl', device_id=dev)

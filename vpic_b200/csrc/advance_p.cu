@@ -71,6 +71,7 @@ __device__ __forceinline__ void run_movers(const PushK &a, const int4 *q0, const
       }
     }
     st_particle(a.pout + 2 * (size_t)i, rr, uu);
+    if (a.keys) a.keys[i] = __float_as_int(rr.w);
   }
 }
 
@@ -176,6 +177,7 @@ __global__ void __launch_bounds__(kBlock, GATHER ? 4 : kMinBlocks) advance_p_ker
       if (inb) {
         const float qw = un.w * a.qsp;
         if (!(dbg & 4)) st_particle(a.pout + 2 * (size_t)i, make_float4(v3, v4, v5n, r.w), un);
+        if (a.keys) a.keys[i] = ii;
         const float v5 = (((qw * ux) * uy) * uz) * one_third;
         streak_currents(qw, ux, uy, uz, v0, v1, v2, v5, j);
       } else {
@@ -282,7 +284,7 @@ extern "C" int vpb_advance_p(const vpb_push_args_t *args, void *stream) {
   // asked for (variant VPB_DEPOSIT_BRICK_TILE, or VPB_BRICK_DEFAULT=1 in the environment).
   static int brick_default = -1;
   if (brick_default < 0) { const char *e = getenv("VPB_BRICK_DEFAULT"); brick_default = e && atoi(e) != 0; }
-  if (!args->perm && (args->variant == VPB_DEPOSIT_BRICK_TILE || (args->variant == VPB_DEPOSIT_DEFAULT && brick_default))) {
+  if (!args->perm && !args->keys_out && (args->variant == VPB_DEPOSIT_BRICK_TILE || (args->variant == VPB_DEPOSIT_DEFAULT && brick_default))) {
     VPB_REQUIRE(args->nx > 0 && args->ny > 0 && args->nz > 0, "vpb_advance_p: Bad grid");
     const int served = (args->debug_skip == 0) ? advance_p_brick(args, k, as_stream(stream)) : 0;
     if (served < 0) return -1;

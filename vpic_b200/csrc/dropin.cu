@@ -389,6 +389,29 @@ size_t fread(void *ptr, size_t size, size_t n, FILE *stream) {
   return real(ptr, size, n, stream);
 }
 
+// The same for the system calls themselves (an MPI shared-memory transport, MPI-IO or a deck's own I/O may hand a tracked
+// array straight to read/write/pread/pwrite): a system call on a device-owned page does not fault, it fails with EFAULT.
+ssize_t write(int fd, const void *buf, size_t n) {
+  static ssize_t (*real)(int, const void *, size_t) = (ssize_t (*)(int, const void *, size_t))next_symbol("write");
+  if (vpb_lazy::active()) vpb_lazy::host_access(buf, n);
+  return real(fd, buf, n);
+}
+ssize_t read(int fd, void *buf, size_t n) {
+  static ssize_t (*real)(int, void *, size_t) = (ssize_t (*)(int, void *, size_t))next_symbol("read");
+  if (vpb_lazy::active()) vpb_lazy::host_access(buf, n);
+  return real(fd, buf, n);
+}
+ssize_t pwrite(int fd, const void *buf, size_t n, off_t off) {
+  static ssize_t (*real)(int, const void *, size_t, off_t) = (ssize_t (*)(int, const void *, size_t, off_t))next_symbol("pwrite");
+  if (vpb_lazy::active()) vpb_lazy::host_access(buf, n);
+  return real(fd, buf, n, off);
+}
+ssize_t pread(int fd, void *buf, size_t n, off_t off) {
+  static ssize_t (*real)(int, void *, size_t, off_t) = (ssize_t (*)(int, void *, size_t, off_t))next_symbol("pread");
+  if (vpb_lazy::active()) vpb_lazy::host_access(buf, n);
+  return real(fd, buf, n, off);
+}
+
 // ---- advance_p: species_advance.h:73-76, advance_p_pipeline.cc:252-340 ------------------------------------
 // In coherent mode the particle array crosses PCIe twice per call; the copy-in, the kernel and the copy-out of
 // successive chunks run on three streams so the three overlap (needs page-locked host memory to be asynchronous).

@@ -64,7 +64,7 @@ struct Lock {
 
 void fatal(const char *msg) {
   if (g_copy.fatal) g_copy.fatal(msg);
-  (void)!write(2, msg, strlen(msg)); (void)!write(2, "\n", 1);
+  (void)!syscall(SYS_write, 2, msg, strlen(msg)); (void)!syscall(SYS_write, 2, "\n", 1);
   _exit(1);
 }
 
@@ -81,15 +81,14 @@ void protect(const Region *r, size_t c0, size_t c1, int prot) {      // chunks [
 // Fill still-protected host pages [a, a+n) from the device.  False when neither protection-blind route works.
 bool fill_protected(char *a, const char *dev, size_t n) {
   if (g_copy.d2h_protected && g_copy.d2h_protected(a, dev, n) == 0) return true;
-  if (g_mem_fd < 0) return false;
-  if (!g_staging) g_staging = (char *)(g_copy.staging_alloc ? g_copy.staging_alloc(kStaging) : malloc(kStaging));
-  if (!g_staging) return false;
+  if (g_mem_fd < 0 || !g_staging) return false;          // the staging buffer is allocated in init(), never in here
   for (size_t off = 0; off < n; off += kStaging) {
     const size_t m = n - off < kStaging ? n - off : kStaging;
     if (g_copy.d2h(g_staging, dev + off, m)) fatal("vpic_b200: device-to-host copy failed while serving a host access");
     size_t done = 0;
     while (done < m) {
-      const ssize_t w = pwrite(g_mem_fd, g_staging + done, m - done, (off_t)(uintptr_t)(a + off + done));
+      // raw system call: the library interposes pwrite(2) for the host program (dropin.cu)
+      const ssize_t w = syscall(SYS_pwrite64, g_mem_fd, g_staging + done, m - done, (off_t)(uintptr_t)(a + off + done));
       if (w <= 0) {
         if (off == 0 && done == 0) { close(g_mem_fd); g_mem_fd = -1; return false; }   // not permitted here: fall back
         fatal("vpic_b200: write through /proc/self/mem failed half way");
@@ -129,8 +128,9 @@ bool still_protected(const Region *r) {
   for (size_t c = 0; c < r->nchunks; c++) {
     if (r->state[c] != DEVICE) continue;
     if (g_probe[1] < 0) return true;
-    const ssize_t n = write(g_probe[1], chunk_lo(r, c), 1);         // the kernel refuses to read PROT_NONE memory
-    if (n == 1) { char b; (void)!read(g_probe[0], &b, 1); return false; }
+    // raw system calls: write(2)/read(2) themselves are interposed for the host program (dropin.cu) and would fetch
+    const ssize_t n = syscall(SYS_write, g_probe[1], chunk_lo(r, c), 1);   // the kernel refuses to read PROT_NONE memory
+    if (n == 1) { char b; (void)!syscall(SYS_read, g_probe[0], &b, 1); return false; }
     return errno == EFAULT;
   }
   return true;
@@ -216,6 +216,8 @@ void init(const Copier &c, size_t chunk_bytes) {
   if (chunk_bytes) g_chunk = chunk_bytes < g_page ? g_page : (chunk_bytes / g_page) * g_page;
   if (pipe2(g_probe, O_NONBLOCK | O_CLOEXEC) != 0) g_probe[0] = g_probe[1] = -1;
   g_mem_fd = open("/proc/self/mem", O_RDWR | O_CLOEXEC);
+  // everything the fault handler needs is set up here, so that the handler itself never allocates
+  if (!g_staging) g_staging = (char *)(g_copy.staging_alloc ? g_copy.staging_alloc(kStaging) : malloc(kStaging));
   install_handler();
   atexit(at_exit);
   g_installed = true;
@@ -342,6 +344,15 @@ int host_access(const void *p, size_t n) {
   if (!n || !g_nregions.load(std::memory_order_acquire)) return 0;
   const char *a = (const char *)p, *b = a + n;
   int touched = 0;
+  {
+    // Without the lock first: this runs under every read(2)/write(2) of the process (dropin.cu interposes them), also
+    // on threads of the CUDA runtime while another thread holds the lock and waits for the device.  A buffer that
+    // overlaps no tracked array must never wait here.  (Regions are only added or removed between entry points.)
+    bool any = false;
+    const int nr0 = g_nregions.load(std::memory_order_acquire);
+    for (int i = 0; i < nr0 && !any; i++) { const Region *r = g_regions[i]; any = r && b > r->lo && a < r->hi; }
+    if (!any) return 0;
+  }
   Lock lk;
   const int nr = g_nregions.load();
   for (int i = 0; i < nr; i++) {

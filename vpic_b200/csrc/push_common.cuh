@@ -26,6 +26,7 @@ __device__ __forceinline__ int fast_div(int v, int d, float inv_d) {
 
 struct PushK {
   float4 *p; int np; int first;
+  int *keys;                      // optional: voxel every particle ends the push with (for a following index sort)
   float4 *pout; const int *perm;  // stores go to pout (== p unless an index sort is being applied: loads from p[perm[k]])
   int4 *pm; int max_nm; int *counters;
   const float *interp; int istride;
@@ -227,6 +228,7 @@ static inline PushK to_push_k(const vpb_push_args_t *args) {
   PushK k;
   k.p = (float4 *)args->p; k.np = args->np; k.first = args->p_first;
   k.perm = args->perm; k.pout = args->perm ? (float4 *)args->p_out : k.p;
+  k.keys = args->keys_out;
   k.pm = (int4 *)args->pm; k.max_nm = args->max_nm; k.counters = args->counters;
   k.interp = args->interp; k.istride = args->interp_stride;
   k.accum = args->accum; k.astride = args->accum_stride;

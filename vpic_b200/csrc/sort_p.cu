@@ -156,6 +156,7 @@ __global__ void __launch_bounds__(kSortBlock) radix_scatter_kernel(const int4 *s
   for (int t0 = lo; t0 < hi; t0 += kSubTile) {
     int4 it[kIPT][VEC];
     int digit[kIPT], rank[kIPT];
+    int wlo = R, whi = -1;                                 // digits this warp touches in this sub-tile
     // warp-striped: warp w owns items [t0 + w*32*kIPT, +32*kIPT); step j covers 32 consecutive items
 #pragma unroll
     for (int j = 0; j < kIPT; j++) {
@@ -178,13 +179,13 @@ __global__ void __launch_bounds__(kSortBlock) radix_scatter_kernel(const int4 *s
       int before = 0;
       if (valid) before = s_wcount[w * R + d];
       __syncwarp();
-      if (valid && lane == __ffs(peers) - 1) {
-        s_wcount[w * R + d] = before + __popc(peers);
-        if (before == 0) { atomicMin(&s_range[0], d); atomicMax(&s_range[1], d); }
-      }
+      if (valid && lane == __ffs(peers) - 1) s_wcount[w * R + d] = before + __popc(peers);
       __syncwarp();
       rank[j] = before + __popc(peers & lt_mask);
+      wlo = min(wlo, __reduce_min_sync(0xffffffffu, valid ? d : R));
+      whi = max(whi, __reduce_max_sync(0xffffffffu, valid ? d : -1));
     }
+    if (lane == 0 && whi >= 0) { atomicMin(&s_range[0], wlo); atomicMax(&s_range[1], whi); }
     __syncthreads();
     // exclusive prefix over warps for every digit in the touched range, one thread per digit: a sub-tile of nearly
     // sorted items touches a few dozen CONSECUTIVE digits (a bitmap walk left them all to one or two threads)
@@ -244,7 +245,7 @@ static int ceil_log2(int64_t x) { int b = 0; while (((int64_t)1 << b) < x) b++; 
 
 struct SortPlan { int nblocks, per_block, scan_tmp; size_t hist_bytes, total_bytes; };
 
-static SortPlan plan_sort(int n, int bits = 11, int n_keys = 0, int sub_tile = kSubTile) {
+static SortPlan plan_sort(int n, int bits = 11, int n_keys = 0, int sub_tile = kSubTile, bool pow2 = false) {
   const int R = 1 << bits;
   SortPlan s;
   int nb = (n + sub_tile - 1) / sub_tile;
@@ -253,6 +254,7 @@ static SortPlan plan_sort(int n, int bits = 11, int n_keys = 0, int sub_tile = k
   int per = (n + nb - 1) / nb;
   per = ((per + sub_tile - 1) / sub_tile) * sub_tile;          // whole sub-tiles per CTA
   if (per < sub_tile) per = sub_tile;
+  if (pow2) { int q = sub_tile; while (q < per) q <<= 1; per = q; }   // output position -> CTA of the next pass by a shift
   nb = (n + per - 1) / per; if (nb < 1) nb = 1;
   s.nblocks = nb; s.per_block = per;
   s.scan_tmp = (R * nb + kScanTile - 1) / kScanTile;
@@ -309,8 +311,14 @@ static int radix_sort(int4 *a, int4 *b, int n, int key_bits, void *scratch, size
 //   key_hist_kernel      voxel of every particle (read from the particles, or from a key array a previous advance_p
 //                        left) -> compact key array, digit-0 histogram per CTA, per-voxel counts for partition[]
 //   pair_scatter_kernel  one stable LSD pass; SRC 0: keys (index implicit) / 1: pairs, DST 0: pairs / 1: index only
-constexpr int kPairIPT = 8;                             // 2048 pairs per sub-tile; 24 registers of items keep 3 CTAs per SM
-constexpr int kPairSubTile = kSortBlock * kPairIPT;
+// Items per thread and sub-tile: the first pass reads bare keys (the index is the position), so it can hold twice as
+// many per thread in the same registers — and its sub-tiles touch digits all over the range (the y and z neighbours of
+// a voxel differ in the low bits), so every sub-tile pays a walk over the whole [warp][digit] counter matrix.
+#ifndef VPB_PAIR_IPT0
+#define VPB_PAIR_IPT0 16
+#endif
+template <int SRC> struct PairTile { static constexpr int kIPT = SRC == 0 ? VPB_PAIR_IPT0 : 8; static constexpr int kItems = kSortBlock * kIPT; };
+constexpr int kPairSubTile = PairTile<0>::kItems;       // per-CTA chunks are whole multiples of the larger sub-tile
 
 template <int BITS>
 __global__ void __launch_bounds__(kSortBlock) key_hist_kernel(const int4 *p, const int *keys_in, int *keys_out, int n,
@@ -342,9 +350,10 @@ __global__ void __launch_bounds__(kSortBlock) key_hist_kernel(const int4 *p, con
 }
 
 template <int BITS, int SRC, int DST>
-__global__ void __launch_bounds__(kSortBlock, 3) pair_scatter_kernel(const void *src_, void *dst_, int n, int per_block,
+__global__ void __launch_bounds__(kSortBlock, (SRC == 0 && VPB_PAIR_IPT0 > 8) ? 2 : 3) pair_scatter_kernel(const void *src_, void *dst_, int n, int per_block,
                                                                   int shift, const int *offs, int *next_hist) {
   constexpr int R = 1 << BITS;
+  constexpr int IPT = PairTile<SRC>::kIPT;
   extern __shared__ int s_dyn[];
   int *s_base = s_dyn;                                  // [R]
   int *s_wcount = s_dyn + R;                            // [kSortWarps][R]
@@ -356,37 +365,38 @@ __global__ void __launch_bounds__(kSortBlock, 3) pair_scatter_kernel(const void 
   if (tid == 0) { s_range[0] = R; s_range[1] = -1; }
   const int lo = blockIdx.x * per_block;
   const int hi = min(n, lo + per_block);
+  const int pb_shift = 31 - __clz(per_block);
   __syncthreads();
 
-  for (int t0 = lo; t0 < hi; t0 += kPairSubTile) {
-    int key[kPairIPT], idx[kPairIPT], rank[kPairIPT];
+  for (int t0 = lo; t0 < hi; t0 += PairTile<SRC>::kItems) {
+    int key[IPT], idx[SRC == 0 ? 1 : IPT], rank[IPT];
     // warp-striped as in radix_scatter_kernel: warp w owns [t0 + w*32*IPT, +32*IPT), step j covers 32 consecutive items
+    const int i0 = t0 + w * 32 * IPT + lane;
 #pragma unroll
-    for (int j = 0; j < kPairIPT; j++) {
-      const int i = t0 + w * 32 * kPairIPT + j * 32 + lane;
-      if (i < hi) {
-        if (SRC == 0) { key[j] = static_cast<const int *>(src_)[i]; idx[j] = i; }
-        else { const int2 v = static_cast<const int2 *>(src_)[i]; key[j] = v.x; idx[j] = v.y; }
-      } else { key[j] = 0; idx[j] = -1; }
+    for (int j = 0; j < IPT; j++) {
+      const int i = i0 + j * 32;
+      if (SRC == 0) { key[j] = i < hi ? static_cast<const int *>(src_)[i] : 0; }
+      else if (i < hi) { const int2 v = static_cast<const int2 *>(src_)[i]; key[j] = v.x; idx[j] = v.y; }
+      else { key[j] = 0; idx[j] = -1; }
     }
+    int wlo = R, whi = -1;                                 // digits this warp touches in this sub-tile
 #pragma unroll
-    for (int j = 0; j < kPairIPT; j++) {
-      const bool valid = idx[j] >= 0;
+    for (int j = 0; j < IPT; j++) {
+      const bool valid = i0 + j * 32 < hi;
       const int d = valid ? ((key[j] >> shift) & (R - 1)) : (R + lane);
       const unsigned peers = __match_any_sync(0xffffffffu, d);
       int before = 0;
       if (valid) before = s_wcount[w * R + d];
       __syncwarp();
-      if (valid && lane == __ffs(peers) - 1) {
-        s_wcount[w * R + d] = before + __popc(peers);
-        if (before == 0) { atomicMin(&s_range[0], d); atomicMax(&s_range[1], d); }
-      }
+      if (valid && lane == __ffs(peers) - 1) s_wcount[w * R + d] = before + __popc(peers);
       __syncwarp();
       rank[j] = before + __popc(peers & lt_mask);
+      wlo = min(wlo, __reduce_min_sync(0xffffffffu, valid ? d : R));
+      whi = max(whi, __reduce_max_sync(0xffffffffu, valid ? d : -1));
     }
+    if (lane == 0 && whi >= 0) { atomicMin(&s_range[0], wlo); atomicMax(&s_range[1], whi); }
     __syncthreads();
-    // exclusive prefix over warps for every digit in the touched range, one thread per digit: a sub-tile of nearly
-    // sorted items touches a few dozen CONSECUTIVE digits (a bitmap walk left them all to one or two threads)
+    // exclusive prefix over warps for every digit in the touched range, one thread per digit
     const int dlo = s_range[0], dhi = s_range[1];
     for (int d = dlo + tid; d <= dhi; d += kSortBlock) {
       int run = s_base[d];
@@ -396,18 +406,19 @@ __global__ void __launch_bounds__(kSortBlock, 3) pair_scatter_kernel(const void 
     }
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < kPairIPT; j++) {
-      const bool valid = idx[j] >= 0;
+    for (int j = 0; j < IPT; j++) {
+      const bool valid = i0 + j * 32 < hi;
       const int o = valid ? s_wcount[w * R + ((key[j] >> shift) & (R - 1))] + rank[j] : 0;
       if (next_hist) {
         const int nd = (key[j] >> (shift + BITS)) & (R - 1);
-        const int cell = valid ? nd * (int)gridDim.x + o / per_block : -1 - lane;
+        const int cell = valid ? nd * (int)gridDim.x + (o >> pb_shift) : -1 - lane;     // per_block is a power of two here
         const unsigned pp = __match_any_sync(0xffffffffu, cell);
         if (valid && lane == __ffs(pp) - 1) atomicAdd(&next_hist[cell], __popc(pp));
       }
       if (valid) {
-        if (DST == 0) static_cast<int2 *>(dst_)[o] = make_int2(key[j], idx[j]);
-        else static_cast<int *>(dst_)[o] = idx[j];
+        const int id = SRC == 0 ? i0 + j * 32 : idx[SRC == 0 ? 0 : j];
+        if (DST == 0) static_cast<int2 *>(dst_)[o] = make_int2(key[j], id);
+        else static_cast<int *>(dst_)[o] = id;
       }
     }
     __syncthreads();
@@ -442,7 +453,7 @@ template <int BITS>
 static int index_sort(const int4 *p, const int *keys_in, int n, int key_bits, int *perm, char *work, void *scratch,
                       size_t scratch_bytes, cudaStream_t st, int *key_count, int n_keys) {
   constexpr int R = 1 << BITS;
-  const SortPlan pl = plan_sort(n, BITS, n_keys, kPairSubTile);
+  const SortPlan pl = plan_sort(n, BITS, n_keys, kPairSubTile, true);
   VPB_REQUIRE(scratch && scratch_bytes >= pl.total_bytes, "sort: scratch too small (%zu < %zu)", scratch_bytes, pl.total_bytes);
   const size_t hb = ((pl.hist_bytes + 255) / 256) * 256;
   int *hist[2] = {(int *)scratch, (int *)((char *)scratch + hb)};
@@ -551,7 +562,7 @@ extern "C" int vpb_sort_p(void *p, int32_t np, void *aux, int32_t *partition, in
 extern "C" size_t vpb_sort_index_work_bytes(int32_t np) { return index_sort_work_bytes(np > 0 ? np : 1); }
 
 extern "C" size_t vpb_sort_index_scratch_bytes(int32_t n_items, int32_t n_keys_hint) {
-  return plan_sort(n_items > 0 ? n_items : 1, 11, n_keys_hint > 0 ? n_keys_hint : 0, kPairSubTile).total_bytes;
+  return plan_sort(n_items > 0 ? n_items : 1, 11, n_keys_hint > 0 ? n_keys_hint : 0, kPairSubTile, true).total_bytes;
 }
 
 extern "C" int vpb_sort_p_index(const void *p, const int32_t *keys, int32_t np, int32_t *perm, int32_t *partition,
@@ -571,7 +582,7 @@ extern "C" int vpb_sort_p_index(const void *p, const int32_t *keys, int32_t np, 
   int r = wide ? index_sort<11>((const int4 *)p, keys, np, kb, perm, (char *)work, scratch, scratch_bytes, st, partition, nv)
                : index_sort<8>((const int4 *)p, keys, np, kb, perm, (char *)work, scratch, scratch_bytes, st, partition, nv);
   if (r) return r;
-  const SortPlan pl = plan_sort(np, wide ? 11 : 8, nv, kPairSubTile);
+  const SortPlan pl = plan_sort(np, wide ? 11 : 8, nv, kPairSubTile, true);
   int *tmp = (int *)((char *)scratch + 2 * (((pl.hist_bytes + 255) / 256) * 256));
   return exclusive_scan_inplace(partition, nv + 1, tmp, st);
 }

@@ -197,6 +197,9 @@ class Species:
         self._p = torch.zeros((self.max_np, 8), dtype=torch.float32, device=dev)
         self._perm = None                 # order of a deferred sort_p the next advance_p applies (sort_p(sp, defer=True))
         self._perm_pending = False
+        self._keys = None                 # voxel of every particle as the last advance_p(emit_keys=True) left it ...
+        self._keys_valid = False          # ... still true: nothing has touched the array since
+        self._keys_np = -1
         self.pm = torch.zeros((self.max_nm, 4), dtype=torch.float32, device=dev)
         self.partition = torch.zeros(g.nv + 1, dtype=torch.int32, device=dev)
         self.counters = torch.zeros(4, dtype=torch.int32, device=dev)
@@ -213,6 +216,7 @@ class Species:
         advance_p that consumes the order sees the array sort_p promised."""
         if self._perm_pending:
             self.settle()
+        self._keys_valid = False          # whoever holds the tensor may write it
         return self._p
 
     def settle(self):
@@ -220,6 +224,7 @@ class Species:
         if not self._perm_pending:
             return
         self._perm_pending = False
+        self._keys_valid = False
         _lib.check(_lib.load().vpb_permute_p(_ptr(self._p), self.np, _ptr(self._perm), _ptr(self._aux), _stream()), "permute_p")
         self._p, self._aux = self._aux, self._p
 
@@ -232,6 +237,7 @@ class Species:
         n = t.shape[0]
         _bad_args(n > self.max_np, "set_particles")
         self._perm_pending = False
+        self._keys_valid = False
         self._p[:n].copy_(t)
         self.np, self.nm = n, 0
         self.partition_np = -1
@@ -252,8 +258,11 @@ class Species:
 
 # ---- operators (same names as the reference's C API) ---------------------------------------------------------
 
-def advance_p(sp: Species, aa: AccumulatorArray, ia: InterpolatorArray, variant=_lib.DEPOSIT_DEFAULT, sync=True):
-    """advance_p(species_t*, accumulator_array_t*, const interpolator_array_t*), species_advance.h:73-76."""
+def advance_p(sp: Species, aa: AccumulatorArray, ia: InterpolatorArray, variant=_lib.DEPOSIT_DEFAULT, sync=True,
+              emit_keys=False):
+    """advance_p(species_t*, accumulator_array_t*, const interpolator_array_t*), species_advance.h:73-76.
+    emit_keys=True (the caller knows a sort_p comes next): the push also leaves every particle's voxel in a compact
+    array, so that sort does not have to read the particles to find it."""
     _bad_args(sp is None or aa is None or ia is None or sp.g is not aa.g or sp.g is not ia.g, "advance_p")
     g = sp.g
     sp.counters.zero_()
@@ -263,7 +272,14 @@ def advance_p(sp: Species, aa: AccumulatorArray, ia: InterpolatorArray, variant=
         a.p, a.np = sp._p.data_ptr(), sp.np
         a.perm, a.p_out = sp._perm.data_ptr(), sp._aux.data_ptr()
     else:
-        a.p, a.np = sp.p.data_ptr(), sp.np
+        sp.settle()
+        a.p, a.np = sp._p.data_ptr(), sp.np
+    sp._keys_valid = False
+    emit_keys = emit_keys and variant in (_lib.DEPOSIT_DEFAULT, 2) and not int(os.environ.get("VPB_DEBUG_SKIP", "0"))
+    if emit_keys:
+        if sp._keys is None:
+            sp._keys = torch.empty(sp.max_np, dtype=torch.int32, device=sp.g.device)
+        a.keys_out = sp._keys.data_ptr()
     a.pm, a.max_nm = sp.pm.data_ptr(), sp.max_nm
     a.counters = sp.counters.data_ptr()
     a.interp, a.interp_stride = ia.i.data_ptr(), ia.stride
@@ -283,6 +299,8 @@ def advance_p(sp: Species, aa: AccumulatorArray, ia: InterpolatorArray, variant=
     if gather:
         sp._perm_pending = False
         sp._p, sp._aux = sp._aux, sp._p
+    sp._keys_valid = bool(emit_keys)      # void again if any mover left the domain (checked by sort_p through sp.nm)
+    sp._keys_np = sp.np
     if sync:
         finish_advance_p(sp)
 
@@ -331,7 +349,10 @@ def sort_p(sp: Species, defer=False):
             sp._perm = torch.empty(sp.max_np, dtype=torch.int32, device=g.device)
         work_bytes = sp._aux.numel() * 4
         _bad_args(work_bytes < L.vpb_sort_index_work_bytes(sp.np), "sort_p")
-        _lib.check(L.vpb_sort_p_index(_ptr(sp._p), None, sp.np, _ptr(sp._perm), _ptr(sp.partition), g.nx, g.ny, g.nz,
+        # the voxels the last push left behind, if nothing has touched the array since (no boundary_p, no host access)
+        keys = _ptr(sp._keys) if (sp._keys_valid and sp.nm == 0 and sp._keys_np == sp.np) else None
+        sp._keys_valid = False
+        _lib.check(L.vpb_sort_p_index(_ptr(sp._p), keys, sp.np, _ptr(sp._perm), _ptr(sp.partition), g.nx, g.ny, g.nz,
                                       _ptr(sp._aux), work_bytes, _ptr(sp._scratch), sp._scratch.numel(), _stream()),
                    "sort_p")
         sp._perm_pending = True

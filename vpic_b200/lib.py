@@ -32,7 +32,7 @@ class PushArgs(C.Structure):
                 ("nx", c_i32), ("ny", c_i32), ("nz", c_i32),
                 ("variant", c_i32), ("p_first", c_i32), ("neighbor_rule", C.POINTER(NeighborRule)), ("debug_skip", c_i32),
                 ("partition", c_vp), ("partition_np", c_i32),
-                ("perm", c_vp), ("p_out", c_vp)]
+                ("perm", c_vp), ("p_out", c_vp), ("keys_out", c_vp)]
 
 
 class BoundaryArgs(C.Structure):

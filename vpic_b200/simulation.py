@@ -80,7 +80,9 @@ class Simulation:
             if self.push_events is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-            E.advance_p(sp, aa, ia, variant=self.deposit_variant, sync=False)
+            # a sort_p of this species opens the next step: let the push leave the voxel keys behind for it
+            keys = self.defer_sort and sp.sort_interval > 0 and (step + 1) % sp.sort_interval == 0
+            E.advance_p(sp, aa, ia, variant=self.deposit_variant, sync=False, emit_keys=keys)
             if self.push_events is not None:
                 e1.record()
                 self.push_events.append((e0, e1, sp.np))
