@@ -44,14 +44,39 @@ def gb(s):
     v, u = s.split(); return float(v.replace(',', '')) * {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1}[u]
 
 
+NOTES = {
+    'r02': ['electron launch, 12 steps after a sort (20 % of particles cross a face per step)', 'ion launch, same step (4 % cross)'],
+    # bench.py defaults of the second session: electrons sorted every 6 steps, ions every 12
+    'r02b': ['electron launch 5 steps after its sort (the last before the next one; also writes the voxel keys for it)',
+             'ion launch, same step (5 steps after its sort)',
+             'electron launch of a sort step: the gather variant applies the order of the index sort (loads p[perm[k]], stores position k of the other buffer)',
+             'ion launch, 6 steps after its sort'],
+}
 rep = f'gpurun_out/{tag}_advance_p.ncu-rep'
 if os.path.exists(rep):
-    summ = summary(rep, ['electron launch, 12 steps after a sort (20 % of particles cross a face per step)', 'ion launch, same step (4 % cross)'])
+    summ = summary(rep, NOTES.get(tag, NOTES['r02']))
     json.dump(summ, open(f'profiles/{tag}_advance_p_ncu_summary.json', 'w'), indent=1)
     tr = [gb(d['dram__bytes_read.sum']) + gb(d['dram__bytes_write.sum']) for d in summ]
-    json.dump({'dram_bytes_per_launch': int(sum(tr) / len(tr)),
-               'source': f'profiles/{tag}_advance_p_ncu_summary.json (ncu --set full, electron and ion launch 12 steps after a sort)',
-               'particles_per_launch': 134217728}, open('profiles/advance_p_traffic.json', 'w'), indent=1)
+    if tag == 'r02b':
+        # launches of a sort cycle: electrons 5 ordinary + 1 gather of 6, ions 11 ordinary + 1 gather of 12 (the ion gather
+        # launch was not captured: the electron launch's excess over an ordinary one is added to an ordinary ion launch)
+        e_ord, i_ord, e_gat = tr[0], tr[1], tr[2]
+        i_gat = i_ord + (e_gat - e_ord)
+        mean = 0.5 * ((5 * e_ord + e_gat) / 6 + (11 * i_ord + i_gat) / 12)
+        json.dump({'dram_bytes_per_launch': int(mean),
+                   'ordinary_launch': int(0.5 * (e_ord + i_ord)), 'sort_step_launch_electrons': int(e_gat),
+                   'source': f'profiles/{tag}_advance_p_ncu_summary.json (ncu --set full): mean over a sort cycle at the bench defaults; '
+                             'the launch that applies a sort reads 2.3x the particle bytes (32-byte gathers fetch 64-byte DRAM atoms)',
+                   'particles_per_launch': 134217728}, open('profiles/advance_p_traffic.json', 'w'), indent=1)
+    else:
+        json.dump({'dram_bytes_per_launch': int(sum(tr) / len(tr)),
+                   'source': f'profiles/{tag}_advance_p_ncu_summary.json (ncu --set full, mean over the captured electron and ion launches)',
+                   'particles_per_launch': 134217728}, open('profiles/advance_p_traffic.json', 'w'), indent=1)
+rep = f'gpurun_out/{tag}_sort.ncu-rep'
+if os.path.exists(rep):
+    json.dump(summary(rep, ['index sort of 134 M particles: voxel keys (left by the previous advance_p) -> digit-0 histogram and per-voxel counts',
+                            'first scatter pass: keys -> (voxel, index) pairs by the low 11 bits', 'second pass: pairs -> perm by the high 11 bits']),
+              open(f'profiles/{tag}_sort_ncu_summary.json', 'w'), indent=1)
 rep = f'gpurun_out/{tag}_advance_p_brick.ncu-rep'
 if os.path.exists(rep):
     json.dump(summary(rep, ['brick/tile kernel (variant 5, VPB_BRICK_CFG=2), electron launch, same step as the linear capture', 'ion launch']),
@@ -73,7 +98,7 @@ if os.path.exists(lc):
     open(f'profiles/{tag}_launch_shares.csv', 'w').write("\n".join(lines) + "\n")
     print("\n".join(lines[:8]))
     open(f'profiles/{tag}_launches_ncu.csv', 'w').write(open(lc).read())
-for f in ('bench', 'bench_reference', 'bench_harris', 'kernel_times', 'bench_2gpu', 'bench_2gpu_counted', 'bench_4gpu', 'bench_8gpu',
+for f in ('bench', 'bench_reference', 'bench_harris', 'bench_sort20', 'bench_sort20_nodefer', 'kernel_times', 'bench_2gpu', 'bench_2gpu_counted', 'bench_4gpu', 'bench_8gpu',
           'bench_8gpu_counted', 'bench_8gpu_strong', 'bench_harris_8gpu', 'c5_1gpu', 'c5_8gpu'):
     src = f'gpurun_out/{tag}_{f}.json'
     if os.path.exists(src) and os.path.getsize(src):
