@@ -7,30 +7,40 @@
 //   src/species_advance/standard/pipeline/hydro_p_pipeline.cc:19-252   accumulate_hydro_p
 //   src/sf_interface/hydro_array.cc:131-309                            synchronize_hydro_array (walls, periodic folds)
 //   src/sf_interface/clear_array.cc / reduce_array.cc                  clear_hydro_array; reduce is the identity here
-// Per-particle arithmetic follows the scalar pipeline exactly (-fmad=false); the sums are atomic, so node values agree
-// with the reference to fp32 summation-order tolerance.  Lanes of a warp that share a voxel (for voxel-sorted
-// particles: all of them, or two or three groups) sum each node's 14 moments with a reduce-scatter butterfly (16
-// shuffles per node instead of 70) and issue one set of REDs per group; lanes in groups of fewer than four go
-// straight to memory.
+// Per-particle arithmetic follows the scalar pipeline (-fmad=false) up to the moments per unit weight; the node sums are
+// formed per voxel group as a small matrix product out of shared memory (see the kernel) and added with vector REDs, so
+// node values agree with the reference to fp32 summation-order tolerance.
 #include "field_common.cuh"
 
 namespace vpb {
 
 constexpr int kHydroFloats = 16;
+constexpr int kHydroWarps = 8;
 
-__global__ void __launch_bounds__(256, 3) accumulate_hydro_p_kernel(float *__restrict__ hydro, const float4 *__restrict__ p, int np,
+// One row of 32 particles at a time per warp.  Node k of a particle receives w_k x {14 moments}, so the contribution of a
+// group of P lanes that share a voxel to its 8 nodes is the product of a [8 x P] weight matrix with a [P x 16] moment
+// matrix.  The warp stages both in shared memory (24 floats per lane) and every lane sums four consecutive moments of
+// one node over the members of the group (two shared-memory loads and four FMAs per member), then issues one 16-byte
+// RED.  (The first version reduced 8 x 16 values across the warp with shuffles: ~1000 instructions per row and 112
+// scalar REDs per group, 8.1 ms per 134 M particles; this one takes 5.2 ms right after a sort and is bound by the
+// shared-memory pipe — 1.2 G wavefronts per launch, ncu — and back at 8.8 ms seven steps later.  Two re-blockings of
+// the inner loop, fixed trip count and two nodes per lane, measured no faster.)  The products are formed as w_k * (q v) instead of the reference's
+// (q w_k) * v and summed with FMAs: node values agree with the reference to fp32 summation-order tolerance, as before.
+__global__ void __launch_bounds__(32 * kHydroWarps, 4) accumulate_hydro_p_kernel(float *__restrict__ hydro, const float4 *__restrict__ p, int np,
                                                                  const float *__restrict__ interp, int istride,
                                                                  float qsp, float mspc, float c, float qdt_2mc, float qdt_4mc2,
                                                                  float r8V, int sy, int sz) {
+  __shared__ __align__(16) float s_w[kHydroWarps][32][8];
+  __shared__ __align__(16) float s_m[kHydroWarps][32][16];
   const float one = 1.0f, one_third = (float)(1.0 / 3.0);
-  const int lane = threadIdx.x & 31;
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int node = lane >> 2, quad = lane & 3;                   // this lane sums four consecutive moments of one node
+  const int node_off = (node & 1) + ((node & 2) ? sy : 0) + ((node & 4) ? sz : 0);
   const long long rows = ((long long)np + 31) / 32;
-  for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows;
-       row += (long long)gridDim.x * (blockDim.x >> 5)) {
+  for (long long row = (long long)blockIdx.x * kHydroWarps + w; row < rows; row += (long long)gridDim.x * kHydroWarps) {
     const long long n = row * 32 + lane;
     const bool valid = n < np;
-    float ux = 0, uy = 0, uz = 0, vx = 0, vy = 0, vz = 0, ke_mc = 0;
-    float wn[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int vox = -1 - lane;
     if (valid) {
       const float4 r = p[2 * n], u = p[2 * n + 1];
@@ -39,13 +49,13 @@ __global__ void __launch_bounds__(256, 3) accumulate_hydro_p_kernel(float *__res
       const float4 *f = reinterpret_cast<const float4 *>(interp + (size_t)vox * istride);
       const float4 fex = __ldg(f), fey = __ldg(f + 1), fez = __ldg(f + 2), fb0 = __ldg(f + 3);
       const float2 fb1 = __ldg(reinterpret_cast<const float2 *>(f + 4));
-      ux = u.x; uy = u.y; uz = u.z;
+      float ux = u.x, uy = u.y, uz = u.z;
       ux += qdt_2mc * ((fex.x + dy * fex.y) + dz * (fex.z + dy * fex.w));        // hydro_p_pipeline.cc:88-95
       uy += qdt_2mc * ((fey.x + dz * fey.y) + dx * (fey.z + dz * fey.w));
       uz += qdt_2mc * ((fez.x + dx * fez.y) + dy * (fez.z + dx * fez.w));
       float w5 = fb0.x + dx * fb0.y, w6 = fb0.z + dy * fb0.w, w7 = fb1.x + dz * fb1.y;
-      ke_mc = (ux * ux + uy * uy) + uz * uz;                                      // :112-115
-      vz = __fsqrt_rn(one + ke_mc);
+      float ke_mc = (ux * ux + uy * uy) + uz * uz;                                // :112-115
+      float vz = __fsqrt_rn(one + ke_mc);
       ke_mc *= __fdiv_rn(c, vz + one);
       vz = __fdiv_rn(c, vz);
       float w0 = qdt_4mc2 * vz;                                                   // half Boris rotation, :121-136
@@ -60,59 +70,41 @@ __global__ void __launch_bounds__(256, 3) accumulate_hydro_p_kernel(float *__res
       ux += w4 * (w1 * w7 - w2 * w6);
       uy += w4 * (w2 * w5 - w0 * w7);
       uz += w4 * (w0 * w6 - w1 * w5);
-      vx = ux * vz; vy = uy * vz; vz = uz * vz;
+      const float vx = ux * vz, vy = uy * vz; vz = uz * vz;
       w0 = r8V * u.w;                                                             // trilinear weights, :152-172
       dx *= w0; w1 = w0 + dx; w0 -= dx;
       w3 = one + dy; w2 = w0 * w3; w3 *= w1;
       dy = one - dy; w0 *= dy; w1 *= dy;
       w7 = one + dz; w4 = w0 * w7; w5 = w1 * w7; w6 = w2 * w7; w7 *= w3;
       dz = one - dz; w0 *= dz; w1 *= dz; w2 *= dz; w3 *= dz;
-      wn[0] = w0; wn[1] = w1; wn[2] = w2; wn[3] = w3; wn[4] = w4; wn[5] = w5; wn[6] = w6; wn[7] = w7;
+      float4 *sw = reinterpret_cast<float4 *>(s_w[w][lane]);
+      sw[0] = make_float4(w0, w1, w2, w3); sw[1] = make_float4(w4, w5, w6, w7);
+      // the 14 moments per unit weight (ACCUM_HYDRO, :178-198), padded to the 16 floats of hydro_t
+      const float tx = mspc * ux, ty = mspc * uy, tz = mspc * uz;
+      float4 *sm = reinterpret_cast<float4 *>(s_m[w][lane]);
+      sm[0] = make_float4(qsp * vx, qsp * vy, qsp * vz, qsp);
+      sm[1] = make_float4(tx, ty, tz, mspc * ke_mc);
+      sm[2] = make_float4(tx * vx, ty * vy, tz * vz, ty * vz);
+      sm[3] = make_float4(tz * vx, tx * vy, 0.0f, 0.0f);
     }
-    // moments of node k of this lane's particle (ACCUM_HYDRO, :178-198), padded to the 16 floats of hydro_t
-    auto moments = [&](int k, float (&m)[16]) {
-      float t = qsp * wn[k];
-      m[0] = t * vx; m[1] = t * vy; m[2] = t * vz; m[3] = t;
-      t = mspc * wn[k];
-      const float tx = t * ux, ty = t * uy, tz = t * uz;
-      m[4] = tx; m[5] = ty; m[6] = tz; m[7] = t * ke_mc;
-      m[8] = tx * vx; m[9] = ty * vy; m[10] = tz * vz;
-      m[11] = ty * vz; m[12] = tz * vx; m[13] = tx * vy;
-      m[14] = 0.0f; m[15] = 0.0f;
-    };
-    const unsigned peers = warp_peers(valid, vox);
-    const bool grouped = valid && __popc(peers) >= 4;
-    if (valid && !grouped) {                                   // stragglers: per-lane REDs
-#pragma unroll 1
-      for (int k = 0; k < 8; k++) {
-        float m[16];
-        moments(k, m);
-        float *h = hydro + (size_t)(vox + (k & 1) + ((k & 2) ? sy : 0) + ((k & 4) ? sz : 0)) * kHydroFloats;
-        red_add_v4(h, m[0], m[1], m[2], m[3]);
-        red_add_v4(h + 4, m[4], m[5], m[6], m[7]);
-        red_add_v4(h + 8, m[8], m[9], m[10], m[11]);
-        red_add(h + 12, m[12]); red_add(h + 13, m[13]);
+    __syncwarp();
+    unsigned rest = __ballot_sync(full, valid);
+    while (rest) {                                               // one pass per voxel present in the row
+      const int leader = __ffs(rest) - 1;
+      const int gv = __shfl_sync(full, vox, leader);
+      unsigned grp = __ballot_sync(full, valid && vox == gv);
+      rest &= ~grp;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      while (grp) {
+        const int l = __ffs(grp) - 1;
+        grp &= grp - 1;
+        const float wk = s_w[w][l][node];
+        const float4 m = *reinterpret_cast<const float4 *>(&s_m[w][l][4 * quad]);
+        a0 = __fmaf_rn(wk, m.x, a0); a1 = __fmaf_rn(wk, m.y, a1); a2 = __fmaf_rn(wk, m.z, a2); a3 = __fmaf_rn(wk, m.w, a3);
       }
+      red_add_v4(hydro + (size_t)(gv + node_off) * kHydroFloats + 4 * quad, a0, a1, a2, a3);
     }
-    unsigned big = __ballot_sync(0xffffffffu, grouped);
-    while (big) {                                              // one pass per voxel shared by >= 4 lanes
-      const int leader = __ffs(big) - 1;
-      const unsigned grp = __shfl_sync(0xffffffffu, peers, leader);
-      const int gv = __shfl_sync(0xffffffffu, vox, leader);
-      const bool mine = grouped && peers == grp;
-#pragma unroll 1                                               // one node at a time keeps the kernel at 3 CTAs per SM
-      for (int k = 0; k < 8; k++) {
-        float m[16];
-        moments(k, m);
-#pragma unroll
-        for (int q = 0; q < 16; q++) m[q] = mine ? m[q] : 0.0f;
-        warp_reduce_scatter<16>(m);                            // total of moment c in lanes 2c, 2c+1
-        const int c = lane >> 1;
-        if (!(lane & 1) && c < 14)
-          red_add(hydro + (size_t)(gv + (k & 1) + ((k & 2) ? sy : 0) + ((k & 4) ? sz : 0)) * kHydroFloats + c, m[0]);
-      }
-      big &= ~grp;
-    }
+    __syncwarp();
   }
 }
 
@@ -201,8 +193,8 @@ extern "C" int vpb_accumulate_hydro_p(float *hydro, const void *p, int32_t np, c
   const float qdt_4mc2 = qdt_2mc / (2 * cvac);                     // :33-35
   const float mspc = cvac * m;
   const long long rows = ((long long)np + 31) / 32;
-  long long grid = (rows + 7) / 8; if (grid > kSMs * 16) grid = kSMs * 16;
-  accumulate_hydro_p_kernel<<<(int)grid, 256, 0, as_stream(stream)>>>(hydro, (const float4 *)p, np, interp, interp_stride,
+  long long grid = (rows + kHydroWarps - 1) / kHydroWarps; if (grid > kSMs * 16) grid = kSMs * 16;
+  accumulate_hydro_p_kernel<<<(int)grid, 32 * kHydroWarps, 0, as_stream(stream)>>>(hydro, (const float4 *)p, np, interp, interp_stride,
                                                                      q, mspc, cvac, qdt_2mc, qdt_4mc2, r8V,
                                                                      nx + 2, (nx + 2) * (ny + 2));
   VPB_LAUNCH_CHECK();
