@@ -247,12 +247,10 @@ def test_dump_deck_files_match_reference(mode):
             shutil.rmtree(d, ignore_errors=True)
 
 
-@pytest.mark.skipif(os.environ.get("VPIC_B200_LONG_TESTS") != "1",
-                    reason="27 000 steps through the drop-in seam; wired and passing on the CPU reference path "
-                           "(tests/test_oracle_vs_ref.py), GPU leg enabled with VPIC_B200_LONG_TESTS=1")
 def test_reference_grid_heating_rate_on_gpu_path():
     """test/unit/grid_heating with the hot path on the GPU: the numerical heating rate over 27 000 steps must stay
-    within the 5 standard deviations the reference's own checker allows around its authors' mean."""
+    within the 5 standard deviations the reference's own checker allows around its authors' mean.  (15 s on a B200,
+    profiles/r02b_grid_heating_gpu.log.)"""
     _need("gridHeatingTestElec.scalar")
     import test_oracle_vs_ref as T
     out, verdict = T._grid_heating({"LD_PRELOAD": LIB, "VPIC_B200_TRACE": "1"}, timeout=3000)
