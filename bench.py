@@ -672,7 +672,7 @@ def main():
                          "reference arm runs the same intervals.  C5 names 20.")
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--e2e", type=int, default=1)
-    ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--e2e-steps", type=int, default=60)
     ap.add_argument("--e2e-energy-interval", type=int, default=10,
                     help="e2e leg: steps between dump_energies-style diagnostics (energy_f + energy_p per species)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -200,9 +200,13 @@ size_t vpb_sort_index_work_bytes(int32_t np);
 size_t vpb_sort_index_scratch_bytes(int32_t n_items, int32_t n_keys_hint);
 int vpb_sort_p_index(const void *p, const int32_t *keys, int32_t np, int32_t *perm, int32_t *partition,
                      int32_t nx, int32_t ny, int32_t nz, void *work, size_t work_bytes,
-                     void *scratch, size_t scratch_bytes, void *stream);
+                     void *scratch, size_t scratch_bytes, void *stream, void *partition_ready_event);
+/* partition_ready_event: optional cudaEvent_t, recorded on `stream` as soon as partition[] is final (before the scatter
+ * passes), so that a caller can copy it elsewhere on another stream while the order is still being computed. */
 /* dst[k] = p[perm[k]] for k < np (dst != p) */
 int vpb_permute_p(const void *p, int32_t np, const int32_t *perm, void *dst, void *stream);
+/* keys[k] = voxel index of p[k] for k < n (refreshes part of a keys_out array after the host edited those particles) */
+int vpb_extract_keys(const void *p, int32_t n, int32_t *keys, void *stream);
 /* the inverse for a few particles: p[perm[k]] = src[k] for k < n (perm may point into the middle of an order) */
 int vpb_unpermute_p(void *p, int32_t n, const int32_t *perm, const void *src, void *stream);
 

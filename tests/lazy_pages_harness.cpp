@@ -45,7 +45,7 @@ struct Reader { const char *p; size_t n; long sum; };
 static void *reader_main(void *arg) { Reader *r = (Reader *)arg; long s = 0; for (size_t i = 0; i < r->n; i++) s += r->p[i]; r->sum = s; return nullptr; }
 
 static int run() {
-  vpb_lazy::Copier cp = {fake_h2d, fake_d2h, fake_fatal, nullptr, nullptr};
+  vpb_lazy::Copier cp = {fake_h2d, fake_d2h, fake_fatal, nullptr, nullptr, nullptr};
   vpb_lazy::init(cp, kChunk);
   uint64_t h2d = 0, d2h = 0;
 
@@ -199,7 +199,7 @@ static uint32_t rnd() { rng_state = rng_state * 6364136223846793005ull + 1442695
 
 static int stress(int iterations, uint64_t seed) {
   rng_state = seed * 2654435761u + 17;
-  vpb_lazy::Copier cp = {fake_h2d, fake_d2h, fake_fatal, nullptr, nullptr};
+  vpb_lazy::Copier cp = {fake_h2d, fake_d2h, fake_fatal, nullptr, nullptr, nullptr};
   vpb_lazy::init(cp, kChunk);
   const size_t pages = 64 + rnd() % 64;
   Arr a = make(pages, 128 * (1 + rnd() % 20), rnd() % 3000);
@@ -255,7 +255,7 @@ static int stress(int iterations, uint64_t seed) {
 // Throughput of the staged fetch path (device -> staging -> /proc/self/mem -> protected pages), the route pageable
 // host arrays take; the copies are memcpy here, so this bounds the host-side overhead of that route.
 static int bandwidth(size_t mb) {
-  vpb_lazy::Copier cp = {fake_h2d, fake_d2h, fake_fatal, nullptr, nullptr};
+  vpb_lazy::Copier cp = {fake_h2d, fake_d2h, fake_fatal, nullptr, nullptr, nullptr};
   vpb_lazy::init(cp, 2u << 20);
   const size_t pages = mb * 256;
   Arr a = make(pages, 128, 0);

@@ -720,6 +720,85 @@ import json; print('RESULT ' + json.dumps(res))
 """
 
 
+_KEYS_SCRIPT = """
+import sys, os, ctypes as C, numpy as np
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, 'tests'))
+import bench, refvpic as R
+from vpic_b200 import lib, grid as G, abi
+mode, scenario = sys.argv[1], sys.argv[2]
+L = lib.load(); orc = R.load_oracle()
+nx, ny, nz, n = 9, 8, 7, 70001
+g = G.partition_periodic_box(0,0,0,nx,ny,nz,nx,ny,nz,1,1,1, dt=G.courant_dt(1,1,1,nx,ny,nz,frac=0.98))
+H = bench.HostWorld(L, g, pinned='register')
+L.vpic_b200_set_lazy_min.argtypes = [C.c_size_t]; L.vpic_b200_set_lazy_min.restype = None
+L.vpic_b200_set_lazy_min(4096)
+L.vpic_b200_sync_to_host.argtypes = [C.c_void_p]; L.vpic_b200_sync_to_host.restype = None
+L.vpic_b200_set_mode(dict(resident=1, auto=2)[mode])
+rng = np.random.default_rng(35)
+fld = R.random_fields(rng, g.nv) * 0.05
+H.fields[:] = fld
+sp = H.new_species('e', -1.0, 1.0, n + 64, n, 3)
+parts = R.random_particles(rng, n, nx, ny, nz, uth=0.3, w=0.5)
+sp.p[:n] = parts.view(np.float32).reshape(-1, 8); sp.c.np = n
+H.load_interpolator()
+interp = np.zeros((g.nv, 20), np.float32)
+orc.vpo_load_interpolator(interp.ctypes.data, 20, fld.ctypes.data, nx, ny, nz)
+f32 = np.float32; dt = f32(g.dt)
+def oracle_push(p2):
+    pm2 = np.zeros(n, dtype=abi.mover_dtype); acc2 = np.zeros(((g.nv + 1)//2*2, 12), np.float32)
+    a = R.OraclePushArgs(p2.ctypes.data, n, pm2.ctypes.data, n, interp.ctypes.data, 20, acc2.ctypes.data, 12,
+                         g.neighbor.ctypes.data, g.rangel, g.rangeh, f32(f32(f32(-1)*dt)/f32(2)), dt, dt, dt, f32(-1))
+    assert orc.vpo_advance_p(C.byref(a), None) == 0
+def oracle_sort(p2):
+    aux = np.zeros_like(p2); part = np.zeros(g.nv + 1, np.int32)
+    orc.vpo_sort_p(p2.ctypes.data, n, aux.ctypes.data, part.ctypes.data, nx, ny, nz)
+    return part
+p2 = parts.copy()
+# step 2 of a species sorted every 3 steps: this push knows that a sort opens the next step
+H.G.step = 2
+L.clear_accumulator_array(C.byref(H.aa)); L.advance_p(C.byref(sp.c), C.byref(H.aa), C.byref(H.ia))
+oracle_push(p2)
+other = int(p2['i'][n // 3])
+if scenario == 'edge_edit' and mode == 'auto':   # the host moves a particle at the unprotected head of the array to another voxel
+    view = sp.p.view(np.int32)
+    view[2, 3] = other; p2['i'][2] = other
+elif scenario == 'interior_edit' and mode == 'auto':      # ... and one in the middle (faults the chunk back)
+    view = sp.p.view(np.int32)
+    view[n // 2, 3] = other; p2['i'][n // 2] = other
+H.G.step = 3
+L.sort_p(C.byref(sp.c))
+part = oracle_sort(p2)
+L.clear_accumulator_array(C.byref(H.aa)); L.advance_p(C.byref(sp.c), C.byref(H.aa), C.byref(H.ia))
+oracle_push(p2)
+if mode == 'resident': L.vpic_b200_sync_to_host(None)
+got = sp.p[:n].reshape(-1).view(abi.particle_dtype)
+bad = np.nonzero(np.any(got.view(np.uint32).reshape(n, 8) != p2.view(np.uint32).reshape(n, 8), axis=1))[0]
+res = dict(particles=int(bad.size), first_bad=[int(x) for x in bad[:5]], partition=bool(np.array_equal(sp.partition[:g.nv], part[:g.nv])))
+L.vpic_b200_set_mode(0)
+import json; print('RESULT ' + json.dumps(res))
+"""
+
+
+@pytest.mark.parametrize("mode", ["auto", "resident"])
+@pytest.mark.parametrize("scenario", ["plain", "edge_edit", "interior_edit"])
+def test_dropin_sort_p_on_the_keys_of_the_last_push(eng, oracle, mode, scenario):
+    """The drop-in advance_p of the step before a sort (g->step + 1 divisible by sp->sort_interval) leaves the voxel
+    keys behind and sort_p sorts those instead of reading the particles — unless the host touched the array in between:
+    an edit at the unprotected head is picked up by re-reading those keys, an edit that faulted a chunk back voids the
+    short cut.  Result after push, sort, push bit-identical to the oracle with the same edits."""
+    import subprocess, sys, os, json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, VPIC_B200_LAZY_CHUNK="16384", VPIC_B200_TRACE="1")
+    r = subprocess.run([sys.executable, "-c", _KEYS_SCRIPT.format(root=root), mode, scenario],
+                       capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("RESULT ")][0][7:])
+    assert res["particles"] == 0 and res["partition"], res
+    trace = [ln for ln in r.stderr.splitlines() if "sort_p_on_keys_of_the_last_push" in ln][0]
+    with_keys = int(trace.split("sort_p_on_keys_of_the_last_push=")[1].split()[0])
+    assert with_keys == (0 if (scenario == "interior_edit" and mode == "auto") else 1), trace
+
+
 @pytest.mark.parametrize("mode", ["auto", "resident"])
 @pytest.mark.parametrize("scenario", ["plain", "edge_read", "edge_write", "interior_read"])
 def test_dropin_deferred_sort_is_invisible_to_the_host(eng, oracle, mode, scenario):

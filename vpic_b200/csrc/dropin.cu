@@ -59,6 +59,7 @@ enum { C_ADVANCE_P, C_SORT_P, C_CENTER_P, C_ENERGY_P, C_RHO_P, C_LOAD_INTERP, C_
        C_ADVANCE_E, C_CLEAR_JF, C_SYNC_JF, C_ENERGY_F, C_DIV_CLEAN, C_HYDRO, C_BOUNDARY_P, C_FIELD_FALLBACK, C_COUNT };
 uint64_t g_calls[C_COUNT];
 uint64_t g_sorts_fused = 0, g_sorts_settled = 0;   // deferred sort_p orders applied inside advance_p / applied on their own
+uint64_t g_sorts_with_keys = 0;                    // index sorts that took their keys from the previous push
 // VPIC_B200_TRACE=1 also accumulates host wall time per phase of the entry points that synchronise with the device
 enum { T_ADV_PREP, T_ADV_KERNEL_WAIT, T_ADV_MOVER_SORT, T_ADV_FINISH, T_BP_PACK, T_BP_EXCHANGE, T_BP_INJECT, T_HALO, T_COUNT };
 double g_phase_s[T_COUNT];
@@ -77,8 +78,8 @@ void trace_report() {
   fprintf(stderr, "vpic_b200 trace[%d]:", rank_for_log());
   for (int i = 0; i < C_COUNT; i++) fprintf(stderr, " %s=%llu", names[i], (unsigned long long)g_calls[i]);
   const vpb_lazy::Stats st = vpb_lazy::stats();
-  fprintf(stderr, " sort_p_fused_into_advance_p=%llu sort_p_applied_separately=%llu", (unsigned long long)g_sorts_fused,
-          (unsigned long long)g_sorts_settled);
+  fprintf(stderr, " sort_p_fused_into_advance_p=%llu sort_p_applied_separately=%llu sort_p_on_keys_of_the_last_push=%llu",
+          (unsigned long long)g_sorts_fused, (unsigned long long)g_sorts_settled, (unsigned long long)g_sorts_with_keys);
   fprintf(stderr, " lazy_faults=%llu lazy_fault_bytes=%llu\n", (unsigned long long)st.faults, (unsigned long long)st.fault_bytes);
   static const char *pn[T_COUNT] = {"advance_p.prepare", "advance_p.kernel+count_read", "advance_p.mover_sort", "advance_p.finish",
                                     "boundary_p.pack", "boundary_p.exchange", "boundary_p.inject", "field_halo_exchange"};
@@ -150,7 +151,20 @@ void settle_dev(const void *d) {
     if ((const char *)d >= a && (const char *)d < a + mi->second.cap) { settle_inplace(mi->second, kv.second); return; }
   }
 }
+// Voxel keys a push left behind for the sort_p that follows it (vpb_push_args_t.keys_out): valid only while nothing has
+// asked for the particle array since (mirror() clears the flag) and no particle left the domain.
+struct KeyInfo { int32_t *keys = nullptr; size_t cap = 0; bool valid = false; int32_t np = 0; };
+std::unordered_map<const void *, KeyInfo> g_keys;              // by host particle array
+int g_nkeys_valid = 0;
+void invalidate_keys(const void *h) {
+  if (!g_nkeys_valid) return;
+  auto it = g_keys.find(h);
+  if (it != g_keys.end() && it->second.valid) { it->second.valid = false; g_nkeys_valid--; }
+}
+
 void cancel_pending(const void *h, bool release) {
+  invalidate_keys(h);
+  if (release) { auto kt = g_keys.find(h); if (kt != g_keys.end()) { if (kt->second.keys) vpb_free(kt->second.keys); g_keys.erase(kt); } }
   auto it = g_pending.find(h);
   if (it == g_pending.end()) return;
   if (it->second.pending) { it->second.pending = false; g_npending--; }
@@ -178,6 +192,17 @@ int lazy_d2h_protected(void *h, const void *d, size_t n) {
       a0.type != cudaMemoryTypeHost || a1.type != cudaMemoryTypeHost) { cudaGetLastError(); return 1; }
   if (cudaMemcpy(h, d, n, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return 1; }
   return 0;
+}
+// The unprotected ends of a tracked array after the device wrote it: queued on the work queue like the kernels; the
+// entry point waits once for all of them (finish_entry) instead of once per copy.
+bool g_copied_back = false;     // an asynchronous device->host copy is in flight: the entry point must not return yet
+int lazy_d2h(void *h, const void *d, size_t n);
+int lazy_d2h_edges(void *h, const void *d, size_t n) {
+  static int async = -1;
+  if (async < 0) { const char *e = getenv("VPIC_B200_EDGE_ASYNC"); async = !(e && atoi(e) == 0); }
+  if (!async) return lazy_d2h(h, d, n);
+  g_copied_back = true;
+  return vpb_memcpy_d2h(h, d, n, nullptr);
 }
 void *lazy_staging(size_t n) {
   void *p = nullptr;
@@ -209,13 +234,12 @@ void lazy_setup() {
   cudaGetDevice(&g_device);
   const char *c = getenv("VPIC_B200_LAZY_CHUNK");
   if (const char *e = getenv("VPIC_B200_LAZY_DMA")) g_dma_into_protected = atoi(e) != 0;
-  vpb_lazy::Copier cp = {lazy_h2d, lazy_d2h, lazy_fatal, lazy_d2h_protected, lazy_staging};
+  vpb_lazy::Copier cp = {lazy_h2d, lazy_d2h, lazy_fatal, lazy_d2h_protected, lazy_staging, lazy_d2h_edges};
   vpb_lazy::init(cp, c ? (size_t)atoll(c) : 0);
 }
 
 // copies every call (coherent mode, and the small arrays of auto mode)
 inline bool strict(const Mirror &m) { return g_mode == VPB_MODE_COHERENT || (g_mode == VPB_MODE_AUTO && !m.lazy); }
-bool g_copied_back = false;     // an asynchronous device->host copy is in flight: the entry point must not return yet
 void finish_entry() { if (g_copied_back) { DEV(vpb_stream_sync(nullptr)); g_copied_back = false; } }
 
 void drop_mirror(Mirror &m, const void *h) {
@@ -227,6 +251,7 @@ void drop_mirror(Mirror &m, const void *h) {
 
 Mirror &mirror(const void *h, size_t bytes, bool may_track = true) {
   settle_host(h);
+  invalidate_keys(h);
   if (g_mirrors.find(h) == g_mirrors.end()) {
     // A host array seen for the first time.  The host reallocates its arrays (boundary_p.cc:470-552 grows sp->p and
     // sp->pm) and frees temporaries; a mirror whose host range overlaps the new array describes memory the allocator
@@ -344,6 +369,8 @@ void vpic_b200_invalidate(const void *h) {
   // the host declares its copy current: an order that was still waiting for the device copy has nothing left to apply to
   if (h) { cancel_pending(h, false); auto it = g_mirrors.find(h); if (it != g_mirrors.end()) drop(it->second); return; }
   for (auto &kv : g_pending) if (kv.second.pending) { kv.second.pending = false; g_npending--; }
+  for (auto &kv : g_keys) kv.second.valid = false;
+  g_nkeys_valid = 0;
   for (auto &kv : g_mirrors) drop(kv.second);
 }
 
@@ -432,6 +459,19 @@ static int chunk_particles() {
   return c;
 }
 
+static cudaStream_t copy_stream = nullptr;      // carries partition[] to the host while the scatter passes of a sort run
+static cudaEvent_t part_ready = nullptr;
+static bool defer_sort_enabled() {
+  static int v = -1;
+  if (v < 0) { const char *e = getenv("VPIC_B200_DEFER_SORT"); v = !(e && atoi(e) == 0); }
+  return v != 0;
+}
+
+static bool env_on(const char *name, int &cache) {             // switches that default to on
+  if (cache < 0) { const char *e = getenv(name); cache = !(e && atoi(e) == 0); }
+  return cache != 0;
+}
+static int g_env_keys = -1, g_env_part_async = -1;
 static std::unordered_map<const void *, bool> g_movers_unsorted;  // species whose sp->pm was filled by an injection
 struct SortInfo { int32_t *part = nullptr; size_t cap = 0; int32_t np = 0; int64_t nv = 0; };
 static std::unordered_map<const void *, SortInfo> g_sort_info;     // by species_t address
@@ -474,6 +514,15 @@ void advance_p(vpb_species_t *sp, vpb_accumulator_array_t *aa, const vpb_interpo
   a.variant = VPB_DEPOSIT_DEFAULT;
 
   const size_t pbytes = (size_t)sp->np * sizeof(vpb_particle_t);
+  // the next step opens with a sort_p of this species (advance.cc:25-29): let the push leave the voxel keys behind
+  KeyInfo *ki = nullptr;
+  if (!coherent && defer_sort_enabled() && env_on("VPIC_B200_SORT_KEYS", g_env_keys) && sp->sort_interval > 0 &&
+      (g->step + 1) % sp->sort_interval == 0) {
+    ki = &g_keys[sp->p];
+    const size_t kbytes = (size_t)sp->max_np * sizeof(int32_t);
+    if (ki->cap < kbytes) { if (ki->keys) vpb_free(ki->keys); ki->keys = nullptr; DEV(vpb_malloc((void **)&ki->keys, kbytes)); ki->cap = kbytes; }
+    a.keys_out = ki->keys;
+  }
   if (!coherent) {
     // the partition of this species' last sort_p (device-private copy) lets advance_p work brick by brick
     auto it = g_sort_info.find(sp);
@@ -567,6 +616,7 @@ void advance_p(vpb_species_t *sp, vpb_accumulator_array_t *aa, const vpb_interpo
   g_movers_unsorted[sp] = false;
   ph.mark(T_ADV_MOVER_SORT);
   sp->nm = nm;
+  if (ki && c[0] == 0) { if (!ki->valid) g_nkeys_valid++; ki->valid = true; ki->np = sp->np; }    // after the mirror() calls above
   if (!coherent) dev_written(sp->p, pbytes);
   dev_written(sp->pm, (size_t)nm * sizeof(vpb_particle_mover_t));
   dev_written(aa->a, (size_t)aa->stride * sizeof(vpb_accumulator_t));
@@ -962,24 +1012,29 @@ int move_p(vpb_particle_t *p0, vpb_particle_mover_t *pm, vpb_accumulator_t *a0, 
 }
 
 // ---- sort_p: species_advance.h:65-66, sort_p_pipeline.cc:220-371 ------------------------------------------
-static bool defer_sort_enabled() {
-  static int v = -1;
-  if (v < 0) { const char *e = getenv("VPIC_B200_DEFER_SORT"); v = !(e && atoi(e) == 0); }
-  return v != 0;
-}
-
 void sort_p(vpb_species_t *sp) {
   if (!sp) DROPIN_ERROR("Bad args.");
   count_call(C_SORT_P);
   const vpb_grid_t *g = sp->g;
   sp->last_sorted = g->step;
   const size_t pbytes = (size_t)sp->np * sizeof(vpb_particle_t), cap = (size_t)sp->max_np * sizeof(vpb_particle_t);
+  // keys the last push left behind: usable if nothing has asked for the array since, no particle left the domain, and
+  // (tracked arrays) the host has not taken a single chunk back; the unprotected ends are re-read below
+  const int32_t *keys = nullptr;
+  if (g_nkeys_valid) {
+    auto kt = g_keys.find(sp->p);
+    auto mt = g_mirrors.find(sp->p);
+    if (kt != g_keys.end() && kt->second.valid && kt->second.np == sp->np && mt != g_mirrors.end() &&
+        (mt->second.lazy ? vpb_lazy::all_device(mt->second.lazy, pbytes) : (g_mode == VPB_MODE_RESIDENT && mt->second.device_valid)))
+      keys = kt->second.keys;
+  }
   void *p = dev_in(sp->p, pbytes, cap);
   int32_t *part = (int32_t *)dev_out_only(sp->partition, ((size_t)g->nv + 1) * sizeof(int32_t));
   Mirror &m = g_mirrors[sp->p];
   // Deferred: only the order is computed here, the advance_p that follows moves the particles (see PendingSort).  Not
   // for arrays that are copied on every call (the host must get the sorted array back now).
   bool defer = defer_sort_enabled() && sp->np > 1 && !strict(m) && (m.lazy || g_mode == VPB_MODE_RESIDENT);
+  bool part_copied = false;
   size_t head_end = 0, tail_begin = pbytes;
   if (defer && m.lazy) {
     vpb_lazy::edges(m.lazy, &head_end, &tail_begin);
@@ -993,7 +1048,37 @@ void sort_p(vpb_species_t *sp) {
     if (ps.aux_cap < vpb_sort_index_work_bytes(sp->np)) defer = false;       // cannot happen for max_np >= np; be safe
     if (defer) {
       const size_t need = vpb_sort_index_scratch_bytes(sp->np, g->nv);
-      DEV(vpb_sort_p_index(p, nullptr, sp->np, ps.perm, part, g->nx, g->ny, g->nz, ps.aux, ps.aux_cap, scratch(2, need), need, nullptr));
+      // partition[] is final early in the sort; when it has to be copied to the host on every call (an array too small to
+      // be tracked), that copy runs on its own stream under the scatter passes
+      Mirror &mpart = g_mirrors[sp->partition];
+      const size_t part_bytes = ((size_t)g->nv + 1) * sizeof(int32_t);
+      const bool part_async = env_on("VPIC_B200_PART_ASYNC", g_env_part_async);
+      if (part_async && strict(mpart) && !mpart.lazy && !mpart.pinned && part_bytes >= (1u << 20)) {
+        // an asynchronous copy into pageable memory is staged by the driver a few KB at a time; page-lock the array once
+        mpart.pinned = cudaHostRegister(sp->partition, part_bytes, cudaHostRegisterDefault) == cudaSuccess;
+        mpart.pinned_bytes = mpart.pinned ? part_bytes : 0;
+        if (!mpart.pinned) cudaGetLastError();
+      }
+      const bool copy_part = part_async && strict(mpart) && !mpart.lazy && mpart.pinned && mpart.pinned_bytes >= part_bytes;
+      if (copy_part && !copy_stream) {
+        if (cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&part_ready, cudaEventDisableTiming) != cudaSuccess) DROPIN_ERROR("cannot create the copy stream");
+      }
+      if (keys && m.lazy) {                                       // the host may have edited particles at the unprotected ends
+        const size_t r0 = head_end < pbytes ? head_end : pbytes, r1 = tail_begin < pbytes ? tail_begin : pbytes;
+        DEV(vpb_extract_keys(p, (int32_t)(r0 / sizeof(vpb_particle_t)), const_cast<int32_t *>(keys), nullptr));
+        DEV(vpb_extract_keys((const char *)p + r1, (int32_t)((pbytes - r1) / sizeof(vpb_particle_t)),
+                             const_cast<int32_t *>(keys) + r1 / sizeof(vpb_particle_t), nullptr));
+      }
+      if (keys) g_sorts_with_keys++;
+      DEV(vpb_sort_p_index(p, keys, sp->np, ps.perm, part, g->nx, g->ny, g->nz, ps.aux, ps.aux_cap, scratch(2, need), need, nullptr,
+                           copy_part ? part_ready : nullptr));
+      if (copy_part) {
+        const size_t bytes = ((size_t)g->nv + 1) * sizeof(int32_t);
+        if (cudaStreamWaitEvent(copy_stream, part_ready, 0) != cudaSuccess) DROPIN_ERROR("CUDA event error");
+        DEV(vpb_memcpy_d2h(sp->partition, part, bytes, copy_stream)); g_d2h += bytes;
+        part_copied = true;
+      }
       ps.pending = true; ps.np = sp->np; g_npending++;
       if (m.lazy) {
         // the unprotected ends of the host array: sorted contents now (a host read there cannot fault)
@@ -1024,7 +1109,14 @@ void sort_p(vpb_species_t *sp) {
     si.np = sp->np; si.nv = g->nv;
   }
   if (!defer) dev_written(sp->p, pbytes);
-  dev_written(sp->partition, ((size_t)g->nv + 1) * sizeof(int32_t));
+  if (part_copied) {                                      // the copy above stands in for dev_written()'s
+    Mirror &mpart = g_mirrors[sp->partition];
+    mpart.device_valid = true; mpart.host_stale = false;
+    if (((size_t)g->nv + 1) * sizeof(int32_t) > mpart.live_bytes) mpart.live_bytes = ((size_t)g->nv + 1) * sizeof(int32_t);
+    if (cudaStreamSynchronize(copy_stream) != cudaSuccess) DROPIN_ERROR("copy of partition[] failed: %s", cudaGetErrorString(cudaGetLastError()));
+  } else {
+    dev_written(sp->partition, ((size_t)g->nv + 1) * sizeof(int32_t));
+  }
   finish_entry();
 }
 

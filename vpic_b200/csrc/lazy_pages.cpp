@@ -307,7 +307,7 @@ void device_wrote(Region *r, size_t bytes, uint64_t *d2h_bytes) {
   char *end = r->h + bytes;
   auto down = [&](char *a, char *b) {
     if (b <= a) return;
-    if (g_copy.d2h(a, r->d + (a - r->h), (size_t)(b - a))) fatal("vpic_b200: device-to-host copy failed");
+    if ((g_copy.d2h_async ? g_copy.d2h_async : g_copy.d2h)(a, r->d + (a - r->h), (size_t)(b - a))) fatal("vpic_b200: device-to-host copy failed");
     if (d2h_bytes) *d2h_bytes += (uint64_t)(b - a);
   };
   down(r->h, end < r->lo ? end : r->lo);
@@ -373,6 +373,18 @@ bool device_owns(Region *r, size_t off) {
   if (a < r->lo || a >= r->hi) return false;            // the edges are always host-owned
   Lock lk;
   return r->ndevice && r->state[chunk_of(r, a)] != HOST;
+}
+
+bool all_device(Region *r, size_t bytes) {
+  if (!r) return false;
+  if (bytes > r->cap) bytes = r->cap;
+  char *end = r->h + bytes;
+  if (end <= r->lo) return true;
+  Lock lk;
+  if (r->ndevice && !still_protected(r)) return false;
+  const size_t c1 = chunk_of(r, (end < r->hi ? end : r->hi) - 1) + 1;
+  for (size_t c = 0; c < c1; c++) if (r->state[c] != DEVICE) return false;
+  return true;
 }
 
 void set_device(Region *r, void *dev) {

@@ -43,6 +43,9 @@ struct Copier {
   // accessible after they hold the data, so a second host thread can never read a half-filled chunk.
   int (*d2h_protected)(void *host, const void *dev, size_t n);
   void *(*staging_alloc)(size_t n);                    // optional (page-locked) staging buffer; malloc when null
+  // Optional: like d2h but may return before the bytes have arrived; the caller of device_wrote() waits for the device's
+  // work queue once, after all the arrays of an entry point (used for the unprotected array ends only).
+  int (*d2h_async)(void *host, const void *dev, size_t n);
 };
 
 struct Region;
@@ -58,6 +61,7 @@ void to_host(Region *r, size_t off, size_t bytes, uint64_t *d2h_bytes);
 void forget_device(Region *r);                         // the host copy is declared current everywhere
 int host_access(const void *p, size_t n);              // [p,p+n) made host-owned in every attached region
 bool device_owns(Region *r, size_t off);               // is the byte at offset `off` currently owned by the device?
+bool all_device(Region *r, size_t bytes);               // every whole page inside [0,bytes) is device-owned (the host has not touched it)
 void set_device(Region *r, void *dev);                 // the device copy now lives at `dev` (same contents, same capacity)
 // the unprotected ends of the array: bytes [0, *head_end) and [*tail_begin, cap) are never device-owned
 void edges(Region *r, size_t *head_end, size_t *tail_begin);

@@ -451,7 +451,7 @@ static size_t index_sort_work_bytes(int n) { return (((size_t)n * 4 + 255) / 256
 
 template <int BITS>
 static int index_sort(const int4 *p, const int *keys_in, int n, int key_bits, int *perm, char *work, void *scratch,
-                      size_t scratch_bytes, cudaStream_t st, int *key_count, int n_keys) {
+                      size_t scratch_bytes, cudaStream_t st, int *key_count, int n_keys, cudaEvent_t partition_ready) {
   constexpr int R = 1 << BITS;
   const SortPlan pl = plan_sort(n, BITS, n_keys, kPairSubTile, true);
   VPB_REQUIRE(scratch && scratch_bytes >= pl.total_bytes, "sort: scratch too small (%zu < %zu)", scratch_bytes, pl.total_bytes);
@@ -463,6 +463,10 @@ static int index_sort(const int4 *p, const int *keys_in, int n, int key_bits, in
   void *pairs[2] = {work + kb_bytes, work + kb_bytes + pb_bytes};
   key_hist_kernel<BITS><<<pl.nblocks, kSortBlock, 0, st>>>(p, keys_in, keys, n, pl.per_block, hist[0], key_count, n_keys);
   VPB_LAUNCH_CHECK();
+  // partition[] = exclusive scan of the per-voxel counts: final here, before the scatter passes, so that a caller who has
+  // to hand it to the host can copy it while they run (partition_ready)
+  { int r = exclusive_scan_inplace(key_count, n_keys + 1, tmp, st); if (r) return r; }
+  if (partition_ready) VPB_CUDA(cudaEventRecord(partition_ready, st));
   const void *src = keys_in ? (const void *)keys_in : (const void *)keys;
   int cur = 0, pc = 0;
   for (int shift = 0; shift < key_bits; shift += BITS) {
@@ -488,6 +492,12 @@ __global__ void __launch_bounds__(256) unpermute_p_kernel(float4 *p, const int *
   float4 r, u;
   ld_particle(src + 2 * (size_t)k, r, u);
   st_particle(p + 2 * (size_t)__ldg(perm + k), r, u);
+}
+
+// keys[k] = p[k].i for a few particles (the ends of an array whose other keys a push left behind)
+__global__ void __launch_bounds__(256) extract_keys_kernel(const int4 *p, int *keys, int n) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) keys[k] = p[2 * (size_t)k].w;
 }
 
 // dst[k] = p[perm[k]]: one 32-byte sector gathered per particle, consecutive stores
@@ -567,30 +577,39 @@ extern "C" size_t vpb_sort_index_scratch_bytes(int32_t n_items, int32_t n_keys_h
 
 extern "C" int vpb_sort_p_index(const void *p, const int32_t *keys, int32_t np, int32_t *perm, int32_t *partition,
                                 int32_t nx, int32_t ny, int32_t nz, void *work, size_t work_bytes,
-                                void *scratch, size_t scratch_bytes, void *stream) {
+                                void *scratch, size_t scratch_bytes, void *stream, void *partition_ready_event) {
   VPB_REQUIRE((p || keys) && perm && partition && np >= 0 && nx > 0 && ny > 0 && nz > 0, "vpb_sort_p_index: Bad args");
   cudaStream_t st = as_stream(stream);
+  cudaEvent_t ev = reinterpret_cast<cudaEvent_t>(partition_ready_event);
   const int64_t nv64 = (int64_t)(nx + 2) * (ny + 2) * (nz + 2);
   VPB_REQUIRE(nv64 < (1ll << 31), "vpb_sort_p_index: too many voxels");
   const int nv = (int)nv64;
-  if (np == 0) { VPB_CUDA(cudaMemsetAsync(partition, 0, ((size_t)nv + 1) * sizeof(int), st)); return 0; }
+  if (np == 0) {
+    VPB_CUDA(cudaMemsetAsync(partition, 0, ((size_t)nv + 1) * sizeof(int), st));
+    if (ev) VPB_CUDA(cudaEventRecord(ev, st));
+    return 0;
+  }
   VPB_REQUIRE(work && work_bytes >= index_sort_work_bytes(np), "vpb_sort_p_index: work area too small (%zu < %zu)",
               work_bytes, index_sort_work_bytes(np));
   const int kb = ceil_log2(nv) > 0 ? ceil_log2(nv) : 1;
   const bool wide = (kb + 10) / 11 < (kb + 7) / 8;
   VPB_CUDA(cudaMemsetAsync(partition, 0, ((size_t)nv + 1) * sizeof(int), st));
-  int r = wide ? index_sort<11>((const int4 *)p, keys, np, kb, perm, (char *)work, scratch, scratch_bytes, st, partition, nv)
-               : index_sort<8>((const int4 *)p, keys, np, kb, perm, (char *)work, scratch, scratch_bytes, st, partition, nv);
-  if (r) return r;
-  const SortPlan pl = plan_sort(np, wide ? 11 : 8, nv, kPairSubTile, true);
-  int *tmp = (int *)((char *)scratch + 2 * (((pl.hist_bytes + 255) / 256) * 256));
-  return exclusive_scan_inplace(partition, nv + 1, tmp, st);
+  return wide ? index_sort<11>((const int4 *)p, keys, np, kb, perm, (char *)work, scratch, scratch_bytes, st, partition, nv, ev)
+              : index_sort<8>((const int4 *)p, keys, np, kb, perm, (char *)work, scratch, scratch_bytes, st, partition, nv, ev);
 }
 
 extern "C" int vpb_permute_p(const void *p, int32_t np, const int32_t *perm, void *dst, void *stream) {
   VPB_REQUIRE(np >= 0 && (np == 0 || (p && perm && dst && p != dst)), "vpb_permute_p: Bad args");
   if (np == 0) return 0;
   permute_p_kernel<<<(np + 255) / 256, 256, 0, as_stream(stream)>>>((const float4 *)p, perm, (float4 *)dst, np);
+  VPB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vpb_extract_keys(const void *p, int32_t n, int32_t *keys, void *stream) {
+  VPB_REQUIRE(n >= 0 && (n == 0 || (p && keys)), "vpb_extract_keys: Bad args");
+  if (n == 0) return 0;
+  extract_keys_kernel<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>((const int4 *)p, keys, n);
   VPB_LAUNCH_CHECK();
   return 0;
 }

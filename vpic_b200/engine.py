@@ -353,7 +353,7 @@ def sort_p(sp: Species, defer=False):
         keys = _ptr(sp._keys) if (sp._keys_valid and sp.nm == 0 and sp._keys_np == sp.np) else None
         sp._keys_valid = False
         _lib.check(L.vpb_sort_p_index(_ptr(sp._p), keys, sp.np, _ptr(sp._perm), _ptr(sp.partition), g.nx, g.ny, g.nz,
-                                      _ptr(sp._aux), work_bytes, _ptr(sp._scratch), sp._scratch.numel(), _stream()),
+                                      _ptr(sp._aux), work_bytes, _ptr(sp._scratch), sp._scratch.numel(), _stream(), None),
                    "sort_p")
         sp._perm_pending = True
     else:

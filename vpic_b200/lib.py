@@ -90,9 +90,10 @@ _PROTOS = {
     "vpb_sort_p": (C.c_int, [c_vp, c_i32, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, C.c_size_t, c_vp]),
     "vpb_sort_index_work_bytes": (C.c_size_t, [c_i32]),
     "vpb_sort_index_scratch_bytes": (C.c_size_t, [c_i32, c_i32]),
-    "vpb_sort_p_index": (C.c_int, [c_vp, c_vp, c_i32, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, C.c_size_t, c_vp, C.c_size_t, c_vp]),
+    "vpb_sort_p_index": (C.c_int, [c_vp, c_vp, c_i32, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, C.c_size_t, c_vp, C.c_size_t, c_vp, c_vp]),
     "vpb_permute_p": (C.c_int, [c_vp, c_i32, c_vp, c_vp, c_vp]),
     "vpb_unpermute_p": (C.c_int, [c_vp, c_i32, c_vp, c_vp, c_vp]),
+    "vpb_extract_keys": (C.c_int, [c_vp, c_i32, c_vp, c_vp]),
     "vpb_load_interpolator": (C.c_int, [c_vp, c_i32, c_vp, c_i32, c_i32, c_i32, c_vp]),
     "vpb_clear_accumulator": (C.c_int, [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "vpb_unload_accumulator": (C.c_int, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_f, c_f, c_f, c_f, c_vp]),
