@@ -8,8 +8,10 @@
 //   (2) exclusive scan of the [digit][CTA] matrix (digit-major),
 //   (3) stable scatter: inside a CTA, items are ranked warp by warp with __match_any_sync against per-warp digit
 //       counters in shared memory, so equal keys keep their input order.
-// Whole 32-byte particles (one DRAM sector each) move in every pass as two 128-bit halves; there is no separate
-// key/index array and no gather pass.  partition[] falls out of the sorted keys (lower bounds).
+// vpb_sort_p moves whole 32-byte particles (one DRAM sector each, 256-bit accesses) in every pass.  vpb_sort_p_index
+// (further down) sorts 8-byte (voxel, index) pairs with the same passes and leaves the particle movement to the
+// advance_p that follows (vpb_push_args_t.perm) — the default of both host layers.  partition[] is the exclusive scan of
+// the per-voxel counts the first histogram gathers on its way.
 #include "vpb_common.cuh"
 
 namespace vpb {
