@@ -51,6 +51,34 @@ def test_bad_args_are_rejected():
     assert L.vpb_vacuum_advance_e(C.byref(a), 1.0, None) != 0
 
 
+def test_index_sort_entry_points_reject_bad_args():
+    """The deferred-sort entry points (vpb_sort_p_index, vpb_permute_p, vpb_unpermute_p, vpb_extract_keys, and
+    vpb_advance_p with perm) validate their arguments before touching the device."""
+    L = lib.load()
+    assert L.vpb_sort_p_index(None, None, 5, None, None, 4, 4, 4, None, 0, None, 0, None, None) != 0
+    assert b"Bad args" in L.vpb_last_error()
+    assert L.vpb_permute_p(None, 5, None, None, None) != 0
+    assert L.vpb_unpermute_p(None, 5, None, None, None) != 0
+    assert L.vpb_extract_keys(None, 5, None, None) != 0
+    assert L.vpb_sort_index_work_bytes(1000) >= 1000 * 20 and L.vpb_sort_index_scratch_bytes(1000, 216) > 0
+    a = lib.PushArgs()
+    buf = (C.c_char * 4096)()
+    base = (C.addressof(buf) + 127) // 128 * 128
+    a.p = a.interp = a.accum = a.neighbor = a.counters = a.pm = base
+    a.np, a.max_nm, a.interp_stride, a.accum_stride, a.nx, a.ny, a.nz = 4, 4, 20, 12, 2, 2, 2
+    a.perm = base                                  # an order without somewhere else to put the particles
+    assert L.vpb_advance_p(C.byref(a), None) != 0 and b"p_out" in L.vpb_last_error()
+    a.p_out = base                                 # ... or onto themselves
+    assert L.vpb_advance_p(C.byref(a), None) != 0 and b"p_out" in L.vpb_last_error()
+
+
+def test_bench_sort_intervals():
+    import types, bench
+    assert bench.sort_intervals(types.SimpleNamespace(sort_interval="20")) == (20, 20)
+    assert bench.sort_intervals(types.SimpleNamespace(sort_interval="6,12")) == (6, 12)
+    assert bench.sort_intervals(types.SimpleNamespace(sort_interval=25)) == (25, 25)
+
+
 @pytest.mark.parametrize("dims", [(6, 5, 4), (8, 1, 8), (64, 64, 1)])
 def test_grid_matches_reference(ref_scalar, dims):
     nx, ny, nz = dims
@@ -122,10 +150,18 @@ def test_simulation_step_follows_advance_cc_order(monkeypatch):
             return call
 
     monkeypatch.setattr(E, "FieldArray", FakeFields)
+    kw = []                                              # (operator, species, keyword arguments) of the particle operators
+    def recorder(name):
+        def call(*a, **k):
+            log.append(name)
+            if name in ("sort_p", "advance_p"):
+                kw.append((name, a[0].name, {x: k[x] for x in ("defer", "emit_keys") if x in k}))
+        return call
     for fn in ("sort_p", "clear_accumulator_array", "advance_p", "reduce_accumulator_array", "unload_accumulator_array",
                "load_interpolator_array", "accumulate_rho_p", "finish_advance_p_all"):
-        monkeypatch.setattr(E, fn, (lambda name: (lambda *a, **k: log.append(name)))(fn))
+        monkeypatch.setattr(E, fn, recorder(fn))
     sim = S.Simulation(dg)
+    assert sim.defer_sort
     for name in ("e", "i"):
         sim.species_list.append(NS(name=name, sort_interval=2, nm=0, np=10))
     sim.clean_div_e_interval, sim.clean_div_b_interval, sim.sync_shared_interval = 2, 3, 4
@@ -152,3 +188,8 @@ def test_simulation_step_follows_advance_cc_order(monkeypatch):
     assert step() == ["sort_p", "sort_p"] + push + fields + div_e + ["load_interpolator_array"]
     assert step() == push + fields + div_b + ["load_interpolator_array"]
     assert sim.step == 4 and [w for _, w, _ in sim.cleaning_log][:3] == ["div_e initial", "div_e cleaned", "div_b initial"]
+    # sort_p only computes the order (the push that follows applies it), and the push of the step before a sort is asked
+    # to leave the voxel keys behind: sort_interval = 2, so the pushes of steps 1 and 3
+    assert all(k == {"defer": True} for n, _, k in kw if n == "sort_p")
+    pushes = [k["emit_keys"] for n, _, k in kw if n == "advance_p"]
+    assert pushes == [False, False, True, True, False, False, True, True]
