@@ -4,6 +4,7 @@
 // Built by `make -C vpic_b200/csrc lazy_test`, run by tests/test_host.py.  Exit code 0 = pass; otherwise the
 // failing line is printed.
 #include "lazy_pages.h"
+#include <vector>
 
 #include <pthread.h>
 #include <signal.h>
@@ -13,11 +14,18 @@
 #include <sys/mman.h>
 #include <time.h>
 #include <unistd.h>
-#include <vector>
 
 static uint64_t g_h2d_calls = 0, g_d2h_calls = 0;
-static int fake_h2d(void *d, const void *h, size_t n) { memcpy(d, h, n); g_h2d_calls++; return 0; }
-static int fake_d2h(void *h, const void *d, size_t n) { memcpy(h, d, n); g_d2h_calls++; return 0; }
+struct Pending { void *h; const void *d; size_t n; };
+static std::vector<Pending> g_pending_copies;
+// one in-order work queue, like a CUDA stream: a copy that is issued later executes after the queued copy-backs
+static void drain_queue() { for (const Pending &p : g_pending_copies) memcpy(p.h, p.d, p.n); g_pending_copies.clear(); }
+static int fake_h2d(void *d, const void *h, size_t n) { drain_queue(); memcpy(d, h, n); g_h2d_calls++; return 0; }
+static int fake_d2h(void *h, const void *d, size_t n) { drain_queue(); memcpy(h, d, n); g_d2h_calls++; return 0; }
+// asynchronous copy-back of the array ends (Copier::d2h_async): the bytes only arrive when the "work queue" drains, which
+// an entry point waits for once before it returns (finish_entry in dropin.cu) and then tells the tracker (after_sync)
+static int fake_d2h_async(void *h, const void *d, size_t n) { g_pending_copies.push_back({h, d, n}); g_d2h_calls++; return 0; }
+static void entry_end() { drain_queue(); vpb_lazy::after_sync(); }
 static void fake_fatal(const char *m) { fprintf(stderr, "FATAL: %s\n", m); _exit(3); }
 
 #define CHECK(c) do { if (!(c)) { fprintf(stderr, "lazy_pages_test: line %d: %s\n", __LINE__, #c); return __LINE__; } } while (0)
@@ -70,14 +78,63 @@ static int run() {
 
   // --- 2. steady state: nothing host-touched means nothing copied ---------------------------------------------
   h2d = d2h = 0;
-  vpb_lazy::to_device(r, a.cap, &h2d);                       // everything host-owned after the read: full upload
-  CHECK(h2d == a.cap);
+  vpb_lazy::to_device(r, a.cap, &h2d);                       // every whole page is host-owned after the read: they go up
+  CHECK(h2d == 38 * kPage);                                  // ... the two ends do not: the host only read them
   for (int step = 0; step < 5; step++) {
     h2d = d2h = 0;
     vpb_lazy::to_device(r, a.cap, &h2d);
     device_kernel(a, a.cap);
     vpb_lazy::device_wrote(r, a.cap, &d2h);
-    CHECK(h2d == (kPage - 128) + (kPage - 1000) && d2h == h2d);      // edges only
+    CHECK(h2d == 0 && d2h == (kPage - 128) + (kPage - 1000));       // the ends come back, nothing goes up
+  }
+  // --- 2b. the unprotected ends: an end goes up again exactly when the host changed it ----------------------------
+  {
+    Arr e = make(12, 128, 1000);
+    fill(e.h, e.cap, 9);
+    vpb_lazy::Region *re = vpb_lazy::attach(e.h, e.cap, e.d);
+    const size_t head = kPage - 128, tail = kPage - 1000;
+    h2d = d2h = 0;
+    vpb_lazy::to_device(re, e.cap, &h2d);
+    CHECK(h2d == e.cap);
+    device_kernel(e, e.cap);
+    vpb_lazy::device_wrote(re, e.cap, &d2h);
+    CHECK(d2h == head + tail);
+    e.h[5] = (char)(e.h[5] + 3);                             // host edit at the head (no fault: the page is not protected)
+    h2d = d2h = 0;
+    vpb_lazy::to_device(re, e.cap, &h2d);
+    CHECK(h2d == head && e.d[5] == e.h[5]);                  // the head went up, the tail did not
+    device_kernel(e, e.cap);
+    vpb_lazy::device_wrote(re, e.cap, &d2h);
+    CHECK(e.h[5] == e.d[5] && d2h == head + tail);
+    e.h[e.cap - 3] = 77;                                     // ... and at the tail
+    h2d = 0;
+    vpb_lazy::to_device(re, e.cap, &h2d);
+    CHECK(h2d == tail && e.d[e.cap - 3] == 77);
+    h2d = 0;
+    vpb_lazy::to_device(re, e.cap, &h2d);                    // a second entry point without a device write in between
+    CHECK(h2d == 0);
+    // a shorter extent compares (and uploads) only what it covers; the rest of the tail stays as the device has it
+    e.h[e.cap - 3] = 78;
+    h2d = 0;
+    vpb_lazy::to_device(re, e.cap - 500, &h2d);
+    CHECK(h2d == 0 && e.d[e.cap - 3] == 77);
+    vpb_lazy::to_device(re, e.cap, &h2d);
+    CHECK(h2d == tail && e.d[e.cap - 3] == 78);
+    // the device writes the ends, the host edits them afterwards: the edit wins at the next upload
+    device_kernel(e, e.cap);
+    vpb_lazy::device_wrote(re, e.cap, &d2h);
+    const char dev_val = e.h[7];
+    e.h[7] = (char)(dev_val + 5);
+    h2d = 0;
+    vpb_lazy::to_device(re, e.cap, &h2d);
+    CHECK(h2d == head && e.d[7] == (char)(dev_val + 5));
+    // forget_device: the host copy is declared current, so everything goes up again, the ends included
+    vpb_lazy::forget_device(re);
+    h2d = 0;
+    vpb_lazy::to_device(re, e.cap, &h2d);
+    CHECK(h2d == e.cap);
+    vpb_lazy::detach(re, true, &d2h);
+    munmap(e.map, 12 * kPage); free(e.d);
   }
   // --- 3. a sparse host write (inject_particle) moves one chunk, and the write survives the next device pass ---
   s0 = vpb_lazy::stats();
@@ -87,7 +144,7 @@ static int run() {
   CHECK(a.h[20 * kPage + 8] == (char)(((((20 * kPage + 8) * 31 + 1) & 0x7f) + 6) & 0xff));   // neighbours are current
   h2d = 0;
   vpb_lazy::to_device(r, a.cap, &h2d);
-  CHECK(h2d == kChunk + (kPage - 128) + (kPage - 1000));
+  CHECK(h2d == kChunk);
   device_kernel(a, a.cap);
   vpb_lazy::device_wrote(r, a.cap, &d2h);
   CHECK(a.h[20 * kPage + 7] == 100);
@@ -197,9 +254,9 @@ static int run() {
 static uint64_t rng_state = 1;
 static uint32_t rnd() { rng_state = rng_state * 6364136223846793005ull + 1442695040888963407ull; return (uint32_t)(rng_state >> 33); }
 
-static int stress(int iterations, uint64_t seed) {
+static int stress(int iterations, uint64_t seed, bool async_ends) {
   rng_state = seed * 2654435761u + 17;
-  vpb_lazy::Copier cp = {fake_h2d, fake_d2h, fake_fatal, nullptr, nullptr, nullptr};
+  vpb_lazy::Copier cp = {fake_h2d, fake_d2h, fake_fatal, nullptr, nullptr, async_ends ? fake_d2h_async : nullptr};
   vpb_lazy::init(cp, kChunk);
   const size_t pages = 64 + rnd() % 64;
   Arr a = make(pages, 128 * (1 + rnd() % 20), rnd() % 3000);
@@ -218,6 +275,15 @@ static int stress(int iterations, uint64_t seed) {
       CHECK(memcmp(a.d, truth.data(), ext) == 0);            // the device sees exactly what the program last had
       for (size_t i = 0; i < ext; i++) { a.d[i] = (char)(a.d[i] + 1); truth[i] = (char)(truth[i] + 1); }
       vpb_lazy::device_wrote(r, ext, &d2h);
+      if (async_ends && op % 2) {                             // an entry point that touches the array twice before it returns
+        const size_t ext2 = 1 + rnd() % a.cap;                // (no wait in between: the copy-backs of the ends are in flight)
+        vpb_lazy::to_device(r, ext2, &h2d);
+        drain_queue();
+        CHECK(memcmp(a.d, truth.data(), ext2) == 0);
+        for (size_t i = 0; i < ext2; i++) { a.d[i] = (char)(a.d[i] + 1); truth[i] = (char)(truth[i] + 1); }
+        vpb_lazy::device_wrote(r, ext2, &d2h);
+      }
+      entry_end();
     } else if (op < 40) {                                     // an entry point that only reads (e.g. interpolators in advance_p)
       const size_t ext = 1 + rnd() % a.cap;
       vpb_lazy::to_device(r, ext, &h2d);
@@ -247,7 +313,8 @@ static int stress(int iterations, uint64_t seed) {
   }
   vpb_lazy::detach(r, true, &d2h);
   CHECK(memcmp(a.h, truth.data(), a.cap) == 0);               // after detach the host holds everything
-  printf("lazy_pages_test: stress ok (%d operations, seed %llu, %llu faults, %.1f MB up, %.1f MB down)\n", iterations,
+  printf("lazy_pages_test: stress ok (%d operations%s, seed %llu, %llu faults, %.1f MB up, %.1f MB down)\n", iterations,
+         async_ends ? ", asynchronous array ends" : "",
          (unsigned long long)seed, (unsigned long long)vpb_lazy::stats().faults, h2d / 1e6, (d2h + vpb_lazy::stats().fault_bytes) / 1e6);
   return 0;
 }
@@ -278,7 +345,8 @@ static int bandwidth(size_t mb) {
 
 int main(int argc, char **argv) {
   if (argc > 2 && !strcmp(argv[1], "--bandwidth")) return bandwidth((size_t)atoi(argv[2]));
-  if (argc > 3 && !strcmp(argv[1], "--stress")) return stress(atoi(argv[2]), strtoull(argv[3], nullptr, 10)) ? 1 : 0;
+  if (argc > 3 && !strcmp(argv[1], "--stress")) return stress(atoi(argv[2]), strtoull(argv[3], nullptr, 10), false) ? 1 : 0;
+  if (argc > 3 && !strcmp(argv[1], "--stress-async")) return stress(atoi(argv[2]), strtoull(argv[3], nullptr, 10), true) ? 1 : 0;
   const int rc = run();
   if (rc) return 1;
   if (argc > 1 && !strcmp(argv[1], "--crash")) {             // a genuine wild access must still kill the process

@@ -125,6 +125,10 @@ def test_lazy_pages_state_machine():
     for seed in (11, 12, 13):
         r = subprocess.run([exe, "--stress", "4000", str(seed)], capture_output=True, text=True, timeout=300)
         assert r.returncode == 0 and "stress ok" in r.stdout, r.stdout + r.stderr
+    # the same with the array ends copied back asynchronously (one wait per entry point, then after_sync)
+    for seed in (21, 22, 23):
+        r = subprocess.run([exe, "--stress-async", "4000", str(seed)], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 and "stress ok" in r.stdout, r.stdout + r.stderr
 
 
 def test_simulation_step_follows_advance_cc_order(monkeypatch):

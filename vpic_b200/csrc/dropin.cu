@@ -240,7 +240,7 @@ void lazy_setup() {
 
 // copies every call (coherent mode, and the small arrays of auto mode)
 inline bool strict(const Mirror &m) { return g_mode == VPB_MODE_COHERENT || (g_mode == VPB_MODE_AUTO && !m.lazy); }
-void finish_entry() { if (g_copied_back) { DEV(vpb_stream_sync(nullptr)); g_copied_back = false; } }
+void finish_entry() { if (g_copied_back) { DEV(vpb_stream_sync(nullptr)); g_copied_back = false; vpb_lazy::after_sync(); } }
 
 void drop_mirror(Mirror &m, const void *h) {
   cancel_pending(h, true);

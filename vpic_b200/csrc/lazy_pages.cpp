@@ -31,6 +31,13 @@ struct Region {
   uint8_t *state = nullptr;
   size_t last_fault_end = (size_t)-1;    // chunk after the last window fetched by the fault handler
   size_t window = 1;
+  // The two unprotected ends are copied both ways on every call.  shadow holds what host and device agreed on at the last
+  // of those copies (head edge first, then the tail edge); the leading head_ok / tail_ok bytes of each are valid.  An
+  // end the host has not changed since (memcmp) is not uploaded again.
+  char *shadow = nullptr;
+  size_t head_ok = 0, tail_ok = 0;
+  bool refresh_head = false, refresh_tail = false;   // shadow to be re-read from the host once the queued copy-back is done
+  size_t refresh_head_len = 0, refresh_tail_len = 0;
 };
 
 namespace {
@@ -48,6 +55,9 @@ Stats g_stats = {0, 0, 0, 0};
 int g_mem_fd = -1;                       // /proc/self/mem: writes through it ignore page protection (FOLL_FORCE)
 char *g_staging = nullptr;
 constexpr size_t kStaging = 8u << 20;
+
+Region *g_refresh[kMaxRegions];          // regions whose shadow waits for an asynchronous copy-back (after_sync)
+int g_nrefresh = 0;
 
 long self_tid() { return (long)syscall(SYS_gettid); }
 
@@ -239,6 +249,7 @@ Region *attach(void *host, size_t cap, void *dev) {
   r->base = (char *)((uintptr_t)lo / g_chunk * g_chunk);
   r->nchunks = ((size_t)(hi - r->base) + g_chunk - 1) / g_chunk;
   r->state = (uint8_t *)calloc(r->nchunks, 1);
+  r->shadow = (char *)malloc((size_t)(lo - h) + (size_t)(h + cap - hi));
   Lock lk;
   int n = g_nregions.load();
   int slot = -1;
@@ -262,8 +273,40 @@ void detach(Region *r, bool sync_host, uint64_t *d2h_bytes) {
     for (int i = 0; i < n; i++) if (g_regions[i] == r) g_regions[i] = nullptr;
     g_stats.regions--;
   }
+  for (int i = 0; i < g_nrefresh; i++) if (g_refresh[i] == r) g_refresh[i] = nullptr;
+  free(r->shadow);
   free(r->state);
   delete r;
+}
+
+// shadow <- host for the ends the device just wrote (the host copy is complete when this runs, and the host program has
+// not run since: after_sync() is called before the entry point returns)
+static void finish_refresh(Region *r) {
+  if (r->refresh_head) { memcpy(r->shadow, r->h, r->refresh_head_len); r->head_ok = r->refresh_head_len; }
+  if (r->refresh_tail) { memcpy(r->shadow + (r->lo - r->h), r->hi, r->refresh_tail_len); r->tail_ok = r->refresh_tail_len; }
+  r->refresh_head = r->refresh_tail = false;
+  r->refresh_head_len = r->refresh_tail_len = 0;
+}
+// a refresh that never got its after_sync(): the host may have run since, so the shadow cannot be trusted
+static void drop_refresh(Region *r) {
+  if (r->refresh_head) r->head_ok = 0;
+  if (r->refresh_tail) r->tail_ok = 0;
+  r->refresh_head = r->refresh_tail = false;
+  r->refresh_head_len = r->refresh_tail_len = 0;
+}
+static void note_refresh(Region *r, bool head, size_t len) {
+  if (head) { r->refresh_head = true; if (len > r->refresh_head_len) r->refresh_head_len = len; r->head_ok = 0; }
+  else { r->refresh_tail = true; if (len > r->refresh_tail_len) r->refresh_tail_len = len; r->tail_ok = 0; }
+  if (!g_copy.d2h_async) { finish_refresh(r); return; }
+  for (int i = 0; i < g_nrefresh; i++) if (g_refresh[i] == r) return;
+  if (g_nrefresh < kMaxRegions) g_refresh[g_nrefresh++] = r; else drop_refresh(r);
+}
+
+void after_sync() {
+  if (!g_nrefresh) return;
+  Lock lk;
+  for (int i = 0; i < g_nrefresh; i++) if (g_refresh[i]) finish_refresh(g_refresh[i]);
+  g_nrefresh = 0;
 }
 
 void to_device(Region *r, size_t bytes, uint64_t *h2d_bytes) {
@@ -275,6 +318,7 @@ void to_device(Region *r, size_t bytes, uint64_t *h2d_bytes) {
     // remapped under us: every chunk is host-owned again, nothing to copy back
     mprotect(r->lo, (size_t)(r->hi - r->lo), PROT_READ | PROT_WRITE);
     memset(r->state, HOST, r->nchunks); r->ndevice = 0; g_stats.remaps++;
+    r->head_ok = r->tail_ok = 0;
   }
   char *end = r->h + bytes;
   auto up = [&](char *a, char *b) {
@@ -282,7 +326,20 @@ void to_device(Region *r, size_t bytes, uint64_t *h2d_bytes) {
     if (g_copy.h2d(r->d + (a - r->h), a, (size_t)(b - a))) fatal("vpic_b200: host-to-device copy failed");
     if (h2d_bytes) *h2d_bytes += (uint64_t)(b - a);
   };
-  up(r->h, end < r->lo ? end : r->lo);                                 // head edge
+  // an unprotected end goes up only if the host changed it since host and device last agreed on it
+  // (An end whose copy-back is still in flight — the array is touched twice inside one entry point — is uploaded
+  // unconditionally: the copy engine reads the host bytes after that copy-back has landed, the CPU cannot compare yet.)
+  const bool in_flight = r->refresh_head || r->refresh_tail;
+  auto up_edge = [&](char *a, char *b, char *sh, size_t &ok) {
+    if (b <= a) return;
+    const size_t len = (size_t)(b - a);
+    if (in_flight || !r->shadow) { up(a, b); ok = 0; return; }
+    if (len <= ok && memcmp(a, sh, len) == 0) return;
+    up(a, b);
+    memcpy(sh, a, len); if (len > ok) ok = len;
+  };
+  drop_refresh(r);
+  up_edge(r->h, end < r->lo ? end : r->lo, r->shadow, r->head_ok);     // head edge
   if (end > r->lo) {
     const size_t c1 = chunk_of(r, (end < r->hi ? end : r->hi) - 1) + 1;
     size_t c = 0;
@@ -297,7 +354,7 @@ void to_device(Region *r, size_t bytes, uint64_t *h2d_bytes) {
       c = e;
     }
   }
-  if (end > r->hi) up(r->hi, end);                                     // tail edge
+  if (end > r->hi) up_edge(r->hi, end, r->shadow ? r->shadow + (r->lo - r->h) : nullptr, r->tail_ok);   // tail edge
 }
 
 void device_wrote(Region *r, size_t bytes, uint64_t *d2h_bytes) {
@@ -310,7 +367,13 @@ void device_wrote(Region *r, size_t bytes, uint64_t *d2h_bytes) {
     if ((g_copy.d2h_async ? g_copy.d2h_async : g_copy.d2h)(a, r->d + (a - r->h), (size_t)(b - a))) fatal("vpic_b200: device-to-host copy failed");
     if (d2h_bytes) *d2h_bytes += (uint64_t)(b - a);
   };
-  down(r->h, end < r->lo ? end : r->lo);
+  // the copies below may be asynchronous (d2h_async): the shadow is re-read from the host in after_sync(), which the
+  // caller runs once the device's work queue has drained, or right here when the copy is synchronous
+  {
+    char *b = end < r->lo ? end : r->lo;
+    down(r->h, b);
+    if (r->shadow && b > r->h) note_refresh(r, true, (size_t)(b - r->h));
+  }
   if (end > r->lo) {
     // every chunk the device wrote must be device-owned (to_device ran first); one that a racing host thread took
     // back in between is handed to the device again — the host copy there is older than what was just written
@@ -318,7 +381,10 @@ void device_wrote(Region *r, size_t bytes, uint64_t *d2h_bytes) {
     for (size_t c = 0; c < c1; c++)
       if (r->state[c] == HOST) { protect(r, c, c + 1, PROT_NONE); r->state[c] = DEVICE; r->ndevice++; }
   }
-  if (end > r->hi) down(r->hi, end);
+  if (end > r->hi) {
+    down(r->hi, end);
+    if (r->shadow) note_refresh(r, false, (size_t)(end - r->hi));
+  }
 }
 
 void to_host(Region *r, size_t off, size_t bytes, uint64_t *d2h_bytes) {
@@ -335,6 +401,7 @@ void to_host(Region *r, size_t off, size_t bytes, uint64_t *d2h_bytes) {
 
 void forget_device(Region *r) {
   Lock lk;
+  r->head_ok = r->tail_ok = 0; r->refresh_head = r->refresh_tail = false;
   if (!r->ndevice) return;
   mprotect(r->lo, (size_t)(r->hi - r->lo), PROT_READ | PROT_WRITE);
   memset(r->state, HOST, r->nchunks); r->ndevice = 0;

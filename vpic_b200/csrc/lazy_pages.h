@@ -13,7 +13,8 @@
 //   * the first host access to a device-owned chunk faults; the SIGSEGV handler copies the chunk back, unprotects
 //     it, and the faulting instruction is retried.  Sequential scans grow the window that is fetched per fault;
 //   * the partial pages at both ends of the array are shared with foreign heap data and are never protected: those
-//     bytes ("edges", < 8 KB per array) are copied both ways on every call, as in coherent mode;
+//     bytes ("edges", < 8 KB per array) come back to the host after every call that wrote the array, and go up again
+//     whenever the host changed them — the tracker keeps a copy of what host and device last agreed on and compares;
 //   * kernel-side accesses do not fault (write(2) on PROT_NONE memory fails with EFAULT), so the library interposes
 //     fwrite/fread, the only I/O calls the reference makes on these arrays, and exports vpic_b200_host_access()
 //     for anything else (MPI on device-owned memory).
@@ -59,6 +60,7 @@ void to_device(Region *r, size_t bytes, uint64_t *h2d_bytes);     // device copy
 void device_wrote(Region *r, size_t bytes, uint64_t *d2h_bytes);  // edge bytes inside [0,bytes) copied back
 void to_host(Region *r, size_t off, size_t bytes, uint64_t *d2h_bytes);
 void forget_device(Region *r);                         // the host copy is declared current everywhere
+void after_sync();                                     // the copy-backs queued by device_wrote() (d2h_async) have completed
 int host_access(const void *p, size_t n);              // [p,p+n) made host-owned in every attached region
 bool device_owns(Region *r, size_t off);               // is the byte at offset `off` currently owned by the device?
 bool all_device(Region *r, size_t bytes);               // every whole page inside [0,bytes) is device-owned (the host has not touched it)
